@@ -1,0 +1,323 @@
+"""ctypes binding of the C oracle (oracle/libbsx_oracle.so).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libbsx_oracle.so")
+
+SUBCHAIN_BYTES = 128
+SIG_OUT_BYTES = 576
+VAL_IN_BYTES = 240
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_max_threads.restype = C.c_int
+        for f in ("orc_sha256_pad_fixed", "orc_sha256_pad_variable", "orc_sha512_pad_variable", "orc_marshal_int64_varint",
+                  "orc_marshal_validator", "orc_verify_header", "orc_verify_skip", "orc_next_header",
+                  "orc_sha256_hash_input_data", "orc_gate_num_constraints", "orc_gate_num_wires"):
+            if hasattr(_lib, f):
+                getattr(_lib, f).restype = C.c_uint32
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u8(b) -> np.ndarray:
+    if isinstance(b, np.ndarray):
+        return np.ascontiguousarray(b, dtype=np.uint8)
+    return np.frombuffer(bytes(b), dtype=np.uint8).copy() if len(b) else np.zeros(0, np.uint8)
+
+
+def sha256(msg: bytes) -> bytes:
+    m = _u8(msg)
+    out = np.zeros(32, np.uint8)
+    lib().orc_sha256(_p(m), C.c_size_t(len(m)), _p(out))
+    return out.tobytes()
+
+
+def sha512(msg: bytes) -> bytes:
+    m = _u8(msg)
+    out = np.zeros(64, np.uint8)
+    lib().orc_sha512(_p(m), C.c_size_t(len(m)), _p(out))
+    return out.tobytes()
+
+
+def sha256_batch(msgs: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    n = len(offsets) - 1
+    out = np.zeros((n, 32), np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint32)
+    lib().orc_sha256_batch(_p(_u8(msgs)), _p(offsets), C.c_uint32(n), _p(out))
+    return out
+
+
+def sha512_batch(msgs: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    n = len(offsets) - 1
+    out = np.zeros((n, 64), np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint32)
+    lib().orc_sha512_batch(_p(_u8(msgs)), _p(offsets), C.c_uint32(n), _p(out))
+    return out
+
+
+def sha256_pad_variable(buf: bytes, length: int):
+    b = _u8(buf)
+    out = np.zeros(len(b) + 192, np.uint8)
+    lc = C.c_uint32(0)
+    n = lib().orc_sha256_pad_variable(_p(b), C.c_uint32(len(b)), C.c_uint32(length), _p(out), C.byref(lc))
+    return out[: 64 * n].tobytes(), lc.value
+
+
+def tm_root_from_slices(items) -> bytes:
+    flat = _u8(b"".join(items))
+    offs = np.zeros(len(items) + 1, np.uint32)
+    offs[1:] = np.cumsum([len(i) for i in items])
+    out = np.zeros(32, np.uint8)
+    lib().orc_tm_root_from_slices(_p(flat), _p(offs), C.c_uint32(len(items)), _p(out))
+    return out.tobytes()
+
+
+def tm_merkle_proof(leaf: bytes, aunts: bytes, depth: int, path_bits: int, hashed_leaf: bool = False):
+    l, a = _u8(leaf), _u8(aunts)
+    nd = 2 * depth + (0 if hashed_leaf else 1)
+    dig = np.zeros((nd, 32), np.uint8)
+    root = np.zeros(32, np.uint8)
+    lib().orc_tm_merkle_proof(_p(l), C.c_uint32(len(l)), _p(a), C.c_uint32(depth), C.c_uint32(path_bits),
+                              C.c_int(int(hashed_leaf)), _p(dig), _p(root))
+    return dig, root.tobytes()
+
+
+def tm_merkle_tree(leaf_digests: np.ndarray, nb_enabled: int):
+    ld = _u8(leaf_digests).reshape(-1, 32)
+    n = ld.shape[0]
+    P = 1
+    while P < n:
+        P *= 2
+    inner = np.zeros((P - 1, 32), np.uint8)
+    root = np.zeros(32, np.uint8)
+    lib().orc_tm_merkle_tree(_p(ld), C.c_uint32(n), C.c_uint64(nb_enabled), _p(inner), _p(root))
+    return inner, root.tobytes()
+
+
+def get_data_commitment(data_hashes: np.ndarray, start: int, end: int):
+    dh = _u8(data_hashes).reshape(-1, 32)
+    B = dh.shape[0]
+    P = 1
+    while P < B:
+        P *= 2
+    dig = np.zeros((B + P - 1, 32), np.uint8)
+    root = np.zeros(32, np.uint8)
+    fail = C.c_uint32(0)
+    lib().orc_get_data_commitment(_p(dh), C.c_uint32(B), C.c_uint64(start), C.c_uint64(end), _p(dig), _p(root), C.byref(fail))
+    return dig, root.tobytes(), fail.value
+
+
+def prove_subchain(B, dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_header, end_header, batch_start, batch_end,
+                   global_end, global_end_header):
+    dig = np.zeros((20 * B - 1, 32), np.uint8)
+    sub = np.zeros(SUBCHAIN_BYTES, np.uint8)
+    lib().orc_prove_subchain(C.c_uint32(B), _p(_u8(dh_leaf)), _p(_u8(dh_aunts)), _p(_u8(lb_leaf)), _p(_u8(lb_aunts)),
+                             _p(_u8(start_header)), _p(_u8(end_header)), C.c_uint64(batch_start), C.c_uint64(batch_end),
+                             C.c_uint64(global_end), _p(_u8(global_end_header)), _p(dig), _p(sub))
+    return dig, sub
+
+
+def prove_data_commitment(n_jobs, B, dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, start_block,
+                          start_header, end_block, end_header, threads=1):
+    map_dig = np.zeros((n_jobs, 20 * B - 1, 32), np.uint8)
+    map_sub = np.zeros((n_jobs, SUBCHAIN_BYTES), np.uint8)
+    red_dig = np.zeros((n_jobs - 1, 32), np.uint8)
+    red_nodes = np.zeros((n_jobs - 1, SUBCHAIN_BYTES), np.uint8)
+    dc = np.zeros(32, np.uint8)
+    fail = C.c_uint32(0)
+    lib().orc_prove_data_commitment(
+        C.c_uint32(n_jobs), C.c_uint32(B), _p(_u8(dh_leaf)), _p(_u8(dh_aunts)), _p(_u8(lb_leaf)), _p(_u8(lb_aunts)),
+        _p(_u8(start_headers)), _p(_u8(end_headers)), C.c_uint64(start_block), _p(_u8(start_header)),
+        C.c_uint64(end_block), _p(_u8(end_header)), _p(map_dig), _p(map_sub), _p(red_dig), _p(red_nodes), _p(dc),
+        C.byref(fail), C.c_int(threads))
+    return dict(map_digests=map_dig, map_subchains=map_sub, reduce_digests=red_dig, reduce_nodes=red_nodes,
+                data_commitment=dc.tobytes(), fail=fail.value)
+
+
+def marshal_int64_varint(v: int):
+    out = np.zeros(9, np.uint8)
+    n = lib().orc_marshal_int64_varint(C.c_uint64(v), _p(out))
+    return out.tobytes(), n
+
+
+def marshal_validator(pubkey: bytes, power: int):
+    out = np.zeros(46, np.uint8)
+    n = lib().orc_marshal_validator(_p(_u8(pubkey)), C.c_uint64(power), _p(out))
+    return out.tobytes(), n
+
+
+def hash_validator_set(pubkeys: np.ndarray, powers: np.ndarray, byte_lengths: np.ndarray, nb_enabled: int):
+    pk = _u8(pubkeys).reshape(-1, 32)
+    n = pk.shape[0]
+    P = 1
+    while P < n:
+        P *= 2
+    dig = np.zeros((n + P - 1, 32), np.uint8)
+    root = np.zeros(32, np.uint8)
+    lib().orc_hash_validator_set(C.c_uint32(n), _p(pk), _p(np.ascontiguousarray(powers, np.uint64)),
+                                 _p(np.ascontiguousarray(byte_lengths, np.uint32)), C.c_uint64(nb_enabled), _p(dig), _p(root))
+    return dig, root.tobytes()
+
+
+def ed25519_witness(pk: bytes, sig: bytes, msg: bytes) -> bytes:
+    out = np.zeros(SIG_OUT_BYTES, np.uint8)
+    m = _u8(msg)
+    lib().orc_ed25519_witness(_p(_u8(pk)), _p(_u8(sig)), _p(m), C.c_uint32(len(m)), _p(out))
+    return out.tobytes()
+
+
+def ed25519_batch(pks, sigs, msgs, msg_lens, active=None, threads=1) -> np.ndarray:
+    pks = _u8(pks).reshape(-1, 32)
+    n = pks.shape[0]
+    out = np.zeros((n, SIG_OUT_BYTES), np.uint8)
+    act = None if active is None else _u8(active)
+    lib().orc_ed25519_batch(C.c_uint32(n), _p(pks), _p(_u8(sigs)), _p(_u8(msgs)), _p(np.ascontiguousarray(msg_lens, np.uint32)),
+                            _p(act), _p(out), C.c_int(threads))
+    return out
+
+
+def ed25519_decompress(b: bytes):
+    xy = np.zeros(64, np.uint8)
+    root = np.zeros(32, np.uint8)
+    lib().orc_ed25519_decompress.restype = C.c_int
+    ok = lib().orc_ed25519_decompress(_p(_u8(b)), _p(xy), _p(root))
+    return xy.tobytes(), root.tobytes(), bool(ok)
+
+
+def ed25519_scalar_mul(scalar: bytes, xy: bytes, affine: bool = False) -> bytes:
+    out = np.zeros(64, np.uint8)
+    f = lib().orc_ed25519_affine_double_and_add if affine else lib().orc_ed25519_scalar_mul
+    f(_p(_u8(scalar)), _p(_u8(xy)), _p(out))
+    return out.tobytes()
+
+
+def ed25519_add(a: bytes, b: bytes) -> bytes:
+    out = np.zeros(64, np.uint8)
+    lib().orc_ed25519_add(_p(_u8(a)), _p(_u8(b)), _p(out))
+    return out.tobytes()
+
+
+class _VerifyHeaderIn(C.Structure):
+    _fields_ = [("n_validators", C.c_uint32), ("validators", C.c_void_p), ("nb_enabled", C.c_uint64),
+                ("header", C.c_void_p), ("height", C.c_uint64), ("round", C.c_uint64), ("chain_id_enc", C.c_void_p),
+                ("chain_id_enc_len", C.c_uint32), ("chain_id_aunts", C.c_void_p), ("height_aunts", C.c_void_p),
+                ("height_enc_len", C.c_uint32), ("validators_hash_proof", C.c_void_p), ("expected_chain_id", C.c_void_p),
+                ("expected_chain_id_len", C.c_uint32)]
+
+
+class _VerifySkipIn(C.Structure):
+    _fields_ = [("target", _VerifyHeaderIn), ("trusted_block", C.c_uint64), ("trusted_header", C.c_void_p),
+                ("skip_max", C.c_uint32), ("trusted_validators_hash_proof", C.c_void_p), ("trusted_pubkeys", C.c_void_p),
+                ("trusted_powers", C.c_void_p), ("trusted_byte_lengths", C.c_void_p), ("trusted_nb_enabled", C.c_uint64)]
+
+
+class _VerifyStepIn(C.Structure):
+    _fields_ = [("next", _VerifyHeaderIn), ("prev_block", C.c_uint64), ("prev_header", C.c_void_p),
+                ("last_block_id_proof", C.c_void_p), ("prev_next_validators_proof", C.c_void_p),
+                ("data_hash_proof", C.c_void_p)]
+
+
+def _hdr_struct(h: dict, keep: list) -> _VerifyHeaderIn:
+    """h: dict of numpy arrays / ints as produced by the input shapers (see tests/helpers.py)."""
+    s = _VerifyHeaderIn()
+    arr = lambda k: keep.append(_u8(h[k])) or keep[-1]
+    s.n_validators = h["n_validators"]
+    s.validators = _p(arr("validators")).value
+    s.nb_enabled = h["nb_enabled"]
+    s.header = _p(arr("header")).value
+    s.height = h["height"]
+    s.round = h["round"]
+    s.chain_id_enc = _p(arr("chain_id_enc")).value
+    s.chain_id_enc_len = h["chain_id_enc_len"]
+    s.chain_id_aunts = _p(arr("chain_id_aunts")).value
+    s.height_aunts = _p(arr("height_aunts")).value
+    s.height_enc_len = h["height_enc_len"]
+    s.validators_hash_proof = _p(arr("validators_hash_proof")).value
+    s.expected_chain_id = _p(arr("expected_chain_id")).value
+    s.expected_chain_id_len = len(h["expected_chain_id"])
+    return s
+
+
+def _n_header_digests(n):
+    P = 1
+    while P < n:
+        P *= 2
+    return n + P - 1 + 9 + 9 + 9
+
+
+def verify_header(h: dict, threads=1):
+    keep = []
+    s = _hdr_struct(h, keep)
+    n = h["n_validators"]
+    dig = np.zeros((_n_header_digests(n), 32), np.uint8)
+    ed = np.zeros((n, SIG_OUT_BYTES), np.uint8)
+    fail = lib().orc_verify_header(C.byref(s), _p(dig), _p(ed), C.c_int(threads))
+    return dict(sha256_digests=dig, ed=ed, fail=fail)
+
+
+def verify_skip(k: dict, threads=1):
+    keep = []
+    s = _VerifySkipIn()
+    s.target = _hdr_struct(k["target"], keep)
+    n = k["target"]["n_validators"]
+    arr = lambda a, dt=np.uint8: keep.append(np.ascontiguousarray(a, dtype=dt)) or keep[-1]
+    s.trusted_block = k["trusted_block"]
+    s.trusted_header = _p(arr(k["trusted_header"])).value
+    s.skip_max = k["skip_max"]
+    s.trusted_validators_hash_proof = _p(arr(k["trusted_validators_hash_proof"])).value
+    s.trusted_pubkeys = _p(arr(k["trusted_pubkeys"])).value
+    s.trusted_powers = _p(arr(k["trusted_powers"], np.uint64)).value
+    s.trusted_byte_lengths = _p(arr(k["trusted_byte_lengths"], np.uint32)).value
+    s.trusted_nb_enabled = k["trusted_nb_enabled"]
+    P = 1
+    while P < n:
+        P *= 2
+    dig = np.zeros((9 + n + P - 1 + _n_header_digests(n), 32), np.uint8)
+    ed = np.zeros((n, SIG_OUT_BYTES), np.uint8)
+    fail = lib().orc_verify_skip(C.byref(s), _p(dig), _p(ed), C.c_int(threads))
+    return dict(sha256_digests=dig, ed=ed, fail=fail)
+
+
+def next_header(k: dict, threads=1):
+    keep = []
+    s = _VerifyStepIn()
+    s.next = _hdr_struct(k["next"], keep)
+    n = k["next"]["n_validators"]
+    arr = lambda a: keep.append(_u8(a)) or keep[-1]
+    s.prev_block = k["prev_block"]
+    s.prev_header = _p(arr(k["prev_header"])).value
+    s.last_block_id_proof = _p(arr(k["last_block_id_proof"])).value
+    s.prev_next_validators_proof = _p(arr(k["prev_next_validators_proof"])).value
+    s.data_hash_proof = _p(arr(k["data_hash_proof"])).value
+    dig = np.zeros((_n_header_digests(n) + 28, 32), np.uint8)
+    ed = np.zeros((n, SIG_OUT_BYTES), np.uint8)
+    dc = np.zeros(32, np.uint8)
+    fail = lib().orc_next_header(C.byref(s), _p(dig), _p(ed), _p(dc), C.c_int(threads))
+    return dict(sha256_digests=dig, ed=ed, data_commitment=dc.tobytes(), fail=fail)
+
+
+def max_threads() -> int:
+    return lib().orc_max_threads()

@@ -1,0 +1,290 @@
+/*
+ * oracle/tendermint.c -- Tendermint (RFC-6962 style) Merkle hashing, both the off-circuit
+ * variable-shape tree (TX/input/tendermint_utils.rs:276-372) and the fixed-shape in-circuit
+ * evaluation (PX/frontend/merkle/tendermint.rs:62-214), plus the Blobstream data-commitment
+ * gadgets (BX/circuits/builder.rs:82-444).  TEST INFRASTRUCTURE ONLY (see bsx_oracle.h).
+ */
+#include "bsx_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* PX/frontend/merkle/tendermint.rs:95-106 ; TX/input/tendermint_utils.rs:358-364 */
+void orc_leaf_hash(const uint8_t *leaf, size_t len, uint8_t out[32]) {
+    uint8_t buf[256];
+    uint8_t *p = len + 1 <= sizeof buf ? buf : (uint8_t *)malloc(len + 1);
+    p[0] = 0x00;
+    if (len) memcpy(p + 1, leaf, len);
+    orc_sha256(p, len + 1, out);
+    if (p != buf) free(p);
+}
+
+/* PX/frontend/merkle/tendermint.rs:108-122 ; TX/input/tendermint_utils.rs:366-372 */
+void orc_inner_hash(const uint8_t l[32], const uint8_t r[32], uint8_t out[32]) {
+    uint8_t buf[65];
+    buf[0] = 0x01;
+    memcpy(buf + 1, l, 32);
+    memcpy(buf + 33, r, 32);
+    orc_sha256(buf, 65, out);
+}
+
+/* TX/input/tendermint_utils.rs:338-349 */
+static uint32_t split_point(uint32_t n) {
+    uint32_t k = 1;
+    while (k * 2 <= n) k *= 2; /* largest power of two <= n */
+    return (k == n) ? k >> 1 : k;
+}
+
+static void root_rec(const uint8_t *items, const uint32_t *off, uint32_t lo, uint32_t hi, uint8_t out[32]) {
+    uint32_t n = hi - lo;
+    if (n == 0) { orc_sha256((const uint8_t *)"", 0, out); return; }
+    if (n == 1) { orc_leaf_hash(items + off[lo], off[lo + 1] - off[lo], out); return; }
+    uint32_t k = split_point(n);
+    uint8_t l[32], r[32];
+    root_rec(items, off, lo, lo + k, l);
+    root_rec(items, off, lo + k, hi, r);
+    orc_inner_hash(l, r, out);
+}
+
+void orc_tm_root_from_slices(const uint8_t *items, const uint32_t *offsets, uint32_t n, uint8_t out[32]) {
+    root_rec(items, offsets, 0, n, out);
+}
+
+/* PX/frontend/merkle/tendermint.rs:62-93: leaf hash, then per level BOTH inner(h,aunt) and
+ * inner(aunt,h) are requested (left form first) and the path bit selects. */
+void orc_tm_merkle_proof(const uint8_t *leaf, uint32_t leaf_len, const uint8_t *aunts, uint32_t depth,
+                         uint32_t path_bits, int hashed_leaf, uint8_t *digests, uint8_t root[32]) {
+    uint8_t h[32];
+    uint8_t *d = digests;
+    if (hashed_leaf) {
+        memcpy(h, leaf, 32);
+    } else {
+        orc_leaf_hash(leaf, leaf_len, h);
+        memcpy(d, h, 32);
+        d += 32;
+    }
+    for (uint32_t i = 0; i < depth; i++) {
+        const uint8_t *aunt = aunts + 32 * i;
+        orc_inner_hash(h, aunt, d);      /* left_hash_pair  */
+        orc_inner_hash(aunt, h, d + 32); /* right_hash_pair */
+        memcpy(h, ((path_bits >> i) & 1) ? d + 32 : d, 32);
+        d += 64;
+    }
+    memcpy(root, h, 32);
+}
+
+/* PX/frontend/merkle/tendermint.rs:124-153,165-204 */
+void orc_tm_merkle_tree(const uint8_t *leaf_digests, uint32_t N, uint64_t nb_enabled, uint8_t *inner,
+                        uint8_t root[32]) {
+    uint32_t P = 1;
+    while (P < N) P *= 2;
+    uint8_t *nodes = (uint8_t *)calloc(P, 32);
+    uint8_t *en = (uint8_t *)malloc(P);
+    memcpy(nodes, leaf_digests, (size_t)N * 32);
+    int is_enabled = 1;
+    for (uint32_t i = 0; i < P; i++) { /* :184-194 running AND of (i != nb_enabled) */
+        if ((uint64_t)i == nb_enabled) is_enabled = 0;
+        en[i] = (uint8_t)is_enabled;
+    }
+    uint8_t *w = inner;
+    for (uint32_t len = P; len > 1; len /= 2) {
+        for (uint32_t i = 0; i < len; i += 2) {
+            uint8_t ih[32];
+            orc_inner_hash(nodes + 32 * (size_t)i, nodes + 32 * (size_t)(i + 1), ih);
+            if (w) { memcpy(w, ih, 32); w += 32; }
+            int both = en[i] && en[i + 1];
+            int none = !en[i] && !en[i + 1];
+            /* select(both_enabled, inner, left) ; enabled' = !both_disabled */
+            if (both) memcpy(nodes + 32 * (size_t)(i / 2), ih, 32);
+            else memmove(nodes + 32 * (size_t)(i / 2), nodes + 32 * (size_t)i, 32);
+            en[i / 2] = (uint8_t)!none;
+        }
+    }
+    memcpy(root, nodes, 32);
+    free(nodes);
+    free(en);
+}
+
+/* BX/circuits/builder.rs:82-103 : 24 zero bytes ‖ u64 BE height ‖ data_hash */
+void orc_encode_data_root_tuple(const uint8_t data_hash[32], uint64_t height, uint8_t out[64]) {
+    memset(out, 0, 24);
+    for (int i = 0; i < 8; i++) out[24 + i] = (uint8_t)(height >> (56 - 8 * i));
+    memcpy(out + 32, data_hash, 32);
+}
+
+/* BX/circuits/builder.rs:105-148 */
+void orc_get_data_commitment(const uint8_t *data_hashes, uint32_t B, uint64_t start, uint64_t end,
+                             uint8_t *digests, uint8_t root[32], uint32_t *fail) {
+    if (end < start && fail) *fail |= ORC_FAIL_END_LT_START;
+    uint64_t nb = end - start; /* wrapping, like the u64 gadget */
+    if ((nb >> 32) && fail) *fail |= ORC_FAIL_END_LT_START;
+    uint64_t nb_enabled = nb & 0xffffffffu; /* limbs[0] */
+    for (uint32_t i = 0; i < B; i++) {
+        uint8_t tup[64];
+        orc_encode_data_root_tuple(data_hashes + 32 * (size_t)i, start + i, tup);
+        orc_leaf_hash(tup, 64, digests + 32 * (size_t)i);
+    }
+    orc_tm_merkle_tree(digests, B, nb_enabled, digests + 32 * (size_t)B, root);
+}
+
+static void put64(uint8_t *p, uint64_t v) { for (int i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (8 * i)); }
+static uint64_t get64(const uint8_t *p) { uint64_t v = 0; for (int i = 7; i >= 0; i--) v = (v << 8) | p[i]; return v; }
+static void put32(uint8_t *p, uint32_t v) { for (int i = 0; i < 4; i++) p[i] = (uint8_t)(v >> (8 * i)); }
+static uint32_t get32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+/* BX/circuits/builder.rs:150-271 */
+void orc_prove_subchain(uint32_t B, const uint8_t *dh_leaf, const uint8_t *dh_aunts, const uint8_t *lb_leaf,
+                        const uint8_t *lb_aunts, const uint8_t start_header[32], const uint8_t end_header[32],
+                        uint64_t batch_start, uint64_t batch_end, uint64_t global_end,
+                        const uint8_t global_end_header[32], uint8_t *digests, uint8_t *subchain) {
+    const uint32_t data_hash_path = 0x6;     /* [0,1,1,0] LSB-first : leaf 6 */
+    const uint32_t last_block_id_path = 0x4; /* [0,0,1,0]           : leaf 4 */
+    uint32_t fail = 0;
+    int is_batch_enabled = batch_start < global_end;
+    int curr_enabled = is_batch_enabled;
+    uint8_t curr_header[32];
+    memcpy(curr_header, start_header, 32);
+    uint64_t last_block_to_process = global_end - 1;
+    uint8_t *d = digests;
+    uint8_t *data_hashes = (uint8_t *)malloc((size_t)B * 32);
+    for (uint32_t i = 0; i < B; i++) {
+        uint64_t curr_idx = batch_start + i;
+        int curr_disabled = !curr_enabled;
+        int is_last = (last_block_to_process == curr_idx);
+        uint8_t dh_root[32], lb_root[32];
+        orc_tm_merkle_proof(dh_leaf + 34 * (size_t)i, 34, dh_aunts + 128 * (size_t)i, 4, data_hash_path, 0, d, dh_root);
+        d += 9 * 32;
+        orc_tm_merkle_proof(lb_leaf + 72 * (size_t)i, 72, lb_aunts + 128 * (size_t)i, 4, last_block_id_path, 0, d, lb_root);
+        d += 9 * 32;
+        const uint8_t *header_hash = lb_leaf + 72 * (size_t)i + 2;
+        if (!(curr_disabled || memcmp(curr_header, header_hash, 32) == 0)) fail |= ORC_FAIL_PREV_HEADER;
+        if (!(curr_disabled || memcmp(dh_root, header_hash, 32) == 0)) fail |= ORC_FAIL_DATA_HASH;
+        if (!(!is_last || memcmp(lb_root, global_end_header, 32) == 0)) fail |= ORC_FAIL_END_HEADER;
+        if (curr_enabled) memcpy(curr_header, lb_root, 32);
+        curr_enabled = curr_enabled && !is_last;
+        memcpy(data_hashes + 32 * (size_t)i, dh_leaf + 34 * (size_t)i + 2, 32);
+    }
+    if (!(!curr_enabled || memcmp(curr_header, end_header, 32) == 0)) fail |= ORC_FAIL_BATCH_END_HEADER;
+    uint64_t temp_end = (batch_end < global_end) ? batch_end : global_end;
+    uint64_t end_block_num = (temp_end < batch_start) ? batch_start : temp_end;
+    uint8_t root[32];
+    orc_get_data_commitment(data_hashes, B, batch_start, end_block_num, d, root, &fail);
+    free(data_hashes);
+    memset(subchain, 0, ORC_SUBCHAIN_BYTES);
+    subchain[0] = (uint8_t)is_batch_enabled;
+    put32(subchain + 4, fail);
+    put64(subchain + 8, batch_start);
+    put64(subchain + 16, end_block_num);
+    memcpy(subchain + 24, start_header, 32);
+    memcpy(subchain + 56, curr_header, 32);
+    memcpy(subchain + 88, root, 32);
+}
+
+/* BX/circuits/builder.rs:337-395 ; the hash is the bit-level sha256 gadget (:363-364) */
+void orc_reduce_subchain(const uint8_t *left, const uint8_t *right, uint8_t *out, uint8_t digest[32]) {
+    uint32_t fail = get32(left + 4) | get32(right + 4);
+    int right_disabled = (right[0] == 0);
+    int headers_linked = memcmp(left + 56, right + 24, 32) == 0;
+    int blocks_linked = get64(left + 16) == get64(right + 8);
+    if (!(right_disabled || (headers_linked && blocks_linked))) fail |= ORC_FAIL_REDUCE_LINK;
+    orc_inner_hash(left + 88, right + 88, digest);
+    memset(out, 0, ORC_SUBCHAIN_BYTES);
+    out[0] = left[0];
+    put32(out + 4, fail);
+    memcpy(out + 8, left + 8, 8);                               /* start_block */
+    memcpy(out + 16, right_disabled ? left + 16 : right + 16, 8); /* end_block */
+    memcpy(out + 24, left + 24, 32);                            /* start_header */
+    memcpy(out + 56, right_disabled ? left + 56 : right + 56, 32);
+    memcpy(out + 88, right_disabled ? left + 88 : digest, 32);
+}
+
+/* BX/circuits/builder.rs:273-409 with PX/frontend/mapreduce/generator.rs:86-151 (map all jobs,
+ * then reduce layer by layer). */
+void orc_prove_data_commitment(uint32_t n_jobs, uint32_t B, const uint8_t *dh_leaf, const uint8_t *dh_aunts,
+                               const uint8_t *lb_leaf, const uint8_t *lb_aunts, const uint8_t *start_headers,
+                               const uint8_t *end_headers, uint64_t start_block, const uint8_t start_header[32],
+                               uint64_t end_block, const uint8_t end_header[32], uint8_t *map_digests,
+                               uint8_t *map_subchains, uint8_t *reduce_digests, uint8_t *reduce_nodes,
+                               uint8_t data_commitment[32], uint32_t *fail, int threads) {
+    uint32_t f = 0;
+    if (!(end_block <= start_block + (uint64_t)n_jobs * B)) f |= ORC_FAIL_RANGE;
+    size_t dig_per_job = (size_t)(20 * B - 1) * 32;
+    (void)threads;
+#pragma omp parallel for schedule(dynamic) num_threads(threads > 0 ? threads : 1)
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        uint64_t bs = start_block + (uint64_t)j * B;
+        uint64_t be = bs + B; /* last_block + 1 */
+        orc_prove_subchain(B, dh_leaf + (size_t)j * B * 34, dh_aunts + (size_t)j * B * 128,
+                           lb_leaf + (size_t)j * B * 72, lb_aunts + (size_t)j * B * 128,
+                           start_headers + 32 * (size_t)j, end_headers + 32 * (size_t)j, bs, be, end_block,
+                           end_header, map_digests + dig_per_job * j, map_subchains + ORC_SUBCHAIN_BYTES * (size_t)j);
+    }
+    uint8_t *cur = (uint8_t *)malloc((size_t)n_jobs * ORC_SUBCHAIN_BYTES);
+    memcpy(cur, map_subchains, (size_t)n_jobs * ORC_SUBCHAIN_BYTES);
+    uint8_t *rd = reduce_digests, *rn = reduce_nodes;
+    for (uint32_t len = n_jobs; len > 1; len /= 2) {
+        for (uint32_t i = 0; i < len; i += 2) {
+            uint8_t node[ORC_SUBCHAIN_BYTES], dg[32];
+            orc_reduce_subchain(cur + ORC_SUBCHAIN_BYTES * (size_t)i, cur + ORC_SUBCHAIN_BYTES * (size_t)(i + 1), node, dg);
+            memcpy(cur + ORC_SUBCHAIN_BYTES * (size_t)(i / 2), node, ORC_SUBCHAIN_BYTES);
+            if (rd) { memcpy(rd, dg, 32); rd += 32; }
+            if (rn) { memcpy(rn, node, ORC_SUBCHAIN_BYTES); rn += ORC_SUBCHAIN_BYTES; }
+        }
+    }
+    f |= get32(cur + 4);
+    /* :398-406 result must match the public inputs */
+    if (get64(cur + 8) != start_block || memcmp(cur + 24, start_header, 32) != 0 ||
+        get64(cur + 16) != end_block || memcmp(cur + 56, end_header, 32) != 0)
+        f |= ORC_FAIL_RESULT;
+    memcpy(data_commitment, cur + 88, 32);
+    free(cur);
+    if (fail) *fail = f;
+}
+
+/* TX/builder/shared.rs:67-156 : 9 bytes always; byte i = septet i, MSB set iff i < index of the
+ * last non-zero septet. */
+uint32_t orc_marshal_int64_varint(uint64_t v, uint8_t out[9]) {
+    uint32_t last = 0;
+    uint8_t sept[9];
+    for (int i = 0; i < 9; i++) {
+        sept[i] = (uint8_t)((v >> (7 * i)) & 0x7f);
+        if (sept[i]) last = (uint32_t)i;
+    }
+    for (uint32_t i = 0; i < 9; i++) out[i] = (uint8_t)(sept[i] | ((i < last) ? 0x80 : 0));
+    return last + 1;
+}
+
+/* TX/builder/validator.rs:185-207 : 0a 22 0a 20 ‖ pk ‖ 10 ‖ varint[9] = 46 bytes */
+uint32_t orc_marshal_validator(const uint8_t pubkey[32], uint64_t power, uint8_t out[46]) {
+    out[0] = 10; out[1] = 34; out[2] = 10; out[3] = 32;
+    memcpy(out + 4, pubkey, 32);
+    out[36] = 16;
+    uint32_t n = orc_marshal_int64_varint(power, out + 37);
+    return 37 + n;
+}
+
+/* TX/builder/validator.rs:209-252 */
+void orc_hash_validator_set(uint32_t N, const uint8_t *pubkeys, const uint64_t *powers,
+                            const uint32_t *byte_lengths, uint64_t nb_enabled, uint8_t *digests,
+                            uint8_t root[32]) {
+    for (uint32_t i = 0; i < N; i++) {
+        uint8_t buf[64];
+        memset(buf, 0, sizeof buf);
+        buf[0] = 0x00;
+        orc_marshal_validator(pubkeys + 32 * (size_t)i, powers[i], buf + 1);
+        /* curta_sha256_variable over the 64-byte buffer: the hint hashes the first len bytes
+         * (PX/frontend/hash/curta/digest_hint.rs:31-33) */
+        orc_sha256(buf, 1 + byte_lengths[i], digests + 32 * (size_t)i);
+    }
+    orc_tm_merkle_tree(digests, N, nb_enabled, digests + 32 * (size_t)N, root);
+}
