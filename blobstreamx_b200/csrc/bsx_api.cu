@@ -1,0 +1,47 @@
+// Context management for libbsx (see include/bsx.h).
+#include "common.cuh"
+
+#include <new>
+
+extern "C" int bsx_version(void) { return BSX_VERSION; }
+
+extern "C" int bsx_init(int device, bsx_ctx **out) {
+    if (!out) return BSX_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return BSX_ERR_NODEVICE;
+    bsx_ctx *ctx = new (std::nothrow) bsx_ctx();
+    if (!ctx) return BSX_ERR_NOMEM;
+    memset(ctx, 0, sizeof *ctx);
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return BSX_ERR_CUDA;
+    }
+    *out = ctx;
+    return BSX_OK;
+}
+
+extern "C" void bsx_destroy(bsx_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->ws) cudaFree(ctx->ws);
+    delete ctx;
+}
+
+extern "C" const char *bsx_last_error(const bsx_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+extern "C" uint64_t bsx_launch_count(const bsx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int bsx_sync(bsx_ctx *ctx) {
+    BSX_REQUIRE(ctx, ctx != nullptr);
+    BSX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BSX_OK;
+}

@@ -1,0 +1,106 @@
+// Internal helpers shared by the kernels: ctx, error plumbing, TMA (cp.async.bulk) staging.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bsx.h"
+
+struct bsx_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;       // the ctx's own stream (host entry points run here)
+    char err[512];
+    uint64_t launches;
+    uint8_t *ws;               // grow-only device workspace for the host entry points
+    size_t ws_cap;
+    size_t ws_off;
+};
+
+namespace bsx {
+
+inline int fail(bsx_ctx *ctx, int code, const char *fmt, const char *a = "", const char *b = "") {
+    if (ctx) snprintf(ctx->err, sizeof ctx->err, fmt, a, b);
+    return code;
+}
+
+#define BSX_CUDA(ctx, call)                                                                           \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return bsx::fail((ctx), BSX_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define BSX_LAUNCHED(ctx)                                                                             \
+    do {                                                                                              \
+        (ctx)->launches++;                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                                          \
+        if (e_ != cudaSuccess) return bsx::fail((ctx), BSX_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+#define BSX_REQUIRE(ctx, cond)                                                                        \
+    do {                                                                                              \
+        if (!(cond)) return bsx::fail((ctx), BSX_ERR_INVALID, "invalid argument: %s", #cond);         \
+    } while (0)
+
+// ---- workspace (host entry points only) ----
+inline int ws_begin(bsx_ctx *ctx, size_t total) {
+    total += 4096;
+    if (total > ctx->ws_cap) {
+        if (ctx->ws) cudaFree(ctx->ws);
+        ctx->ws = nullptr;
+        ctx->ws_cap = 0;
+        size_t cap = total + total / 4;
+        cudaError_t e = cudaMalloc(&ctx->ws, cap);
+        if (e != cudaSuccess) return fail(ctx, BSX_ERR_NOMEM, "cudaMalloc workspace: %s", cudaGetErrorString(e));
+        ctx->ws_cap = cap;
+    }
+    ctx->ws_off = 0;
+    return BSX_OK;
+}
+template <typename T>
+inline T *ws_take(bsx_ctx *ctx, size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T *p = reinterpret_cast<T *>(ctx->ws + ctx->ws_off);
+    ctx->ws_off += bytes;
+    return p;
+}
+inline size_t ws_size(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+// shared -> global bulk store (async proxy); caller fences + waits
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace bsx

@@ -1,0 +1,478 @@
+// prove_subchain<B> (the header_range map circuit) and the mapreduce reduce stage, fused per job.
+//   BX/circuits/builder.rs:150-271 (map), :337-395 (reduce), :273-409 (prove_data_commitment)
+// One CTA per map job: 2B threads verify the 2B Merkle inclusion proofs (leaf hash + 4 levels,
+// both orderings per level), then the same CTA hashes the B data-root tuples and evaluates the
+// fixed-shape Tendermint tree.  Inputs of the job are staged into shared memory with TMA bulk
+// copies; every digest of the Curta request schedule is written out.
+#include "common.cuh"
+#include "sha256.cuh"
+#include "tm_tree.cuh"
+
+namespace bsx {
+
+struct SubchainArgs {
+    const uint8_t *dh_leaf, *dh_aunts, *lb_leaf, *lb_aunts, *start_headers, *end_headers;
+    // explicit per-job scalars (range_jobs == 0) ...
+    const uint64_t *batch_start, *batch_end, *global_end;
+    const uint8_t *global_end_header;
+    // ... or derived from per-range public inputs (range_jobs = jobs per range)
+    uint32_t range_jobs;
+    const uint64_t *start_blocks, *end_blocks;
+    const uint8_t *range_end_header;
+    uint8_t *digests, *subchains;
+};
+
+__device__ __forceinline__ void load_words_be(const uint8_t *p, uint32_t d[8]) {  // any alignment
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        d[k] = ((uint32_t)p[4 * k] << 24) | ((uint32_t)p[4 * k + 1] << 16) | ((uint32_t)p[4 * k + 2] << 8) | p[4 * k + 3];
+}
+
+template <int B, bool TMA>
+__global__ void __launch_bounds__((2 * B < 32) ? 32 : 2 * B) prove_subchain_kernel(SubchainArgs a) {
+    constexpr int LEAF_DH = 34, LEAF_LB = 72;
+    constexpr uint32_t SZ_DHL = (B * LEAF_DH + 15) & ~15u, SZ_LBL = (B * LEAF_LB + 15) & ~15u, SZ_AUNT = B * 128;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t *s_dh_leaf = smem_raw;
+    uint8_t *s_lb_leaf = s_dh_leaf + SZ_DHL;
+    uint8_t *s_dh_aunts = s_lb_leaf + SZ_LBL;
+    uint8_t *s_lb_aunts = s_dh_aunts + SZ_AUNT;
+    uint32_t *s_dh_root = reinterpret_cast<uint32_t *>(s_lb_aunts + SZ_AUNT);
+    uint32_t *s_lb_root = s_dh_root + 8 * B;
+    uint32_t *s_A = s_lb_root + 8 * B;
+    uint32_t *s_Bf = s_A + 8 * B;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_Bf + 4 * B + 4);
+    uint32_t *s_fail = reinterpret_cast<uint32_t *>(s_bar + 1);
+
+    const uint32_t tid = threadIdx.x;
+    const size_t job = blockIdx.x;
+    const uint8_t *g_dh_leaf = a.dh_leaf + job * (B * LEAF_DH), *g_lb_leaf = a.lb_leaf + job * (B * LEAF_LB);
+    const uint8_t *g_dh_aunts = a.dh_aunts + job * SZ_AUNT, *g_lb_aunts = a.lb_aunts + job * SZ_AUNT;
+
+    if (TMA) {
+        if (tid == 0) {
+            *s_fail = 0;
+            mbar_init(s_bar, 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(s_bar, B * LEAF_DH + B * LEAF_LB + 2 * SZ_AUNT);
+            bulk_g2s(s_dh_leaf, g_dh_leaf, B * LEAF_DH, s_bar);
+            bulk_g2s(s_lb_leaf, g_lb_leaf, B * LEAF_LB, s_bar);
+            bulk_g2s(s_dh_aunts, g_dh_aunts, SZ_AUNT, s_bar);
+            bulk_g2s(s_lb_aunts, g_lb_aunts, SZ_AUNT, s_bar);
+        }
+        mbar_wait(s_bar, 0);
+    } else {
+        if (tid == 0) *s_fail = 0;
+        for (uint32_t k = tid; k < B * LEAF_DH; k += blockDim.x) s_dh_leaf[k] = g_dh_leaf[k];
+        for (uint32_t k = tid; k < B * LEAF_LB; k += blockDim.x) s_lb_leaf[k] = g_lb_leaf[k];
+        for (uint32_t k = tid; k < SZ_AUNT; k += blockDim.x) { s_dh_aunts[k] = g_dh_aunts[k]; s_lb_aunts[k] = g_lb_aunts[k]; }
+        __syncthreads();
+    }
+
+    // per-job scalars
+    uint64_t batch_start, batch_end, global_end;
+    const uint8_t *g_end_hdr;
+    if (a.range_jobs) {
+        size_t r = job / a.range_jobs, j = job % a.range_jobs;
+        batch_start = a.start_blocks[r] + (uint64_t)j * B;
+        batch_end = batch_start + B;
+        global_end = a.end_blocks[r];
+        g_end_hdr = a.range_end_header + 32 * r;
+    } else {
+        batch_start = a.batch_start[job];
+        batch_end = a.batch_end[job];
+        global_end = a.global_end[job];
+        g_end_hdr = a.global_end_header + 32 * job;
+    }
+    uint8_t *out = a.digests + job * (size_t)(20 * B - 1) * 32;
+
+    // ---- phase 1: the 2B inclusion proofs (tendermint.rs:62-93) ----
+    if (tid < 2 * B) {
+        const uint32_t kind = tid / B, i = tid % B;  // 0: data_hash proof, 1: last_block_id proof
+        const uint8_t *leaf = kind ? s_lb_leaf + LEAF_LB * i : s_dh_leaf + LEAF_DH * i;
+        const uint8_t *aunts = (kind ? s_lb_aunts : s_dh_aunts) + 128 * i;
+        const uint32_t bits = kind ? 0x4u : 0x6u;  // path of leaf 4 / leaf 6, LSB first (builder.rs:166-169)
+        uint8_t *o = out + 32 * (size_t)(18 * i + 9 * kind);
+        uint32_t h[8];
+        tm_leaf_hash([&](uint32_t k) -> uint8_t { return leaf[k]; }, kind ? LEAF_LB : LEAF_DH, h);
+        store_digest_be(o, h);
+#pragma unroll 1
+        for (int l = 0; l < 4; l++) {
+            uint32_t au[8], left[8], right[8];
+            const uint4 *ap = reinterpret_cast<const uint4 *>(aunts + 32 * l);
+            uint4 a0 = ap[0], a1 = ap[1];
+            au[0] = bswap32(a0.x); au[1] = bswap32(a0.y); au[2] = bswap32(a0.z); au[3] = bswap32(a0.w);
+            au[4] = bswap32(a1.x); au[5] = bswap32(a1.y); au[6] = bswap32(a1.z); au[7] = bswap32(a1.w);
+            tm_inner_hash(h, au, left);
+            tm_inner_hash(au, h, right);
+            store_digest_be(o + 32 + 64 * l, left);
+            store_digest_be(o + 64 + 64 * l, right);
+            bool sel = (bits >> l) & 1;
+#pragma unroll
+            for (int k = 0; k < 8; k++) h[k] = sel ? right[k] : left[k];
+        }
+        uint32_t *r = (kind ? s_lb_root : s_dh_root) + 8 * i;
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[k] = h[k];
+    }
+    __syncthreads();
+
+    // ---- phase 2: link checks (builder.rs:174-232) + tuple leaves (:133-139) ----
+    const bool batch_enabled = batch_start < global_end;
+    const uint64_t last = global_end - 1;           // last_block_to_process
+    const uint64_t kk = last - batch_start;         // index of the last enabled iteration (if enabled)
+    if (tid < B) {
+        const uint32_t i = tid;
+        uint32_t f = 0;
+        const bool e_i = batch_enabled && (uint64_t)i <= kk;
+        const bool is_last = (last == batch_start + i);
+        uint32_t hh[8], cur[8];
+        load_words_be(s_lb_leaf + LEAF_LB * i + 2, hh);  // header hash of block curr_idx inside last_block_id
+        if (i == 0) load_words_be(a.start_headers + 32 * job, cur);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) cur[k] = s_lb_root[8 * (i - 1) + k];
+        }
+        if (e_i && !digest_eq(cur, hh)) f |= BSX_FAIL_PREV_HEADER;
+        if (e_i && !digest_eq(s_dh_root + 8 * i, hh)) f |= BSX_FAIL_DATA_HASH;
+        if (is_last) {
+            uint32_t ge[8];
+            load_words_be(g_end_hdr, ge);
+            if (!digest_eq(s_lb_root + 8 * i, ge)) f |= BSX_FAIL_END_HEADER;
+        }
+        if (f) atomicOr(s_fail, f);
+        // tuple leaf: 0x00 ‖ 0^24 ‖ u64be(batch_start+i) ‖ data_hash_i   (data_hash = dh_leaf[2..34])
+        uint32_t x[8], d[8], w[16];
+        load_words_be(s_dh_leaf + LEAF_DH * i + 2, x);
+        const uint64_t hgt = batch_start + i;
+#pragma unroll
+        for (int k = 0; k < 6; k++) w[k] = 0;
+        w[6] = (uint32_t)(hgt >> 40);
+        w[7] = (uint32_t)(hgt >> 8);
+        w[8] = ((uint32_t)hgt << 24) | (x[0] >> 8);
+#pragma unroll
+        for (int k = 1; k < 8; k++) w[8 + k] = __funnelshift_r(x[k], x[k - 1], 8);
+        sha256_init(d);
+        sha256_compress(d, w);
+        w[0] = (x[7] << 24) | 0x00800000u;
+#pragma unroll
+        for (int k = 1; k < 15; k++) w[k] = 0;
+        w[15] = 65 * 8;
+        sha256_compress(d, w);
+        store_digest_be(out + 32 * (size_t)(18 * B + i), d);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_A[8 * i + k] = d[k];
+    }
+    __syncthreads();
+
+    // ---- phase 3: data-commitment tree over the batch (builder.rs:234-252, tendermint.rs:165-204) ----
+    const uint64_t temp_end = batch_end < global_end ? batch_end : global_end;
+    const uint64_t end_block = temp_end < batch_start ? batch_start : temp_end;
+    const uint64_t nb_blocks = end_block - batch_start;
+    uint32_t root[8];
+    tm_tree_cta(s_A, s_Bf, B, nb_blocks & 0xffffffffull, out + 32 * (size_t)(19 * B), root);
+
+    if (tid == 0) {
+        uint32_t f = *s_fail;
+        if (nb_blocks >> 32) f |= BSX_FAIL_END_LT_START;
+        // curr_header after the loop and the batch-end check (:228-232)
+        uint32_t cur[8], eh[8];
+        if (batch_enabled) {
+            uint64_t idx = kk < (uint64_t)(B - 1) ? kk : (uint64_t)(B - 1);
+#pragma unroll
+            for (int k = 0; k < 8; k++) cur[k] = s_lb_root[8 * idx + k];
+        } else {
+            load_words_be(a.start_headers + 32 * job, cur);
+        }
+        const bool e_B = batch_enabled && (uint64_t)B <= kk;
+        load_words_be(a.end_headers + 32 * job, eh);
+        if (e_B && !digest_eq(cur, eh)) f |= BSX_FAIL_BATCH_END_HEADER;
+        uint32_t *rec = reinterpret_cast<uint32_t *>(a.subchains + job * BSX_SUBCHAIN_BYTES);
+        rec[0] = batch_enabled ? 1u : 0u;
+        rec[1] = f;
+        rec[2] = (uint32_t)batch_start; rec[3] = (uint32_t)(batch_start >> 32);
+        rec[4] = (uint32_t)end_block;   rec[5] = (uint32_t)(end_block >> 32);
+        const uint32_t *sh = reinterpret_cast<const uint32_t *>(a.start_headers + 32 * job);
+#pragma unroll
+        for (int k = 0; k < 8; k++) rec[6 + k] = sh[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) rec[14 + k] = bswap32(cur[k]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) rec[22 + k] = bswap32(root[k]);
+        rec[30] = 0; rec[31] = 0;
+    }
+}
+
+// ---- reduce stage: one CTA per range, records are 32 little-endian words ----
+// rec[0] is_enabled, [1] fail, [2,3] start_block, [4,5] end_block, [6..14) start_header,
+// [14..22) end_header, [22..30) data_merkle_root (header/root words hold raw digest bytes).
+__global__ void reduce_subchains_kernel(uint32_t n_jobs, uint32_t B, const uint8_t *__restrict__ map_subchains,
+                                        const uint64_t *__restrict__ start_blocks, const uint8_t *__restrict__ start_header,
+                                        const uint64_t *__restrict__ end_blocks, const uint8_t *__restrict__ end_header,
+                                        uint8_t *__restrict__ reduce_digests, uint8_t *__restrict__ reduce_nodes,
+                                        uint8_t *__restrict__ data_commitments, uint32_t *__restrict__ fail) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t *src = smem, *dst = smem + 32 * (size_t)n_jobs;
+    const size_t r = blockIdx.x;
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(map_subchains + r * n_jobs * BSX_SUBCHAIN_BYTES);
+    for (uint32_t k = threadIdx.x; k < 32 * n_jobs; k += blockDim.x) src[k] = g[k];
+    __syncthreads();
+    uint32_t off = 0;
+    for (uint32_t len = n_jobs; len > 1; len /= 2) {
+        for (uint32_t i = threadIdx.x; i < len / 2; i += blockDim.x) {
+            const uint32_t *L = src + 64 * i, *R = L + 32;
+            uint32_t f = L[1] | R[1];
+            const bool right_disabled = (R[0] == 0);
+            bool linked = (L[4] == R[2]) && (L[5] == R[3]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) linked = linked && (L[14 + k] == R[6 + k]);
+            if (!(right_disabled || linked)) f |= BSX_FAIL_REDUCE_LINK;
+            uint32_t lr[8], rr[8], p[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { lr[k] = bswap32(L[22 + k]); rr[k] = bswap32(R[22 + k]); }
+            tm_inner_hash(lr, rr, p);  // sha256(0x01 ‖ left.root ‖ right.root), builder.rs:357-364
+            if (reduce_digests) store_digest_be(reduce_digests + 32 * (r * (n_jobs - 1) + off + i), p);
+            uint32_t o[32];
+            o[0] = L[0]; o[1] = f; o[2] = L[2]; o[3] = L[3];
+            o[4] = right_disabled ? L[4] : R[4];
+            o[5] = right_disabled ? L[5] : R[5];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                o[6 + k] = L[6 + k];
+                o[14 + k] = right_disabled ? L[14 + k] : R[14 + k];
+                o[22 + k] = right_disabled ? L[22 + k] : bswap32(p[k]);
+            }
+            o[30] = 0; o[31] = 0;
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst + 32 * i);
+            uint4 *g4 = reduce_nodes ? reinterpret_cast<uint4 *>(reduce_nodes + BSX_SUBCHAIN_BYTES * (r * (n_jobs - 1) + off + i)) : nullptr;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                uint4 v = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+                d4[k] = v;
+                if (g4) g4[k] = v;
+            }
+        }
+        off += len / 2;
+        uint32_t *t = src; src = dst; dst = t;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t f = src[1];
+        const uint64_t sb = start_blocks[r], eb = end_blocks[r];
+        if (!(eb <= sb + (uint64_t)n_jobs * B)) f |= BSX_FAIL_RANGE;  // builder.rs:291-297
+        const uint32_t *sh = reinterpret_cast<const uint32_t *>(start_header + 32 * r);
+        const uint32_t *eh = reinterpret_cast<const uint32_t *>(end_header + 32 * r);
+        bool ok = src[2] == (uint32_t)sb && src[3] == (uint32_t)(sb >> 32) && src[4] == (uint32_t)eb && src[5] == (uint32_t)(eb >> 32);
+#pragma unroll
+        for (int k = 0; k < 8; k++) ok = ok && src[6 + k] == sh[k] && src[14 + k] == eh[k];
+        if (!ok) f |= BSX_FAIL_RESULT;  // builder.rs:398-406
+        uint32_t *dc = reinterpret_cast<uint32_t *>(data_commitments + 32 * r);
+#pragma unroll
+        for (int k = 0; k < 8; k++) dc[k] = src[22 + k];
+        if (fail) fail[r] = f;
+    }
+}
+
+template <int B>
+static int launch_subchain(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const SubchainArgs &a, bool aligned) {
+    constexpr uint32_t SZ_DHL = (B * 34 + 15) & ~15u, SZ_LBL = (B * 72 + 15) & ~15u, SZ_AUNT = B * 128;
+    const size_t smem = SZ_DHL + SZ_LBL + 2 * SZ_AUNT + 4 * (8 * B + 8 * B + 8 * B + 4 * B + 4) + 16;
+    const int threads = (2 * B < 32) ? 32 : 2 * B;
+    constexpr bool CAN_TMA = (B * 34) % 16 == 0;
+    if (CAN_TMA && aligned) {
+        auto k = prove_subchain_kernel<B, CAN_TMA>;
+        if (smem > 48 * 1024) BSX_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<n_jobs, threads, smem, st>>>(a);
+    } else {
+        auto k = prove_subchain_kernel<B, false>;
+        if (smem > 48 * 1024) BSX_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<n_jobs, threads, smem, st>>>(a);
+    }
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+static int dispatch_subchain(bsx_ctx *ctx, cudaStream_t st, uint32_t B, uint32_t n_jobs, const SubchainArgs &a) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a.dh_leaf) | reinterpret_cast<uintptr_t>(a.dh_aunts) |
+                         reinterpret_cast<uintptr_t>(a.lb_leaf) | reinterpret_cast<uintptr_t>(a.lb_aunts);
+    const bool aligned = (al & 15) == 0;
+    switch (B) {
+        case 1: return launch_subchain<1>(ctx, st, n_jobs, a, aligned);
+        case 2: return launch_subchain<2>(ctx, st, n_jobs, a, aligned);
+        case 4: return launch_subchain<4>(ctx, st, n_jobs, a, aligned);
+        case 8: return launch_subchain<8>(ctx, st, n_jobs, a, aligned);
+        case 16: return launch_subchain<16>(ctx, st, n_jobs, a, aligned);
+        case 32: return launch_subchain<32>(ctx, st, n_jobs, a, aligned);
+        case 64: return launch_subchain<64>(ctx, st, n_jobs, a, aligned);
+        case 128: return launch_subchain<128>(ctx, st, n_jobs, a, aligned);
+        case 256: return launch_subchain<256>(ctx, st, n_jobs, a, aligned);
+        default: return fail(ctx, BSX_ERR_INVALID, "BATCH_SIZE must be a power of two in [1,256]%s%s");
+    }
+}
+
+}  // namespace bsx
+
+using namespace bsx;
+
+extern "C" int bsx_prove_subchain_batch_dev(bsx_ctx *ctx, void *stream, uint32_t B, uint32_t n_jobs,
+                                            const uint8_t *dh_leaf, const uint8_t *dh_aunts, const uint8_t *lb_leaf,
+                                            const uint8_t *lb_aunts, const uint8_t *start_headers,
+                                            const uint8_t *end_headers, const uint64_t *batch_start,
+                                            const uint64_t *batch_end, const uint64_t *global_end,
+                                            const uint8_t *global_end_header, uint8_t *digests, uint8_t *subchains) {
+    BSX_REQUIRE(ctx, ctx && dh_leaf && dh_aunts && lb_leaf && lb_aunts && start_headers && end_headers && batch_start &&
+                         batch_end && global_end && global_end_header && digests && subchains);
+    BSX_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(digests) | reinterpret_cast<uintptr_t>(subchains)) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(start_headers) & 3) == 0);
+    if (n_jobs == 0) return BSX_OK;
+    SubchainArgs a{dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, batch_start, batch_end, global_end,
+                   global_end_header, 0, nullptr, nullptr, nullptr, digests, subchains};
+    return dispatch_subchain(ctx, (cudaStream_t)stream, B, n_jobs, a);
+}
+
+extern "C" int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs,
+                                        const uint8_t *map_subchains, const uint64_t *start_blocks,
+                                        const uint8_t *start_header, const uint64_t *end_blocks,
+                                        const uint8_t *end_header, uint32_t B, uint8_t *reduce_digests,
+                                        uint8_t *reduce_nodes, uint8_t *data_commitments, uint32_t *fail) {
+    BSX_REQUIRE(ctx, ctx && map_subchains && start_blocks && start_header && end_blocks && end_header && data_commitments);
+    BSX_REQUIRE(ctx, n_jobs >= 1 && n_jobs <= 1024 && (n_jobs & (n_jobs - 1)) == 0);
+    BSX_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(map_subchains) | reinterpret_cast<uintptr_t>(reduce_digests) |
+                       reinterpret_cast<uintptr_t>(reduce_nodes)) & 15) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(start_header) | reinterpret_cast<uintptr_t>(end_header) |
+                           reinterpret_cast<uintptr_t>(data_commitments)) & 3) == 0);
+    if (n_ranges == 0) return BSX_OK;
+    uint32_t threads = n_jobs / 2 < 32 ? 32 : n_jobs / 2;
+    size_t smem = 4 * (32 * (size_t)n_jobs + 16 * (size_t)n_jobs);
+    if (smem > 48 * 1024)
+        BSX_CUDA(ctx, cudaFuncSetAttribute(reduce_subchains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reduce_subchains_kernel<<<n_ranges, threads, smem, (cudaStream_t)stream>>>(
+        n_jobs, B, map_subchains, start_blocks, start_header, end_blocks, end_header, reduce_digests, reduce_nodes,
+        data_commitments, fail);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+extern "C" int bsx_prove_data_commitment_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs, uint32_t B,
+                                             const uint8_t *dh_leaf, const uint8_t *dh_aunts, const uint8_t *lb_leaf,
+                                             const uint8_t *lb_aunts, const uint8_t *start_headers,
+                                             const uint8_t *end_headers, const uint64_t *start_blocks,
+                                             const uint8_t *start_header, const uint64_t *end_blocks,
+                                             const uint8_t *end_header, uint8_t *map_digests, uint8_t *map_subchains,
+                                             uint8_t *reduce_digests, uint8_t *reduce_nodes, uint8_t *data_commitments,
+                                             uint32_t *fail) {
+    BSX_REQUIRE(ctx, ctx && dh_leaf && dh_aunts && lb_leaf && lb_aunts && start_headers && end_headers && start_blocks &&
+                         start_header && end_blocks && end_header && map_digests && map_subchains && data_commitments);
+    BSX_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(map_digests) | reinterpret_cast<uintptr_t>(map_subchains)) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(start_headers) & 3) == 0);
+    BSX_REQUIRE(ctx, n_jobs >= 1 && (n_jobs & (n_jobs - 1)) == 0);
+    if (n_ranges == 0) return BSX_OK;
+    SubchainArgs a{dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, nullptr, nullptr, nullptr, nullptr,
+                   n_jobs, start_blocks, end_blocks, end_header, map_digests, map_subchains};
+    int rc = dispatch_subchain(ctx, (cudaStream_t)stream, B, n_ranges * n_jobs, a);
+    if (rc) return rc;
+    return bsx_reduce_subchains_dev(ctx, stream, n_ranges, n_jobs, map_subchains, start_blocks, start_header, end_blocks,
+                                    end_header, B, reduce_digests, reduce_nodes, data_commitments, fail);
+}
+
+// ---- host-buffer entry points ----
+namespace {
+struct SubchainSizes {
+    size_t dhl, aunt, lbl, hdr, dig, sub;
+};
+SubchainSizes subchain_sizes(uint32_t B, size_t jobs) {
+    return {jobs * B * 34, jobs * B * 128, jobs * B * 72, jobs * 32, jobs * (size_t)(20 * B - 1) * 32, jobs * BSX_SUBCHAIN_BYTES};
+}
+}  // namespace
+
+extern "C" int bsx_prove_subchain_batch(bsx_ctx *ctx, uint32_t B, uint32_t n_jobs, const uint8_t *dh_leaf,
+                                        const uint8_t *dh_aunts, const uint8_t *lb_leaf, const uint8_t *lb_aunts,
+                                        const uint8_t *start_headers, const uint8_t *end_headers,
+                                        const uint64_t *batch_start, const uint64_t *batch_end,
+                                        const uint64_t *global_end, const uint8_t *global_end_header, uint8_t *digests,
+                                        uint8_t *subchains) {
+    BSX_REQUIRE(ctx, ctx && dh_leaf && dh_aunts && lb_leaf && lb_aunts && start_headers && end_headers && batch_start &&
+                         batch_end && global_end && global_end_header && digests && subchains);
+    if (n_jobs == 0) return BSX_OK;
+    BSX_CUDA(ctx, cudaSetDevice(ctx->device));
+    SubchainSizes s = subchain_sizes(B, n_jobs);
+    int rc = ws_begin(ctx, ws_size(s.dhl) + 2 * ws_size(s.aunt) + ws_size(s.lbl) + 3 * ws_size(s.hdr) + 3 * ws_size(8 * (size_t)n_jobs) +
+                               ws_size(s.dig) + ws_size(s.sub));
+    if (rc) return rc;
+    uint8_t *d_dhl = ws_take<uint8_t>(ctx, s.dhl), *d_dha = ws_take<uint8_t>(ctx, s.aunt);
+    uint8_t *d_lbl = ws_take<uint8_t>(ctx, s.lbl), *d_lba = ws_take<uint8_t>(ctx, s.aunt);
+    uint8_t *d_sh = ws_take<uint8_t>(ctx, s.hdr), *d_eh = ws_take<uint8_t>(ctx, s.hdr), *d_geh = ws_take<uint8_t>(ctx, s.hdr);
+    uint64_t *d_bs = ws_take<uint64_t>(ctx, n_jobs), *d_be = ws_take<uint64_t>(ctx, n_jobs), *d_ge = ws_take<uint64_t>(ctx, n_jobs);
+    uint8_t *d_dig = ws_take<uint8_t>(ctx, s.dig), *d_sub = ws_take<uint8_t>(ctx, s.sub);
+    cudaStream_t st = ctx->stream;
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_dhl, dh_leaf, s.dhl, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_dha, dh_aunts, s.aunt, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_lbl, lb_leaf, s.lbl, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_lba, lb_aunts, s.aunt, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_sh, start_headers, s.hdr, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_eh, end_headers, s.hdr, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_geh, global_end_header, s.hdr, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_bs, batch_start, 8 * (size_t)n_jobs, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_be, batch_end, 8 * (size_t)n_jobs, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_ge, global_end, 8 * (size_t)n_jobs, cudaMemcpyHostToDevice, st));
+    rc = bsx_prove_subchain_batch_dev(ctx, st, B, n_jobs, d_dhl, d_dha, d_lbl, d_lba, d_sh, d_eh, d_bs, d_be, d_ge, d_geh,
+                                      d_dig, d_sub);
+    if (rc) return rc;
+    BSX_CUDA(ctx, cudaMemcpyAsync(digests, d_dig, s.dig, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(subchains, d_sub, s.sub, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaStreamSynchronize(st));
+    return BSX_OK;
+}
+
+extern "C" int bsx_prove_data_commitment(bsx_ctx *ctx, uint32_t n_ranges, uint32_t n_jobs, uint32_t B,
+                                         const uint8_t *dh_leaf, const uint8_t *dh_aunts, const uint8_t *lb_leaf,
+                                         const uint8_t *lb_aunts, const uint8_t *start_headers,
+                                         const uint8_t *end_headers, const uint64_t *start_blocks,
+                                         const uint8_t *start_header, const uint64_t *end_blocks,
+                                         const uint8_t *end_header, uint8_t *map_digests, uint8_t *map_subchains,
+                                         uint8_t *reduce_digests, uint8_t *reduce_nodes, uint8_t *data_commitments,
+                                         uint32_t *fail) {
+    BSX_REQUIRE(ctx, ctx && dh_leaf && dh_aunts && lb_leaf && lb_aunts && start_headers && end_headers && start_blocks &&
+                         start_header && end_blocks && end_header && data_commitments);
+    BSX_REQUIRE(ctx, n_jobs >= 1 && (n_jobs & (n_jobs - 1)) == 0);
+    if (n_ranges == 0) return BSX_OK;
+    BSX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t jobs = (size_t)n_ranges * n_jobs, R = n_ranges;
+    SubchainSizes s = subchain_sizes(B, jobs);
+    const size_t s_rd = R * (n_jobs - 1) * 32, s_rn = R * (n_jobs - 1) * BSX_SUBCHAIN_BYTES;
+    int rc = ws_begin(ctx, ws_size(s.dhl) + 2 * ws_size(s.aunt) + ws_size(s.lbl) + 2 * ws_size(s.hdr) + 3 * ws_size(32 * R) +
+                               2 * ws_size(8 * R) + ws_size(s.dig) + ws_size(s.sub) + ws_size(s_rd) + ws_size(s_rn) + ws_size(4 * R));
+    if (rc) return rc;
+    uint8_t *d_dhl = ws_take<uint8_t>(ctx, s.dhl), *d_dha = ws_take<uint8_t>(ctx, s.aunt);
+    uint8_t *d_lbl = ws_take<uint8_t>(ctx, s.lbl), *d_lba = ws_take<uint8_t>(ctx, s.aunt);
+    uint8_t *d_sh = ws_take<uint8_t>(ctx, s.hdr), *d_eh = ws_take<uint8_t>(ctx, s.hdr);
+    uint8_t *d_rsh = ws_take<uint8_t>(ctx, 32 * R), *d_reh = ws_take<uint8_t>(ctx, 32 * R), *d_dc = ws_take<uint8_t>(ctx, 32 * R);
+    uint64_t *d_sb = ws_take<uint64_t>(ctx, R), *d_eb = ws_take<uint64_t>(ctx, R);
+    uint8_t *d_dig = ws_take<uint8_t>(ctx, s.dig), *d_sub = ws_take<uint8_t>(ctx, s.sub);
+    uint8_t *d_rd = ws_take<uint8_t>(ctx, s_rd), *d_rn = ws_take<uint8_t>(ctx, s_rn);
+    uint32_t *d_fail = ws_take<uint32_t>(ctx, R);
+    cudaStream_t st = ctx->stream;
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_dhl, dh_leaf, s.dhl, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_dha, dh_aunts, s.aunt, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_lbl, lb_leaf, s.lbl, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_lba, lb_aunts, s.aunt, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_sh, start_headers, s.hdr, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_eh, end_headers, s.hdr, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_rsh, start_header, 32 * R, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_reh, end_header, 32 * R, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_sb, start_blocks, 8 * R, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_eb, end_blocks, 8 * R, cudaMemcpyHostToDevice, st));
+    rc = bsx_prove_data_commitment_dev(ctx, st, n_ranges, n_jobs, B, d_dhl, d_dha, d_lbl, d_lba, d_sh, d_eh, d_sb, d_rsh, d_eb,
+                                       d_reh, d_dig, d_sub, d_rd, d_rn, d_dc, d_fail);
+    if (rc) return rc;
+    if (map_digests) BSX_CUDA(ctx, cudaMemcpyAsync(map_digests, d_dig, s.dig, cudaMemcpyDeviceToHost, st));
+    if (map_subchains) BSX_CUDA(ctx, cudaMemcpyAsync(map_subchains, d_sub, s.sub, cudaMemcpyDeviceToHost, st));
+    if (reduce_digests && s_rd) BSX_CUDA(ctx, cudaMemcpyAsync(reduce_digests, d_rd, s_rd, cudaMemcpyDeviceToHost, st));
+    if (reduce_nodes && s_rn) BSX_CUDA(ctx, cudaMemcpyAsync(reduce_nodes, d_rn, s_rn, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(data_commitments, d_dc, 32 * R, cudaMemcpyDeviceToHost, st));
+    if (fail) BSX_CUDA(ctx, cudaMemcpyAsync(fail, d_fail, 4 * R, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaStreamSynchronize(st));
+    return BSX_OK;
+}

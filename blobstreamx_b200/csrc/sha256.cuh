@@ -1,0 +1,129 @@
+// SHA-256 device primitives for sm_100a.
+//
+// Replaces the per-request CPU hint  HashDigestHint<SHA256>::hint -> SHA256::hash
+// (PX/frontend/hash/curta/digest_hint.rs:30-38, PX/frontend/hash/sha/sha256/curta.rs:94-102).
+// All state lives in registers; the 64 round constants are folded into immediates by full
+// unrolling; rotations are funnel shifts (SHF), Ch/Maj/xor3 are single LOP3s.
+#pragma once
+#include <stdint.h>
+
+namespace bsx {
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+__device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t ch32(uint32_t e, uint32_t f, uint32_t g) {
+    uint32_t r;  // (e & f) | (~e & g)  == 0xCA
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(e), "r"(f), "r"(g));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;  // majority == 0xE8
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+__device__ __forceinline__ void sha256_init(uint32_t st[8]) {
+    st[0] = 0x6a09e667u; st[1] = 0xbb67ae85u; st[2] = 0x3c6ef372u; st[3] = 0xa54ff53au;
+    st[4] = 0x510e527fu; st[5] = 0x9b05688cu; st[6] = 0x1f83d9abu; st[7] = 0x5be0cd19u;
+}
+
+// One compression.  w[16] is the big-endian-decoded chunk and is clobbered (rolling schedule).
+__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+    constexpr uint32_t K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+        0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+        0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+        0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+        0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+        0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+        0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+        0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            uint32_t s0 = xor3(rotr32(w15, 7), rotr32(w15, 18), w15 >> 3);
+            uint32_t s1 = xor3(rotr32(w2, 17), rotr32(w2, 19), w2 >> 10);
+            w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+        }
+        uint32_t t1 = h + xor3(rotr32(e, 6), rotr32(e, 11), rotr32(e, 25)) + ch32(e, f, g) + K[i] + w[i & 15];
+        uint32_t t2 = xor3(rotr32(a, 2), rotr32(a, 13), rotr32(a, 22)) + maj32(a, b, c);
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+// Tendermint inner node  sha256(0x01 ‖ l ‖ r)  on big-endian state words (65 bytes = 2 chunks).
+// PX/frontend/merkle/tendermint.rs:108-122
+__device__ __forceinline__ void tm_inner_hash(const uint32_t l[8], const uint32_t r[8], uint32_t out[8]) {
+    uint32_t w[16];
+    w[0] = 0x01000000u | (l[0] >> 8);
+#pragma unroll
+    for (int i = 1; i < 8; i++) w[i] = __funnelshift_r(l[i], l[i - 1], 8);
+    w[8] = __funnelshift_r(r[0], l[7], 8);
+#pragma unroll
+    for (int i = 1; i < 8; i++) w[8 + i] = __funnelshift_r(r[i], r[i - 1], 8);
+    sha256_init(out);
+    sha256_compress(out, w);
+    w[0] = (r[7] << 24) | 0x00800000u;
+#pragma unroll
+    for (int i = 1; i < 15; i++) w[i] = 0;
+    w[15] = 65 * 8;
+    sha256_compress(out, w);
+}
+
+// sha256 of `len` bytes given through a byte getter (any address space); generic path used for
+// leaves and variable-length requests.  get(i) must be valid for i < len.
+template <typename Get>
+__device__ __forceinline__ void sha256_bytes(Get get, uint32_t len, uint32_t out[8]) {
+    sha256_init(out);
+    uint32_t nblk = (len + 9 + 63) >> 6;
+    for (uint32_t b = 0; b < nblk; b++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t idx = b * 64 + k * 4 + j;
+                uint32_t byte = idx < len ? (uint32_t)get(idx) : (idx == len ? 0x80u : 0u);
+                v = (v << 8) | byte;
+            }
+            w[k] = v;
+        }
+        if (b == nblk - 1) { w[14] = 0; w[15] = len << 3; }  // len < 2^29
+        sha256_compress(out, w);
+    }
+}
+
+// Leaf node sha256(0x00 ‖ leaf) with leaf bytes behind a getter.  tendermint.rs:95-106
+template <typename Get>
+__device__ __forceinline__ void tm_leaf_hash(Get get, uint32_t leaf_len, uint32_t out[8]) {
+    sha256_bytes([&](uint32_t i) -> uint8_t { return i == 0 ? (uint8_t)0 : get(i - 1); }, leaf_len + 1, out);
+}
+
+__device__ __forceinline__ void load_digest_be(const uint8_t* p, uint32_t d[8]) {  // p 4-byte aligned
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = bswap32(q[i]);
+}
+__device__ __forceinline__ void store_digest_be(uint8_t* p, const uint32_t d[8]) {  // p 16-byte aligned
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(bswap32(d[0]), bswap32(d[1]), bswap32(d[2]), bswap32(d[3]));
+    q[1] = make_uint4(bswap32(d[4]), bswap32(d[5]), bswap32(d[6]), bswap32(d[7]));
+}
+__device__ __forceinline__ bool digest_eq(const uint32_t a[8], const uint32_t b[8]) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x |= a[i] ^ b[i];
+    return x == 0;
+}
+
+}  // namespace bsx

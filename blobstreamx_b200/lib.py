@@ -1,0 +1,197 @@
+"""ctypes loader for libbsx.so (the C ABI in include/bsx.h).
+
+There is NO CPU fallback: if the CUDA library is missing or no device is present every call
+raises.  PyTorch is not needed here; callers that want device-resident buffers pass raw device
+pointers (e.g. tensor.data_ptr()) and a stream handle to the `*_dev` entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbsx.so")
+
+SUBCHAIN_BYTES = 128
+SIG_OUT_BYTES = 576
+VAL_IN_BYTES = 240
+
+
+class BsxError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BsxError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.bsx_last_error.restype = C.c_char_p
+        _lib.bsx_launch_count.restype = C.c_uint64
+        _lib.bsx_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    return _lib
+
+
+def _ptr(a) -> C.c_void_p:
+    """numpy array -> host pointer; int -> raw (device) pointer; None -> NULL."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _in(a, dtype=np.uint8) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def pow2_ceil(n: int) -> int:
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+class Context:
+    """One per GPU and per calling thread (a ctx is not thread-safe, like the reference's witness loop)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.bsx_init(int(device), C.byref(h))
+        if rc != 0:
+            raise BsxError(f"bsx_init(device={device}) failed with status {rc} (no CUDA device? there is no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bsx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- plumbing --
+    def _call(self, name: str, *args):
+        rc = getattr(self._lib, name)(self._h, *args)
+        if rc != 0:
+            raise BsxError(f"{name} failed ({rc}): {self._lib.bsx_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.bsx_launch_count(self._h))
+
+    def sync(self):
+        self._call("bsx_sync")
+
+    # -- K1 --
+    def sha256_batch(self, msgs, offsets) -> np.ndarray:
+        offsets = _in(offsets, np.uint32)
+        n = len(offsets) - 1
+        out = np.zeros((n, 32), np.uint8)
+        self._call("bsx_sha256_batch", _ptr(_in(msgs)), _ptr(offsets), C.c_uint32(n), _ptr(out))
+        return out
+
+    def sha512_batch(self, msgs, offsets) -> np.ndarray:
+        offsets = _in(offsets, np.uint32)
+        n = len(offsets) - 1
+        out = np.zeros((n, 64), np.uint8)
+        self._call("bsx_sha512_batch", _ptr(_in(msgs)), _ptr(offsets), C.c_uint32(n), _ptr(out))
+        return out
+
+    # -- K3 --
+    def tm_merkle_proofs(self, leaves, leaf_len: int, aunts, depth: int, path_bits, hashed_leaf: bool = False):
+        path_bits = _in(path_bits, np.uint32)
+        n = len(path_bits)
+        nd = 2 * depth + (0 if hashed_leaf else 1)
+        dig = np.zeros((n, nd, 32), np.uint8)
+        roots = np.zeros((n, 32), np.uint8)
+        self._call("bsx_tm_merkle_proofs", _ptr(_in(leaves)), C.c_uint32(leaf_len), _ptr(_in(aunts)), C.c_uint32(depth),
+                   _ptr(path_bits), C.c_uint32(n), C.c_int(int(hashed_leaf)), _ptr(dig), _ptr(roots))
+        return dig, roots
+
+    # -- K2 --
+    def tm_merkle_tree(self, leaf_digests, N: int, nb_enabled):
+        nb_enabled = _in(nb_enabled, np.uint64)
+        t = len(nb_enabled)
+        P = pow2_ceil(N)
+        inner = np.zeros((t, P - 1, 32), np.uint8)
+        roots = np.zeros((t, 32), np.uint8)
+        self._call("bsx_tm_merkle_tree", _ptr(_in(leaf_digests)), C.c_uint32(N), C.c_uint32(t), _ptr(nb_enabled), _ptr(inner),
+                   _ptr(roots))
+        return inner, roots
+
+    def data_commitment_batch(self, data_hashes, N: int, start_blocks, end_blocks):
+        start_blocks, end_blocks = _in(start_blocks, np.uint64), _in(end_blocks, np.uint64)
+        t = len(start_blocks)
+        P = pow2_ceil(N)
+        dig = np.zeros((t, N + P - 1, 32), np.uint8)
+        roots = np.zeros((t, 32), np.uint8)
+        fail = np.zeros(t, np.uint32)
+        self._call("bsx_data_commitment_batch", _ptr(_in(data_hashes)), C.c_uint32(N), C.c_uint32(t), _ptr(start_blocks),
+                   _ptr(end_blocks), _ptr(dig), _ptr(roots), _ptr(fail))
+        return dig, roots, fail
+
+    # -- map circuit --
+    def prove_subchain_batch(self, B: int, dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, batch_start,
+                             batch_end, global_end, global_end_header):
+        batch_start = _in(batch_start, np.uint64)
+        n = len(batch_start)
+        dig = np.zeros((n, 20 * B - 1, 32), np.uint8)
+        sub = np.zeros((n, SUBCHAIN_BYTES), np.uint8)
+        self._call("bsx_prove_subchain_batch", C.c_uint32(B), C.c_uint32(n), _ptr(_in(dh_leaf)), _ptr(_in(dh_aunts)),
+                   _ptr(_in(lb_leaf)), _ptr(_in(lb_aunts)), _ptr(_in(start_headers)), _ptr(_in(end_headers)),
+                   _ptr(batch_start), _ptr(_in(batch_end, np.uint64)), _ptr(_in(global_end, np.uint64)),
+                   _ptr(_in(global_end_header)), _ptr(dig), _ptr(sub))
+        return dig, sub
+
+    def prove_data_commitment(self, n_ranges: int, n_jobs: int, B: int, dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers,
+                              end_headers, start_blocks, start_header, end_blocks, end_header):
+        R = n_ranges
+        out = dict(map_digests=np.zeros((R, n_jobs, 20 * B - 1, 32), np.uint8),
+                   map_subchains=np.zeros((R, n_jobs, SUBCHAIN_BYTES), np.uint8),
+                   reduce_digests=np.zeros((R, n_jobs - 1, 32), np.uint8),
+                   reduce_nodes=np.zeros((R, n_jobs - 1, SUBCHAIN_BYTES), np.uint8),
+                   data_commitments=np.zeros((R, 32), np.uint8), fail=np.zeros(R, np.uint32))
+        self._call("bsx_prove_data_commitment", C.c_uint32(R), C.c_uint32(n_jobs), C.c_uint32(B), _ptr(_in(dh_leaf)),
+                   _ptr(_in(dh_aunts)), _ptr(_in(lb_leaf)), _ptr(_in(lb_aunts)), _ptr(_in(start_headers)),
+                   _ptr(_in(end_headers)), _ptr(_in(start_blocks, np.uint64)), _ptr(_in(start_header)),
+                   _ptr(_in(end_blocks, np.uint64)), _ptr(_in(end_header)), _ptr(out["map_digests"]),
+                   _ptr(out["map_subchains"]), _ptr(out["reduce_digests"]), _ptr(out["reduce_nodes"]),
+                   _ptr(out["data_commitments"]), _ptr(out["fail"]))
+        return out
+
+    # -- raw access for device-pointer entry points (bench / multi-GPU) --
+    def call_dev(self, name: str, stream: int, *args):
+        """Call a `*_dev` entry point; integer args that are pointers must be wrapped with ptr()."""
+        self._call(name, C.c_void_p(int(stream)), *args)
+
+
+def ptr(x) -> C.c_void_p:
+    return _ptr(x)
+
+
+def u32(x) -> C.c_uint32:
+    return C.c_uint32(int(x))
+
+
+def u64(x) -> C.c_uint64:
+    return C.c_uint64(int(x))

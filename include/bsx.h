@@ -1,0 +1,174 @@
+/*
+ * bsx.h -- C ABI of libbsx, the B200 (sm_100a) witness-generation library for the Blobstream X
+ * header_range / next_header / data_commitment circuits.
+ *
+ * This is the drop-in boundary: a plonky2x `Hint` on the Rust side packs the queued
+ * requests of one accelerator and calls ONE of these entry points instead of looping over
+ * per-request hints.  Each entry point cites the reference interface it replaces
+ * (PX = contracts/lib/succinctx/plonky2x/core/src, TX = contracts/lib/tendermintx/circuits,
+ * BX = blobstreamx root; all under /root/reference).  INTEGRATION.md shows the Rust binding.
+ *
+ * Conventions
+ *   - every function returns 0 (BSX_OK) or a negative bsx_status; bsx_last_error(ctx) gives text.
+ *   - plain pointers + sizes only; the caller owns every buffer.
+ *   - functions without a suffix take HOST pointers and are synchronous (H2D, kernels, D2H).
+ *   - `_dev` twins take DEVICE pointers plus a cudaStream_t (passed as void*) and only enqueue
+ *     work; no allocation, no sync.  They are what the host entry points call internally.
+ *   - one bsx_ctx per GPU; a ctx is NOT thread-safe (the reference's witness loop is single
+ *     threaded: PX/backend/circuit/witness.rs:144-199); use one ctx per calling thread.
+ *   - digests are raw big-endian SHA bytes (what `Bytes32Variable` holds); curve field elements
+ *     are 32 little-endian canonical bytes (= 16 u16 limbs of `FieldVariable`,
+ *     PX/frontend/curta/field/variable.rs:38-103); integers are little-endian.
+ *   - circuit assertions never abort: they are reported as bit masks (BSX_FAIL_* / BSX_VFAIL_*),
+ *     0 meaning the reference circuit would have accepted the witness.
+ */
+#ifndef BSX_H
+#define BSX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSX_VERSION 100
+
+typedef enum {
+    BSX_OK = 0,
+    BSX_ERR_INVALID = -1, /* bad argument */
+    BSX_ERR_CUDA = -2,    /* CUDA runtime failure, see bsx_last_error */
+    BSX_ERR_NOMEM = -3,
+    BSX_ERR_NODEVICE = -4
+} bsx_status;
+
+typedef struct bsx_ctx bsx_ctx;
+
+int bsx_init(int device, bsx_ctx **out);
+void bsx_destroy(bsx_ctx *ctx);
+const char *bsx_last_error(const bsx_ctx *ctx);
+int bsx_version(void);
+/* number of kernels this ctx has launched since init (bench.py's gpu_launches) */
+uint64_t bsx_launch_count(const bsx_ctx *ctx);
+/* block until everything enqueued on the ctx's own stream is done */
+int bsx_sync(bsx_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  batched SHA-256 / SHA-512 digests
+ * replaces: one HashDigestHint::hint per request (PX/frontend/hash/curta/digest_hint.rs:30-38,
+ *           emitted by PX/frontend/hash/curta/builder.rs:26-49); fixed requests pass the whole
+ *           message, variable requests pass the first `len` bytes (digest_hint.rs:31-33).
+ * msgs: concatenated messages; offsets[n+1]; digests: n*32 (n*64) raw bytes.
+ * ------------------------------------------------------------------------------------------ */
+int bsx_sha256_batch(bsx_ctx *ctx, const uint8_t *msgs, const uint32_t *offsets, uint32_t n, uint8_t *digests);
+int bsx_sha512_batch(bsx_ctx *ctx, const uint8_t *msgs, const uint32_t *offsets, uint32_t n, uint8_t *digests);
+int bsx_sha256_batch_dev(bsx_ctx *ctx, void *stream, const uint8_t *msgs, const uint32_t *offsets, uint32_t n,
+                         uint8_t *digests);
+int bsx_sha512_batch_dev(bsx_ctx *ctx, void *stream, const uint8_t *msgs, const uint32_t *offsets, uint32_t n,
+                         uint8_t *digests);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  Tendermint Merkle inclusion proofs, fixed-shape evaluation
+ * replaces: get_root_from_merkle_proof / _hashed_leaf (PX/frontend/merkle/tendermint.rs:62-93):
+ *           leaf hash, then per level BOTH inner(h,aunt) and inner(aunt,h); path bit selects.
+ * leaves: n*leaf_len (or n*32 leaf digests when hashed_leaf); aunts: n*depth*32;
+ * path_bits[n]: bit i = path_indices[i]; digests: n*(2*depth + !hashed_leaf)*32 in request
+ * order; roots: n*32.  depth <= 32.
+ * ------------------------------------------------------------------------------------------ */
+int bsx_tm_merkle_proofs(bsx_ctx *ctx, const uint8_t *leaves, uint32_t leaf_len, const uint8_t *aunts, uint32_t depth,
+                         const uint32_t *path_bits, uint32_t n, int hashed_leaf, uint8_t *digests, uint8_t *roots);
+int bsx_tm_merkle_proofs_dev(bsx_ctx *ctx, void *stream, const uint8_t *leaves, uint32_t leaf_len,
+                             const uint8_t *aunts, uint32_t depth, const uint32_t *path_bits, uint32_t n,
+                             int hashed_leaf, uint8_t *digests, uint8_t *roots);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  Tendermint Merkle tree over hashed leaves, fixed-shape evaluation
+ * replaces: get_root_from_hashed_leaves<N> + hash_merkle_layer (tendermint.rs:124-204).
+ * t trees of N leaf digests each (padded internally to P = 2^ceil(log2 N) with zero digests);
+ * nb_enabled[t] (field element; >= P means all enabled); inner: t*(P-1)*32 raw inner hashes,
+ * layer-major (EVERY pair is hashed); roots: t*32 after select.  N <= 4096.
+ * ------------------------------------------------------------------------------------------ */
+int bsx_tm_merkle_tree(bsx_ctx *ctx, const uint8_t *leaf_digests, uint32_t N, uint32_t t, const uint64_t *nb_enabled,
+                       uint8_t *inner, uint8_t *roots);
+int bsx_tm_merkle_tree_dev(bsx_ctx *ctx, void *stream, const uint8_t *leaf_digests, uint32_t N, uint32_t t,
+                           const uint64_t *nb_enabled, uint8_t *inner, uint8_t *roots);
+
+/* ------------------------------------------------------------------------------------------
+ * get_data_commitment<N>  (BX/circuits/builder.rs:105-148 with encode_data_root_tuple :82-103)
+ * t independent trees; data_hashes: t*N*32; start/end: t u64 each;
+ * digests: t*(N + P-1)*32 = N leaf digests then P-1 inner (layer-major); roots: t*32;
+ * fail[t]: BSX_FAIL_END_LT_START when end < start or end-start >= 2^32.
+ * ------------------------------------------------------------------------------------------ */
+int bsx_data_commitment_batch(bsx_ctx *ctx, const uint8_t *data_hashes, uint32_t N, uint32_t t,
+                              const uint64_t *start_blocks, const uint64_t *end_blocks, uint8_t *digests,
+                              uint8_t *roots, uint32_t *fail);
+int bsx_data_commitment_batch_dev(bsx_ctx *ctx, void *stream, const uint8_t *data_hashes, uint32_t N, uint32_t t,
+                                  const uint64_t *start_blocks, const uint64_t *end_blocks, uint8_t *digests,
+                                  uint8_t *roots, uint32_t *fail);
+
+/* ------------------------------------------------------------------------------------------
+ * prove_subchain<B>  -- the map circuit of header_range (BX/circuits/builder.rs:150-271)
+ * n_jobs independent map jobs of B headers each (B in {1,2,4,...,256}).
+ *   dh_leaf  n_jobs*B*34   protobuf data_hash leaves        dh_aunts n_jobs*B*4*32
+ *   lb_leaf  n_jobs*B*72   protobuf last_block_id leaves    lb_aunts n_jobs*B*4*32
+ *   start_headers/end_headers n_jobs*32 (DataCommitmentProofVariable.{start,end}_header)
+ *   batch_start/batch_end/global_end: n_jobs u64;  global_end_header: n_jobs*32
+ * outputs
+ *   digests   n_jobs*(20B-1)*32 in Curta request order: per header 9 data_hash-proof
+ *             digests then 9 last_block_id-proof digests; then B tuple-leaf digests; then B-1 inner.
+ *   subchains n_jobs*BSX_SUBCHAIN_BYTES  MapReduceSubchainVariable (BX/circuits/vars.rs:29-36):
+ *             [0] is_enabled, [4..8) fail mask, [8..16) start_block, [16..24) end_block,
+ *             [24..56) start_header, [56..88) end_header, [88..120) data_merkle_root.
+ * ------------------------------------------------------------------------------------------ */
+#define BSX_SUBCHAIN_BYTES 128
+#define BSX_FAIL_PREV_HEADER 1u       /* builder.rs:204-207 */
+#define BSX_FAIL_DATA_HASH 2u         /* :209-212 */
+#define BSX_FAIL_END_HEADER 4u        /* :214-219 */
+#define BSX_FAIL_BATCH_END_HEADER 8u  /* :228-232 */
+#define BSX_FAIL_END_LT_START 16u     /* :111-128 */
+#define BSX_FAIL_REDUCE_LINK 32u      /* :349-355 */
+#define BSX_FAIL_RANGE 64u            /* :291-297 */
+#define BSX_FAIL_RESULT 128u          /* :398-406 */
+int bsx_prove_subchain_batch(bsx_ctx *ctx, uint32_t B, uint32_t n_jobs, const uint8_t *dh_leaf,
+                             const uint8_t *dh_aunts, const uint8_t *lb_leaf, const uint8_t *lb_aunts,
+                             const uint8_t *start_headers, const uint8_t *end_headers, const uint64_t *batch_start,
+                             const uint64_t *batch_end, const uint64_t *global_end, const uint8_t *global_end_header,
+                             uint8_t *digests, uint8_t *subchains);
+int bsx_prove_subchain_batch_dev(bsx_ctx *ctx, void *stream, uint32_t B, uint32_t n_jobs, const uint8_t *dh_leaf,
+                                 const uint8_t *dh_aunts, const uint8_t *lb_leaf, const uint8_t *lb_aunts,
+                                 const uint8_t *start_headers, const uint8_t *end_headers,
+                                 const uint64_t *batch_start, const uint64_t *batch_end, const uint64_t *global_end,
+                                 const uint8_t *global_end_header, uint8_t *digests, uint8_t *subchains);
+
+/* ------------------------------------------------------------------------------------------
+ * prove_data_commitment<NB_MAP_JOBS,B>  -- map + reduce of n_ranges independent header ranges
+ * (BX/circuits/builder.rs:273-409; PX/frontend/mapreduce/generator.rs:86-151).  Job j of range r
+ * covers [start+jB, start+(j+1)B); arrays are range-major then job-major.
+ *   start_blocks/end_blocks: n_ranges u64; start_header/end_header: n_ranges*32 (public inputs)
+ * outputs (per range): map_digests n_jobs*(20B-1)*32, map_subchains n_jobs*128,
+ *   reduce_digests (n_jobs-1)*32 layer-major (the bit-level sha256 of builder.rs:363-364),
+ *   reduce_nodes (n_jobs-1)*128, data_commitments 32, fail u32.  n_jobs must be a power of two.
+ * ------------------------------------------------------------------------------------------ */
+int bsx_prove_data_commitment(bsx_ctx *ctx, uint32_t n_ranges, uint32_t n_jobs, uint32_t B, const uint8_t *dh_leaf,
+                              const uint8_t *dh_aunts, const uint8_t *lb_leaf, const uint8_t *lb_aunts,
+                              const uint8_t *start_headers, const uint8_t *end_headers, const uint64_t *start_blocks,
+                              const uint8_t *start_header, const uint64_t *end_blocks, const uint8_t *end_header,
+                              uint8_t *map_digests, uint8_t *map_subchains, uint8_t *reduce_digests,
+                              uint8_t *reduce_nodes, uint8_t *data_commitments, uint32_t *fail);
+int bsx_prove_data_commitment_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs, uint32_t B,
+                                  const uint8_t *dh_leaf, const uint8_t *dh_aunts, const uint8_t *lb_leaf,
+                                  const uint8_t *lb_aunts, const uint8_t *start_headers, const uint8_t *end_headers,
+                                  const uint64_t *start_blocks, const uint8_t *start_header,
+                                  const uint64_t *end_blocks, const uint8_t *end_header, uint8_t *map_digests,
+                                  uint8_t *map_subchains, uint8_t *reduce_digests, uint8_t *reduce_nodes,
+                                  uint8_t *data_commitments, uint32_t *fail);
+/* reduce stage alone over already-computed map outputs (used after the multi-GPU all-gather):
+ * map_subchains n_ranges*n_jobs*128 -> reduce_* / data_commitments / fail as above. */
+int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs,
+                             const uint8_t *map_subchains, const uint64_t *start_blocks, const uint8_t *start_header,
+                             const uint64_t *end_blocks, const uint8_t *end_header, uint32_t B, uint8_t *reduce_digests,
+                             uint8_t *reduce_nodes, uint8_t *data_commitments, uint32_t *fail);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSX_H */
