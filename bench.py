@@ -342,8 +342,63 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_ed25519(args):
+    """Config 5: Ed25519 witness batch, sigs/s (device-resident inputs), next to the CPU oracle."""
+    import torch
+    from blobstreamx_b200 import lib, synthetic as S
+    from blobstreamx_b200.lib import ptr, u32
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = lib.Context(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    base = S.ed25519_batch_inputs(min(args.sigs, 2000))
+    rep = -(-args.sigs // len(base[0]))
+    pks, sigs, msgs, lens, active = (np.concatenate([a] * rep)[: args.sigs] for a in base)
+    d = [torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev) for a in (pks, sigs, msgs, lens, active)]
+    out = torch.zeros(args.sigs * 576, dtype=torch.uint8, device=dev)
+    P = lambda t: ptr(t.data_ptr())
+
+    def step():
+        ctx.call_dev("bsx_ed25519_batch_dev", stream, u32(args.sigs), P(d[0]), P(d[1]), P(d[2]), u32(124), P(d[3]), P(d[4]), P(out))
+
+    step()
+    torch.cuda.synchronize()
+    rec = out.cpu().numpy().reshape(-1, 576)
+    assert (rec[:, 520] == 0xF).all(), "signatures did not verify on the GPU"
+    if not args.no_check:
+        from oracle import cbind as orc
+        k = min(args.sigs, 200)
+        want = orc.ed25519_batch(pks[:k], sigs[:k], msgs[:k], lens[:k], active[:k], threads=8)
+        assert (rec[:k] == want).all(), "GPU Ed25519 records differ from the oracle"
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with ClockSampler(0) as clk:
+        ev[0].record()
+        for _ in range(args.steps):
+            step()
+        ev[1].record()
+        torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cbind as orc
+        k = min(args.sigs, 200)
+        t0 = time.perf_counter()
+        orc.ed25519_batch(pks[:k], sigs[:k], msgs[:k], lens[:k], active[:k], threads=1)
+        cpu = {"value": k / (time.perf_counter() - t0), "unit": "sigs/s", "cores": 1, "kind": "port", "sample": f"{k} signatures"}
+    print(json.dumps({"metric": "sigs/sec, Ed25519 witness batch", "value": args.sigs / (ms * 1e-3), "unit": "sigs/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "i32x10 limbs / i64 accumulate", "data": "synthetic",
+                      "config": {"workload": f"ed25519 witness batch, {args.sigs} signatures/step (CanonicalVote messages, 1% dummy lanes)"},
+                      "gpu_launches": args.steps, "clocks": clk.summary(), "cpu_baseline": cpu}))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519"])
+    ap.add_argument("--sigs", type=int, default=100000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
@@ -358,6 +413,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "ed25519":
+        run_ed25519(args)
     else:
         run_gpu(args)
 

@@ -33,6 +33,7 @@ extern "C" void bsx_destroy(bsx_ctx *ctx) {
         cudaStreamDestroy(ctx->stream);
     }
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->ed_table) cudaFree(ctx->ed_table);
     delete ctx;
 }
 

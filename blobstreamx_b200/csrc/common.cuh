@@ -16,6 +16,7 @@ struct bsx_ctx {
     uint8_t *ws;               // grow-only device workspace for the host entry points
     size_t ws_cap;
     size_t ws_off;
+    void *ed_table;            // s*G window table (k_ed25519.cu), built on first use
 };
 
 namespace bsx {

@@ -1,0 +1,511 @@
+// Ed25519 witness arithmetic for sm_100a: every value the plonky2x EC hints produce for one signature.
+//   EcOpResultHint::{ScalarMul, Decompress, Add}   PX/frontend/ecc/curve25519/curta/result_hint.rs:21-50
+//   verification schedule                           PX/frontend/ecc/curve25519/ed25519/eddsa.rs:161-203
+//   h = LE512(SHA512(R‖A‖M)) div/rem l              PX/frontend/uint/num/biguint/mod.rs:451-488
+//
+// Design (one thread per signature, FMA-pipe bound):
+//   * field elements are 10 signed limbs of 26/25 bits; products accumulate in 64 bits (IMAD.WIDE);
+//     limb bounds follow the classic scheme: mul/sq accept |limb| <= 1.65*2^26 (even) / 2^25 (odd) and
+//     return |limb| <= 1.01*2^25 / 2^24; add/sub take mul outputs and feed only mul inputs.
+//   * fe_mul / fe_sq / fe_sqn are real calls (by-value structs travel in registers), so the whole
+//     kernel stays a few thousand instructions and lives in the instruction cache -- fully inlined
+//     it would be >1 MB of SASS.
+//   * s*G: 64 unsigned 4-bit windows over a precomputed affine table ((y+x, y-x, 2dxy) entries, built
+//     once per context on the device); h*A: 16-entry cached table in local memory, 4 doublings + 1
+//     addition per window, extended coordinates; all three projective results share ONE inversion.
+//   * h, div: Barrett division of the 512-bit digest by l with a 264-bit reciprocal.
+// Affine results in canonical form are unique, so parity with the reference's BigUint affine
+// arithmetic (starkyx, un-vendored) is exact; `decompress` returns the EVEN root.
+//
+// The same source compiles for the host (plain g++) in tests/host_check: that build is TEST
+// infrastructure that checks this arithmetic against the oracle on a machine without a GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BSX_HD __host__ __device__ __forceinline__
+#define BSX_CALL static __host__ __device__ __noinline__
+#else
+#define BSX_HD static inline
+#define BSX_CALL static __attribute__((noinline))
+#endif
+
+namespace bsx {
+namespace ed {
+
+struct fe { int32_t v[10]; };
+
+// ---------------------------------------------------------------------------------------------
+// field arithmetic mod p = 2^255 - 19
+// ---------------------------------------------------------------------------------------------
+BSX_HD fe fe_zero() { fe r; for (int i = 0; i < 10; i++) r.v[i] = 0; return r; }
+BSX_HD fe fe_one() { fe r = fe_zero(); r.v[0] = 1; return r; }
+BSX_HD fe fe_add(const fe &a, const fe &b) { fe r; for (int i = 0; i < 10; i++) r.v[i] = a.v[i] + b.v[i]; return r; }
+BSX_HD fe fe_sub(const fe &a, const fe &b) { fe r; for (int i = 0; i < 10; i++) r.v[i] = a.v[i] - b.v[i]; return r; }
+BSX_HD fe fe_neg(const fe &a) { fe r; for (int i = 0; i < 10; i++) r.v[i] = -a.v[i]; return r; }
+BSX_HD fe fe_select(bool c, const fe &a, const fe &b) { fe r; for (int i = 0; i < 10; i++) r.v[i] = c ? a.v[i] : b.v[i]; return r; }
+
+// balanced carry chain on 64-bit limbs -> |even| <= 2^25, |odd| <= 2^24 (+ a few units)
+BSX_HD fe fe_carry64(int64_t h[10]) {
+    int64_t c;
+#define BSX_FE_CARRY(i, bits, nxt, mul)                      \
+    c = (h[i] + ((int64_t)1 << ((bits)-1))) >> (bits);       \
+    h[nxt] += c * (mul);                                     \
+    h[i] -= c << (bits);
+    BSX_FE_CARRY(0, 26, 1, 1) BSX_FE_CARRY(4, 26, 5, 1)
+    BSX_FE_CARRY(1, 25, 2, 1) BSX_FE_CARRY(5, 25, 6, 1)
+    BSX_FE_CARRY(2, 26, 3, 1) BSX_FE_CARRY(6, 26, 7, 1)
+    BSX_FE_CARRY(3, 25, 4, 1) BSX_FE_CARRY(7, 25, 8, 1)
+    BSX_FE_CARRY(4, 26, 5, 1) BSX_FE_CARRY(8, 26, 9, 1)
+    BSX_FE_CARRY(9, 25, 0, 19)
+    BSX_FE_CARRY(0, 26, 1, 1)
+#undef BSX_FE_CARRY
+    fe r;
+    for (int i = 0; i < 10; i++) r.v[i] = (int32_t)h[i];
+    return r;
+}
+
+// re-balance an add/sub result (same value mod p, limbs back within the mul-output bounds)
+BSX_HD fe fe_reduce(const fe &f) {
+    int64_t h[10];
+    for (int i = 0; i < 10; i++) h[i] = f.v[i];
+    return fe_carry64(h);
+}
+
+BSX_CALL fe fe_mul(const fe f, const fe g) {
+    int32_t g19[10], f2[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) { g19[i] = 19 * g.v[i]; f2[i] = 2 * f.v[i]; }
+    int64_t h[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        int64_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            const int j = (k - i + 10) % 10;
+            const bool wrap = (i + j) >= 10, dbl = (i & 1) && (j & 1);
+            acc += (int64_t)(dbl ? f2[i] : f.v[i]) * (wrap ? g19[j] : g.v[j]);
+        }
+        h[k] = acc;
+    }
+    return fe_carry64(h);
+}
+
+// h = f*f (times 2 when `twice`), using the symmetry of the product
+template <bool TWICE>
+BSX_HD fe fe_sq_impl(const fe &f) {
+    int32_t f2[10], f19[10], f38[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) { f2[i] = 2 * f.v[i]; f19[i] = 19 * f.v[i]; f38[i] = 38 * f.v[i]; }
+    int64_t h[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        int64_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            const int j = (k - i + 10) % 10;
+            if (i > j) continue;
+            const bool wrap = (i + j) >= 10, dbl = (i & 1) && (j & 1);
+            // term = f_i f_j * (dbl?2:1) * (wrap?19:1) * (i<j?2:1)
+            int32_t a, b;
+            if (i == j) { a = f.v[i]; b = wrap ? (dbl ? f38[i] : f19[i]) : (dbl ? f2[i] : f.v[i]); }
+            else if (wrap && (j & 1)) { a = dbl ? f2[i] : f.v[i]; b = f38[j]; }   // 38 f_j fits only for odd j
+            else if (wrap) { a = f2[i]; b = f19[j]; }
+            else { a = dbl ? f2[i] : f.v[i]; b = f2[j]; }
+            acc += (int64_t)a * b;
+        }
+        h[k] = TWICE ? acc * 2 : acc;
+    }
+    return fe_carry64(h);
+}
+BSX_CALL fe fe_sq(const fe f) { return fe_sq_impl<false>(f); }
+BSX_CALL fe fe_sq2(const fe f) { return fe_sq_impl<true>(f); }
+// n >= 1 successive squarings (one call for the long chains of inversion / square roots)
+BSX_CALL fe fe_sqn(fe f, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) f = fe_sq_impl<false>(f);
+    return f;
+}
+
+// 32 little-endian bytes (bit 255 ignored) -> balanced limbs
+BSX_HD fe fe_frombytes(const uint8_t *s) {
+    uint64_t w[4];
+    for (int i = 0; i < 4; i++) {
+        uint64_t x = 0;
+        for (int j = 7; j >= 0; j--) x = (x << 8) | s[8 * i + j];
+        w[i] = x;
+    }
+    w[3] &= 0x7fffffffffffffffULL;
+    int64_t h[10];
+    const int off[10] = {0, 26, 51, 77, 102, 128, 153, 179, 204, 230};
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const int o = off[i], wi = o >> 6, sh = o & 63, bits = (i & 1) ? 25 : 26;
+        uint64_t x = w[wi] >> sh;
+        if (sh + bits > 64 && wi < 3) x |= w[wi + 1] << (64 - sh);
+        h[i] = (int64_t)(x & (((uint64_t)1 << bits) - 1));
+    }
+    return fe_carry64(h);
+}
+
+// canonical little-endian bytes in [0, p); input within the mul-output bounds
+BSX_HD void fe_tobytes(uint8_t *s, const fe &f) {
+    int32_t h[10];
+    for (int i = 0; i < 10; i++) h[i] = f.v[i];
+    int32_t q = (19 * h[9] + (1 << 24)) >> 25;
+#pragma unroll
+    for (int i = 0; i < 10; i++) q = (h[i] + q) >> ((i & 1) ? 25 : 26);
+    h[0] += 19 * q;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const int bits = (i & 1) ? 25 : 26;
+        int32_t c = h[i] >> bits;
+        if (i < 9) h[i + 1] += c;
+        h[i] -= c << bits;
+    }
+    uint64_t w[4] = {0, 0, 0, 0};
+    const int off[10] = {0, 26, 51, 77, 102, 128, 153, 179, 204, 230};
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const int o = off[i], wi = o >> 6, sh = o & 63;
+        w[wi] |= (uint64_t)(uint32_t)h[i] << sh;
+        if (sh + 26 > 64 && wi < 3) w[wi + 1] |= (uint64_t)(uint32_t)h[i] >> (64 - sh);
+    }
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 8; j++) s[8 * i + j] = (uint8_t)(w[i] >> (8 * j));
+}
+
+BSX_HD bool fe_iszero_bytes(const uint8_t *s) {
+    uint8_t x = 0;
+    for (int i = 0; i < 32; i++) x |= s[i];
+    return x == 0;
+}
+BSX_HD bool bytes_eq32(const uint8_t *a, const uint8_t *b) {
+    uint8_t x = 0;
+    for (int i = 0; i < 32; i++) x |= a[i] ^ b[i];
+    return x == 0;
+}
+
+// z^(2^252 - 3) = z^((p-5)/8)
+BSX_HD fe fe_pow22523(const fe &z) {
+    fe t0 = fe_sq(z);                 // 2
+    fe t1 = fe_sqn(t0, 2);            // 8
+    t1 = fe_mul(z, t1);               // 9
+    t0 = fe_mul(t0, t1);              // 11
+    t0 = fe_sq(t0);                   // 22
+    t0 = fe_mul(t1, t0);              // 31 = 2^5-1
+    t1 = fe_sqn(t0, 5);
+    t0 = fe_mul(t1, t0);              // 2^10-1
+    t1 = fe_sqn(t0, 10);
+    t1 = fe_mul(t1, t0);              // 2^20-1
+    fe t2 = fe_sqn(t1, 20);
+    t1 = fe_mul(t2, t1);              // 2^40-1
+    t1 = fe_sqn(t1, 10);
+    t0 = fe_mul(t1, t0);              // 2^50-1
+    t1 = fe_sqn(t0, 50);
+    t1 = fe_mul(t1, t0);              // 2^100-1
+    t2 = fe_sqn(t1, 100);
+    t1 = fe_mul(t2, t1);              // 2^200-1
+    t1 = fe_sqn(t1, 50);
+    t0 = fe_mul(t1, t0);              // 2^250-1
+    t0 = fe_sqn(t0, 2);               // 2^252-4
+    return fe_mul(t0, z);             // 2^252-3
+}
+
+// z^(p-2)
+BSX_HD fe fe_invert(const fe &z) {
+    fe t0 = fe_sq(z);                 // 2
+    fe t1 = fe_sqn(t0, 2);            // 8
+    t1 = fe_mul(z, t1);               // 9
+    t0 = fe_mul(t0, t1);              // 11
+    fe t2 = fe_sq(t0);                // 22
+    t1 = fe_mul(t1, t2);              // 31
+    t2 = fe_sqn(t1, 5);
+    t1 = fe_mul(t2, t1);              // 2^10-1
+    t2 = fe_sqn(t1, 10);
+    t2 = fe_mul(t2, t1);              // 2^20-1
+    fe t3 = fe_sqn(t2, 20);
+    t2 = fe_mul(t3, t2);              // 2^40-1
+    t2 = fe_sqn(t2, 10);
+    t1 = fe_mul(t2, t1);              // 2^50-1
+    t2 = fe_sqn(t1, 50);
+    t2 = fe_mul(t2, t1);              // 2^100-1
+    t3 = fe_sqn(t2, 100);
+    t2 = fe_mul(t3, t2);              // 2^200-1
+    t2 = fe_sqn(t2, 50);
+    t1 = fe_mul(t2, t1);              // 2^250-1
+    t1 = fe_sqn(t1, 5);               // 2^255-32
+    return fe_mul(t1, t0);            // 2^255-21
+}
+
+BSX_HD fe fe_const(const int32_t c[10]) { fe r; for (int i = 0; i < 10; i++) r.v[i] = c[i]; return r; }
+#define BSX_FE_D {56195235, 13857412, 51736253, 6949390, 114729, 24766616, 60832955, 30306712, 48412415, 21499315}
+#define BSX_FE_2D {45281625, 27714825, 36363642, 13898781, 229458, 15978800, 54557047, 27058993, 29715967, 9444199}
+#define BSX_FE_SQRTM1 {34513072, 25610706, 9377949, 3500415, 12389472, 33281959, 41962654, 31548777, 326685, 11406482}
+#define BSX_FE_GX {52811034, 25909283, 16144682, 17082669, 27570973, 30858332, 40966398, 8378388, 20764389, 8758491}
+#define BSX_FE_GY {40265304, 26843545, 13421772, 20132659, 26843545, 6710886, 53687091, 13421772, 40265318, 26843545}
+
+// ---------------------------------------------------------------------------------------------
+// points: extended twisted Edwards coordinates, a = -1
+// ---------------------------------------------------------------------------------------------
+struct ge_p3 { fe X, Y, Z, T; };           // x = X/Z, y = Y/Z, xy = T/Z
+struct ge_p1p1 { fe X, Y, Z, T; };         // completed: x = X/Z, y = Y/T
+struct ge_cached { fe YpX, YmX, Z, T2d; };
+struct ge_niels { fe ypx, ymx, xy2d; };    // affine precomputed (Z = 1)
+
+BSX_HD ge_p3 ge_identity() { ge_p3 r; r.X = fe_zero(); r.Y = fe_one(); r.Z = fe_one(); r.T = fe_zero(); return r; }
+BSX_HD ge_p3 ge_from_affine(const fe &x, const fe &y) { ge_p3 r; r.X = x; r.Y = y; r.Z = fe_one(); r.T = fe_mul(x, y); return r; }
+BSX_HD ge_cached ge_to_cached(const ge_p3 &p) {
+    const int32_t d2[10] = BSX_FE_2D;
+    ge_cached c; c.YpX = fe_add(p.Y, p.X); c.YmX = fe_sub(p.Y, p.X); c.Z = p.Z; c.T2d = fe_mul(p.T, fe_const(d2));
+    return c;
+}
+// completed -> extended (4M); with_t=false skips T (3M) when the next operation is a doubling
+BSX_HD ge_p3 ge_p1p1_to_p3(const ge_p1p1 &p, bool with_t) {
+    ge_p3 r; r.X = fe_mul(p.X, p.T); r.Y = fe_mul(p.Y, p.Z); r.Z = fe_mul(p.Z, p.T);
+    r.T = with_t ? fe_mul(p.X, p.Y) : fe_zero();
+    return r;
+}
+// doubling (uses X, Y, Z only): 3S + 1 S2
+BSX_HD ge_p1p1 ge_dbl(const ge_p3 &p) {
+    ge_p1p1 r;
+    fe xx = fe_sq(p.X), yy = fe_sq(p.Y), zz2 = fe_sq2(p.Z);
+    fe a = fe_sq(fe_add(p.X, p.Y));
+    r.Y = fe_add(yy, xx); r.Z = fe_sub(yy, xx); r.X = fe_sub(a, r.Y); r.T = fe_sub(zz2, r.Z);
+    return r;
+}
+// p + q, q cached: 4M
+BSX_HD ge_p1p1 ge_add_cached(const ge_p3 &p, const ge_cached &q) {
+    ge_p1p1 r;
+    fe a = fe_mul(fe_add(p.Y, p.X), q.YpX), b = fe_mul(fe_sub(p.Y, p.X), q.YmX);
+    fe c = fe_mul(q.T2d, p.T), zz = fe_mul(p.Z, q.Z);
+    fe d = fe_add(zz, zz);
+    r.X = fe_sub(a, b); r.Y = fe_add(a, b); r.Z = fe_add(d, c); r.T = fe_sub(d, c);
+    return r;
+}
+// p + q, q affine precomputed: 3M
+BSX_HD ge_p1p1 ge_add_niels(const ge_p3 &p, const ge_niels &q) {
+    ge_p1p1 r;
+    fe a = fe_mul(fe_add(p.Y, p.X), q.ypx), b = fe_mul(fe_sub(p.Y, p.X), q.ymx);
+    fe c = fe_mul(q.xy2d, p.T);
+    fe d = fe_add(p.Z, p.Z);
+    r.X = fe_sub(a, b); r.Y = fe_add(a, b); r.Z = fe_add(d, c); r.T = fe_sub(d, c);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decompress (starkyx chip::ec::edwards::ed25519::decompress, call site result_hint.rs:40):
+// returns the affine point and `root` = the EVEN square root of (y^2-1)/(d y^2+1); x = root when
+// the sign bit is 0, p - root otherwise.  ok=false when the ratio is not a square (the reference
+// panics there); the outputs are then the identity and root = 0 (same convention in the oracle).
+// ---------------------------------------------------------------------------------------------
+BSX_HD bool ge_decompress(const uint8_t *in, fe &x, fe &y, uint8_t x_bytes[32], uint8_t y_bytes[32], uint8_t root_bytes[32]) {
+    const int32_t dc[10] = BSX_FE_D, sm1[10] = BSX_FE_SQRTM1;
+    const bool sign = (in[31] >> 7) != 0;
+    y = fe_frombytes(in);
+    fe yy = fe_sq(y);
+    fe u = fe_sub(yy, fe_one());
+    fe v = fe_add(fe_mul(yy, fe_const(dc)), fe_one());
+    fe v3 = fe_mul(fe_sq(v), v);
+    fe uv7 = fe_mul(fe_mul(fe_sq(v3), v), u);
+    fe r = fe_mul(fe_mul(fe_pow22523(uv7), v3), u);   // u v^3 (u v^7)^((p-5)/8)
+    fe vxx = fe_mul(fe_sq(r), v);
+    uint8_t a[32], b[32];
+    fe_tobytes(a, fe_reduce(fe_sub(vxx, u)));  // v r^2 - u
+    bool ok = fe_iszero_bytes(a);
+    if (!ok) {
+        fe_tobytes(b, fe_reduce(fe_add(vxx, u)));  // v r^2 + u
+        if (fe_iszero_bytes(b)) { r = fe_mul(r, fe_const(sm1)); ok = true; }
+    }
+    if (!ok) {
+        x = fe_zero(); y = fe_one();
+        for (int i = 0; i < 32; i++) { x_bytes[i] = 0; y_bytes[i] = 0; root_bytes[i] = 0; }
+        y_bytes[0] = 1;
+        return false;
+    }
+    fe_tobytes(root_bytes, r);
+    if (root_bytes[0] & 1) { r = fe_neg(r); fe_tobytes(root_bytes, r); }
+    x = sign ? fe_neg(r) : r;
+    if (sign) fe_tobytes(x_bytes, x); else for (int i = 0; i < 32; i++) x_bytes[i] = root_bytes[i];
+    fe_tobytes(y_bytes, y);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar multiplication
+// ---------------------------------------------------------------------------------------------
+#define BSX_ED_BASE_WINDOWS 64
+#define BSX_ED_BASE_ENTRIES 15
+// table[w*15 + (d-1)] = d * 16^w * G   (d = 1..15), affine precomputed form
+BSX_HD ge_p3 ge_scalarmult_base(const uint8_t s[32], const ge_niels *table) {
+    ge_p3 acc = ge_identity();
+#pragma unroll 1
+    for (int w = 0; w < BSX_ED_BASE_WINDOWS; w++) {
+        const uint32_t dgt = (s[w >> 1] >> ((w & 1) * 4)) & 15;
+        if (dgt) {
+            const ge_niels q = table[w * BSX_ED_BASE_ENTRIES + (dgt - 1)];
+            acc = ge_p1p1_to_p3(ge_add_niels(acc, q), true);
+        }
+    }
+    return acc;
+}
+
+// scalar * P for an arbitrary 256-bit scalar (EcOpResultHint::ScalarMul takes the U256 unreduced)
+BSX_HD ge_p3 ge_scalarmult(const uint8_t s[32], const ge_p3 &P) {
+    ge_cached tab[15];                       // tab[d-1] = d*P
+    {
+        ge_p3 cur = P;
+        tab[0] = ge_to_cached(cur);
+#pragma unroll 1
+        for (int d = 2; d <= 15; d++) {
+            cur = ge_p1p1_to_p3(ge_add_cached(cur, tab[0]), true);
+            tab[d - 1] = ge_to_cached(cur);
+        }
+    }
+    ge_p3 acc = ge_identity();
+#pragma unroll 1
+    for (int w = 63; w >= 0; w--) {
+        if (w != 63) {
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) acc = ge_p1p1_to_p3(ge_dbl(acc), k == 3);
+        }
+        const uint32_t dgt = (s[w >> 1] >> ((w & 1) * 4)) & 15;
+        // T is consumed only by additions: the 4th doubling of a window produces it, an addition
+        // drops it again (the next step is a doubling) except in the last window.
+        if (dgt) acc = ge_p1p1_to_p3(ge_add_cached(acc, tab[dgt - 1]), w == 0);
+    }
+    return acc;
+}
+
+// one entry of the s*G table: d * 16^w * G in affine precomputed form (run once per context)
+BSX_HD ge_niels ge_base_table_entry(int w, int d) {
+    const int32_t gx[10] = BSX_FE_GX, gy[10] = BSX_FE_GY, d2[10] = BSX_FE_2D;
+    uint8_t s[32];
+    for (int i = 0; i < 32; i++) s[i] = 0;
+    s[w >> 1] = (uint8_t)(d << ((w & 1) * 4));
+    ge_p3 r = ge_scalarmult(s, ge_from_affine(fe_const(gx), fe_const(gy)));
+    fe zi = fe_invert(r.Z);
+    fe x = fe_mul(r.X, zi), y = fe_mul(r.Y, zi);
+    ge_niels n;
+    n.ypx = fe_reduce(fe_add(y, x)); n.ymx = fe_reduce(fe_sub(y, x)); n.xy2d = fe_mul(fe_mul(x, y), fe_const(d2));
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 512-bit digest div/rem l  (l = 2^252 + 27742317777372353535851937790883648493)
+// ---------------------------------------------------------------------------------------------
+BSX_HD void sc_divrem_l(const uint8_t digest[64], uint8_t rem[32], uint8_t div[40]) {
+    const uint32_t L[9] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0u, 0u, 0u, 0x10000000u, 0u};
+    const uint32_t MU[9] = {0xa2c131b3u, 0xd9ce5a30u, 0x86329a7eu, 0x106215d0u, 0xfffffeb2u, 0xffffffffu,
+                            0xffffffffu, 0xffffffffu, 0xffu};  // floor(2^516 / l)
+    uint32_t x[16];
+    for (int i = 0; i < 16; i++)
+        x[i] = (uint32_t)digest[4 * i] | ((uint32_t)digest[4 * i + 1] << 8) | ((uint32_t)digest[4 * i + 2] << 16) |
+               ((uint32_t)digest[4 * i + 3] << 24);
+    // x1 = x >> 248 (9 limbs)
+    uint32_t x1[9];
+    for (int i = 0; i < 9; i++) {
+        uint32_t lo = x[7 + i] >> 24, hi = (7 + i + 1 < 16) ? (x[8 + i] << 8) : 0u;
+        x1[i] = lo | hi;
+    }
+    // t = x1 * MU (18 limbs); q = t >> 268
+    uint32_t t[18];
+    for (int i = 0; i < 18; i++) t[i] = 0;
+    for (int i = 0; i < 9; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 9; j++) {
+            uint64_t m = (uint64_t)x1[i] * MU[j] + t[i + j] + carry;
+            t[i + j] = (uint32_t)m;
+            carry = m >> 32;
+        }
+        t[i + 9] = (uint32_t)carry;
+    }
+    uint32_t q[9];
+    for (int i = 0; i < 9; i++) {  // shift right by 268 = 8 limbs + 12 bits
+        uint32_t lo = t[8 + i] >> 12, hi = (9 + i < 18) ? (t[9 + i] << 20) : 0u;
+        q[i] = lo | hi;
+    }
+    // r = x - q*l  (mod 2^288)
+    uint32_t ql[9];
+    for (int i = 0; i < 9; i++) ql[i] = 0;
+    for (int i = 0; i < 9; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; i + j < 9; j++) {
+            uint64_t m = (uint64_t)q[i] * L[j] + ql[i + j] + carry;
+            ql[i + j] = (uint32_t)m;
+            carry = m >> 32;
+        }
+    }
+    uint32_t r[9];
+    {
+        uint64_t borrow = 0;
+        for (int i = 0; i < 9; i++) {
+            uint64_t dd = (uint64_t)x[i] - ql[i] - borrow;
+            r[i] = (uint32_t)dd;
+            borrow = (dd >> 32) & 1;
+        }
+    }
+    // at most one correction (q_hat in {q-1, q})
+    for (int it = 0; it < 2; it++) {
+        bool ge = true;
+        for (int i = 8; i >= 0; i--) {
+            if (r[i] != L[i]) { ge = r[i] > L[i]; break; }
+        }
+        if (!ge) break;
+        uint64_t borrow = 0;
+        for (int i = 0; i < 9; i++) {
+            uint64_t dd = (uint64_t)r[i] - L[i] - borrow;
+            r[i] = (uint32_t)dd;
+            borrow = (dd >> 32) & 1;
+        }
+        for (int i = 0; i < 9; i++) { if (++q[i] != 0) break; }
+    }
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 4; j++) rem[4 * i + j] = (uint8_t)(r[i] >> (8 * j));
+    for (int i = 0; i < 9; i++) for (int j = 0; j < 4; j++) div[4 * i + j] = (uint8_t)(q[i] >> (8 * j));
+    for (int j = 36; j < 40; j++) div[j] = 0;
+}
+
+BSX_HD bool sc_lt_l(const uint8_t s[32]) {
+    const uint8_t Lb[32] = {0xed, 0xd3, 0xf5, 0x5c, 0x1a, 0x63, 0x12, 0x58, 0xd6, 0x9c, 0xf7, 0xa2, 0xde, 0xf9, 0xde, 0x14,
+                            0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x10};
+    for (int i = 31; i >= 0; i--) {
+        if (s[i] != Lb[i]) return s[i] < Lb[i];
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one signature: the record of include/bsx.h (BSX_SIG_OUT_BYTES) from pk, sig and the SHA-512 digest
+//   [0..64) digest  [64..96) h  [96..136) div  [136..200) sG  [200..264) A  [264..296) A_root
+//   [296..360) hA  [360..424) Rp  [424..456) R_root  [456..520) Rp+hA  [520..524) flags
+// flags: 1 s<l, 2 A decompressed, 4 R decompressed, 8 sG == Rp+hA
+// ---------------------------------------------------------------------------------------------
+BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], const uint8_t digest[64],
+                                 const ge_niels *base_table, uint8_t *out) {
+    for (int i = 0; i < 64; i++) out[i] = digest[i];
+    sc_divrem_l(digest, out + 64, out + 96);
+    uint32_t flags = sc_lt_l(sig + 32) ? 1u : 0u;
+    // A, Rp
+    fe ax, ay, rx, ry;
+    if (ge_decompress(pk, ax, ay, out + 200, out + 232, out + 264)) flags |= 2u;
+    if (ge_decompress(sig, rx, ry, out + 360, out + 392, out + 424)) flags |= 4u;
+    // sG, hA, Rp + hA in projective form
+    ge_p3 sg = ge_scalarmult_base(sig + 32, base_table);
+    ge_p3 ha = ge_scalarmult(out + 64, ge_from_affine(ax, ay));
+    ge_p3 sum = ge_p1p1_to_p3(ge_add_cached(ha, ge_to_cached(ge_from_affine(rx, ry))), false);
+    // one inversion for the three Z's
+    fe z12 = fe_mul(sg.Z, ha.Z);
+    fe inv = fe_invert(fe_mul(z12, sum.Z));
+    fe isum = fe_mul(inv, z12);
+    fe i12 = fe_mul(inv, sum.Z);
+    fe isg = fe_mul(i12, ha.Z), iha = fe_mul(i12, sg.Z);
+    fe_tobytes(out + 136, fe_mul(sg.X, isg)); fe_tobytes(out + 168, fe_mul(sg.Y, isg));
+    fe_tobytes(out + 296, fe_mul(ha.X, iha)); fe_tobytes(out + 328, fe_mul(ha.Y, iha));
+    fe_tobytes(out + 456, fe_mul(sum.X, isum)); fe_tobytes(out + 488, fe_mul(sum.Y, isum));
+    if (bytes_eq32(out + 136, out + 456) && bytes_eq32(out + 168, out + 488)) flags |= 8u;
+    out[520] = (uint8_t)flags; out[521] = 0; out[522] = 0; out[523] = 0;
+    for (int i = 524; i < 576; i++) out[i] = 0;
+}
+
+}  // namespace ed
+}  // namespace bsx

@@ -1,0 +1,114 @@
+// K4+K5: batched Ed25519 witness generation (one thread per signature).
+// Replaces, per signature, the CPU hints of curta_eddsa_verify_sigs (PX/frontend/ecc/curve25519/
+// ed25519/eddsa.rs:161-203): HashDigestHint<SHA512> (PX/frontend/hash/sha/sha512/curta.rs:103-111),
+// BigUintDivRemGenerator (PX/frontend/uint/num/biguint/mod.rs:451-488) and the seven EcOpResultHint
+// calls (PX/frontend/ecc/curve25519/curta/result_hint.rs:21-50).  Inactive lanes run on the DUMMY
+// triple exactly like curta_eddsa_verify_sigs_conditional (eddsa.rs:72-127).
+#include "common.cuh"
+#include "ed25519.cuh"
+#include "sha512.cuh"
+
+namespace bsx {
+
+using namespace ed;
+
+__device__ __constant__ uint8_t DUMMY_PK[32] = {138, 136, 227, 221, 116, 9, 241, 149, 253, 82, 219, 45, 60, 186, 93, 114,
+                                                 202, 103, 9, 191, 29, 148, 18, 27, 243, 116, 136, 1, 180, 15, 111, 92};
+__device__ __constant__ uint8_t DUMMY_SIG[64] = {55, 20, 104, 158, 84, 120, 194, 17, 6, 237, 157, 164, 85, 88, 158, 137,
+                                                  187, 119, 187, 240, 159, 73, 80, 63, 133, 162, 74, 91, 48, 53, 6, 138,
+                                                  1, 41, 22, 121, 249, 46, 198, 145, 155, 102, 3, 210, 168, 135, 173, 55,
+                                                  252, 72, 45, 126, 169, 178, 191, 7, 153, 67, 112, 90, 150, 33, 140, 7};
+
+__global__ void __launch_bounds__(64) ed25519_base_table_kernel(ge_niels *table) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES) return;
+    table[i] = ge_base_table_entry(i / BSX_ED_BASE_ENTRIES, i % BSX_ED_BASE_ENTRIES + 1);
+}
+
+__global__ void __launch_bounds__(64) ed25519_batch_kernel(uint32_t n, const uint8_t *__restrict__ pks,
+                                                           const uint8_t *__restrict__ sigs,
+                                                           const uint8_t *__restrict__ msgs, uint32_t msg_stride,
+                                                           const uint32_t *__restrict__ msg_lens,
+                                                           const uint8_t *__restrict__ active,
+                                                           const ge_niels *__restrict__ table, uint8_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t pk[32], sig[64];
+    const bool on = !active || active[i];
+    const uint8_t *m = msgs + (size_t)msg_stride * i;
+    uint32_t len = msg_lens ? msg_lens[i] : msg_stride;
+    if (len > msg_stride) len = msg_stride;
+    if (on) {
+        for (int k = 0; k < 32; k++) pk[k] = pks[32 * (size_t)i + k];
+        for (int k = 0; k < 64; k++) sig[k] = sigs[64 * (size_t)i + k];
+    } else {
+        for (int k = 0; k < 32; k++) pk[k] = DUMMY_PK[k];
+        for (int k = 0; k < 64; k++) sig[k] = DUMMY_SIG[k];
+        len = 32;  // DUMMY_MSG_LENGTH_BYTES: 32 zero bytes (eddsa.rs:28-30,62-63)
+    }
+    uint64_t st[8];
+    sha512_bytes(
+        [&](uint32_t k) -> uint8_t { return k < 32 ? sig[k] : (k < 64 ? pk[k - 32] : (on ? m[k - 64] : (uint8_t)0)); },
+        64 + len, st);
+    uint8_t digest[64];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) digest[8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
+    ed25519_witness_core(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
+}
+
+}  // namespace bsx
+
+using namespace bsx;
+
+// the s*G table lives in the ctx (built on first use)
+static int ensure_base_table(bsx_ctx *ctx, cudaStream_t st) {
+    if (ctx->ed_table) return BSX_OK;
+    const int entries = BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES;
+    BSX_CUDA(ctx, cudaMalloc(&ctx->ed_table, sizeof(ed::ge_niels) * entries));
+    ed25519_base_table_kernel<<<(entries + 63) / 64, 64, 0, st>>>(reinterpret_cast<ed::ge_niels *>(ctx->ed_table));
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+extern "C" int bsx_ed25519_batch_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, const uint8_t *sigs,
+                                     const uint8_t *msgs, uint32_t msg_stride, const uint32_t *msg_lens,
+                                     const uint8_t *active, uint8_t *out) {
+    BSX_REQUIRE(ctx, ctx && pks && sigs && (msgs || msg_stride == 0) && out);
+    if (n == 0) return BSX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_base_table(ctx, st);
+    if (rc) return rc;
+    ed25519_batch_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, pks, sigs, msgs, msg_stride, msg_lens, active,
+                                                       reinterpret_cast<const ed::ge_niels *>(ctx->ed_table), out);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+extern "C" int bsx_ed25519_batch(bsx_ctx *ctx, uint32_t n, const uint8_t *pks, const uint8_t *sigs, const uint8_t *msgs,
+                                 uint32_t msg_stride, const uint32_t *msg_lens, const uint8_t *active, uint8_t *out) {
+    BSX_REQUIRE(ctx, ctx && pks && sigs && (msgs || msg_stride == 0) && out);
+    if (n == 0) return BSX_OK;
+    BSX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t N = n, s_msg = N * msg_stride;
+    int rc = ws_begin(ctx, ws_size(32 * N) + ws_size(64 * N) + ws_size(s_msg + 16) + ws_size(4 * N) + ws_size(N) +
+                               ws_size(BSX_SIG_OUT_BYTES * N));
+    if (rc) return rc;
+    uint8_t *d_pk = ws_take<uint8_t>(ctx, 32 * N), *d_sig = ws_take<uint8_t>(ctx, 64 * N);
+    uint8_t *d_msg = ws_take<uint8_t>(ctx, s_msg + 16);
+    uint32_t *d_len = ws_take<uint32_t>(ctx, N);
+    uint8_t *d_act = ws_take<uint8_t>(ctx, N), *d_out = ws_take<uint8_t>(ctx, BSX_SIG_OUT_BYTES * N);
+    cudaStream_t st = ctx->stream;
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_pk, pks, 32 * N, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_sig, sigs, 64 * N, cudaMemcpyHostToDevice, st));
+    if (s_msg) BSX_CUDA(ctx, cudaMemcpyAsync(d_msg, msgs, s_msg, cudaMemcpyHostToDevice, st));
+    if (msg_lens) BSX_CUDA(ctx, cudaMemcpyAsync(d_len, msg_lens, 4 * N, cudaMemcpyHostToDevice, st));
+    if (active) BSX_CUDA(ctx, cudaMemcpyAsync(d_act, active, N, cudaMemcpyHostToDevice, st));
+    rc = bsx_ed25519_batch_dev(ctx, st, n, d_pk, d_sig, d_msg, msg_stride, msg_lens ? d_len : nullptr,
+                               active ? d_act : nullptr, d_out);
+    if (rc) return rc;
+    BSX_CUDA(ctx, cudaMemcpyAsync(out, d_out, BSX_SIG_OUT_BYTES * N, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaStreamSynchronize(st));
+    return BSX_OK;
+}

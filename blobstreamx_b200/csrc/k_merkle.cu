@@ -88,11 +88,7 @@ __global__ void data_commitment_kernel(const uint8_t *__restrict__ data_hashes, 
             for (int k = 1; k < 8; k++) w[8 + k] = __funnelshift_r(x[k], x[k - 1], 8);
             sha256_init(d);
             sha256_compress(d, w);
-            w[0] = (x[7] << 24) | 0x00800000u;                   // d31 80 00 00
-#pragma unroll
-            for (int k = 1; k < 15; k++) w[k] = 0;
-            w[15] = 65 * 8;
-            sha256_compress(d, w);
+            sha256_tail65(d, x[7] & 0xffu);
             store_digest_be(out + 32 * (size_t)i, d);
         } else {
 #pragma unroll

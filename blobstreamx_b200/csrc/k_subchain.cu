@@ -156,11 +156,7 @@ __global__ void __launch_bounds__((2 * B < 32) ? 32 : 2 * B) prove_subchain_kern
         for (int k = 1; k < 8; k++) w[8 + k] = __funnelshift_r(x[k], x[k - 1], 8);
         sha256_init(d);
         sha256_compress(d, w);
-        w[0] = (x[7] << 24) | 0x00800000u;
-#pragma unroll
-        for (int k = 1; k < 15; k++) w[k] = 0;
-        w[15] = 65 * 8;
-        sha256_compress(d, w);
+        sha256_tail65(d, x[7] & 0xffu);
         store_digest_be(out + 32 * (size_t)(18 * B + i), d);
 #pragma unroll
         for (int k = 0; k < 8; k++) s_A[8 * i + k] = d[k];

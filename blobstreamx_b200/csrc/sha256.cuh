@@ -34,7 +34,7 @@ __device__ __forceinline__ void sha256_init(uint32_t st[8]) {
 }
 
 // One compression.  w[16] is the big-endian-decoded chunk and is clobbered (rolling schedule).
-__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+__device__ __forceinline__ void sha256_rounds(uint32_t st[8], uint32_t w[16]) {
     constexpr uint32_t K[64] = {
         0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
         0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
@@ -60,6 +60,64 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) 
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
+// The 64 unrolled rounds are ~1500 instructions (24 KB).  Inlined at every hash site a kernel grows
+// to hundreds of KB and stalls on instruction fetch (r01a profile: 52 % of samples `no_instructions`),
+// so the compression is ONE real function per module; state and block travel by value in registers.
+//   BSX_SHA_VARIANT 0: inline everywhere (the r01a build)   1: one generic function
+//                   2: generic + a function specialised for the constant tail block of 65-byte messages
+#ifndef BSX_SHA_VARIANT
+#define BSX_SHA_VARIANT 2
+#endif
+struct sha256_state { uint32_t s[8]; };
+struct sha256_block { uint32_t w[16]; };
+#if BSX_SHA_VARIANT >= 1
+static __device__ __noinline__ sha256_state sha256_compress_fn(sha256_state st, sha256_block blk) {
+    sha256_rounds(st.s, blk.w);
+    return st;
+}
+__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
+    sha256_state s; sha256_block b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s.s[i] = st[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++) b.w[i] = w[i];
+    s = sha256_compress_fn(s, b);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = s.s[i];
+}
+#else
+__device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) { sha256_rounds(st, w); }
+#endif
+// second block of a 65-byte message (inner nodes, data-root tuples): byte 64, 0x80, zeros, bit length 520
+#if BSX_SHA_VARIANT >= 2
+static __device__ __noinline__ sha256_state sha256_tail65_fn(sha256_state st, uint32_t last_byte) {
+    uint32_t w[16];
+    w[0] = (last_byte << 24) | 0x00800000u;
+#pragma unroll
+    for (int i = 1; i < 15; i++) w[i] = 0;
+    w[15] = 65 * 8;
+    sha256_rounds(st.s, w);
+    return st;
+}
+__device__ __forceinline__ void sha256_tail65(uint32_t st[8], uint32_t last_byte) {
+    sha256_state s;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s.s[i] = st[i];
+    s = sha256_tail65_fn(s, last_byte);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = s.s[i];
+}
+#else
+__device__ __forceinline__ void sha256_tail65(uint32_t st[8], uint32_t last_byte) {
+    uint32_t w[16];
+    w[0] = (last_byte << 24) | 0x00800000u;
+#pragma unroll
+    for (int i = 1; i < 15; i++) w[i] = 0;
+    w[15] = 65 * 8;
+    sha256_compress(st, w);
+}
+#endif
+
 // Tendermint inner node  sha256(0x01 ‖ l ‖ r)  on big-endian state words (65 bytes = 2 chunks).
 // PX/frontend/merkle/tendermint.rs:108-122
 __device__ __forceinline__ void tm_inner_hash(const uint32_t l[8], const uint32_t r[8], uint32_t out[8]) {
@@ -72,11 +130,7 @@ __device__ __forceinline__ void tm_inner_hash(const uint32_t l[8], const uint32_
     for (int i = 1; i < 8; i++) w[8 + i] = __funnelshift_r(r[i], r[i - 1], 8);
     sha256_init(out);
     sha256_compress(out, w);
-    w[0] = (r[7] << 24) | 0x00800000u;
-#pragma unroll
-    for (int i = 1; i < 15; i++) w[i] = 0;
-    w[15] = 65 * 8;
-    sha256_compress(out, w);
+    sha256_tail65(out, r[7] & 0xffu);
 }
 
 // sha256 of `len` bytes given through a byte getter (any address space); generic path used for

@@ -13,7 +13,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbsx.so")
+# BSX_LIB_PATH selects an alternative build of the SAME CUDA library (kernel-variant experiments)
+LIB_PATH = os.environ.get("BSX_LIB_PATH") or os.path.join(_HERE, "libbsx.so")
 
 SUBCHAIN_BYTES = 128
 SIG_OUT_BYTES = 576
@@ -177,6 +178,20 @@ class Context:
                    _ptr(_in(end_blocks, np.uint64)), _ptr(_in(end_header)), _ptr(out["map_digests"]),
                    _ptr(out["map_subchains"]), _ptr(out["reduce_digests"]), _ptr(out["reduce_nodes"]),
                    _ptr(out["data_commitments"]), _ptr(out["fail"]))
+        return out
+
+    # -- K4+K5 --
+    def ed25519_batch(self, pks, sigs, msgs, msg_lens=None, active=None) -> np.ndarray:
+        """n signatures -> [n, 576] witness records (layout: include/bsx.h).  msgs is [n, stride]."""
+        pks = _in(pks).reshape(-1, 32)
+        n = pks.shape[0]
+        msgs = _in(msgs).reshape(n, -1) if n else _in(msgs)
+        stride = msgs.shape[1] if n else 0
+        out = np.zeros((n, SIG_OUT_BYTES), np.uint8)
+        lens = None if msg_lens is None else _in(msg_lens, np.uint32)
+        act = None if active is None else _in(active)
+        self._call("bsx_ed25519_batch", C.c_uint32(n), _ptr(pks), _ptr(_in(sigs)), _ptr(msgs), C.c_uint32(stride), _ptr(lens),
+                   _ptr(act), _ptr(out))
         return out
 
     # -- raw access for device-pointer entry points (bench / multi-GPU) --

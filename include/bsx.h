@@ -168,6 +168,35 @@ int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint
                              const uint64_t *end_blocks, const uint8_t *end_header, uint32_t B, uint8_t *reduce_digests,
                              uint8_t *reduce_nodes, uint8_t *data_commitments, uint32_t *fail);
 
+/* ------------------------------------------------------------------------------------------
+ * K4+K5  batched Ed25519 witness generation
+ * replaces, per signature of curta_eddsa_verify_sigs[_conditional]
+ *   (PX/frontend/ecc/curve25519/ed25519/eddsa.rs:72-127,131-204):
+ *   HashDigestHint<SHA512>            PX/frontend/hash/sha/sha512/curta.rs:103-111
+ *   BigUintDivRemGenerator            PX/frontend/uint/num/biguint/mod.rs:451-488
+ *   7 x EcOpResultHint::hint          PX/frontend/ecc/curve25519/curta/result_hint.rs:21-50
+ *     order: ScalarMul(s,G), Decompress(pk), IsValid, ScalarMul(h,A), Decompress(R), IsValid, Add
+ * pks n*32 (compressed), sigs n*64 (R ‖ s little-endian), msgs n*msg_stride (MAX_MSG_LENGTH_BYTES),
+ * msg_lens[n] (NULL = every message is msg_stride long), active[n] (NULL = all; 0 = run the lane on
+ * DUMMY_PUBLIC_KEY / DUMMY_SIGNATURE / 32 zero bytes, eddsa.rs:28-42,102-115).
+ * out: n * BSX_SIG_OUT_BYTES records, all values little-endian canonical (x,y = 16 u16 limbs each):
+ *   [0..64) sha512 digest   [64..96) h = LE512(digest) mod l   [96..136) div = LE512(digest) / l
+ *   [136..200) s*G (x,y)    [200..264) A (x,y)   [264..296) A_root   [296..360) h*A
+ *   [360..424) Rp (x,y)     [424..456) R_root    [456..520) Rp + h*A   [520..524) flags
+ * flags: BSX_SIG_S_LT_L | BSX_SIG_A_OK | BSX_SIG_R_OK | BSX_SIG_EQ ; 0xF = the circuit accepts.
+ * A point that fails to decompress (the reference panics) is reported as the identity with root 0.
+ * ------------------------------------------------------------------------------------------ */
+#define BSX_SIG_OUT_BYTES 576
+#define BSX_SIG_S_LT_L 1u
+#define BSX_SIG_A_OK 2u
+#define BSX_SIG_R_OK 4u
+#define BSX_SIG_EQ 8u
+int bsx_ed25519_batch(bsx_ctx *ctx, uint32_t n, const uint8_t *pks, const uint8_t *sigs, const uint8_t *msgs,
+                      uint32_t msg_stride, const uint32_t *msg_lens, const uint8_t *active, uint8_t *out);
+int bsx_ed25519_batch_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, const uint8_t *sigs,
+                          const uint8_t *msgs, uint32_t msg_stride, const uint32_t *msg_lens, const uint8_t *active,
+                          uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

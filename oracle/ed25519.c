@@ -147,6 +147,10 @@ int orc_ed25519_decompress(const uint8_t in[32], uint8_t xy[64], uint8_t root_ou
     fe_neg(&negx2, &x2);
     if (fe_eq(&chk, &negx2) && !fe_iszero(&x2)) { fe_mul(&beta, &beta, &sm1); fe_sq(&chk, &beta); }
     int ok = fe_eq(&chk, &x2);
+    if (!ok) { /* the reference panics here; convention shared with the CUDA kernel: identity, root 0 */
+        memset(xy, 0, 64); xy[32] = 1; memset(root_out, 0, 32);
+        return 0;
+    }
     if (fe_isodd(&beta)) fe_neg(&beta, &beta);
     fe x = beta;
     if (sign) fe_neg(&x, &beta);

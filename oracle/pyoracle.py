@@ -246,6 +246,8 @@ def ed_decompress(b: bytes):
     if (beta * beta) % P25519 == (-x2) % P25519 and x2 != 0:
         beta = beta * SQRT_M1 % P25519
     ok = (beta * beta) % P25519 == x2
+    if not ok:  # the reference panics; shared convention: identity point, root 0
+        return (0, 1), 0, False
     if beta & 1:
         beta = (P25519 - beta) % P25519
     x = (P25519 - beta) % P25519 if sign else beta

@@ -1,0 +1,48 @@
+// TEST INFRASTRUCTURE: compiles the kernel-side Ed25519 arithmetic (blobstreamx_b200/csrc/ed25519.cuh)
+// for the HOST with plain g++, so its logic can be checked against the oracle on a machine without a
+// GPU.  Never linked into libbsx.so; the product has no CPU path.
+#include "../../blobstreamx_b200/csrc/ed25519.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+using namespace bsx::ed;
+
+static ge_niels *g_table = nullptr;
+
+static void build_table() {
+    if (g_table) return;
+    g_table = (ge_niels *)malloc(sizeof(ge_niels) * BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES);
+    for (int w = 0; w < BSX_ED_BASE_WINDOWS; w++)
+        for (int d = 1; d <= BSX_ED_BASE_ENTRIES; d++) g_table[w * BSX_ED_BASE_ENTRIES + d - 1] = ge_base_table_entry(w, d);
+}
+
+extern "C" {
+void hc_ed25519_witness(const uint8_t *pk, const uint8_t *sig, const uint8_t *digest, uint8_t *out) {
+    build_table();
+    ed25519_witness_core(pk, sig, digest, g_table, out);
+}
+void hc_fe_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) { fe_tobytes(out, fe_mul(fe_frombytes(a), fe_frombytes(b))); }
+void hc_fe_sq(const uint8_t *a, uint8_t *out, int twice) {
+    fe f = fe_frombytes(a);
+    fe_tobytes(out, twice ? fe_sq2(f) : fe_sq(f));
+}
+void hc_fe_invert(const uint8_t *a, uint8_t *out) { fe_tobytes(out, fe_invert(fe_frombytes(a))); }
+void hc_fe_addsub_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) {
+    // worst-case limb growth the point formulas rely on: (a+b)*(a-b)
+    fe x = fe_frombytes(a), y = fe_frombytes(b);
+    fe_tobytes(out, fe_mul(fe_add(x, y), fe_sub(x, y)));
+}
+void hc_divrem_l(const uint8_t *digest, uint8_t *rem, uint8_t *div) { sc_divrem_l(digest, rem, div); }
+void hc_scalarmult(const uint8_t *s, const uint8_t *xy, uint8_t *out, int base) {
+    build_table();
+    ge_p3 r = base ? ge_scalarmult_base(s, g_table) : ge_scalarmult(s, ge_from_affine(fe_frombytes(xy), fe_frombytes(xy + 32)));
+    fe zi = fe_invert(r.Z);
+    fe_tobytes(out, fe_mul(r.X, zi));
+    fe_tobytes(out + 32, fe_mul(r.Y, zi));
+}
+int hc_decompress(const uint8_t *in, uint8_t *xy, uint8_t *root) {
+    fe x, y;
+    return ge_decompress(in, x, y, xy, xy + 32, root) ? 1 : 0;
+}
+}

@@ -1,0 +1,144 @@
+"""The kernel-side Ed25519 arithmetic (blobstreamx_b200/csrc/ed25519.cuh) compiled for the HOST and
+checked against the oracle.  This validates the code the GPU runs (same source, same limb schedule)
+without a GPU; the GPU parity test (tests/test_gpu_ed25519.py) repeats it through the C ABI."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_check")
+P = 2**255 - 19
+L = 2**252 + 27742317777372353535851937790883648493
+
+
+@pytest.fixture(scope="module")
+def hc():
+    subprocess.check_call(["make", "-C", HERE, "-s"], stderr=subprocess.DEVNULL)
+    return C.CDLL(os.path.join(HERE, "libed_host_check.so"))
+
+
+def _buf(b):
+    return (C.c_uint8 * len(b)).from_buffer_copy(bytes(b))
+
+
+def _out(n):
+    return (C.c_uint8 * n)()
+
+
+def _fe_cases(rng, n):
+    special = [0, 1, 2, 19, P - 1, P - 2, P, P + 1, 2**255 - 1, 2**255 - 20, (1 << 254), (1 << 255) - (1 << 200),
+               int("aa" * 32, 16) >> 1, int("55" * 32, 16), (1 << 26) - 1, ((1 << 255) - 1) ^ ((1 << 51) - 1)]
+    return special + [int.from_bytes(rng.bytes(32), "little") >> 1 for _ in range(n)]
+
+
+def test_field_ops(hc):
+    rng = np.random.default_rng(5)
+    xs = _fe_cases(rng, 200)
+    ys = list(reversed(_fe_cases(rng, 200)))
+    for a, b in zip(xs, ys):
+        ab, bb = a.to_bytes(32, "little"), b.to_bytes(32, "little")
+        o = _out(32)
+        hc.hc_fe_mul(_buf(ab), _buf(bb), o)
+        assert int.from_bytes(bytes(o), "little") == (a * b) % P
+        hc.hc_fe_sq(_buf(ab), o, 0)
+        assert int.from_bytes(bytes(o), "little") == (a * a) % P
+        hc.hc_fe_sq(_buf(ab), o, 1)
+        assert int.from_bytes(bytes(o), "little") == (2 * a * a) % P
+        hc.hc_fe_addsub_mul(_buf(ab), _buf(bb), o)
+        assert int.from_bytes(bytes(o), "little") == ((a + b) * (a - b)) % P
+    for a in xs[:40]:
+        if a % P == 0:
+            continue
+        o = _out(32)
+        hc.hc_fe_invert(_buf(a.to_bytes(32, "little")), o)
+        assert int.from_bytes(bytes(o), "little") == pow(a, P - 2, P)
+
+
+def test_divrem_l(hc):
+    rng = np.random.default_rng(6)
+    cases = [0, 1, L - 1, L, L + 1, 2 * L - 1, 2 * L, 2**512 - 1, 2**511, L * L, L * L - 1, (2**260 - 1) * L, (2**260 - 1) * L + L - 1,
+             2**252, 2**253 - 1, 2**504]
+    cases += [int.from_bytes(rng.bytes(64), "little") for _ in range(2000)]
+    cases += [int.from_bytes(rng.bytes(64), "little") >> int(s) for s in rng.integers(0, 300, 300)]
+    cases += [k * L + d for k in (1, 2**100, 2**259 + 12345) for d in (-1, 0, 1)]
+    for x in cases:
+        x %= 2**512
+        rem, div = _out(32), _out(40)
+        hc.hc_divrem_l(_buf(x.to_bytes(64, "little")), rem, div)
+        q, r = divmod(x, L)
+        assert int.from_bytes(bytes(rem), "little") == r and int.from_bytes(bytes(div), "little") == q, hex(x)
+
+
+def test_decompress_and_scalarmult(hc):
+    from oracle import cbind as orc, pyoracle as po
+    rng = np.random.default_rng(7)
+    pts = []
+    cands = [bytes(32), (1).to_bytes(32, "little"), (P - 1).to_bytes(32, "little"), (2**255 - 1).to_bytes(32, "little"),
+             po.GY.to_bytes(32, "little"), (po.GY | (1 << 255)).to_bytes(32, "little"), (1 | (1 << 255)).to_bytes(32, "little"),
+             (P + 1).to_bytes(32, "little")] + [rng.bytes(32) for _ in range(60)]
+    n_ok = n_bad = 0
+    for c in cands:
+        xy, root = _out(64), _out(32)
+        ok = hc.hc_decompress(_buf(c), xy, root)
+        wxy, wroot, wok = orc.ed25519_decompress(c)
+        assert bool(ok) == wok and bytes(xy) == wxy and bytes(root) == wroot, c.hex()
+        (px, py), proot, pok = po.ed_decompress(c)
+        assert pok == wok and px.to_bytes(32, "little") + py.to_bytes(32, "little") == wxy and proot.to_bytes(32, "little") == wroot
+        if ok:
+            n_ok += 1
+            pts.append(bytes(xy))
+        else:
+            n_bad += 1
+    assert n_ok > 20 and n_bad > 10
+    scalars = [0, 1, 2, 15, 16, 17, L - 1, L, L + 1, 2**256 - 1, 2**255, 8, 2**252] + [int.from_bytes(rng.bytes(32), "little") for _ in range(12)]
+    g = po.ed_point_bytes(po.G)
+    for k in scalars:
+        kb = k.to_bytes(32, "little")
+        o = _out(64)
+        hc.hc_scalarmult(_buf(kb), _buf(g), o, 1)
+        assert bytes(o) == orc.ed25519_scalar_mul(kb, g), k
+    for i, k in enumerate(scalars):
+        kb = k.to_bytes(32, "little")
+        pt = pts[i % len(pts)]
+        o = _out(64)
+        hc.hc_scalarmult(_buf(kb), _buf(pt), o, 0)
+        assert bytes(o) == orc.ed25519_scalar_mul(kb, pt), (k, pt.hex())
+
+
+def test_witness_records(hc):
+    """Full per-signature record vs the C oracle and the Python-int oracle: valid signatures, the
+    DUMMY triple, corrupted signatures (must not verify), s >= l, undecodable points."""
+    from nacl.signing import SigningKey
+    from oracle import cbind as orc, pyoracle as po
+    rng = np.random.default_rng(8)
+    cases = []
+    for i in range(24):
+        sk = SigningKey(hashlib.sha256(b"hc%d" % i).digest())
+        msg = rng.bytes(int(rng.integers(0, 124)))
+        sig = sk.sign(msg).signature
+        cases.append((bytes(sk.verify_key), sig, msg))
+    cases.append((po.DUMMY_PUBLIC_KEY, po.DUMMY_SIGNATURE, bytes(32)))
+    pk, sig, msg = cases[0]
+    cases.append((pk, sig[:5] + bytes([sig[5] ^ 1]) + sig[6:], msg))                 # R corrupted
+    cases.append((pk, sig[:40] + bytes([sig[40] ^ 4]) + sig[41:], msg))              # s corrupted
+    cases.append((pk, sig, msg + b"x"))                                              # message changed
+    cases.append((pk, sig[:32] + (2**256 - 1).to_bytes(32, "little"), msg))          # s = 2^256-1
+    cases.append((pk, sig[:32] + L.to_bytes(32, "little"), msg))                     # s = l
+    cases.append(((2).to_bytes(32, "little"), sig, msg))                             # pk not on curve
+    cases.append((pk, (2).to_bytes(32, "little") + sig[32:], msg))                   # R not on curve
+    for j in range(6):
+        cases.append((rng.bytes(32), rng.bytes(64), rng.bytes(50)))
+    seen = set()
+    for pk, sig, msg in cases:
+        digest = hashlib.sha512(sig[:32] + pk + msg).digest()
+        out = _out(576)
+        hc.hc_ed25519_witness(_buf(pk), _buf(sig), _buf(digest), out)
+        want = orc.ed25519_witness(pk, sig, msg)
+        assert bytes(out) == want, (pk.hex(), sig.hex())
+        if (want[520] & 6) == 6:
+            assert want == po.ed_witness_bytes(pk, sig, msg)
+        seen.add(want[520])
+    assert 0xF in seen and 0x7 in seen and any(not (f & 1) for f in seen) and any(not (f & 2) for f in seen)
