@@ -25,22 +25,27 @@ __global__ void __launch_bounds__(64) ed25519_base_table_kernel(ge_niels *table)
     table[i] = ge_base_table_entry(i / BSX_ED_BASE_ENTRIES, i % BSX_ED_BASE_ENTRIES + 1);
 }
 
-__global__ void __launch_bounds__(64) ed25519_batch_kernel(uint32_t n, const uint8_t *__restrict__ pks,
-                                                           const uint8_t *__restrict__ sigs,
-                                                           const uint8_t *__restrict__ msgs, uint32_t msg_stride,
-                                                           const uint32_t *__restrict__ msg_lens,
-                                                           const uint8_t *__restrict__ active,
-                                                           const ge_niels *__restrict__ table, uint8_t *__restrict__ out) {
+struct EdIn {
+    const uint8_t *pks, *sigs, *msgs, *lens, *active;   // lens: u32 LE at lens + i*len_stride (NULL = msg_max)
+    uint32_t pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride;
+};
+
+__global__ void __launch_bounds__(64) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels *__restrict__ table,
+                                                           uint8_t *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t pk[32], sig[64];
-    const bool on = !active || active[i];
-    const uint8_t *m = msgs + (size_t)msg_stride * i;
-    uint32_t len = msg_lens ? msg_lens[i] : msg_stride;
-    if (len > msg_stride) len = msg_stride;
+    const bool on = !in.active || in.active[(size_t)in.active_stride * i];
+    const uint8_t *m = in.msgs + (size_t)in.msg_stride * i;
+    uint32_t len = in.msg_max;
+    if (in.lens) {
+        const uint8_t *lp = in.lens + (size_t)in.len_stride * i;
+        len = (uint32_t)lp[0] | ((uint32_t)lp[1] << 8) | ((uint32_t)lp[2] << 16) | ((uint32_t)lp[3] << 24);
+    }
+    if (len > in.msg_max) len = in.msg_max;
     if (on) {
-        for (int k = 0; k < 32; k++) pk[k] = pks[32 * (size_t)i + k];
-        for (int k = 0; k < 64; k++) sig[k] = sigs[64 * (size_t)i + k];
+        for (int k = 0; k < 32; k++) pk[k] = in.pks[(size_t)in.pk_stride * i + k];
+        for (int k = 0; k < 64; k++) sig[k] = in.sigs[(size_t)in.sig_stride * i + k];
     } else {
         for (int k = 0; k < 32; k++) pk[k] = DUMMY_PK[k];
         for (int k = 0; k < 64; k++) sig[k] = DUMMY_SIG[k];
@@ -72,18 +77,27 @@ static int ensure_base_table(bsx_ctx *ctx, cudaStream_t st) {
     return BSX_OK;
 }
 
-extern "C" int bsx_ed25519_batch_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, const uint8_t *sigs,
-                                     const uint8_t *msgs, uint32_t msg_stride, const uint32_t *msg_lens,
-                                     const uint8_t *active, uint8_t *out) {
-    BSX_REQUIRE(ctx, ctx && pks && sigs && (msgs || msg_stride == 0) && out);
+// strided form: used by the verify_* entry points to run straight over validator records
+extern "C" int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, uint32_t pk_stride,
+                                       const uint8_t *sigs, uint32_t sig_stride, const uint8_t *msgs, uint32_t msg_stride,
+                                       uint32_t msg_max, const uint8_t *msg_lens, uint32_t len_stride, const uint8_t *active,
+                                       uint32_t active_stride, uint8_t *out) {
+    BSX_REQUIRE(ctx, ctx && pks && sigs && (msgs || msg_max == 0) && out);
     if (n == 0) return BSX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_base_table(ctx, st);
     if (rc) return rc;
-    ed25519_batch_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, pks, sigs, msgs, msg_stride, msg_lens, active,
-                                                       reinterpret_cast<const ed::ge_niels *>(ctx->ed_table), out);
+    EdIn in{pks, sigs, msgs, msg_lens, active, pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride};
+    ed25519_batch_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, in, reinterpret_cast<const ed::ge_niels *>(ctx->ed_table), out);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
+}
+
+extern "C" int bsx_ed25519_batch_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, const uint8_t *sigs,
+                                     const uint8_t *msgs, uint32_t msg_stride, const uint32_t *msg_lens,
+                                     const uint8_t *active, uint8_t *out) {
+    return bsx_ed25519_strided_dev(ctx, stream, n, pks, 32, sigs, 64, msgs, msg_stride, msg_stride,
+                                   reinterpret_cast<const uint8_t *>(msg_lens), 4, active, 1, out);
 }
 
 extern "C" int bsx_ed25519_batch(bsx_ctx *ctx, uint32_t n, const uint8_t *pks, const uint8_t *sigs, const uint8_t *msgs,

@@ -154,7 +154,7 @@ extern "C" int bsx_tm_merkle_proofs(bsx_ctx *ctx, const uint8_t *leaves, uint32_
 }
 
 static int tree_launch_cfg(bsx_ctx *ctx, const void *kernel, uint32_t P, uint32_t *threads, size_t *smem) {
-    *threads = P / 2 < 32 ? 32 : (P / 2 > 1024 ? 1024 : P / 2);
+    *threads = P / 2 < 32 ? 32 : (P / 2 > 512 ? 512 : P / 2);  // <= 512 threads: up to 128 registers each
     *smem = 32 * (size_t)P + 16 * (size_t)P;
     if (*smem > 48 * 1024) BSX_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
     return BSX_OK;
@@ -208,7 +208,7 @@ extern "C" int bsx_data_commitment_batch_dev(bsx_ctx *ctx, void *stream, const u
     size_t smem;
     int rc = tree_launch_cfg(ctx, (const void *)data_commitment_kernel, P, &threads, &smem);
     if (rc) return rc;
-    if (threads < P && P <= 1024) threads = P;  // one tuple leaf per thread
+    if (threads < P && P <= 512) threads = P;  // one tuple leaf per thread
     data_commitment_kernel<<<t, threads, smem, (cudaStream_t)stream>>>(data_hashes, N, P, start_blocks, end_blocks, digests,
                                                                        roots, fail);
     BSX_LAUNCHED(ctx);

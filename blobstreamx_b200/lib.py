@@ -38,6 +38,7 @@ def load() -> C.CDLL:
         _lib.bsx_last_error.restype = C.c_char_p
         _lib.bsx_launch_count.restype = C.c_uint64
         _lib.bsx_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        _lib.bsx_verify_digest_count.restype = C.c_uint32
     return _lib
 
 
@@ -194,10 +195,104 @@ class Context:
                    _ptr(act), _ptr(out))
         return out
 
+    # -- verify_header / verify_skip / next_header --
+    def _verify(self, mode: int, items, N: int):
+        """items: list of dicts as produced by blobstreamx_b200.inputs.get_skip_inputs / get_step_inputs /
+        _header_common (one per instance).  Returns dict(sha256_digests [n,D,32], ed [n,N,576], fail [n], ...)."""
+        n = len(items)
+        key = {0: None, 1: "target", 2: "next"}[mode]
+        hdr = pack_header_in([it[key] if key else it for it in items])
+        vals = np.stack([_in((it[key] if key else it)["validators"]).reshape(N, VAL_IN_BYTES) for it in items])
+        D = int(self._lib.bsx_verify_digest_count(C.c_int(mode), C.c_uint32(N)))
+        dig = np.zeros((n, D, 32), np.uint8)
+        ed = np.zeros((n, N, SIG_OUT_BYTES), np.uint8)
+        fail = np.zeros(n, np.uint32)
+        out = dict(sha256_digests=dig, ed=ed, fail=fail)
+        if mode == 0:
+            self._call("bsx_verify_header", C.c_uint32(n), C.c_uint32(N), _ptr(hdr), _ptr(vals), _ptr(dig), _ptr(ed), _ptr(fail))
+        elif mode == 1:
+            skip = pack_skip_in(items)
+            tpk = np.stack([_in(it["trusted_pubkeys"]).reshape(N, 32) for it in items])
+            tpw = np.stack([_in(it["trusted_powers"], np.uint64) for it in items])
+            tbl = np.stack([_in(it["trusted_byte_lengths"], np.uint32) for it in items])
+            self._call("bsx_verify_skip", C.c_uint32(n), C.c_uint32(N), _ptr(hdr), _ptr(vals), _ptr(skip), _ptr(tpk), _ptr(tpw),
+                       _ptr(tbl), _ptr(dig), _ptr(ed), _ptr(fail))
+        else:
+            step = pack_step_in(items)
+            dc = np.zeros((n, 32), np.uint8)
+            self._call("bsx_next_header", C.c_uint32(n), C.c_uint32(N), _ptr(hdr), _ptr(vals), _ptr(step), _ptr(dig), _ptr(ed),
+                       _ptr(dc), _ptr(fail))
+            out["data_commitments"] = dc
+        return out
+
+    def verify_header(self, items, N: int = 100):
+        return self._verify(0, items, N)
+
+    def verify_skip(self, items, N: int = 100):
+        return self._verify(1, items, N)
+
+    def next_header(self, items, N: int = 100):
+        return self._verify(2, items, N)
+
     # -- raw access for device-pointer entry points (bench / multi-GPU) --
     def call_dev(self, name: str, stream: int, *args):
         """Call a `*_dev` entry point; integer args that are pointers must be wrapped with ptr()."""
         self._call(name, C.c_void_p(int(stream)), *args)
+
+
+# struct layouts of include/bsx.h
+HEADER_IN = np.dtype([("header", "u1", 32), ("height", "<u8"), ("round", "<u8"), ("nb_enabled", "<u8"),
+                      ("chain_id_enc", "u1", 64), ("chain_id_enc_len", "<u4"), ("height_enc_len", "<u4"),
+                      ("chain_id_aunts", "u1", 128), ("height_aunts", "u1", 128), ("validators_hash_proof", "u1", 168),
+                      ("expected_chain_id", "u1", 56), ("expected_chain_id_len", "<u4"), ("_pad", "<u4")])
+SKIP_IN = np.dtype([("trusted_block", "<u8"), ("trusted_nb_enabled", "<u8"), ("skip_max", "<u4"), ("_pad", "<u4"),
+                    ("trusted_header", "u1", 32), ("trusted_validators_hash_proof", "u1", 168)])
+STEP_IN = np.dtype([("prev_block", "<u8"), ("prev_header", "u1", 32), ("last_block_id_proof", "u1", 200),
+                    ("prev_next_validators_proof", "u1", 168), ("data_hash_proof", "u1", 168)])
+assert HEADER_IN.itemsize == 616 and SKIP_IN.itemsize == 224 and STEP_IN.itemsize == 576
+
+
+def _put(dst, src):
+    src = np.asarray(src, np.uint8).reshape(-1)
+    dst[: len(src)] = src
+
+
+def pack_header_in(hs) -> np.ndarray:
+    a = np.zeros(len(hs), HEADER_IN)
+    for i, h in enumerate(hs):
+        r = a[i]
+        _put(r["header"], h["header"])
+        r["height"], r["round"], r["nb_enabled"] = h["height"], h["round"], h["nb_enabled"]
+        _put(r["chain_id_enc"], h["chain_id_enc"])
+        r["chain_id_enc_len"], r["height_enc_len"] = h["chain_id_enc_len"], h["height_enc_len"]
+        _put(r["chain_id_aunts"], h["chain_id_aunts"])
+        _put(r["height_aunts"], h["height_aunts"])
+        _put(r["validators_hash_proof"], h["validators_hash_proof"])
+        _put(r["expected_chain_id"], h["expected_chain_id"])
+        r["expected_chain_id_len"] = len(h["expected_chain_id"])
+    return a
+
+
+def pack_skip_in(ks) -> np.ndarray:
+    a = np.zeros(len(ks), SKIP_IN)
+    for i, k in enumerate(ks):
+        r = a[i]
+        r["trusted_block"], r["trusted_nb_enabled"], r["skip_max"] = k["trusted_block"], k["trusted_nb_enabled"], k["skip_max"]
+        _put(r["trusted_header"], k["trusted_header"])
+        _put(r["trusted_validators_hash_proof"], k["trusted_validators_hash_proof"])
+    return a
+
+
+def pack_step_in(ks) -> np.ndarray:
+    a = np.zeros(len(ks), STEP_IN)
+    for i, k in enumerate(ks):
+        r = a[i]
+        r["prev_block"] = k["prev_block"]
+        _put(r["prev_header"], k["prev_header"])
+        _put(r["last_block_id_proof"], k["last_block_id_proof"])
+        _put(r["prev_next_validators_proof"], k["prev_next_validators_proof"])
+        _put(r["data_hash_proof"], k["data_hash_proof"])
+    return a
 
 
 def ptr(x) -> C.c_void_p:

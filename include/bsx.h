@@ -197,6 +197,91 @@ int bsx_ed25519_batch_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t 
                           const uint8_t *msgs, uint32_t msg_stride, const uint32_t *msg_lens, const uint8_t *active,
                           uint8_t *out);
 
+/* ------------------------------------------------------------------------------------------
+ * verify_header / verify_skip / verify_step (+ prove_next_header_data_commitment)
+ * replaces every Curta SHA-256 / SHA-512 / EC hint of
+ *   TendermintVerify::verify_header   TX/builder/verify.rs:225-329   (n_digests = N + P-1 + 27)
+ *   TendermintVerify::verify_skip     TX/builder/verify.rs:527-564   (9 + N + P-1 + the above)
+ *   TendermintVerify::verify_step     TX/builder/verify.rs:468-505 followed by
+ *   prove_next_header_data_commitment BX/circuits/builder.rs:411-443 (the above + 28)
+ * for n independent instances with VALIDATOR_SET_SIZE_MAX = N (P = next power of two).
+ * validators: n*N records of BSX_VAL_IN_BYTES (ValidatorVariable, TX/variables.rs:72-83):
+ *   [0..32) pubkey  [32..96) signature R‖s  [96..220) message  [220..224) message_byte_length LE
+ *   [224..232) voting_power LE  [232..236) validator_byte_length LE  [236] signed  [237] present_on_trusted_header
+ * digests: SHA-256 digests in Curta request order;
+ * ed_out: n*N Ed25519 records (BSX_SIG_OUT_BYTES); fail[n]: BSX_VFAIL_* mask, 0 = circuit accepts.
+ * ------------------------------------------------------------------------------------------ */
+#define BSX_VAL_IN_BYTES 240
+typedef struct bsx_header_in {        /* one header to verify; 616 bytes, 8-byte aligned */
+    uint8_t header[32];               /* expected header hash */
+    uint64_t height, round;           /* block height; commit round */
+    uint64_t nb_enabled;              /* nb_enabled_validators */
+    uint8_t chain_id_enc[64];         /* ChainIdProofVariable.enc_chain_id_bytes (52 used), zero padded */
+    uint32_t chain_id_enc_len;        /* enc_chain_id_byte_length */
+    uint32_t height_enc_len;          /* HeightProofVariable.enc_height_byte_length */
+    uint8_t chain_id_aunts[128];
+    uint8_t height_aunts[128];
+    uint8_t validators_hash_proof[168]; /* leaf[34] ‖ aunts[128] ‖ pad */
+    uint8_t expected_chain_id[56];    /* circuit constant CHAIN_ID_BYTES */
+    uint32_t expected_chain_id_len;
+    uint32_t _pad;
+} bsx_header_in;
+typedef struct bsx_skip_in {          /* VerifySkipVariable extras (TX/variables.rs:98-111) */
+    uint64_t trusted_block;
+    uint64_t trusted_nb_enabled;
+    uint32_t skip_max;
+    uint32_t _pad;
+    uint8_t trusted_header[32];
+    uint8_t trusted_validators_hash_proof[168];
+} bsx_skip_in;
+typedef struct bsx_step_in {          /* VerifyStepVariable extras + DataCommitmentProofVariable<1> */
+    uint64_t prev_block;
+    uint8_t prev_header[32];
+    uint8_t last_block_id_proof[200];          /* leaf[72] ‖ aunts[128], against the next header */
+    uint8_t prev_next_validators_proof[168];   /* leaf[34] ‖ aunts[128] ‖ pad, against prev header */
+    uint8_t data_hash_proof[168];              /* leaf[34] ‖ aunts[128] ‖ pad, against prev header */
+} bsx_step_in;
+#define BSX_VFAIL_SIG 1u
+#define BSX_VFAIL_VALHASH 2u
+#define BSX_VFAIL_VALHASH_PROOF 4u
+#define BSX_VFAIL_THRESHOLD 8u
+#define BSX_VFAIL_MESSAGE 16u
+#define BSX_VFAIL_CHAIN_ID 32u
+#define BSX_VFAIL_HEIGHT 64u
+#define BSX_VFAIL_TRUSTED_PROOF 128u
+#define BSX_VFAIL_TRUSTED_VALHASH 256u
+#define BSX_VFAIL_TRUSTED_PRESENT 512u
+#define BSX_VFAIL_TRUSTED_THRESHOLD 1024u
+#define BSX_VFAIL_SKIP_DISTANCE 2048u
+#define BSX_VFAIL_PREV_HEADER 4096u
+#define BSX_VFAIL_NEXT_VALS 8192u
+#define BSX_VFAIL_DATA_HASH_PROOF 16384u
+/* mode 0 verify_header, 1 verify_skip, 2 next_header -> SHA-256 digests per instance */
+uint32_t bsx_verify_digest_count(int mode, uint32_t N);
+int bsx_verify_header(bsx_ctx *ctx, uint32_t n, uint32_t N, const bsx_header_in *hdr, const uint8_t *validators,
+                      uint8_t *digests, uint8_t *ed_out, uint32_t *fail);
+int bsx_verify_skip(bsx_ctx *ctx, uint32_t n, uint32_t N, const bsx_header_in *hdr, const uint8_t *validators,
+                    const bsx_skip_in *skip, const uint8_t *trusted_pubkeys /*n*N*32*/,
+                    const uint64_t *trusted_powers /*n*N*/, const uint32_t *trusted_byte_lengths /*n*N*/,
+                    uint8_t *digests, uint8_t *ed_out, uint32_t *fail);
+int bsx_next_header(bsx_ctx *ctx, uint32_t n, uint32_t N, const bsx_header_in *hdr, const uint8_t *validators,
+                    const bsx_step_in *step, uint8_t *digests, uint8_t *ed_out, uint8_t *data_commitments /*n*32*/,
+                    uint32_t *fail);
+int bsx_verify_header_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const bsx_header_in *hdr,
+                          const uint8_t *validators, uint8_t *digests, uint8_t *ed_out, uint32_t *fail);
+int bsx_verify_skip_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const bsx_header_in *hdr,
+                        const uint8_t *validators, const bsx_skip_in *skip, const uint8_t *trusted_pubkeys,
+                        const uint64_t *trusted_powers, const uint32_t *trusted_byte_lengths, uint8_t *digests,
+                        uint8_t *ed_out, uint32_t *fail);
+int bsx_next_header_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const bsx_header_in *hdr,
+                        const uint8_t *validators, const bsx_step_in *step, uint8_t *digests, uint8_t *ed_out,
+                        uint8_t *data_commitments, uint32_t *fail);
+/* Ed25519 over strided records (what the verify_* entry points run over the validator array) */
+int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, uint32_t pk_stride,
+                            const uint8_t *sigs, uint32_t sig_stride, const uint8_t *msgs, uint32_t msg_stride,
+                            uint32_t msg_max, const uint8_t *msg_lens, uint32_t len_stride, const uint8_t *active,
+                            uint32_t active_stride, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif
