@@ -395,9 +395,83 @@ def run_ed25519(args):
                       "gpu_launches": args.steps, "clocks": clk.summary(), "cpu_baseline": cpu}))
 
 
+def run_gates(args):
+    """constraints/sec: U32ArithmeticGate (3 ops/row, 114 wires, 108 constraints) over 2^k rows, HBM roofline."""
+    import torch
+    from blobstreamx_b200 import lib
+    from blobstreamx_b200.lib import ptr, u32
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = lib.Context(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    rows, gate, p0, p1 = args.rows, 0, 3, 0
+    nw, ncn = ctx.gate_num_wires(gate, p0, p1), ctx.gate_num_constraints(gate, p0, p1)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    wires = torch.zeros(nw * rows, dtype=torch.int64, device=dev)
+    wv = wires.view(nw, rows)
+    for i in range(p0):   # random u32 inputs of valid operations; the generator kernel fills the rest
+        wv[6 * i:6 * i + 3] = torch.randint(0, 2**32, (3, rows), generator=g, device=dev, dtype=torch.int64)
+    cons = torch.zeros(ncn * rows, dtype=torch.int64, device=dev)
+    P = lambda t: ptr(t.data_ptr())
+    ctx.call_dev("bsx_gl_gate_witness_dev", stream, u32(gate), u32(p0), u32(p1), P(wires), u32(rows))
+
+    def step():
+        ctx.call_dev("bsx_gl_gate_eval_dev", stream, u32(gate), u32(p0), u32(p1), P(wires), u32(rows), P(cons))
+
+    step()
+    torch.cuda.synchronize()
+    assert int(cons.abs().max().item()) == 0, "valid witness must satisfy every constraint"
+    if not args.no_check:
+        from oracle import cbind as orc
+        k = 512
+        sub = wv[:, :k].contiguous().cpu().numpy().view(np.uint64)
+        sub[5, 7] += np.uint64(1)  # one broken row so the comparison is not all zeros
+        got = ctx.gl_gate_eval(gate, p0, p1, sub)
+        assert (got == orc.gate_eval(gate, p0, p1, sub, threads=4)).all() and got[:, 7].any()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with ClockSampler(0) as clk:
+        ev[0].record()
+        for _ in range(args.steps):
+            step()
+        ev[1].record()
+        torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    alg = 8 * (nw + ncn) * rows
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cbind as orc
+        k = 1 << 14
+        sub = wv[:, :k].contiguous().cpu().numpy().view(np.uint64)
+        t0 = time.perf_counter()
+        orc.gate_eval(gate, p0, p1, sub, threads=1)
+        cpu = {"value": ncn * k / (time.perf_counter() - t0), "unit": "constraints/s", "cores": 1, "kind": "port", "sample": f"{k} rows"}
+    print(json.dumps({"metric": "constraints/sec, U32ArithmeticGate eval_unfiltered_base_batch", "value": ncn * rows / (ms * 1e-3),
+                      "unit": "constraints/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                      "higher_is_better": True, "dtype": "u64 mod 2^64-2^32+1", "data": "synthetic",
+                      "config": {"workload": f"U32ArithmeticGate num_ops=3, {rows} rows x 114 wires -> 108 constraints/row",
+                                 "l2": f"{alg / 1e6:.0f} MB per step > 126 MB L2"},
+                      "gpu_launches": args.steps, "clocks": clk.summary(),
+                      "roofline": {"kernel": "gl_gate_eval_kernel<0>", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                                   "algorithmic_bytes_per_launch": alg},
+                      "cpu_baseline": cpu}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519"])
+    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates"])
+    ap.add_argument("--rows", type=int, default=1 << 20)
     ap.add_argument("--sigs", type=int, default=100000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -415,6 +489,8 @@ def main():
         run_reference(args)
     elif args.mode == "ed25519":
         run_ed25519(args)
+    elif args.mode == "gates":
+        run_gates(args)
     else:
         run_gpu(args)
 

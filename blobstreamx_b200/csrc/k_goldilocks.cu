@@ -1,0 +1,448 @@
+// K6/K7/K8: Goldilocks u32-gate constraint evaluation, gate witness generators, Poseidon sponge.
+//   U32ArithmeticGate   PX/frontend/uint/num/u32/gates/arithmetic_u32.rs:280-349 (eval), 383-431 (generator)
+//   U32AddManyGate      PX/frontend/uint/num/u32/gates/add_many_u32.rs:107-146, 340-391
+//   U32SubtractionGate  PX/frontend/uint/num/u32/gates/subtraction_u32.rs:101-135, 305-350
+//   ComparisonGate      PX/frontend/uint/num/u32/gates/comparison.rs:118-195, 441-540
+//   U32RangeCheckGate   PX/frontend/uint/num/u32/gates/range_check_u32.rs:69-91, 202-224
+//   Poseidon            plonky2 0.2.1 hash_n_to_hash_no_pad (call sites PX/frontend/hash/poseidon/poseidon256.rs:68,
+//                       PX/utils/poseidon/mod.rs:31-36,54-59)
+// Gate kernels: one thread per row over plonky2's wire-major batch layout (wires[w*rows + r],
+// constraints[c*rows + r]) so that every load and store of a warp is one contiguous 256-byte segment;
+// the traffic is streamed (ld.global.cs / st.global.cs, nothing is reused).  ~1.8 KB of traffic against
+// ~400 field multiplications per row puts the arithmetic gate near the HBM/ALU balance point.
+#include "common.cuh"
+#include "poseidon_constants.cuh"
+
+namespace bsx {
+
+constexpr uint64_t GL_P = 0xFFFFFFFF00000001ULL;
+constexpr uint64_t GL_EPS = 0xFFFFFFFFULL;
+
+// all values canonical (< p)
+__device__ __forceinline__ uint64_t gl_canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
+__device__ __forceinline__ uint64_t gl_add(uint64_t a, uint64_t b) {
+    uint64_t s = a + b;
+    return (s < a) ? s + GL_EPS : gl_canon(s);
+}
+__device__ __forceinline__ uint64_t gl_sub(uint64_t a, uint64_t b) {
+    uint64_t d = a - b;
+    return (a < b) ? d - GL_EPS : d;
+}
+__device__ __forceinline__ uint64_t gl_reduce128(uint64_t hi, uint64_t lo) {
+    const uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
+    uint64_t t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= GL_EPS;
+    const uint64_t t1 = hi_lo * GL_EPS;
+    uint64_t t2 = t0 + t1;
+    if (t2 < t1) t2 += GL_EPS;
+    return gl_canon(t2);
+}
+__device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128(__umul64hi(a, b), a * b); }
+__device__ __forceinline__ uint64_t gl_dbl(uint64_t a) { return gl_add(a, a); }
+__device__ __forceinline__ uint64_t gl_mul4(uint64_t a) { return gl_dbl(gl_dbl(a)); }
+__device__ __forceinline__ uint64_t gl_inv(uint64_t a) {  // a^(p-2), p-2 = 0xFFFFFFFEFFFFFFFF
+    uint64_t r = 1;
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        r = gl_mul(r, r);
+        if ((0xFFFFFFFEFFFFFFFFULL >> i) & 1) r = gl_mul(r, a);
+    }
+    return r;
+}
+// prod_{x < 4} (l - x)
+__device__ __forceinline__ uint64_t limb_product4(uint64_t l) {
+    return gl_mul(gl_mul(l, gl_sub(l, 1)), gl_mul(gl_sub(l, 2), gl_sub(l, 3)));
+}
+__device__ __forceinline__ uint64_t limb_product(uint64_t l, uint32_t base) {
+    uint64_t p = l;
+    for (uint32_t x = 1; x < base; x++) p = gl_mul(p, gl_sub(l, x));
+    return p;
+}
+
+struct RowIO {
+    const uint64_t *wires;
+    uint64_t *out;
+    size_t rows, r;
+    uint32_t c;
+    __device__ __forceinline__ uint64_t w(uint32_t col) const { return gl_canon(__ldcs(wires + (size_t)col * rows + r)); }
+    __device__ __forceinline__ void put(uint64_t v) { __stcs(out + (size_t)(c++) * rows + r, v); }
+};
+
+__device__ __forceinline__ void eval_arithmetic(RowIO &io, uint32_t num_ops) {
+    for (uint32_t i = 0; i < num_ops; i++) {
+        const uint64_t m0 = io.w(6 * i), m1 = io.w(6 * i + 1), addend = io.w(6 * i + 2);
+        const uint64_t out_lo = io.w(6 * i + 3), out_hi = io.w(6 * i + 4), inverse = io.w(6 * i + 5);
+        const uint64_t computed = gl_add(gl_mul(m0, m1), addend);
+        const uint64_t hi_not_max = gl_sub(gl_mul(inverse, gl_sub(GL_EPS, out_hi)), 1);
+        io.put(gl_mul(hi_not_max, out_lo));
+        io.put(gl_sub(gl_add(gl_mul(out_hi, 1ULL << 32), out_lo), computed));
+        uint64_t lo = 0, hi = 0;
+#pragma unroll 8
+        for (int j = 31; j >= 0; j--) {
+            const uint64_t limb = io.w(6 * num_ops + 32 * i + j);
+            io.put(limb_product4(limb));
+            if (j < 16) lo = gl_add(gl_mul4(lo), limb);
+            else hi = gl_add(gl_mul4(hi), limb);
+        }
+        io.put(gl_sub(lo, out_lo));
+        io.put(gl_sub(hi, out_hi));
+    }
+}
+
+__device__ __forceinline__ void eval_add_many(RowIO &io, uint32_t na, uint32_t num_ops) {
+    for (uint32_t i = 0; i < num_ops; i++) {
+        const uint32_t b = (na + 3) * i;
+        uint64_t computed = 0;
+        for (uint32_t j = 0; j <= na; j++) computed = gl_add(computed, io.w(b + j));
+        const uint64_t out_res = io.w(b + na + 1), out_carry = io.w(b + na + 2);
+        io.put(gl_sub(gl_add(gl_mul(out_carry, 1ULL << 32), out_res), computed));
+        uint64_t res = 0, carry = 0;
+#pragma unroll
+        for (int j = 18; j >= 0; j--) {
+            const uint64_t limb = io.w((na + 3) * num_ops + 19 * i + j);
+            io.put(limb_product4(limb));
+            if (j < 16) res = gl_add(gl_mul4(res), limb);
+            else carry = gl_add(gl_mul4(carry), limb);
+        }
+        io.put(gl_sub(res, out_res));
+        io.put(gl_sub(carry, out_carry));
+    }
+}
+
+__device__ __forceinline__ void eval_subtraction(RowIO &io, uint32_t num_ops) {
+    for (uint32_t i = 0; i < num_ops; i++) {
+        const uint64_t x = io.w(5 * i), y = io.w(5 * i + 1), bin = io.w(5 * i + 2), out_res = io.w(5 * i + 3),
+                       out_b = io.w(5 * i + 4);
+        const uint64_t initial = gl_sub(gl_sub(x, y), bin);
+        io.put(gl_sub(out_res, gl_add(initial, gl_mul(1ULL << 32, out_b))));
+        uint64_t comb = 0;
+#pragma unroll
+        for (int j = 15; j >= 0; j--) {
+            const uint64_t limb = io.w(5 * num_ops + 16 * i + j);
+            io.put(limb_product4(limb));
+            comb = gl_add(gl_mul4(comb), limb);
+        }
+        io.put(gl_sub(comb, out_res));
+        io.put(gl_mul(out_b, gl_sub(1, out_b)));
+    }
+}
+
+__device__ __forceinline__ void eval_comparison(RowIO &io, uint32_t num_bits, uint32_t nc) {
+    const uint32_t cb = (num_bits + nc - 1) / nc;
+    const uint64_t chunk_size = 1ULL << cb;
+    uint64_t fc = 0, sc = 0;
+    for (int i = (int)nc - 1; i >= 0; i--) {
+        fc = gl_add(gl_mul(fc, chunk_size), io.w(4 + i));
+        sc = gl_add(gl_mul(sc, chunk_size), io.w(4 + nc + i));
+    }
+    io.put(gl_sub(fc, io.w(0)));
+    io.put(gl_sub(sc, io.w(1)));
+    uint64_t msd_so_far = 0;
+    for (uint32_t i = 0; i < nc; i++) {
+        const uint64_t f = io.w(4 + i), s = io.w(4 + nc + i);
+        io.put(limb_product(f, (uint32_t)chunk_size));
+        io.put(limb_product(s, (uint32_t)chunk_size));
+        const uint64_t diff = gl_sub(s, f), dummy = io.w(4 + 2 * nc + i), eq = io.w(4 + 3 * nc + i);
+        io.put(gl_sub(gl_mul(diff, dummy), gl_sub(1, eq)));
+        io.put(gl_mul(eq, diff));
+        const uint64_t inter = io.w(4 + 4 * nc + i);
+        io.put(gl_sub(inter, gl_mul(eq, msd_so_far)));
+        msd_so_far = gl_add(inter, gl_mul(gl_sub(1, eq), diff));
+    }
+    const uint64_t msd = io.w(3);
+    io.put(gl_sub(msd, msd_so_far));
+    for (uint32_t i = 0; i <= cb; i++) {
+        const uint64_t bit = io.w(4 + 5 * nc + i);
+        io.put(gl_mul(bit, gl_sub(1, bit)));
+    }
+    uint64_t bits = 0;
+    for (int i = (int)cb; i >= 0; i--) bits = gl_add(gl_dbl(bits), io.w(4 + 5 * nc + i));
+    io.put(gl_sub(gl_add(chunk_size, msd), bits));
+    io.put(gl_sub(io.w(2), io.w(4 + 5 * nc + cb)));
+}
+
+__device__ __forceinline__ void eval_range_check(RowIO &io, uint32_t nl) {
+    for (uint32_t i = 0; i < nl; i++) {
+        uint64_t sum = 0;
+        uint64_t aux[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) aux[j] = io.w(nl + 16 * i + j);
+#pragma unroll
+        for (int j = 15; j >= 0; j--) sum = gl_add(gl_mul4(sum), aux[j]);
+        io.put(gl_sub(sum, io.w(i)));
+#pragma unroll
+        for (int j = 0; j < 16; j++) io.put(limb_product4(aux[j]));
+    }
+}
+
+template <int GATE>
+__global__ void __launch_bounds__(128) gl_gate_eval_kernel(uint32_t p0, uint32_t p1, const uint64_t *__restrict__ wires,
+                                                           uint32_t rows, uint64_t *__restrict__ constraints) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    RowIO io{wires, constraints, rows, r, 0};
+    if (GATE == BSX_GATE_U32_ARITHMETIC) eval_arithmetic(io, p0);
+    else if (GATE == BSX_GATE_U32_ADD_MANY) eval_add_many(io, p0, p1);
+    else if (GATE == BSX_GATE_U32_SUBTRACTION) eval_subtraction(io, p0);
+    else if (GATE == BSX_GATE_U32_COMPARISON) eval_comparison(io, p0, p1);
+    else eval_range_check(io, p0);
+}
+
+// ---- witness generators (SimpleGenerator::run_once): fill the dependent wires of each row in place ----
+struct RowRW {
+    uint64_t *wires;
+    size_t rows, r;
+    __device__ __forceinline__ uint64_t get(uint32_t col) const { return gl_canon(wires[(size_t)col * rows + r]); }
+    __device__ __forceinline__ void set(uint32_t col, uint64_t v) { wires[(size_t)col * rows + r] = v; }
+    __device__ __forceinline__ void split(uint64_t v, uint32_t n, uint32_t bits, uint32_t col0) {
+        for (uint32_t j = 0; j < n; j++) { set(col0 + j, v & ((1ULL << bits) - 1)); v >>= bits; }
+    }
+};
+
+__global__ void __launch_bounds__(128) gl_gate_witness_kernel(uint32_t gate, uint32_t p0, uint32_t p1, uint64_t *wires,
+                                                              uint32_t rows) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    RowRW w{wires, rows, r};
+    if (gate == BSX_GATE_U32_ARITHMETIC) {
+        for (uint32_t i = 0; i < p0; i++) {
+            const uint64_t out = gl_add(gl_mul(w.get(6 * i), w.get(6 * i + 1)), w.get(6 * i + 2));
+            const uint64_t hi = out >> 32, lo = out & GL_EPS;
+            w.set(6 * i + 3, lo);
+            w.set(6 * i + 4, hi);
+            const uint64_t diff = GL_EPS - hi;
+            w.set(6 * i + 5, diff == 0 ? 0 : gl_inv(diff));
+            w.split(out, 32, 2, 6 * p0 + 32 * i);
+        }
+    } else if (gate == BSX_GATE_U32_ADD_MANY) {
+        const uint32_t na = p0;
+        for (uint32_t i = 0; i < p1; i++) {
+            uint64_t out = 0;
+            for (uint32_t j = 0; j <= na; j++) out = gl_add(out, w.get((na + 3) * i + j));
+            const uint64_t carry = out >> 32, res = out & GL_EPS;
+            w.set((na + 3) * i + na + 1, res);
+            w.set((na + 3) * i + na + 2, carry);
+            w.split(res, 16, 2, (na + 3) * p1 + 19 * i);
+            w.split(carry, 3, 2, (na + 3) * p1 + 19 * i + 16);
+        }
+    } else if (gate == BSX_GATE_U32_SUBTRACTION) {
+        for (uint32_t i = 0; i < p0; i++) {
+            const uint64_t initial = gl_sub(gl_sub(w.get(5 * i), w.get(5 * i + 1)), w.get(5 * i + 2));
+            const uint64_t borrow = initial > (1ULL << 32) ? 1 : 0;  // subtraction_u32.rs:319 (strict >)
+            const uint64_t res = gl_add(initial, gl_mul(1ULL << 32, borrow));
+            w.set(5 * i + 3, res);
+            w.set(5 * i + 4, borrow);
+            w.split(res, 16, 2, 5 * p0 + 16 * i);
+        }
+    } else if (gate == BSX_GATE_U32_COMPARISON) {
+        const uint32_t nc = p1, cb = (p0 + p1 - 1) / p1;
+        const uint64_t a = w.get(0), b = w.get(1);
+        uint64_t msd = 0;
+        w.set(2, a <= b ? 1 : 0);
+        for (uint32_t i = 0; i < nc; i++) {
+            const uint32_t sh = cb * i;
+            const uint64_t f = sh < 64 ? (a >> sh) & ((1ULL << cb) - 1) : 0, s = sh < 64 ? (b >> sh) & ((1ULL << cb) - 1) : 0;
+            w.set(4 + i, f);
+            w.set(4 + nc + i, s);
+            w.set(4 + 2 * nc + i, f == s ? 1 : gl_inv(gl_sub(s, f)));
+            w.set(4 + 3 * nc + i, f == s ? 1 : 0);
+            if (f != s) { msd = gl_sub(s, f); w.set(4 + 4 * nc + i, 0); }
+            else w.set(4 + 4 * nc + i, msd);
+        }
+        w.set(3, msd);
+        uint64_t t = gl_add(1ULL << cb, msd);
+        for (uint32_t i = 0; i <= cb; i++) { w.set(4 + 5 * nc + i, t & 1); t >>= 1; }
+    } else {
+        for (uint32_t i = 0; i < p0; i++) w.split((uint32_t)w.get(i), 16, 2, p0 + 16 * i);
+    }
+}
+
+// ---- Poseidon (width 12, x^7, 4 + 22 + 4 rounds) ----
+__device__ __forceinline__ uint64_t gl_pow7(uint64_t x) {
+    const uint64_t x2 = gl_mul(x, x), x4 = gl_mul(x2, x2);
+    return gl_mul(gl_mul(x4, x2), x);
+}
+
+__device__ __forceinline__ void poseidon_mds(uint64_t s[12]) {
+    constexpr uint32_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    uint32_t lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { lo[i] = (uint32_t)s[i]; hi[i] = (uint32_t)(s[i] >> 32); }
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        uint64_t al = 0, ah = 0;  // sums of 32-bit halves times 6-bit constants: < 2^42
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            al += (uint64_t)lo[(i + k) % 12] * CIRC[i];
+            ah += (uint64_t)hi[(i + k) % 12] * CIRC[i];
+        }
+        if (k == 0) { al += (uint64_t)lo[0] * 8; ah += (uint64_t)hi[0] * 8; }  // MDS_MATRIX_DIAG = [8, 0, ...]
+        const uint64_t l = al + (ah << 32);
+        const uint64_t h = (ah >> 32) + (l < al ? 1 : 0);
+        s[k] = gl_reduce128(h, l);
+    }
+}
+
+__device__ __forceinline__ void poseidon_permute(uint64_t s[12]) {
+#pragma unroll 1
+    for (int r = 0; r < 30; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], BSX_POSEIDON_RC[12 * r + i]);
+        if (r < 4 || r >= 26) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
+        } else {
+            s[0] = gl_pow7(s[0]);
+        }
+        poseidon_mds(s);
+    }
+}
+
+// hash_n_to_hash_no_pad: rate 8, overwrite mode; one thread per hash
+__global__ void __launch_bounds__(128) gl_poseidon_batch_kernel(const uint64_t *__restrict__ in, const uint32_t *__restrict__ offsets,
+                                                                uint32_t n, uint64_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = offsets[i], e = offsets[i + 1];
+    uint64_t s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = 0;
+#pragma unroll 1
+    for (uint32_t p = b; p < e; p += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (p + k < e) s[k] = gl_canon(in[p + k]);
+        poseidon_permute(s);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[4 * (size_t)i + k] = s[k];
+}
+
+}  // namespace bsx
+
+using namespace bsx;
+
+extern "C" uint32_t bsx_gate_num_wires(uint32_t gate, uint32_t p0, uint32_t p1) {
+    switch (gate) {
+        case BSX_GATE_U32_ARITHMETIC: return p0 * 38;
+        case BSX_GATE_U32_ADD_MANY: return p1 * (p0 + 3 + 19);
+        case BSX_GATE_U32_SUBTRACTION: return p0 * 21;
+        case BSX_GATE_U32_COMPARISON: return p1 ? 4 + 5 * p1 + (p0 + p1 - 1) / p1 + 1 : 0;
+        case BSX_GATE_U32_RANGE_CHECK: return p0 * 17;
+    }
+    return 0;
+}
+extern "C" uint32_t bsx_gate_num_constraints(uint32_t gate, uint32_t p0, uint32_t p1) {
+    switch (gate) {
+        case BSX_GATE_U32_ARITHMETIC: return p0 * 36;
+        case BSX_GATE_U32_ADD_MANY: return p1 * 22;
+        case BSX_GATE_U32_SUBTRACTION: return p0 * 19;
+        case BSX_GATE_U32_COMPARISON: return p1 ? 6 + 5 * p1 + (p0 + p1 - 1) / p1 : 0;
+        case BSX_GATE_U32_RANGE_CHECK: return p0 * 17;
+    }
+    return 0;
+}
+
+static int gate_args_ok(bsx_ctx *ctx, uint32_t gate, uint32_t p0, uint32_t p1) {
+    BSX_REQUIRE(ctx, gate <= BSX_GATE_U32_RANGE_CHECK && p0 >= 1);
+    BSX_REQUIRE(ctx, gate != BSX_GATE_U32_ADD_MANY || (p0 <= 64 && p1 >= 1));
+    BSX_REQUIRE(ctx, gate != BSX_GATE_U32_COMPARISON || (p1 >= 1 && p0 <= 63 && (p0 + p1 - 1) / p1 <= 16));
+    return BSX_OK;
+}
+
+extern "C" int bsx_gl_gate_eval_dev(bsx_ctx *ctx, void *stream, uint32_t gate, uint32_t p0, uint32_t p1, const uint64_t *wires,
+                                    uint32_t rows, uint64_t *constraints) {
+    BSX_REQUIRE(ctx, ctx && wires && constraints);
+    int rc = gate_args_ok(ctx, gate, p0, p1);
+    if (rc) return rc;
+    if (rows == 0) return BSX_OK;
+    const uint32_t blocks = (rows + 127) / 128;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (gate) {
+        case BSX_GATE_U32_ARITHMETIC: gl_gate_eval_kernel<BSX_GATE_U32_ARITHMETIC><<<blocks, 128, 0, st>>>(p0, p1, wires, rows, constraints); break;
+        case BSX_GATE_U32_ADD_MANY: gl_gate_eval_kernel<BSX_GATE_U32_ADD_MANY><<<blocks, 128, 0, st>>>(p0, p1, wires, rows, constraints); break;
+        case BSX_GATE_U32_SUBTRACTION: gl_gate_eval_kernel<BSX_GATE_U32_SUBTRACTION><<<blocks, 128, 0, st>>>(p0, p1, wires, rows, constraints); break;
+        case BSX_GATE_U32_COMPARISON: gl_gate_eval_kernel<BSX_GATE_U32_COMPARISON><<<blocks, 128, 0, st>>>(p0, p1, wires, rows, constraints); break;
+        default: gl_gate_eval_kernel<BSX_GATE_U32_RANGE_CHECK><<<blocks, 128, 0, st>>>(p0, p1, wires, rows, constraints); break;
+    }
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+extern "C" int bsx_gl_gate_witness_dev(bsx_ctx *ctx, void *stream, uint32_t gate, uint32_t p0, uint32_t p1, uint64_t *wires,
+                                       uint32_t rows) {
+    BSX_REQUIRE(ctx, ctx && wires);
+    int rc = gate_args_ok(ctx, gate, p0, p1);
+    if (rc) return rc;
+    if (rows == 0) return BSX_OK;
+    gl_gate_witness_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gate, p0, p1, wires, rows);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+extern "C" int bsx_gl_poseidon_batch_dev(bsx_ctx *ctx, void *stream, const uint64_t *in, const uint32_t *offsets, uint32_t n,
+                                         uint64_t *out) {
+    BSX_REQUIRE(ctx, ctx && offsets && out);
+    if (n == 0) return BSX_OK;
+    gl_poseidon_batch_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, offsets, n, out);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+// ---- host-buffer entry points ----
+extern "C" int bsx_gl_gate_eval(bsx_ctx *ctx, uint32_t gate, uint32_t p0, uint32_t p1, const uint64_t *wires, uint32_t rows,
+                                uint64_t *constraints) {
+    BSX_REQUIRE(ctx, ctx && wires && constraints);
+    int rc = gate_args_ok(ctx, gate, p0, p1);
+    if (rc) return rc;
+    if (rows == 0) return BSX_OK;
+    BSX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t sw = 8 * (size_t)bsx_gate_num_wires(gate, p0, p1) * rows, sc = 8 * (size_t)bsx_gate_num_constraints(gate, p0, p1) * rows;
+    rc = ws_begin(ctx, ws_size(sw) + ws_size(sc));
+    if (rc) return rc;
+    uint64_t *d_w = ws_take<uint64_t>(ctx, sw / 8), *d_c = ws_take<uint64_t>(ctx, sc / 8);
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_w, wires, sw, cudaMemcpyHostToDevice, ctx->stream));
+    rc = bsx_gl_gate_eval_dev(ctx, ctx->stream, gate, p0, p1, d_w, rows, d_c);
+    if (rc) return rc;
+    BSX_CUDA(ctx, cudaMemcpyAsync(constraints, d_c, sc, cudaMemcpyDeviceToHost, ctx->stream));
+    BSX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BSX_OK;
+}
+
+extern "C" int bsx_gl_gate_witness(bsx_ctx *ctx, uint32_t gate, uint32_t p0, uint32_t p1, uint64_t *wires, uint32_t rows) {
+    BSX_REQUIRE(ctx, ctx && wires);
+    int rc = gate_args_ok(ctx, gate, p0, p1);
+    if (rc) return rc;
+    if (rows == 0) return BSX_OK;
+    BSX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t sw = 8 * (size_t)bsx_gate_num_wires(gate, p0, p1) * rows;
+    rc = ws_begin(ctx, ws_size(sw));
+    if (rc) return rc;
+    uint64_t *d_w = ws_take<uint64_t>(ctx, sw / 8);
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_w, wires, sw, cudaMemcpyHostToDevice, ctx->stream));
+    rc = bsx_gl_gate_witness_dev(ctx, ctx->stream, gate, p0, p1, d_w, rows);
+    if (rc) return rc;
+    BSX_CUDA(ctx, cudaMemcpyAsync(wires, d_w, sw, cudaMemcpyDeviceToHost, ctx->stream));
+    BSX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BSX_OK;
+}
+
+extern "C" int bsx_gl_poseidon_batch(bsx_ctx *ctx, const uint64_t *in, const uint32_t *offsets, uint32_t n, uint64_t *out) {
+    BSX_REQUIRE(ctx, ctx && offsets && out);
+    if (n == 0) return BSX_OK;
+    BSX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t total = offsets[n];
+    BSX_REQUIRE(ctx, total == 0 || in);
+    int rc = ws_begin(ctx, ws_size(8 * total + 8) + ws_size(4 * (size_t)(n + 1)) + ws_size(32 * (size_t)n));
+    if (rc) return rc;
+    uint64_t *d_in = ws_take<uint64_t>(ctx, total + 1);
+    uint32_t *d_off = ws_take<uint32_t>(ctx, n + 1);
+    uint64_t *d_out = ws_take<uint64_t>(ctx, 4 * (size_t)n);
+    if (total) BSX_CUDA(ctx, cudaMemcpyAsync(d_in, in, 8 * total, cudaMemcpyHostToDevice, ctx->stream));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_off, offsets, 4 * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    rc = bsx_gl_poseidon_batch_dev(ctx, ctx->stream, d_in, d_off, n, d_out);
+    if (rc) return rc;
+    BSX_CUDA(ctx, cudaMemcpyAsync(out, d_out, 32 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    BSX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BSX_OK;
+}

@@ -39,6 +39,8 @@ def load() -> C.CDLL:
         _lib.bsx_launch_count.restype = C.c_uint64
         _lib.bsx_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         _lib.bsx_verify_digest_count.restype = C.c_uint32
+        _lib.bsx_gate_num_wires.restype = C.c_uint32
+        _lib.bsx_gate_num_constraints.restype = C.c_uint32
     return _lib
 
 
@@ -193,6 +195,34 @@ class Context:
         act = None if active is None else _in(active)
         self._call("bsx_ed25519_batch", C.c_uint32(n), _ptr(pks), _ptr(_in(sigs)), _ptr(msgs), C.c_uint32(stride), _ptr(lens),
                    _ptr(act), _ptr(out))
+        return out
+
+    # -- K6/K7/K8 --
+    def gate_num_wires(self, gate: int, p0: int, p1: int = 0) -> int:
+        return int(self._lib.bsx_gate_num_wires(C.c_uint32(gate), C.c_uint32(p0), C.c_uint32(p1)))
+
+    def gate_num_constraints(self, gate: int, p0: int, p1: int = 0) -> int:
+        return int(self._lib.bsx_gate_num_constraints(C.c_uint32(gate), C.c_uint32(p0), C.c_uint32(p1)))
+
+    def gl_gate_eval(self, gate: int, p0: int, p1: int, wires) -> np.ndarray:
+        """wires [n_wires, rows] u64 wire-major -> constraints [n_constraints, rows]."""
+        wires = _in(wires, np.uint64)
+        assert wires.shape[0] == self.gate_num_wires(gate, p0, p1)
+        rows = wires.shape[1]
+        out = np.zeros((self.gate_num_constraints(gate, p0, p1), rows), np.uint64)
+        self._call("bsx_gl_gate_eval", C.c_uint32(gate), C.c_uint32(p0), C.c_uint32(p1), _ptr(wires), C.c_uint32(rows), _ptr(out))
+        return out
+
+    def gl_gate_witness(self, gate: int, p0: int, p1: int, wires) -> np.ndarray:
+        wires = _in(wires, np.uint64).copy()
+        self._call("bsx_gl_gate_witness", C.c_uint32(gate), C.c_uint32(p0), C.c_uint32(p1), _ptr(wires), C.c_uint32(wires.shape[1]))
+        return wires
+
+    def gl_poseidon_batch(self, inputs, offsets) -> np.ndarray:
+        offsets = _in(offsets, np.uint32)
+        n = len(offsets) - 1
+        out = np.zeros((n, 4), np.uint64)
+        self._call("bsx_gl_poseidon_batch", _ptr(_in(inputs, np.uint64)), _ptr(offsets), C.c_uint32(n), _ptr(out))
         return out
 
     # -- verify_header / verify_skip / next_header --

@@ -282,6 +282,44 @@ int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_
                             uint32_t msg_max, const uint8_t *msg_lens, uint32_t len_stride, const uint8_t *active,
                             uint32_t active_stride, uint8_t *out);
 
+/* ------------------------------------------------------------------------------------------
+ * K6/K7  Goldilocks u32 gates: constraint evaluation and witness generators
+ * replaces: Gate::eval_unfiltered_base_batch -> PackedEvaluableBase::eval_unfiltered_base_packed and the per-gate
+ *   SimpleGenerator::run_once of the five vendored gates:
+ *   U32ArithmeticGate{num_ops=p0}                 PX/frontend/uint/num/u32/gates/arithmetic_u32.rs:280-349, 383-431
+ *   U32AddManyGate{num_addends=p0, num_ops=p1}    PX/frontend/uint/num/u32/gates/add_many_u32.rs:107-146, 340-391
+ *   U32SubtractionGate{num_ops=p0}                PX/frontend/uint/num/u32/gates/subtraction_u32.rs:101-135, 305-350
+ *   ComparisonGate{num_bits=p0, num_chunks=p1}    PX/frontend/uint/num/u32/gates/comparison.rs:118-195, 441-540
+ *   U32RangeCheckGate{num_input_limbs=p0}         PX/frontend/uint/num/u32/gates/range_check_u32.rs:69-91, 202-224
+ * wires: bsx_gate_num_wires x rows u64, WIRE-major (wires[w*rows + r], plonky2's EvaluationVarsBaseBatch view);
+ * constraints: bsx_gate_num_constraints x rows, constraints[c*rows + r], canonical (< p = 2^64 - 2^32 + 1), in the
+ * order the gate yields them.  bsx_gl_gate_witness fills the generator-owned wires of every row in place.
+ * ------------------------------------------------------------------------------------------ */
+#define BSX_GATE_U32_ARITHMETIC 0
+#define BSX_GATE_U32_ADD_MANY 1
+#define BSX_GATE_U32_SUBTRACTION 2
+#define BSX_GATE_U32_COMPARISON 3
+#define BSX_GATE_U32_RANGE_CHECK 4
+uint32_t bsx_gate_num_wires(uint32_t gate, uint32_t p0, uint32_t p1);
+uint32_t bsx_gate_num_constraints(uint32_t gate, uint32_t p0, uint32_t p1);
+int bsx_gl_gate_eval(bsx_ctx *ctx, uint32_t gate, uint32_t p0, uint32_t p1, const uint64_t *wires, uint32_t rows,
+                     uint64_t *constraints);
+int bsx_gl_gate_eval_dev(bsx_ctx *ctx, void *stream, uint32_t gate, uint32_t p0, uint32_t p1, const uint64_t *wires,
+                         uint32_t rows, uint64_t *constraints);
+int bsx_gl_gate_witness(bsx_ctx *ctx, uint32_t gate, uint32_t p0, uint32_t p1, uint64_t *wires, uint32_t rows);
+int bsx_gl_gate_witness_dev(bsx_ctx *ctx, void *stream, uint32_t gate, uint32_t p0, uint32_t p1, uint64_t *wires,
+                            uint32_t rows);
+
+/* ------------------------------------------------------------------------------------------
+ * K8  Poseidon sponge over Goldilocks (width 12, rate 8, no padding, overwrite mode, 4 outputs)
+ * replaces: plonky2 hash_n_to_hash_no_pad::<PoseidonPermutation> behind poseidon_hash / poseidon_hash_pair
+ *   (PX/frontend/hash/poseidon/poseidon256.rs:61-86) and mapreduce_merkle_tree_root (PX/utils/poseidon/mod.rs:9-66).
+ * in: concatenated field elements; offsets[n+1]; out: n x 4 canonical elements.
+ * ------------------------------------------------------------------------------------------ */
+int bsx_gl_poseidon_batch(bsx_ctx *ctx, const uint64_t *in, const uint32_t *offsets, uint32_t n, uint64_t *out);
+int bsx_gl_poseidon_batch_dev(bsx_ctx *ctx, void *stream, const uint64_t *in, const uint32_t *offsets, uint32_t n,
+                              uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -319,5 +319,58 @@ def next_header(k: dict, threads=1):
     return dict(sha256_digests=dig, ed=ed, data_commitment=dc.tobytes(), fail=fail)
 
 
+GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_COMPARISON, GATE_U32_RANGE_CHECK = range(5)
+
+
+def gate_num_wires(gate, p0, p1=0) -> int:
+    return lib().orc_gate_num_wires(C.c_uint32(gate), C.c_uint32(p0), C.c_uint32(p1))
+
+
+def gate_num_constraints(gate, p0, p1=0) -> int:
+    return lib().orc_gate_num_constraints(C.c_uint32(gate), C.c_uint32(p0), C.c_uint32(p1))
+
+
+def gate_eval(gate, p0, p1, wires: np.ndarray, threads=1) -> np.ndarray:
+    """wires [n_wires, rows] u64 (wire-major) -> constraints [n_constraints, rows]."""
+    wires = np.ascontiguousarray(wires, np.uint64)
+    rows = wires.shape[1]
+    out = np.zeros((gate_num_constraints(gate, p0, p1), rows), np.uint64)
+    rc = lib().orc_gate_eval(C.c_uint32(gate), C.c_uint32(p0), C.c_uint32(p1), _p(wires), C.c_uint32(rows), _p(out), C.c_int(threads))
+    assert rc == 0
+    return out
+
+
+def gate_witness(gate, p0, p1, wires: np.ndarray, threads=1) -> np.ndarray:
+    wires = np.ascontiguousarray(wires, np.uint64).copy()
+    rc = lib().orc_gate_witness(C.c_uint32(gate), C.c_uint32(p0), C.c_uint32(p1), _p(wires), C.c_uint32(wires.shape[1]), C.c_int(threads))
+    assert rc == 0
+    return wires
+
+
+def poseidon_permute(state) -> np.ndarray:
+    s = np.ascontiguousarray(state, np.uint64).copy()
+    lib().orc_poseidon_permute(_p(s))
+    return s
+
+
+def poseidon_batch(inputs: np.ndarray, offsets: np.ndarray, threads=1) -> np.ndarray:
+    inputs = np.ascontiguousarray(inputs, np.uint64)
+    offsets = np.ascontiguousarray(offsets, np.uint32)
+    n = len(offsets) - 1
+    out = np.zeros((n, 4), np.uint64)
+    lib().orc_poseidon_batch(_p(inputs), _p(offsets), C.c_uint32(n), _p(out), C.c_int(threads))
+    return out
+
+
+def poseidon_hash_no_pad(inputs) -> np.ndarray:
+    a = np.ascontiguousarray(inputs, np.uint64)
+    return poseidon_batch(a, np.array([0, len(a)], np.uint32))[0]
+
+
+def poseidon_round_constants() -> np.ndarray:
+    lib().orc_poseidon_round_constants.restype = C.POINTER(C.c_uint64)
+    return np.array(lib().orc_poseidon_round_constants()[:360], np.uint64)
+
+
 def max_threads() -> int:
     return lib().orc_max_threads()
