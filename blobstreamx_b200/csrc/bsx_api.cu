@@ -17,7 +17,10 @@ extern "C" int bsx_init(int device, bsx_ctx **out) {
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return BSX_ERR_CUDA;
     }
@@ -32,6 +35,12 @@ extern "C" void bsx_destroy(bsx_ctx *ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    if (ctx->stream2) {
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamDestroy(ctx->stream2);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ed_table) cudaFree(ctx->ed_table);
     delete ctx;

@@ -17,6 +17,8 @@ struct bsx_ctx {
     size_t ws_cap;
     size_t ws_off;
     void *ed_table;            // s*G window table (k_ed25519.cu), built on first use
+    cudaStream_t stream2;      // second stream + events: bsx_header_range runs its two halves concurrently
+    cudaEvent_t ev_fork, ev_join;
 };
 
 namespace bsx {

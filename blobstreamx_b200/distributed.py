@@ -1,0 +1,139 @@
+"""Multi-GPU header_range: the map jobs of prove_data_commitment sharded over ranks, ONE all-gather of the
+per-job MapReduceSubchainVariable records, then the reduce tree.
+
+Reference shape: `MapReduceGenerator::run_once` proves the NB_MAP_JOBS map circuits independently
+(PX/frontend/mapreduce/generator.rs:97-111) -- each consumes only the shared ctx (start/end block + header) and its
+own BATCH_SIZE headers -- and then log2(jobs) reduce layers (generator.rs:113-151, closure BX/circuits/builder.rs:
+337-395).  The reference's only multi-worker story is `PROVER=remote` (HTTP, PX/backend/prover/remote.rs:98-153).
+Here rank r of W owns jobs [r*J/W, (r+1)*J/W) of EVERY range in flight (contiguous job slice = contiguous header
+range), the 128-byte subchain records are exchanged with one `all_gather_into_tensor` (NCCL over NVLink on GPUs,
+gloo in the CPU tests), and rank r reduces ranges [r*R/W, (r+1)*R/W).  No other collective is on the data path.
+
+The compute backend is injected: `CudaBackend` (below) drives libbsx through device pointers on torch's current
+stream; the CPU tests pass an oracle-backed stand-in that lives under tests/ (the product has no CPU path).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+SUBCHAIN_BYTES = 128
+MAP_FIELDS = ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers")
+_ROW = {"dh_leaf": 34, "dh_aunts": 128, "lb_leaf": 72, "lb_aunts": 128}
+
+
+def job_slice(n_jobs: int, rank: int, world: int) -> slice:
+    if n_jobs % world:
+        raise ValueError(f"NB_MAP_JOBS={n_jobs} is not divisible by world size {world}")
+    per = n_jobs // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def shard_map_inputs(host: Dict[str, np.ndarray], n_ranges: int, n_jobs: int, batch: int, rank: int, world: int):
+    """host: the flat arrays of ALL `n_ranges` ranges (range-major, job-major; see include/bsx.h
+    bsx_prove_data_commitment).  Returns this rank's job slice of every range plus the explicit per-job scalars
+    bsx_prove_subchain_batch wants."""
+    js = job_slice(n_jobs, rank, world)
+    per = js.stop - js.start
+    out = {}
+    for f in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts"):
+        a = np.ascontiguousarray(host[f], np.uint8).reshape(n_ranges, n_jobs, batch, _ROW[f])
+        out[f] = np.ascontiguousarray(a[:, js]).reshape(n_ranges * per * batch, _ROW[f])
+    for f in ("start_headers", "end_headers"):
+        a = np.ascontiguousarray(host[f], np.uint8).reshape(n_ranges, n_jobs, 32)
+        out[f] = np.ascontiguousarray(a[:, js]).reshape(n_ranges * per, 32)
+    sb = np.ascontiguousarray(host["start_blocks"], np.uint64).reshape(n_ranges)
+    eb = np.ascontiguousarray(host["end_blocks"], np.uint64).reshape(n_ranges)
+    j = np.arange(js.start, js.stop, dtype=np.uint64)
+    bs = (sb[:, None] + j[None, :] * np.uint64(batch)).reshape(-1)
+    out["batch_start"] = bs
+    out["batch_end"] = bs + np.uint64(batch)
+    out["global_end"] = np.repeat(eb, per)
+    out["global_end_header"] = np.repeat(np.ascontiguousarray(host["end_header"], np.uint8).reshape(n_ranges, 32), per, axis=0)
+    return out
+
+
+class CudaBackend:
+    """libbsx through the `_dev` entry points on torch's current CUDA stream."""
+
+    def __init__(self, device_index: int):
+        from . import lib
+        self.lib = lib
+        self.ctx = lib.Context(device_index)
+        self.device = torch.device("cuda", device_index)
+
+    def tensor(self, a: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(self.device)
+
+    def empty(self, nbytes: int) -> torch.Tensor:
+        return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+
+    def map(self, B, n_jobs, t, digests, subchains):
+        P = lambda x: self.lib.ptr(x.data_ptr())
+        self.ctx.call_dev("bsx_prove_subchain_batch_dev", torch.cuda.current_stream().cuda_stream, self.lib.u32(B), self.lib.u32(n_jobs),
+                          P(t["dh_leaf"]), P(t["dh_aunts"]), P(t["lb_leaf"]), P(t["lb_aunts"]), P(t["start_headers"]),
+                          P(t["end_headers"]), P(t["batch_start"]), P(t["batch_end"]), P(t["global_end"]),
+                          P(t["global_end_header"]), P(digests), P(subchains))
+
+    def reduce(self, n_ranges, n_jobs, B, subchains, t, reduce_digests, reduce_nodes, dcs, fail):
+        P = lambda x: self.lib.ptr(x.data_ptr())
+        self.ctx.call_dev("bsx_reduce_subchains_dev", torch.cuda.current_stream().cuda_stream, self.lib.u32(n_ranges), self.lib.u32(n_jobs),
+                          P(subchains), P(t["start_blocks"]), P(t["start_header"]), P(t["end_blocks"]), P(t["end_header"]),
+                          self.lib.u32(B), P(reduce_digests), P(reduce_nodes), P(dcs), P(fail))
+
+
+class ShardedHeaderRange:
+    """One step = all map jobs of `n_ranges` ranges (this rank's slice), all-gather, reduce of this rank's ranges."""
+
+    def __init__(self, backend, n_ranges: int, n_jobs: int, batch: int, rank: int = 0, world: int = 1, group=None):
+        if n_ranges % world:
+            raise ValueError("the number of ranges in flight must be divisible by the world size")
+        self.be, self.R, self.J, self.B, self.rank, self.world, self.group = backend, n_ranges, n_jobs, batch, rank, world, group
+        self.per = n_jobs // world
+        self.own = slice(rank * (n_ranges // world), (rank + 1) * (n_ranges // world))
+        R, per, B = n_ranges, self.per, batch
+        e = backend.empty
+        self.map_digests = e(R * per * (20 * B - 1) * 32)
+        self.local_sub = e(R * per * SUBCHAIN_BYTES)
+        self.gathered = e(world * R * per * SUBCHAIN_BYTES) if world > 1 else None
+        self.all_sub = e(R * n_jobs * SUBCHAIN_BYTES) if world > 1 else self.local_sub
+        Ro = R // world
+        self.reduce_digests = e(Ro * max(n_jobs - 1, 1) * 32)
+        self.reduce_nodes = e(Ro * max(n_jobs - 1, 1) * SUBCHAIN_BYTES)
+        self.data_commitments = e(Ro * 32)
+        self.fail = e(Ro * 4)
+        self.t: Optional[dict] = None
+
+    def load(self, host: Dict[str, np.ndarray]):
+        """host arrays of ALL ranges -> device-resident shard + this rank's public inputs for the reduce."""
+        sh = shard_map_inputs(host, self.R, self.J, self.B, self.rank, self.world)
+        t = {k: self.be.tensor(v) for k, v in sh.items()}
+        o = self.own
+        t["start_blocks"] = self.be.tensor(np.ascontiguousarray(host["start_blocks"], np.uint64)[o])
+        t["end_blocks"] = self.be.tensor(np.ascontiguousarray(host["end_blocks"], np.uint64)[o])
+        t["start_header"] = self.be.tensor(np.ascontiguousarray(host["start_header"], np.uint8).reshape(self.R, 32)[o])
+        t["end_header"] = self.be.tensor(np.ascontiguousarray(host["end_header"], np.uint8).reshape(self.R, 32)[o])
+        self.t = t
+
+    def step(self):
+        R, J, per, W = self.R, self.J, self.per, self.world
+        self.be.map(self.B, R * per, self.t, self.map_digests, self.local_sub)
+        if W > 1:
+            dist.all_gather_into_tensor(self.gathered, self.local_sub, group=self.group)
+            # [W, R, per, 128] -> [R, W*per, 128]: job j of range r lives on rank j // per
+            g = self.gathered.view(W, R, per * SUBCHAIN_BYTES).permute(1, 0, 2)
+            self.all_sub.view(R, W, per * SUBCHAIN_BYTES).copy_(g)
+        o = self.own
+        sub = self.all_sub.view(R, J * SUBCHAIN_BYTES)[o].reshape(-1)
+        self.be.reduce(R // W, J, self.B, sub, self.t, self.reduce_digests, self.reduce_nodes, self.data_commitments, self.fail)
+
+    def results(self):
+        Ro = self.R // self.world
+        return dict(data_commitments=self.data_commitments.cpu().numpy().reshape(Ro, 32),
+                    fail=self.fail.cpu().numpy().view(np.uint32).reshape(Ro),
+                    reduce_nodes=self.reduce_nodes.cpu().numpy().reshape(Ro, max(self.J - 1, 1), SUBCHAIN_BYTES),
+                    map_subchains=self.all_sub.cpu().numpy().reshape(self.R, self.J, SUBCHAIN_BYTES)[self.own],
+                    local_map_digests=self.map_digests.cpu().numpy().reshape(self.R, self.per, 20 * self.B - 1, 32))

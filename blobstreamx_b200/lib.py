@@ -264,10 +264,62 @@ class Context:
     def next_header(self, items, N: int = 100):
         return self._verify(2, items, N)
 
+    # -- header_range = skip + prove_data_commitment --
+    def header_range(self, skip_items, m, N: int = 100):
+        """One or more header ranges.  skip_items: list of get_skip_inputs dicts; m: dict of the flat map arrays
+        (as bench.tile_ranges / inputs.HeaderRangeMapInputs fields) incl. n_jobs, batch."""
+        n, J, B = len(skip_items), int(m["n_jobs"]), int(m["batch"])
+        keep = dict(
+            hdr=pack_header_in([k["target"] for k in skip_items]),
+            validators=np.stack([_in(k["target"]["validators"]).reshape(N, VAL_IN_BYTES) for k in skip_items]),
+            skip=pack_skip_in(skip_items),
+            trusted_pubkeys=np.stack([_in(k["trusted_pubkeys"]).reshape(N, 32) for k in skip_items]),
+            trusted_powers=np.stack([_in(k["trusted_powers"], np.uint64) for k in skip_items]),
+            trusted_byte_lengths=np.stack([_in(k["trusted_byte_lengths"], np.uint32) for k in skip_items]))
+        D = int(self._lib.bsx_verify_digest_count(C.c_int(1), C.c_uint32(N)))
+        so = dict(digests=np.zeros((n, D, 32), np.uint8), ed_out=np.zeros((n, N, SIG_OUT_BYTES), np.uint8), fail=np.zeros(n, np.uint32))
+        sb = fill_struct(SkipBatch(), **keep, **so)
+        mi = {f: _in(m[f]) for f in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers", "start_header", "end_header")}
+        mi["start_blocks"], mi["end_blocks"] = _in(m["start_blocks"], np.uint64), _in(m["end_blocks"], np.uint64)
+        mo = dict(map_digests=np.zeros((n, J, 20 * B - 1, 32), np.uint8), map_subchains=np.zeros((n, J, SUBCHAIN_BYTES), np.uint8),
+                  reduce_digests=np.zeros((n, max(J - 1, 1), 32), np.uint8), reduce_nodes=np.zeros((n, max(J - 1, 1), SUBCHAIN_BYTES), np.uint8),
+                  data_commitments=np.zeros((n, 32), np.uint8), fail=np.zeros(n, np.uint32))
+        rb = fill_struct(RangeBatch(), **mi, **mo)
+        self._call("bsx_header_range", C.c_uint32(n), C.c_uint32(N), C.c_uint32(J), C.c_uint32(B), C.byref(sb), C.byref(rb))
+        return dict(skip=dict(sha256_digests=so["digests"], ed=so["ed_out"], fail=so["fail"]), **mo)
+
     # -- raw access for device-pointer entry points (bench / multi-GPU) --
     def call_dev(self, name: str, stream: int, *args):
         """Call a `*_dev` entry point; integer args that are pointers must be wrapped with ptr()."""
         self._call(name, C.c_void_p(int(stream)), *args)
+
+
+class SkipBatch(C.Structure):
+    """bsx_skip_batch"""
+    _fields_ = [(k, C.c_void_p) for k in ("hdr", "validators", "skip", "trusted_pubkeys", "trusted_powers",
+                                          "trusted_byte_lengths", "digests", "ed_out", "fail")]
+
+
+class RangeBatch(C.Structure):
+    """bsx_range_batch"""
+    _fields_ = [(k, C.c_void_p) for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers",
+                                          "start_blocks", "end_blocks", "start_header", "end_header", "map_digests",
+                                          "map_subchains", "reduce_digests", "reduce_nodes", "data_commitments", "fail")]
+
+
+def _addr(a) -> int:
+    if a is None:
+        return 0
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    return a.ctypes.data
+
+
+def fill_struct(st, **ptrs):
+    """numpy arrays / raw device addresses -> the pointer fields of a SkipBatch / RangeBatch."""
+    for k, v in ptrs.items():
+        setattr(st, k, _addr(v))
+    return st
 
 
 # struct layouts of include/bsx.h

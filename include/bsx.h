@@ -320,6 +320,41 @@ int bsx_gl_poseidon_batch(bsx_ctx *ctx, const uint64_t *in, const uint32_t *offs
 int bsx_gl_poseidon_batch_dev(bsx_ctx *ctx, void *stream, const uint64_t *in, const uint32_t *offsets, uint32_t n,
                               uint64_t *out);
 
+/* ------------------------------------------------------------------------------------------
+ * header_range = skip + prove_data_commitment for n independent ranges in ONE call
+ * replaces every accelerator hint of CombinedSkipCircuit::define (BX/circuits/header_range.rs:32-59):
+ *   builder.skip(..)                    TX/skip.rs:29-58 -> verify_skip (TX/builder/verify.rs:527-564)
+ *   builder.prove_data_commitment(..)   BX/circuits/builder.rs:273-409 (32 map jobs + reduce tree)
+ * The two argument blocks are plain structs of pointers (repr(C) on the Rust side); every pointer has the
+ * meaning and size of the like-named parameter of bsx_verify_skip / bsx_prove_data_commitment.
+ * The skip half and the map/reduce half run concurrently on two streams of the ctx.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bsx_skip_batch {
+    const bsx_header_in *hdr;           /* n */
+    const uint8_t *validators;          /* n*N*BSX_VAL_IN_BYTES */
+    const bsx_skip_in *skip;            /* n */
+    const uint8_t *trusted_pubkeys;     /* n*N*32 */
+    const uint64_t *trusted_powers;     /* n*N */
+    const uint32_t *trusted_byte_lengths; /* n*N */
+    uint8_t *digests;                   /* out: n*bsx_verify_digest_count(1,N)*32 */
+    uint8_t *ed_out;                    /* out: n*N*BSX_SIG_OUT_BYTES */
+    uint32_t *fail;                     /* out: n, BSX_VFAIL_* */
+} bsx_skip_batch;
+typedef struct bsx_range_batch {
+    const uint8_t *dh_leaf, *dh_aunts, *lb_leaf, *lb_aunts; /* n*n_jobs*B*{34,128,72,128} */
+    const uint8_t *start_headers, *end_headers;             /* n*n_jobs*32 */
+    const uint64_t *start_blocks, *end_blocks;              /* n */
+    const uint8_t *start_header, *end_header;               /* n*32 */
+    uint8_t *map_digests, *map_subchains;                   /* out: n*n_jobs*(20B-1)*32, n*n_jobs*128 */
+    uint8_t *reduce_digests, *reduce_nodes;                 /* out: n*(n_jobs-1)*32, n*(n_jobs-1)*128 */
+    uint8_t *data_commitments;                              /* out: n*32 */
+    uint32_t *fail;                                         /* out: n, BSX_FAIL_* */
+} bsx_range_batch;
+int bsx_header_range(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n_jobs, uint32_t B, const bsx_skip_batch *skip,
+                     const bsx_range_batch *range);
+int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, uint32_t n_jobs, uint32_t B,
+                         const bsx_skip_batch *skip, const bsx_range_batch *range);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,11 @@ void orc_prove_data_commitment(uint32_t n_jobs, uint32_t B, const uint8_t *dh_le
                                uint8_t *map_subchains, uint8_t *reduce_digests, uint8_t *reduce_nodes,
                                uint8_t data_commitment[32], uint32_t *fail, int threads);
 
+/* reduce tree alone over map outputs (what every rank runs after the all-gather) */
+void orc_reduce_subchains(uint32_t n_jobs, uint32_t B, const uint8_t *map_subchains, uint64_t start_block,
+                          const uint8_t start_header[32], uint64_t end_block, const uint8_t end_header[32],
+                          uint8_t *reduce_digests, uint8_t *reduce_nodes, uint8_t data_commitment[32], uint32_t *fail);
+
 /* ---- tendermintx gadgets (TX/builder/{validator,shared,verify}.rs) ---- */
 /* marshal_int64_varint: always 9 output bytes; returns significant length */
 uint32_t orc_marshal_int64_varint(uint64_t v, uint8_t out[9]);

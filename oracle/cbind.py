@@ -157,6 +157,17 @@ def prove_data_commitment(n_jobs, B, dh_leaf, dh_aunts, lb_leaf, lb_aunts, start
                 data_commitment=dc.tobytes(), fail=fail.value)
 
 
+def reduce_subchains(n_jobs, B, map_subchains, start_block, start_header, end_block, end_header):
+    red_dig = np.zeros((max(n_jobs - 1, 1), 32), np.uint8)
+    red_nodes = np.zeros((max(n_jobs - 1, 1), SUBCHAIN_BYTES), np.uint8)
+    dc = np.zeros(32, np.uint8)
+    fail = C.c_uint32(0)
+    lib().orc_reduce_subchains(C.c_uint32(n_jobs), C.c_uint32(B), _p(_u8(map_subchains)), C.c_uint64(start_block),
+                               _p(_u8(start_header)), C.c_uint64(end_block), _p(_u8(end_header)), _p(red_dig), _p(red_nodes),
+                               _p(dc), C.byref(fail))
+    return dict(reduce_digests=red_dig, reduce_nodes=red_nodes, data_commitment=dc.tobytes(), fail=fail.value)
+
+
 def marshal_int64_varint(v: int):
     out = np.zeros(9, np.uint8)
     n = lib().orc_marshal_int64_varint(C.c_uint64(v), _p(out))

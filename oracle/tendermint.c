@@ -217,7 +217,6 @@ void orc_prove_data_commitment(uint32_t n_jobs, uint32_t B, const uint8_t *dh_le
                                uint8_t *map_subchains, uint8_t *reduce_digests, uint8_t *reduce_nodes,
                                uint8_t data_commitment[32], uint32_t *fail, int threads) {
     uint32_t f = 0;
-    if (!(end_block <= start_block + (uint64_t)n_jobs * B)) f |= ORC_FAIL_RANGE;
     size_t dig_per_job = (size_t)(20 * B - 1) * 32;
     (void)threads;
 #pragma omp parallel for schedule(dynamic) num_threads(threads > 0 ? threads : 1)
@@ -229,6 +228,18 @@ void orc_prove_data_commitment(uint32_t n_jobs, uint32_t B, const uint8_t *dh_le
                            start_headers + 32 * (size_t)j, end_headers + 32 * (size_t)j, bs, be, end_block,
                            end_header, map_digests + dig_per_job * j, map_subchains + ORC_SUBCHAIN_BYTES * (size_t)j);
     }
+    uint32_t fr = 0;
+    orc_reduce_subchains(n_jobs, B, map_subchains, start_block, start_header, end_block, end_header, reduce_digests,
+                         reduce_nodes, data_commitment, &fr);
+    if (fail) *fail = f | fr;
+}
+
+/* the reduce tree alone (BX/circuits/builder.rs:337-409) over already-computed map outputs */
+void orc_reduce_subchains(uint32_t n_jobs, uint32_t B, const uint8_t *map_subchains, uint64_t start_block,
+                          const uint8_t start_header[32], uint64_t end_block, const uint8_t end_header[32],
+                          uint8_t *reduce_digests, uint8_t *reduce_nodes, uint8_t data_commitment[32], uint32_t *fail) {
+    uint32_t f = 0;
+    if (!(end_block <= start_block + (uint64_t)n_jobs * B)) f |= ORC_FAIL_RANGE;
     uint8_t *cur = (uint8_t *)malloc((size_t)n_jobs * ORC_SUBCHAIN_BYTES);
     memcpy(cur, map_subchains, (size_t)n_jobs * ORC_SUBCHAIN_BYTES);
     uint8_t *rd = reduce_digests, *rn = reduce_nodes;

@@ -1,0 +1,49 @@
+"""ShardedHeaderRange with the CUDA backend on one GPU (world 1) and, when the box has 2+ GPUs, over NCCL with two
+ranks -- results equal the oracle's.  The N>1 host logic is also covered on CPU by tests/test_distributed_gloo.py."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_world1_cuda():
+    import bench
+    from blobstreamx_b200 import synthetic as S
+    from blobstreamx_b200.distributed import CudaBackend, ShardedHeaderRange
+    from oracle import cbind as orc
+    R, J, B = 3, 8, 16
+    vs = S.ValidatorSet.make(S.SEED, n=4)
+    ms = [S.header_range_inputs(J, B, nb, start=5_000_000 + 1000 * r, seed=S.SEED + r, valset=vs, with_skip=False)[0]
+          for r, nb in enumerate((None, 100, 3))]
+    eng = ShardedHeaderRange(CudaBackend(0), R, J, B)
+    eng.load(bench.tile_ranges(ms, R))
+    eng.step()
+    res = eng.results()
+    for r, m in enumerate(ms):
+        w = orc.prove_data_commitment(J, B, m.dh_leaf, m.dh_aunts, m.lb_leaf, m.lb_aunts, m.start_headers, m.end_headers,
+                                      m.start_block, m.start_header, m.end_block, m.end_header, threads=4)
+        assert res["fail"][r] == 0 == w["fail"]
+        assert res["data_commitments"][r].tobytes() == w["data_commitment"]
+        assert (res["reduce_nodes"][r] == w["reduce_nodes"]).all() and (res["local_map_digests"][r] == w["map_digests"]).all()
+
+
+def test_bench_two_ranks_nccl():
+    """bench.py under torchrun with 2 ranks (its correctness gate compares every rank's outputs with the oracle)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "3",
+                          "--warmup", "3", "--ranges", "16", "--e2e-ranges", "4", "--distinct", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert '"n_gpus": 2' in out.stdout

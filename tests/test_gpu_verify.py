@@ -110,3 +110,27 @@ def test_verify_header_small_validator_sets(ctx, orc, golden, n_max):
     assert want["fail"] == 0
     g2, w2 = ctx.verify_header([k["next"]], N=n_max), orc.verify_header(k["next"], threads=4)
     _same(g2, w2)
+
+
+def test_header_range_combined(ctx, orc):
+    """bsx_header_range: skip + map/reduce of several ranges in one call (the two halves run on two streams);
+    every output equals the oracle's, and the skip target header is the range's end header."""
+    import bench
+    from blobstreamx_b200 import synthetic as S
+    vs = S.ValidatorSet.make()
+    J, B = 4, 8
+    sets = [S.header_range_inputs(J, B, nb, start=3_000_000 + 1000 * r, seed=S.SEED + r, valset=vs) for r, nb in enumerate((None, 19, 2))]
+    ms, skips = [x[0] for x in sets], [x[1] for x in sets]
+    m = bench.tile_ranges(ms, len(ms))
+    m["n_jobs"], m["batch"] = J, B
+    got = ctx.header_range(skips, m)
+    for r, (mm, k) in enumerate(zip(ms, skips)):
+        ws = orc.verify_skip(k, threads=8)
+        assert ws["fail"] == 0 and got["skip"]["fail"][r] == 0
+        assert (got["skip"]["sha256_digests"][r] == ws["sha256_digests"]).all() and (got["skip"]["ed"][r] == ws["ed"]).all()
+        wm = orc.prove_data_commitment(J, B, mm.dh_leaf, mm.dh_aunts, mm.lb_leaf, mm.lb_aunts, mm.start_headers, mm.end_headers,
+                                       mm.start_block, mm.start_header, mm.end_block, mm.end_header)
+        assert wm["fail"] == 0 and got["fail"][r] == 0
+        assert (got["map_digests"][r] == wm["map_digests"]).all() and (got["reduce_nodes"][r] == wm["reduce_nodes"]).all()
+        assert got["data_commitments"][r].tobytes() == wm["data_commitment"]
+        assert k["target"]["header"].tobytes() == mm.end_header.tobytes()   # circuit wiring: skip output = range end header

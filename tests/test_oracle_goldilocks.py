@@ -92,7 +92,7 @@ def py_gate_eval(gate, p0, p1, w):
 
 
 GATES = [(orc.GATE_U32_ARITHMETIC, 3, 0), (orc.GATE_U32_ADD_MANY, 2, 5), (orc.GATE_U32_ADD_MANY, 4, 3), (orc.GATE_U32_ADD_MANY, 16, 3),
-         (orc.GATE_U32_SUBTRACTION, 6, 0), (orc.GATE_U32_COMPARISON, 32, 16), (orc.GATE_U32_COMPARISON, 64, 32),
+         (orc.GATE_U32_SUBTRACTION, 6, 0), (orc.GATE_U32_COMPARISON, 32, 16), (orc.GATE_U32_COMPARISON, 62, 31),
          (orc.GATE_U32_RANGE_CHECK, 7, 0), (orc.GATE_U32_RANGE_CHECK, 8, 0)]
 
 
