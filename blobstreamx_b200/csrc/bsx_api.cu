@@ -5,6 +5,16 @@
 
 extern "C" int bsx_version(void) { return BSX_VERSION; }
 
+// stream2 carries the Ed25519 half of bsx_header_range.  That kernel is latency-bound with few, fat CTAs (202
+// registers/thread); giving it the highest priority makes the block scheduler place its CTAs first, and the SHA-256
+// map kernel (ALU pipe, thousands of small CTAs) fills the rest of every SM around them.
+static cudaError_t create_priority_stream(cudaStream_t *st) {
+    int lo = 0, hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e != cudaSuccess) return e;
+    return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, hi);
+}
+
 extern "C" int bsx_init(int device, bsx_ctx **out) {
     if (!out) return BSX_ERR_INVALID;
     *out = nullptr;
@@ -18,9 +28,11 @@ extern "C" int bsx_init(int device, bsx_ctx **out) {
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        create_priority_stream(&ctx->stream2) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return BSX_ERR_CUDA;
     }
@@ -41,6 +53,8 @@ extern "C" void bsx_destroy(bsx_ctx *ctx) {
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ed_table) cudaFree(ctx->ed_table);
     delete ctx;

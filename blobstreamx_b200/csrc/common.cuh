@@ -18,8 +18,17 @@ struct bsx_ctx {
     size_t ws_off;
     void *ed_table;            // s*G window table (k_ed25519.cu), built on first use
     cudaStream_t stream2;      // second stream + events: bsx_header_range runs its two halves concurrently
-    cudaEvent_t ev_fork, ev_join;
+    cudaEvent_t ev_fork, ev_join;     // bsx_header_range (host path: two copy+compute pipelines)
+    cudaEvent_t ev_fork2, ev_join2;   // verify_*: Ed25519 kernel on stream2 beside the SHA-256 schedule
 };
+
+// stages of verify_* (k_verify.cu), reused by bsx_header_range_dev
+int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out);
+int bsx_verify_launch_hash(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t N, const bsx_header_in *hdr,
+                           const uint8_t *validators, const bsx_skip_in *skip, const uint8_t *trusted_pubkeys,
+                           const uint64_t *trusted_powers, const uint32_t *trusted_byte_lengths, const bsx_step_in *step,
+                           uint8_t *digests, uint8_t *data_commitments, uint32_t *fail);
+int bsx_verify_launch_flags(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *ed_out, uint32_t *fail);
 
 namespace bsx {
 

@@ -18,19 +18,27 @@ static int fork_join_end(bsx_ctx *ctx, cudaStream_t main) {
 extern "C" int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, uint32_t n_jobs, uint32_t B,
                                     const bsx_skip_batch *s, const bsx_range_batch *m) {
     BSX_REQUIRE(ctx, ctx && s && m);
+    BSX_REQUIRE(ctx, s->hdr && s->validators && s->skip && s->trusted_pubkeys && s->trusted_powers && s->trusted_byte_lengths &&
+                         s->digests && s->ed_out && s->fail);
     if (n == 0) return BSX_OK;
     cudaStream_t main = (cudaStream_t)stream;
     int rc = fork_join_begin(ctx, main);
     if (rc) return rc;
-    rc = bsx_verify_skip_dev(ctx, ctx->stream2, n, N, s->hdr, s->validators, s->skip, s->trusted_pubkeys, s->trusted_powers,
-                             s->trusted_byte_lengths, s->digests, s->ed_out, s->fail);
+    // high-priority stream: the Ed25519 kernel only (few fat CTAs, latency-bound)
+    rc = bsx_verify_launch_ed(ctx, ctx->stream2, n, N, s->validators, s->ed_out);
+    if (rc) return rc;
+    // caller's stream: every SHA-256 kernel -- the skip schedule, then map and reduce
+    rc = bsx_verify_launch_hash(ctx, main, 1, n, N, s->hdr, s->validators, s->skip, s->trusted_pubkeys, s->trusted_powers,
+                                s->trusted_byte_lengths, nullptr, s->digests, nullptr, s->fail);
     if (rc) return rc;
     rc = bsx_prove_data_commitment_dev(ctx, main, n, n_jobs, B, m->dh_leaf, m->dh_aunts, m->lb_leaf, m->lb_aunts,
                                        m->start_headers, m->end_headers, m->start_blocks, m->start_header, m->end_blocks,
                                        m->end_header, m->map_digests, m->map_subchains, m->reduce_digests, m->reduce_nodes,
                                        m->data_commitments, m->fail);
     if (rc) return rc;
-    return fork_join_end(ctx, main);
+    rc = fork_join_end(ctx, main);
+    if (rc) return rc;
+    return bsx_verify_launch_flags(ctx, main, n, N, s->ed_out, s->fail);
 }
 
 namespace {

@@ -8,6 +8,8 @@
 #include "sha256.cuh"
 #include "tm_tree.cuh"
 
+#include <stdlib.h>
+
 namespace bsx {
 
 struct SubchainArgs {
@@ -271,6 +273,215 @@ __global__ void reduce_subchains_kernel(uint32_t n_jobs, uint32_t B, const uint8
     }
 }
 
+// =============================================================================================
+// Split form of the map stage (default): 90 % of a job's hashing is its 2B inclusion proofs, which need no
+// cooperation at all -- so they get their own kernel, one proof per thread, no shared memory, no barriers,
+// full warps.  A second, much smaller kernel packs the tuple leaves / trees / link checks of G jobs per CTA so
+// that the shrinking tree levels still fill warps.  (The fused one-CTA-per-job kernel above spent 27 % of its
+// issue slots waiting at barriers and ran its tree levels at 16, 8, 4, 2, 1 active lanes; profiles/r01b.)
+// =============================================================================================
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) subchain_proofs_kernel(SubchainArgs a, uint32_t B, uint32_t n_jobs) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n_jobs * 2 * B) return;
+    const size_t job = t / (2 * B);
+    const uint32_t r = (uint32_t)(t % (2 * B)), kind = r / B, i = r % B;   // B = 32: a warp is all-data_hash or all-last_block_id
+    const size_t hdr = job * B + i;
+    const uint8_t *leaf = kind ? a.lb_leaf + hdr * 72 : a.dh_leaf + hdr * 34;
+    const uint8_t *aunts = (kind ? a.lb_aunts : a.dh_aunts) + hdr * 128;
+    const uint32_t bits = kind ? 0x4u : 0x6u;  // path of leaf 4 / leaf 6, LSB first (builder.rs:166-169)
+    uint8_t *o = a.digests + (job * (size_t)(20 * B - 1) + 18 * i + 9 * kind) * 32;
+    uint32_t h[8];
+    tm_leaf_hash([&](uint32_t k) -> uint8_t { return __ldg(leaf + k); }, kind ? 72u : 34u, h);
+    store_digest_be(o, h);
+#pragma unroll 1
+    for (int l = 0; l < 4; l++) {
+        uint32_t au[8], left[8], right[8];
+        load_words_be(aunts + 32 * l, au);
+        tm_inner_hash(h, au, left);
+        tm_inner_hash(au, h, right);
+        store_digest_be(o + 32 + 64 * l, left);
+        store_digest_be(o + 64 + 64 * l, right);
+        const bool sel = (bits >> l) & 1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) h[k] = sel ? right[k] : left[k];
+    }
+}
+
+// G jobs per CTA, one thread per header: link checks (builder.rs:174-232), tuple leaves (:133-139), the G
+// data-commitment trees evaluated as one forest (tendermint.rs:165-204), subchain records.
+// Proof roots are read back from the digests the proofs kernel wrote (level-3 "left" digest: bit 3 of both paths is 0).
+template <int B, int G>
+__global__ void __launch_bounds__(B * G < 32 ? 32 : B * G) subchain_commit_kernel(SubchainArgs a, uint32_t n_jobs) {
+    constexpr int T = B * G;
+    __shared__ __align__(16) uint32_t s_dh_root[8 * T];
+    __shared__ __align__(16) uint32_t s_lb_root[8 * T];
+    __shared__ __align__(16) uint32_t s_A[8 * T];
+    __shared__ __align__(16) uint32_t s_Bf[4 * T + 8];
+    __shared__ uint32_t s_fail[G];
+    const uint32_t tid = threadIdx.x, g = tid / B, i = tid % B;
+    const size_t job = (size_t)blockIdx.x * G + g;
+    const bool live = tid < T && job < n_jobs;
+    if (tid < G) s_fail[tid] = 0;
+
+    uint64_t batch_start = 0, batch_end = 0, global_end = 0;
+    const uint8_t *g_end_hdr = nullptr;
+    uint8_t *out = nullptr;
+    if (live) {
+        if (a.range_jobs) {
+            const size_t r = job / a.range_jobs, j = job % a.range_jobs;
+            batch_start = a.start_blocks[r] + (uint64_t)j * B;
+            batch_end = batch_start + B;
+            global_end = a.end_blocks[r];
+            g_end_hdr = a.range_end_header + 32 * r;
+        } else {
+            batch_start = a.batch_start[job];
+            batch_end = a.batch_end[job];
+            global_end = a.global_end[job];
+            g_end_hdr = a.global_end_header + 32 * job;
+        }
+        out = a.digests + job * (size_t)(20 * B - 1) * 32;
+        load_words_be(out + 32 * (size_t)(18 * i + 7), s_dh_root + 8 * tid);
+        load_words_be(out + 32 * (size_t)(18 * i + 9 + 7), s_lb_root + 8 * tid);
+    }
+    __syncthreads();
+
+    const bool batch_enabled = batch_start < global_end;
+    const uint64_t last = global_end - 1;          // last_block_to_process
+    const uint64_t kk = last - batch_start;        // index of the last enabled iteration (if enabled)
+    if (live) {
+        uint32_t f = 0;
+        const bool e_i = batch_enabled && (uint64_t)i <= kk;
+        const bool is_last = (last == batch_start + i);
+        const uint8_t *lbl = a.lb_leaf + (job * B + i) * 72, *dhl = a.dh_leaf + (job * B + i) * 34;
+        uint32_t hh[8], cur[8];
+        load_words_be(lbl + 2, hh);                // header hash of block curr_idx inside last_block_id
+        if (i == 0) load_words_be(a.start_headers + 32 * job, cur);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) cur[k] = s_lb_root[8 * (tid - 1) + k];
+        }
+        if (e_i && !digest_eq(cur, hh)) f |= BSX_FAIL_PREV_HEADER;
+        if (e_i && !digest_eq(s_dh_root + 8 * tid, hh)) f |= BSX_FAIL_DATA_HASH;
+        if (is_last) {
+            uint32_t ge[8];
+            load_words_be(g_end_hdr, ge);
+            if (!digest_eq(s_lb_root + 8 * tid, ge)) f |= BSX_FAIL_END_HEADER;
+        }
+        if (f) atomicOr(&s_fail[g], f);
+        // tuple leaf: 0x00 ‖ 0^24 ‖ u64be(batch_start+i) ‖ data_hash_i   (data_hash = dh_leaf[2..34])
+        uint32_t x[8], d[8], w[16];
+        load_words_be(dhl + 2, x);
+        const uint64_t hgt = batch_start + i;
+#pragma unroll
+        for (int k = 0; k < 6; k++) w[k] = 0;
+        w[6] = (uint32_t)(hgt >> 40);
+        w[7] = (uint32_t)(hgt >> 8);
+        w[8] = ((uint32_t)hgt << 24) | (x[0] >> 8);
+#pragma unroll
+        for (int k = 1; k < 8; k++) w[8 + k] = __funnelshift_r(x[k], x[k - 1], 8);
+        sha256_init(d);
+        sha256_compress(d, w);
+        sha256_tail65(d, x[7] & 0xffu);
+        store_digest_be(out + 32 * (size_t)(18 * B + i), d);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_A[8 * tid + k] = d[k];
+    } else if (tid < T) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s_A[8 * tid + k] = 0;
+    }
+    __syncthreads();
+
+    // the forest: level arrays of G*B, G*B/2, ... , G nodes; pairs never straddle trees because B is a power of two
+    uint32_t *src = s_A, *dst = s_Bf;
+    uint32_t off = 0, shift = 0;
+#pragma unroll 1
+    for (uint32_t len = B; len > 1; len >>= 1) {          // len = nodes per tree on the source level
+        const uint32_t half = len >> 1;
+        if (tid < G * half) {
+            const uint32_t tg = tid / half, j = tid % half;  // tree, node within the tree's next level
+            const size_t tjob = (size_t)blockIdx.x * G + tg;
+            uint32_t l[8], r[8], p[8];
+            const uint4 *sp = reinterpret_cast<const uint4 *>(src + 16 * tid);
+            const uint4 v0 = sp[0], v1 = sp[1], v2 = sp[2], v3 = sp[3];
+            l[0] = v0.x; l[1] = v0.y; l[2] = v0.z; l[3] = v0.w; l[4] = v1.x; l[5] = v1.y; l[6] = v1.z; l[7] = v1.w;
+            r[0] = v2.x; r[1] = v2.y; r[2] = v2.z; r[3] = v2.w; r[4] = v3.x; r[5] = v3.y; r[6] = v3.z; r[7] = v3.w;
+            tm_inner_hash(l, r, p);
+            uint64_t nb = 0;
+            if (tjob < n_jobs) {
+                uint64_t bs, be, ge;
+                if (a.range_jobs) {
+                    const size_t rr = tjob / a.range_jobs, jj = tjob % a.range_jobs;
+                    bs = a.start_blocks[rr] + (uint64_t)jj * B; be = bs + B; ge = a.end_blocks[rr];
+                } else { bs = a.batch_start[tjob]; be = a.batch_end[tjob]; ge = a.global_end[tjob]; }
+                const uint64_t te = be < ge ? be : ge, eb = te < bs ? bs : te;
+                nb = (eb - bs) & 0xffffffffull;
+                store_digest_be(a.digests + (tjob * (size_t)(20 * B - 1) + 19 * B + off + j) * 32, p);
+            }
+            const bool both = ((uint64_t)(2 * j + 1) << shift) < nb;
+            uint4 *o4 = reinterpret_cast<uint4 *>(dst + 8 * tid);
+            o4[0] = both ? make_uint4(p[0], p[1], p[2], p[3]) : v0;
+            o4[1] = both ? make_uint4(p[4], p[5], p[6], p[7]) : v1;
+        }
+        off += half;
+        shift++;
+        uint32_t *tmp = src; src = dst; dst = tmp;
+        __syncthreads();
+    }
+
+    if (tid < G && (size_t)blockIdx.x * G + tid < n_jobs) {
+        const size_t j2 = (size_t)blockIdx.x * G + tid;
+        uint64_t bs, be, ge;
+        if (a.range_jobs) {
+            const size_t rr = j2 / a.range_jobs, jj = j2 % a.range_jobs;
+            bs = a.start_blocks[rr] + (uint64_t)jj * B; be = bs + B; ge = a.end_blocks[rr];
+        } else { bs = a.batch_start[j2]; be = a.batch_end[j2]; ge = a.global_end[j2]; }
+        const bool en = bs < ge;
+        const uint64_t k2 = ge - 1 - bs;
+        const uint64_t te = be < ge ? be : ge, end_block = te < bs ? bs : te, nb_blocks = end_block - bs;
+        uint32_t f = s_fail[tid];
+        if (nb_blocks >> 32) f |= BSX_FAIL_END_LT_START;
+        uint32_t cur[8], eh[8];
+        if (en) {
+            const uint64_t idx = k2 < (uint64_t)(B - 1) ? k2 : (uint64_t)(B - 1);
+#pragma unroll
+            for (int k = 0; k < 8; k++) cur[k] = s_lb_root[8 * (tid * B + idx) + k];
+        } else {
+            load_words_be(a.start_headers + 32 * j2, cur);
+        }
+        const bool e_B = en && (uint64_t)B <= k2;
+        load_words_be(a.end_headers + 32 * j2, eh);
+        if (e_B && !digest_eq(cur, eh)) f |= BSX_FAIL_BATCH_END_HEADER;
+        uint32_t *rec = reinterpret_cast<uint32_t *>(a.subchains + j2 * BSX_SUBCHAIN_BYTES);
+        rec[0] = en ? 1u : 0u;
+        rec[1] = f;
+        rec[2] = (uint32_t)bs; rec[3] = (uint32_t)(bs >> 32);
+        rec[4] = (uint32_t)end_block; rec[5] = (uint32_t)(end_block >> 32);
+        const uint32_t *sh = reinterpret_cast<const uint32_t *>(a.start_headers + 32 * j2);
+#pragma unroll
+        for (int k = 0; k < 8; k++) rec[6 + k] = sh[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) rec[14 + k] = bswap32(cur[k]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) rec[22 + k] = bswap32(src[8 * tid + k]);   // tree g's root sits at src[g]
+        rec[30] = 0; rec[31] = 0;
+    }
+}
+
+template <int B>
+static int launch_subchain_split(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const SubchainArgs &a) {
+    const size_t total = (size_t)n_jobs * 2 * B;
+    static const int occ = [] { const char *e = getenv("BSX_PROOFS_OCC"); return e ? atoi(e) : 8; }();
+    if (occ >= 8) subchain_proofs_kernel<8><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, B, n_jobs);   // 64 registers
+    else subchain_proofs_kernel<6><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, B, n_jobs);             // 80 registers
+    BSX_LAUNCHED(ctx);
+    constexpr int G = B >= 128 ? 1 : 128 / B;
+    constexpr int T = B * G < 32 ? 32 : B * G;
+    subchain_commit_kernel<B, G><<<(n_jobs + G - 1) / G, T, 0, st>>>(a, n_jobs);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
 template <int B>
 static int launch_subchain(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const SubchainArgs &a, bool aligned) {
     constexpr uint32_t SZ_DHL = (B * 34 + 15) & ~15u, SZ_LBL = (B * 72 + 15) & ~15u, SZ_AUNT = B * 128;
@@ -290,7 +501,26 @@ static int launch_subchain(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const
     return BSX_OK;
 }
 
+static bool use_fused_map() {  // BSX_SUBCHAIN_FUSED=1 selects the one-CTA-per-job kernel (A/B measurements)
+    static const bool v = [] { const char *e = getenv("BSX_SUBCHAIN_FUSED"); return e && e[0] == '1'; }();
+    return v;
+}
+
 static int dispatch_subchain(bsx_ctx *ctx, cudaStream_t st, uint32_t B, uint32_t n_jobs, const SubchainArgs &a) {
+    if (!use_fused_map()) {
+        switch (B) {
+            case 1: return launch_subchain_split<1>(ctx, st, n_jobs, a);
+            case 2: return launch_subchain_split<2>(ctx, st, n_jobs, a);
+            case 4: return launch_subchain_split<4>(ctx, st, n_jobs, a);
+            case 8: return launch_subchain_split<8>(ctx, st, n_jobs, a);
+            case 16: return launch_subchain_split<16>(ctx, st, n_jobs, a);
+            case 32: return launch_subchain_split<32>(ctx, st, n_jobs, a);
+            case 64: return launch_subchain_split<64>(ctx, st, n_jobs, a);
+            case 128: return launch_subchain_split<128>(ctx, st, n_jobs, a);
+            case 256: return launch_subchain_split<256>(ctx, st, n_jobs, a);
+            default: return fail(ctx, BSX_ERR_INVALID, "BATCH_SIZE must be a power of two in [1,256]%s%s");
+        }
+    }
     const uintptr_t al = reinterpret_cast<uintptr_t>(a.dh_leaf) | reinterpret_cast<uintptr_t>(a.dh_aunts) |
                          reinterpret_cast<uintptr_t>(a.lb_leaf) | reinterpret_cast<uintptr_t>(a.lb_aunts);
     const bool aligned = (al & 15) == 0;

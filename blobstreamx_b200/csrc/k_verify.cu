@@ -189,9 +189,8 @@ __global__ void __launch_bounds__(256) verify_kernel(VerifyArgs a) {
     }
 
     // ---- verify_header ----
-    // (1) EdDSA batch: flags of the records written by ed25519_batch_kernel (:239-251)
-    for (uint32_t i = tid; i < N; i += blockDim.x)
-        if ((a.ed_out[(inst * N + i) * BSX_SIG_OUT_BYTES + 520] & 0xf) != 0xf) atomicOr(&s_fail, BSX_VFAIL_SIG);
+    // (1) EdDSA batch (:239-251): the records come from ed25519_batch_kernel, which runs CONCURRENTLY on the ctx's
+    //     high-priority stream; ed25519_flags_kernel folds their flags into fail[] after both have finished.
     // (2) validators hash (:253-267)
     validator_set_cta(N, P, vals, BSX_VAL_IN_BYTES, vals + 224, BSX_VAL_IN_BYTES, vals + 232, BSX_VAL_IN_BYTES, H->nb_enabled, sA,
                       sB, out, root);
@@ -275,6 +274,13 @@ __global__ void __launch_bounds__(256) verify_kernel(VerifyArgs a) {
     if (tid == 0) a.fail[inst] = s_fail;
 }
 
+// fail[inst] |= BSX_VFAIL_SIG unless every lane's record says "s < l, A and R decompressed, sG == R + hA"
+__global__ void ed25519_flags_kernel(uint32_t n, uint32_t N, const uint8_t *__restrict__ ed_out, uint32_t *__restrict__ fail) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * N) return;
+    if ((ed_out[(size_t)i * BSX_SIG_OUT_BYTES + 520] & 0xf) != 0xf) atomicOr(fail + i / N, BSX_VFAIL_SIG);
+}
+
 static int launch_verify(bsx_ctx *ctx, cudaStream_t st, int mode, uint32_t n, VerifyArgs a) {
     uint32_t P = 1;
     while (P < a.N) P <<= 1;
@@ -294,6 +300,13 @@ static int launch_verify(bsx_ctx *ctx, cudaStream_t st, int mode, uint32_t n, Ve
 
 using namespace bsx;
 
+int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out);
+int bsx_verify_launch_hash(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t N, const bsx_header_in *hdr,
+                           const uint8_t *validators, const bsx_skip_in *skip, const uint8_t *trusted_pubkeys,
+                           const uint64_t *trusted_powers, const uint32_t *trusted_byte_lengths, const bsx_step_in *step,
+                           uint8_t *digests, uint8_t *data_commitments, uint32_t *fail);
+int bsx_verify_launch_flags(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *ed_out, uint32_t *fail);
+
 extern "C" uint32_t bsx_verify_digest_count(int mode, uint32_t N) {
     uint32_t P = 1;
     while (P < N) P <<= 1;
@@ -312,14 +325,40 @@ static int verify_dev(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t
     BSX_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(digests) | reinterpret_cast<uintptr_t>(data_commitments)) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(hdr) & 7) == 0);
     if (n == 0) return BSX_OK;
-    // curta_eddsa_verify_sigs_conditional over the validators (is_active = signed), verify.rs:239-251
-    int rc = bsx_ed25519_strided_dev(ctx, stream, n * N, validators, BSX_VAL_IN_BYTES, validators + 32, BSX_VAL_IN_BYTES,
-                                     validators + 96, BSX_VAL_IN_BYTES, 124, validators + 220, BSX_VAL_IN_BYTES,
-                                     validators + 236, BSX_VAL_IN_BYTES, ed_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    // fork: Ed25519 (FMA pipe, latency-bound) on the high-priority stream, the SHA-256 schedule on the caller's stream
+    BSX_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, st));
+    BSX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork2, 0));
+    int rc = bsx_verify_launch_ed(ctx, ctx->stream2, n, N, validators, ed_out);
     if (rc) return rc;
-    VerifyArgs a{N, 0, hdr, validators, skip, trusted_pubkeys, trusted_powers, trusted_byte_lengths, step, digests, ed_out,
+    rc = bsx_verify_launch_hash(ctx, stream, mode, n, N, hdr, validators, skip, trusted_pubkeys, trusted_powers,
+                                trusted_byte_lengths, step, digests, data_commitments, fail);
+    if (rc) return rc;
+    BSX_CUDA(ctx, cudaEventRecord(ctx->ev_join2, ctx->stream2));
+    BSX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+    return bsx_verify_launch_flags(ctx, stream, n, N, ed_out, fail);
+}
+
+// the three stages, also used by bsx_header_range_dev to interleave them with the map/reduce kernels
+int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out) {
+    // curta_eddsa_verify_sigs_conditional over the validators (is_active = signed), verify.rs:239-251
+    return bsx_ed25519_strided_dev(ctx, stream, n * N, validators, BSX_VAL_IN_BYTES, validators + 32, BSX_VAL_IN_BYTES,
+                                   validators + 96, BSX_VAL_IN_BYTES, 124, validators + 220, BSX_VAL_IN_BYTES,
+                                   validators + 236, BSX_VAL_IN_BYTES, ed_out);
+}
+int bsx_verify_launch_hash(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t N, const bsx_header_in *hdr,
+                           const uint8_t *validators, const bsx_skip_in *skip, const uint8_t *trusted_pubkeys,
+                           const uint64_t *trusted_powers, const uint32_t *trusted_byte_lengths, const bsx_step_in *step,
+                           uint8_t *digests, uint8_t *data_commitments, uint32_t *fail) {
+    VerifyArgs a{N, 0, hdr, validators, skip, trusted_pubkeys, trusted_powers, trusted_byte_lengths, step, digests, nullptr,
                  data_commitments, fail};
     return launch_verify(ctx, (cudaStream_t)stream, mode, n, a);
+}
+int bsx_verify_launch_flags(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *ed_out, uint32_t *fail) {
+    const uint32_t total = n * N;
+    bsx::ed25519_flags_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, N, ed_out, fail);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
 }
 
 extern "C" int bsx_verify_header_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const bsx_header_in *hdr,
