@@ -225,6 +225,34 @@ class Context:
         self._call("bsx_gl_poseidon_batch", _ptr(_in(inputs, np.uint64)), _ptr(offsets), C.c_uint32(n), _ptr(out))
         return out
 
+    # -- witness data formats --
+    def hash_input_data(self, bufs, buf_offsets, lens, kinds, sha512: bool = False):
+        """HashInputData of one SHA accelerator -> dict(padded_chunks [chunks,16], end_bits, digest_bits, digest_indices)."""
+        buf_offsets, lens, kinds = _in(buf_offsets, np.uint32), _in(lens, np.uint32), _in(kinds, np.uint8)
+        n = len(kinds)
+        total = C.c_uint32(0)
+        a = (C.c_int(int(sha512)), C.c_uint32(n), _ptr(_in(bufs)), _ptr(buf_offsets), _ptr(lens), _ptr(kinds))
+        self._call("bsx_hash_input_data", *a, _ptr(None), _ptr(None), _ptr(None), _ptr(None), C.byref(total))
+        t = total.value
+        pc = np.zeros((t, 16), np.uint64 if sha512 else np.uint32)
+        eb, db, di = np.zeros(t, np.uint8), np.zeros(t, np.uint8), np.zeros(n, np.uint32)
+        if n:
+            self._call("bsx_hash_input_data", *a, _ptr(pc), _ptr(eb), _ptr(db), _ptr(di), C.byref(total))
+        return dict(padded_chunks=pc, end_bits=eb, digest_bits=db, digest_indices=di)
+
+    def witness_pack_bytes(self, data) -> np.ndarray:
+        data = _in(data).reshape(-1)
+        out = np.zeros((len(data), 8), np.uint64)
+        self._call("bsx_witness_pack_bytes", _ptr(data), C.c_size_t(len(data)), _ptr(out))
+        return out
+
+    def witness_unpack_bytes(self, elements):
+        el = _in(elements, np.uint64).reshape(-1, 8)
+        out = np.zeros(len(el), np.uint8)
+        bad = C.c_uint32(0)
+        self._call("bsx_witness_unpack_bytes", _ptr(el), C.c_size_t(len(el)), _ptr(out), C.byref(bad))
+        return out, bool(bad.value)
+
     # -- verify_header / verify_skip / next_header --
     def _verify(self, mode: int, items, N: int):
         """items: list of dicts as produced by blobstreamx_b200.inputs.get_skip_inputs / get_step_inputs /

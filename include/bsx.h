@@ -355,6 +355,36 @@ int bsx_header_range(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n_jobs, uint
 int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, uint32_t n_jobs, uint32_t B,
                          const bsx_skip_batch *skip, const bsx_range_batch *range);
 
+/* ------------------------------------------------------------------------------------------
+ * Witness data formats
+ * HashInputData: the STARK public-input layout of one SHA accelerator, built from its request list
+ *   replaces get_hash_data (PX/frontend/hash/curta/mod.rs:95-192; stream order PX/frontend/hash/curta/data.rs:63-78)
+ *   with the padding of PX/frontend/hash/sha/sha256/pad.rs:15-157 / sha512/pad.rs:13-58.
+ *   sha512 = 0: 64-byte chunks, padded_chunks = u32 big-endian words (16 per chunk);
+ *   sha512 = 1: 128-byte chunks, padded_chunks = u64 big-endian words (16 per chunk).
+ *   bufs: concatenated request buffers (fixed request: the message; variable: the whole buffer), buf_offsets[n+1];
+ *   lens[n]: message length of variable requests (ignored for fixed); kinds[n]: 0 fixed, 1 variable.
+ *   outputs: padded_chunks (total*16 words), end_bits / digest_bits (one per chunk), digest_indices (one per request).
+ *   Call with padded_chunks = NULL to obtain *total_chunks only.  bsx_hash_input_chunks gives one request's chunk count
+ *   (a circuit constant), from which the caller of the _dev form builds chunk_offsets[n+1].
+ * Field-element encodings: ByteVariable = 8 big-endian bit elements (PX/frontend/vars/byte.rs:49-66);
+ *   SHA-256 digest = 8 big-endian u32 words, one element each (PX/frontend/hash/sha/sha256/curta.rs:81-92).
+ * ------------------------------------------------------------------------------------------ */
+uint32_t bsx_hash_input_chunks(int sha512, uint32_t buf_len, int variable);
+int bsx_hash_input_data(bsx_ctx *ctx, int sha512, uint32_t n_req, const uint8_t *bufs, const uint32_t *buf_offsets,
+                        const uint32_t *lens, const uint8_t *kinds, void *padded_chunks, uint8_t *end_bits,
+                        uint8_t *digest_bits, uint32_t *digest_indices, uint32_t *total_chunks);
+int bsx_hash_input_data_dev(bsx_ctx *ctx, void *stream, int sha512, uint32_t n_req, const uint8_t *bufs,
+                            const uint32_t *buf_offsets, const uint32_t *lens, const uint8_t *kinds,
+                            const uint32_t *chunk_offsets, uint32_t total_chunks, void *padded_chunks, uint8_t *end_bits,
+                            uint8_t *digest_bits, uint32_t *digest_indices);
+int bsx_witness_pack_bytes(bsx_ctx *ctx, const uint8_t *bytes, size_t n, uint64_t *elements /* n*8 */);
+int bsx_witness_unpack_bytes(bsx_ctx *ctx, const uint64_t *elements, size_t n, uint8_t *bytes, uint32_t *not_bits);
+int bsx_witness_pack_bytes_dev(bsx_ctx *ctx, void *stream, const uint8_t *bytes, size_t n, uint64_t *elements);
+int bsx_witness_unpack_bytes_dev(bsx_ctx *ctx, void *stream, const uint64_t *elements, size_t n, uint8_t *bytes,
+                                 uint32_t *not_bits);
+int bsx_witness_pack_u32_be_dev(bsx_ctx *ctx, void *stream, const uint8_t *bytes, size_t n_words, uint64_t *elements);
+
 #ifdef __cplusplus
 }
 #endif

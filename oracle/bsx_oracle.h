@@ -197,6 +197,10 @@ uint32_t orc_sha256_hash_input_data(uint32_t n_req, const uint8_t *bufs, const u
                                     const uint32_t *lens, const uint8_t *kinds, uint32_t *padded_chunks,
                                     uint8_t *end_bits, uint8_t *digest_bits, uint32_t *digest_indices);
 
+uint32_t orc_sha512_hash_input_data(uint32_t n_req, const uint8_t *bufs, const uint32_t *buf_offsets,
+                                    const uint32_t *lens, const uint8_t *kinds, uint64_t *padded_chunks,
+                                    uint8_t *end_bits, uint8_t *digest_bits, uint32_t *digest_indices);
+
 /* ---- Goldilocks / gates / Poseidon (PX/frontend/uint/num/u32/gates/*.rs; plonky2 0.2.1) ---- */
 #define ORC_GATE_U32_ARITHMETIC 0
 #define ORC_GATE_U32_ADD_MANY 1

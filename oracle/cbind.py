@@ -32,7 +32,7 @@ def lib():
         _lib.orc_max_threads.restype = C.c_int
         for f in ("orc_sha256_pad_fixed", "orc_sha256_pad_variable", "orc_sha512_pad_variable", "orc_marshal_int64_varint",
                   "orc_marshal_validator", "orc_verify_header", "orc_verify_skip", "orc_next_header",
-                  "orc_sha256_hash_input_data", "orc_gate_num_constraints", "orc_gate_num_wires"):
+                  "orc_sha256_hash_input_data", "orc_sha512_hash_input_data", "orc_gate_num_constraints", "orc_gate_num_wires"):
             if hasattr(_lib, f):
                 getattr(_lib, f).restype = C.c_uint32
     return _lib
@@ -328,6 +328,21 @@ def next_header(k: dict, threads=1):
     dc = np.zeros(32, np.uint8)
     fail = lib().orc_next_header(C.byref(s), _p(dig), _p(ed), _p(dc), C.c_int(threads))
     return dict(sha256_digests=dig, ed=ed, data_commitment=dc.tobytes(), fail=fail)
+
+
+def hash_input_data(bufs, buf_offsets, lens, kinds, sha512=False):
+    """HashInputData (PX/frontend/hash/curta/mod.rs:95-192) for a request list."""
+    buf_offsets = np.ascontiguousarray(buf_offsets, np.uint32)
+    lens = np.ascontiguousarray(lens, np.uint32)
+    kinds = np.ascontiguousarray(kinds, np.uint8)
+    n = len(kinds)
+    chunk = 128 if sha512 else 64
+    cap = int(sum((int(buf_offsets[i + 1] - buf_offsets[i]) + 2 * chunk + chunk) // chunk + 1 for i in range(n))) + 1
+    pc = np.zeros((cap, 16), np.uint64 if sha512 else np.uint32)
+    eb, db, di = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8), np.zeros(n, np.uint32)
+    f = lib().orc_sha512_hash_input_data if sha512 else lib().orc_sha256_hash_input_data
+    t = f(C.c_uint32(n), _p(_u8(bufs)), _p(buf_offsets), _p(lens), _p(kinds), _p(pc), _p(eb), _p(db), _p(di))
+    return dict(padded_chunks=pc[:t], end_bits=eb[:t], digest_bits=db[:t], digest_indices=di)
 
 
 GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_SUBTRACTION, GATE_U32_COMPARISON, GATE_U32_RANGE_CHECK = range(5)

@@ -224,3 +224,41 @@ uint32_t orc_sha256_hash_input_data(uint32_t n_req, const uint8_t *bufs, const u
     free(tmp);
     return cur;
 }
+
+/* SHA-512 accelerator: 128-byte chunks of big-endian u64 words; fixed padding FIPS 180-4 (sha512/pad.rs:13-41),
+ * variable padding orc_sha512_pad_variable.  PX/frontend/hash/curta/mod.rs:95-192 */
+uint32_t orc_sha512_hash_input_data(uint32_t n_req, const uint8_t *bufs, const uint32_t *buf_offsets,
+                                    const uint32_t *lens, const uint8_t *kinds, uint64_t *padded_chunks,
+                                    uint8_t *end_bits, uint8_t *digest_bits, uint32_t *digest_indices) {
+    uint32_t cur = 0;
+    for (uint32_t r = 0; r < n_req; r++) {
+        const uint8_t *b = bufs + buf_offsets[r];
+        uint32_t blen = buf_offsets[r + 1] - buf_offsets[r];
+        uint8_t *tmp = (uint8_t *)calloc((size_t)blen + 400, 1);
+        uint32_t nch, lc;
+        if (kinds[r] == 0) {
+            nch = (blen + 17 + 127) / 128;
+            if (blen) memcpy(tmp, b, blen);
+            tmp[blen] = 0x80;
+            uint64_t bits = (uint64_t)blen * 8;
+            for (int i = 0; i < 8; i++) tmp[(size_t)nch * 128 - 1 - i] = (uint8_t)(bits >> (8 * i));
+            lc = nch - 1;
+        } else {
+            nch = orc_sha512_pad_variable(b, blen, lens[r], tmp, &lc);
+        }
+        for (uint32_t j = 0; j < nch; j++) {
+            for (int w = 0; w < 16; w++) {
+                const uint8_t *p = tmp + 128 * (size_t)j + 8 * w;
+                uint64_t v = 0;
+                for (int k = 0; k < 8; k++) v = (v << 8) | p[k];
+                padded_chunks[(size_t)(cur + j) * 16 + w] = v;
+            }
+            end_bits[cur + j] = (j == nch - 1);
+            digest_bits[cur + j] = (j == lc);
+        }
+        digest_indices[r] = cur + lc;
+        cur += nch;
+        free(tmp);
+    }
+    return cur;
+}
