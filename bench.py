@@ -163,7 +163,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import cbind as orc
-    threads = min(orc.max_threads(), len(os.sched_getaffinity(0)))
+    threads = len(os.sched_getaffinity(0))   # every host core this process may use (torchrun's OMP_NUM_THREADS=1 is ignored)
     ms, skips = make_ranges(2)
     sample = args.cpu_ranges
     for _ in range(args.warmup):
@@ -334,7 +334,7 @@ def run_gpu(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("prove_subchain_kernel<32>", {}).get("dram_bytes_per_launch_R256")
+            traffic = json.load(f).get("prove_subchain (subchain_proofs_kernel<8>)", {}).get("dram_bytes_per_launch_R256")
     except Exception:
         pass
 
@@ -395,12 +395,18 @@ def run_gpu(args):
                        "l2": f"inputs+outputs per step per GPU = {resident / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"kernel": "prove_subchain_kernel<32>", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "map stage: subchain_proofs_kernel<8> + subchain_commit_kernel<32,4>", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-                         "note": "SHA-256 is ~25 int ops/byte: the int32 ALU pipe, not HBM, is the physical bound (DESIGN.md)"},
-            "kernels_alone_ms": {"prove_subchain_kernel<32> (map)": k_ms, "verify_skip (ed25519_batch_kernel + verify_kernel<1>)": skip_ms},
+                         "note": "SHA-256 is ~23 int ops/byte: the int32 ALU pipe (93 % busy in the proofs kernel, profiles/r01e), not HBM, "
+                                 "is the physical bound"},
+            "roofline_ed25519": {"kernel": "ed25519_batch_kernel (+ verify_kernel<1> beside it)", "bound": "hbm",
+                                 "achieved": 704 * R * N_VAL / (skip_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": 704 * R * N_VAL / (skip_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                                 "note": "704 B/signature against ~3700 field multiplications: bound by the integer-multiply (fmaheavy) "
+                                         "pipe, 73 % busy (profiles/r01b); the HBM fraction is <<1 % by construction"},
+            "kernels_alone_ms": {"map stage (proofs + commit kernels)": k_ms, "verify_skip (ed25519_batch_kernel beside verify_kernel<1>)": skip_ms},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ranges_per_step": Re},
             "cpu_baseline": cpu,
@@ -484,19 +490,25 @@ def run_gates(args):
     P = lambda t: ptr(t.data_ptr())
     ctx.call_dev("bsx_gl_gate_witness_dev", stream, u32(gate), u32(p0), u32(p1), P(wires), u32(rows))
 
-    def step():
-        ctx.call_dev("bsx_gl_gate_eval_dev", stream, u32(gate), u32(p0), u32(p1), P(wires), u32(rows), P(cons))
+    def step(w=None):
+        ctx.call_dev("bsx_gl_gate_eval_dev", stream, u32(gate), u32(p0), u32(p1), P(wires if w is None else w), u32(rows), P(cons))
 
     step()
     torch.cuda.synchronize()
     assert int(cons.abs().max().item()) == 0, "valid witness must satisfy every constraint"
+    # timed input: uniform random canonical field elements on every wire -- what the gate sees on the points of the
+    # low-degree extension inside the quotient computation (no constraint is zero there)
+    rnd = (torch.randint(0, 2**62, (nw * rows,), generator=g, device=dev, dtype=torch.int64) * 4 +
+           torch.randint(0, 4, (nw * rows,), generator=g, device=dev, dtype=torch.int64))
+    pm = torch.tensor(-(2**32) + 1, dtype=torch.int64, device=dev)   # p as a signed 64-bit pattern = 0xFFFFFFFF00000001
+    rnd = torch.where((rnd < 0) & (rnd >= pm), rnd - pm, rnd)        # values >= p (unsigned) wrapped into [0, p)
+    wires_valid, wires = wires, rnd
     if not args.no_check:
         from oracle import cbind as orc
         k = 512
-        sub = wv[:, :k].contiguous().cpu().numpy().view(np.uint64)
-        sub[5, 7] += np.uint64(1)  # one broken row so the comparison is not all zeros
+        sub = wires.view(nw, rows)[:, :k].contiguous().cpu().numpy().view(np.uint64)
         got = ctx.gl_gate_eval(gate, p0, p1, sub)
-        assert (got == orc.gate_eval(gate, p0, p1, sub, threads=4)).all() and got[:, 7].any()
+        assert (got == orc.gate_eval(gate, p0, p1, sub, threads=4)).all() and got.any()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -520,14 +532,14 @@ def run_gates(args):
     if not args.no_cpu:
         from oracle import cbind as orc
         k = 1 << 14
-        sub = wv[:, :k].contiguous().cpu().numpy().view(np.uint64)
+        sub = wires.view(nw, rows)[:, :k].contiguous().cpu().numpy().view(np.uint64)
         t0 = time.perf_counter()
         orc.gate_eval(gate, p0, p1, sub, threads=1)
         cpu = {"value": ncn * k / (time.perf_counter() - t0), "unit": "constraints/s", "cores": 1, "kind": "port", "sample": f"{k} rows"}
     print(json.dumps({"metric": "constraints/sec, U32ArithmeticGate eval_unfiltered_base_batch", "value": ncn * rows / (ms * 1e-3),
                       "unit": "constraints/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                       "higher_is_better": True, "dtype": "u64 mod 2^64-2^32+1", "data": "synthetic",
-                      "config": {"workload": f"U32ArithmeticGate num_ops=3, {rows} rows x 114 wires -> 108 constraints/row",
+                      "config": {"workload": f"U32ArithmeticGate num_ops=3, {rows} rows x 114 wires (uniform random field elements) -> 108 constraints/row",
                                  "l2": f"{alg / 1e6:.0f} MB per step > 126 MB L2"},
                       "gpu_launches": args.steps, "clocks": clk.summary(),
                       "roofline": {"kernel": "gl_gate_eval_kernel<0>", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,

@@ -49,10 +49,45 @@ __device__ __forceinline__ uint64_t gl_inv(uint64_t a) {  // a^(p-2), p-2 = 0xFF
     }
     return r;
 }
-// prod_{x < 4} (l - x)
-__device__ __forceinline__ uint64_t limb_product4(uint64_t l) {
-    return gl_mul(gl_mul(l, gl_sub(l, 1)), gl_mul(gl_sub(l, 2), gl_sub(l, 3)));
+// ---- lazy 128-bit forms used by the gate kernels (fewer reductions per constraint) ----
+// weak reduction: any u64 representative of (hi*2^64 + lo) mod p (no final conditional subtraction)
+__device__ __forceinline__ uint64_t gl_reduce128_weak(uint64_t hi, uint64_t lo) {
+    const uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
+    uint64_t t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= GL_EPS;
+    const uint64_t t1 = hi_lo * GL_EPS;
+    uint64_t t2 = t0 + t1;
+    if (t2 < t1) t2 += GL_EPS;
+    return t2;
 }
+// prod_{x < 4} (l - x) for canonical l, with two multiplications and two reductions:
+//   u = l^2 - 3l  (computed as l^2 + 3(p - l) >= 0),   l(l-1)(l-2)(l-3) = u (u + 2) = u^2 + 2u
+// u may be any 64-bit representative: u^2 + 2u <= 2^128 - 1 never overflows.
+__device__ __forceinline__ uint64_t limb_product4(uint64_t l) {
+    const uint64_t m = GL_P - l;                              // in (0, p]
+    uint64_t lo = l * l, hi = __umul64hi(l, l);
+    const uint64_t m3lo = m * 3, m3hi = __umul64hi(m, 3);     // 3m < 2^66
+    lo += m3lo;
+    hi += m3hi + (lo < m3lo ? 1 : 0);
+    const uint64_t u = gl_reduce128_weak(hi, lo);
+    lo = u * u;
+    hi = __umul64hi(u, u);
+    const uint64_t u2lo = u << 1, u2hi = u >> 63;
+    lo += u2lo;
+    hi += u2hi + (lo < u2lo ? 1 : 0);
+    return gl_canon(gl_reduce128_weak(hi, lo));
+}
+// sum_j limb_j * 4^j accumulated as a plain 128-bit integer (16 canonical limbs: < 2^97), one reduction at the end
+struct Horner4 {
+    uint64_t hi = 0, lo = 0;
+    __device__ __forceinline__ void push(uint64_t limb) {      // acc = 4*acc + limb  (limbs arrive most significant first)
+        hi = (hi << 2) | (lo >> 62);
+        lo <<= 2;
+        lo += limb;
+        hi += (lo < limb ? 1 : 0);
+    }
+    __device__ __forceinline__ uint64_t value() const { return gl_canon(gl_reduce128_weak(hi, lo)); }
+};
 __device__ __forceinline__ uint64_t limb_product(uint64_t l, uint32_t base) {
     uint64_t p = l;
     for (uint32_t x = 1; x < base; x++) p = gl_mul(p, gl_sub(l, x));
@@ -76,16 +111,16 @@ __device__ __forceinline__ void eval_arithmetic(RowIO &io, uint32_t num_ops) {
         const uint64_t hi_not_max = gl_sub(gl_mul(inverse, gl_sub(GL_EPS, out_hi)), 1);
         io.put(gl_mul(hi_not_max, out_lo));
         io.put(gl_sub(gl_add(gl_mul(out_hi, 1ULL << 32), out_lo), computed));
-        uint64_t lo = 0, hi = 0;
+        Horner4 lo, hi;
 #pragma unroll 8
         for (int j = 31; j >= 0; j--) {
             const uint64_t limb = io.w(6 * num_ops + 32 * i + j);
             io.put(limb_product4(limb));
-            if (j < 16) lo = gl_add(gl_mul4(lo), limb);
-            else hi = gl_add(gl_mul4(hi), limb);
+            if (j < 16) lo.push(limb);
+            else hi.push(limb);
         }
-        io.put(gl_sub(lo, out_lo));
-        io.put(gl_sub(hi, out_hi));
+        io.put(gl_sub(lo.value(), out_lo));
+        io.put(gl_sub(hi.value(), out_hi));
     }
 }
 
@@ -96,16 +131,16 @@ __device__ __forceinline__ void eval_add_many(RowIO &io, uint32_t na, uint32_t n
         for (uint32_t j = 0; j <= na; j++) computed = gl_add(computed, io.w(b + j));
         const uint64_t out_res = io.w(b + na + 1), out_carry = io.w(b + na + 2);
         io.put(gl_sub(gl_add(gl_mul(out_carry, 1ULL << 32), out_res), computed));
-        uint64_t res = 0, carry = 0;
+        Horner4 res, carry;
 #pragma unroll
         for (int j = 18; j >= 0; j--) {
             const uint64_t limb = io.w((na + 3) * num_ops + 19 * i + j);
             io.put(limb_product4(limb));
-            if (j < 16) res = gl_add(gl_mul4(res), limb);
-            else carry = gl_add(gl_mul4(carry), limb);
+            if (j < 16) res.push(limb);
+            else carry.push(limb);
         }
-        io.put(gl_sub(res, out_res));
-        io.put(gl_sub(carry, out_carry));
+        io.put(gl_sub(res.value(), out_res));
+        io.put(gl_sub(carry.value(), out_carry));
     }
 }
 
@@ -115,14 +150,14 @@ __device__ __forceinline__ void eval_subtraction(RowIO &io, uint32_t num_ops) {
                        out_b = io.w(5 * i + 4);
         const uint64_t initial = gl_sub(gl_sub(x, y), bin);
         io.put(gl_sub(out_res, gl_add(initial, gl_mul(1ULL << 32, out_b))));
-        uint64_t comb = 0;
+        Horner4 comb;
 #pragma unroll
         for (int j = 15; j >= 0; j--) {
             const uint64_t limb = io.w(5 * num_ops + 16 * i + j);
             io.put(limb_product4(limb));
-            comb = gl_add(gl_mul4(comb), limb);
+            comb.push(limb);
         }
-        io.put(gl_sub(comb, out_res));
+        io.put(gl_sub(comb.value(), out_res));
         io.put(gl_mul(out_b, gl_sub(1, out_b)));
     }
 }
@@ -163,13 +198,13 @@ __device__ __forceinline__ void eval_comparison(RowIO &io, uint32_t num_bits, ui
 
 __device__ __forceinline__ void eval_range_check(RowIO &io, uint32_t nl) {
     for (uint32_t i = 0; i < nl; i++) {
-        uint64_t sum = 0;
+        Horner4 sum;
         uint64_t aux[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) aux[j] = io.w(nl + 16 * i + j);
 #pragma unroll
-        for (int j = 15; j >= 0; j--) sum = gl_add(gl_mul4(sum), aux[j]);
-        io.put(gl_sub(sum, io.w(i)));
+        for (int j = 15; j >= 0; j--) sum.push(aux[j]);
+        io.put(gl_sub(sum.value(), io.w(i)));
 #pragma unroll
         for (int j = 0; j < 16; j++) io.put(limb_product4(aux[j]));
     }
