@@ -8,6 +8,8 @@
 #include "ed25519.cuh"
 #include "sha512.cuh"
 
+#include <stdlib.h>
+
 namespace bsx {
 
 using namespace ed;
@@ -30,7 +32,8 @@ struct EdIn {
     uint32_t pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride;
 };
 
-__global__ void __launch_bounds__(64) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels *__restrict__ table,
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels *__restrict__ table,
                                                            uint8_t *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -88,7 +91,12 @@ extern "C" int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, c
     int rc = ensure_base_table(ctx, st);
     if (rc) return rc;
     EdIn in{pks, sigs, msgs, msg_lens, active, pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride};
-    ed25519_batch_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, in, reinterpret_cast<const ed::ge_niels *>(ctx->ed_table), out);
+    // register budget per thread: 4 CTAs/SM -> 202 registers, 6 -> 168, 8 -> 128 (with spills); BSX_ED_OCC selects (A/B)
+    static const int occ = [] { const char *e = getenv("BSX_ED_OCC"); return e ? atoi(e) : 4; }();
+    const ed::ge_niels *tab = reinterpret_cast<const ed::ge_niels *>(ctx->ed_table);
+    if (occ >= 8) ed25519_batch_kernel<8><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+    else if (occ >= 6) ed25519_batch_kernel<6><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+    else ed25519_batch_kernel<4><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }

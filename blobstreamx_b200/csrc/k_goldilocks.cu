@@ -95,8 +95,8 @@ __device__ __forceinline__ uint64_t limb_product(uint64_t l, uint32_t base) {
 }
 
 struct RowIO {
-    const uint64_t *wires;
-    uint64_t *out;
+    const uint64_t *__restrict__ wires;
+    uint64_t *__restrict__ out;
     size_t rows, r;
     uint32_t c;
     __device__ __forceinline__ uint64_t w(uint32_t col) const { return gl_canon(__ldcs(wires + (size_t)col * rows + r)); }
@@ -112,12 +112,17 @@ __device__ __forceinline__ void eval_arithmetic(RowIO &io, uint32_t num_ops) {
         io.put(gl_mul(hi_not_max, out_lo));
         io.put(gl_sub(gl_add(gl_mul(out_hi, 1ULL << 32), out_lo), computed));
         Horner4 lo, hi;
-#pragma unroll 8
-        for (int j = 31; j >= 0; j--) {
-            const uint64_t limb = io.w(6 * num_ops + 32 * i + j);
-            io.put(limb_product4(limb));
-            if (j < 16) lo.push(limb);
-            else hi.push(limb);
+#pragma unroll
+        for (int h = 1; h >= 0; h--) {            // 16 limbs at a time: all loads issued before the arithmetic (memory-level parallelism)
+            uint64_t limb[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) limb[j] = io.w(6 * num_ops + 32 * i + 16 * h + j);
+#pragma unroll
+            for (int j = 15; j >= 0; j--) {
+                io.put(limb_product4(limb[j]));
+                if (h == 0) lo.push(limb[j]);
+                else hi.push(limb[j]);
+            }
         }
         io.put(gl_sub(lo.value(), out_lo));
         io.put(gl_sub(hi.value(), out_hi));
@@ -151,11 +156,13 @@ __device__ __forceinline__ void eval_subtraction(RowIO &io, uint32_t num_ops) {
         const uint64_t initial = gl_sub(gl_sub(x, y), bin);
         io.put(gl_sub(out_res, gl_add(initial, gl_mul(1ULL << 32, out_b))));
         Horner4 comb;
+        uint64_t limb[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) limb[j] = io.w(5 * num_ops + 16 * i + j);
 #pragma unroll
         for (int j = 15; j >= 0; j--) {
-            const uint64_t limb = io.w(5 * num_ops + 16 * i + j);
-            io.put(limb_product4(limb));
-            comb.push(limb);
+            io.put(limb_product4(limb[j]));
+            comb.push(limb[j]);
         }
         io.put(gl_sub(comb.value(), out_res));
         io.put(gl_mul(out_b, gl_sub(1, out_b)));
