@@ -631,7 +631,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ranges", type=int, default=256, help="independent header ranges per step per GPU")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic chains (tiled to --ranges)")
-    ap.add_argument("--e2e-ranges", type=int, default=64)
+    ap.add_argument("--e2e-ranges", type=int, default=256)
     ap.add_argument("--cpu-ranges", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")

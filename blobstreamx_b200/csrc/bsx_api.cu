@@ -1,6 +1,8 @@
 // Context management for libbsx (see include/bsx.h).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <new>
 
 extern "C" int bsx_version(void) { return BSX_VERSION; }
@@ -36,6 +38,13 @@ extern "C" int bsx_init(int device, bsx_ctx **out) {
         delete ctx;
         return BSX_ERR_CUDA;
     }
+    for (int i = 0; i < BSX_PIPE_STREAMS; i++) {
+        if (cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming) != cudaSuccess) {
+            bsx_destroy(ctx);
+            return BSX_ERR_CUDA;
+        }
+    }
     *out = ctx;
     return BSX_OK;
 }
@@ -51,6 +60,15 @@ extern "C" void bsx_destroy(bsx_ctx *ctx) {
         cudaStreamSynchronize(ctx->stream2);
         cudaStreamDestroy(ctx->stream2);
     }
+    for (int i = 0; i < BSX_PIPE_STREAMS; i++) {
+        if (ctx->pipe[i]) {
+            cudaStreamSynchronize(ctx->pipe[i]);
+            cudaStreamDestroy(ctx->pipe[i]);
+        }
+        if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
+    }
+    for (uint32_t i = 0; i < ctx->n_ev_chunk; i++) cudaEventDestroy(ctx->ev_chunk[i]);
+    free(ctx->ev_chunk);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);

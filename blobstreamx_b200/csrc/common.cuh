@@ -3,9 +3,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/bsx.h"
+
+#define BSX_PIPE_STREAMS 3
 
 struct bsx_ctx {
     int device;
@@ -20,6 +23,13 @@ struct bsx_ctx {
     cudaStream_t stream2;      // second stream + events: bsx_header_range runs its two halves concurrently
     cudaEvent_t ev_fork, ev_join;     // bsx_header_range (host path: two copy+compute pipelines)
     cudaEvent_t ev_fork2, ev_join2;   // verify_*: Ed25519 kernel on stream2 beside the SHA-256 schedule
+    // bsx_header_range (host buffers): the map half is cut into chunks of ranges that flow through three streams by
+    // role (0: H2D copies, 1: kernels, 2: D2H copies), so the H2D copy of chunk k+1, the kernels of chunk k and the
+    // D2H copy of chunk k-1 run at the same time; ev_chunk[2k] = chunk k uploaded, ev_chunk[2k+1] = chunk k computed
+    cudaStream_t pipe[BSX_PIPE_STREAMS];
+    cudaEvent_t ev_pipe[BSX_PIPE_STREAMS];
+    cudaEvent_t *ev_chunk;
+    uint32_t n_ev_chunk;
 };
 
 // stages of verify_* (k_verify.cu), reused by bsx_header_range_dev
@@ -53,6 +63,22 @@ inline int fail(bsx_ctx *ctx, int code, const char *fmt, const char *a = "", con
 #define BSX_REQUIRE(ctx, cond)                                                                        \
     do {                                                                                              \
         if (!(cond)) return bsx::fail((ctx), BSX_ERR_INVALID, "invalid argument: %s", #cond);         \
+    } while (0)
+
+// One shared-memory carveout for every kernel that can share an SM with another one.  An SM re-partitions its
+// L1/shared memory only when it is empty, so two kernels whose preferred carveouts differ cannot be co-resident: the
+// Ed25519 kernel (no shared memory, prefers all-L1) then keeps the SHA-256 commit/reduce/verify kernels (shared-memory
+// trees) off every SM it occupies.  Pinning all of them to the same preference lets the halves of bsx_header_range
+// really overlap.  BSX_CARVEOUT overrides the percentage (negative = leave the driver's default per kernel).
+template <typename K>
+inline void pin_carveout(K kernel) {
+    static const int pct = [] { const char *e = getenv("BSX_CARVEOUT"); return e ? atoi(e) : 50; }();
+    if (pct >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+#define BSX_PIN_CARVEOUT(kernel)                       \
+    do {                                               \
+        static const bool once_ = (bsx::pin_carveout(kernel), true); \
+        (void)once_;                                   \
     } while (0)
 
 // ---- workspace (host entry points only) ----

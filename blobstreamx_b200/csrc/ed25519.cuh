@@ -72,6 +72,64 @@ BSX_HD fe fe_reduce(const fe &f) {
     return fe_carry64(h);
 }
 
+// One parallel carry round in 32-bit arithmetic: same value mod p, every limb back in [-38, 2^26 + 19] (even) /
+// [-2, 2^25 + 1] (odd) for inputs up to 3 "units".  Used on the one factor of a 3-unit x 3-unit product that
+// becomes the g-side of fe_mul (see its bounds).  ~30 ALU-pipe operations, no dependent chain.
+BSX_HD fe fe_tighten(const fe &f) {
+    fe r;
+    int32_t c[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) c[i] = f.v[i] >> ((i & 1) ? 25 : 26);
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const int32_t lowpart = f.v[i] & ((i & 1) ? 0x1ffffff : 0x3ffffff);
+        r.v[i] = lowpart + (i == 0 ? 19 * c[9] : c[i - 1]);
+    }
+    return r;
+}
+
+#ifndef BSX_FE_SCHOOLBOOK
+// h = f*g.  The limbs are read as five pairs (a_k + 2^26 b_k) 2^(51k); each pair product costs THREE
+// 32x32->64 multiplications (Karatsuba on the pair: a c, b d, (a+b)(c+d)) instead of four, so the product is
+// 75 IMAD.WIDE instead of 100 -- the fmaheavy pipe IMAD.WIDE runs on is what bounds this kernel.
+//   LL_n = sum a_k c_m, HH_n = sum b_k d_m, SS_n = sum (a_k+b_k)(c_m+d_m)   over k+m = n (mod 5), x19 on wrap
+//   h[2n+1] = SS_n - LL_n - HH_n;  h[2n] = LL_n + 2 HH_{n-1};  h[0] = LL_0 + 38 HH_4
+// Bounds: g at most 2 units (|g_even| <= 2.02*2^25, |g_odd| <= 2.02*2^24: one add/sub of carried values, or a
+// fe_tighten output) so that 19 (c_m + d_m) < 2^31; f at most 3 units.  Sums stay below 2^61.
+BSX_CALL fe fe_mul(const fe f, const fe g) {
+    int32_t fs[5], gs[5], c19[5], d19[5], gs19[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        fs[k] = f.v[2 * k] + f.v[2 * k + 1];
+        gs[k] = g.v[2 * k] + g.v[2 * k + 1];
+        c19[k] = 19 * g.v[2 * k];
+        d19[k] = 19 * g.v[2 * k + 1];
+        gs19[k] = c19[k] + d19[k];
+    }
+    int64_t LL[5], HH[5], SS[5];
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+        int64_t ll = 0, hh = 0, ss = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const int m = (n - k + 5) % 5;
+            const bool wrap = (k + m) >= 5;
+            ll += (int64_t)f.v[2 * k] * (wrap ? c19[m] : g.v[2 * m]);
+            hh += (int64_t)f.v[2 * k + 1] * (wrap ? d19[m] : g.v[2 * m + 1]);
+            ss += (int64_t)fs[k] * (wrap ? gs19[m] : gs[m]);
+        }
+        LL[n] = ll; HH[n] = hh; SS[n] = ss;
+    }
+    int64_t h[10];
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+        h[2 * n + 1] = SS[n] - LL[n] - HH[n];
+        h[2 * n] = LL[n] + (n == 0 ? 38 * HH[4] : 2 * HH[n - 1]);
+    }
+    return fe_carry64(h);
+}
+
+#else
 BSX_CALL fe fe_mul(const fe f, const fe g) {
     int32_t g19[10], f2[10];
 #pragma unroll
@@ -91,12 +149,16 @@ BSX_CALL fe fe_mul(const fe f, const fe g) {
     return fe_carry64(h);
 }
 
-// h = f*f (times 2 when `twice`), using the symmetry of the product
+#endif
+
+// h = f*f (times 2 when `twice`), using the symmetry of the product: 55 IMAD.WIDE.  (The pair-Karatsuba form of the
+// squaring is 45 IMAD.WIDE but measured slower on B200 at every occupancy -- 376 vs 341 cycles per squaring per SM
+// sub-partition at 8 warps, 438 vs 413 at 2 -- because its extra additions land on the same pipe; profiles/r01j_ubench_femul.txt.)
 template <bool TWICE>
 BSX_HD fe fe_sq_impl(const fe &f) {
     int32_t f2[10], f19[10], f38[10];
 #pragma unroll
-    for (int i = 0; i < 10; i++) { f2[i] = 2 * f.v[i]; f19[i] = 19 * f.v[i]; f38[i] = 38 * f.v[i]; }
+    for (int i = 0; i < 10; i++) { f2[i] = 2 * f.v[i]; f19[i] = 19 * f.v[i]; f38[i] = (i & 1) ? 38 * f.v[i] : 0; }   // 38 f_i fits (and is used) only for odd i
     int64_t h[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) {
@@ -261,8 +323,11 @@ BSX_HD ge_cached ge_to_cached(const ge_p3 &p) {
     return c;
 }
 // completed -> extended (4M); with_t=false skips T (3M) when the next operation is a doubling
+// Operand order follows fe_mul's bounds: X and T of a completed point are 3-unit values (a - (yy + xx),
+// 2zz - (yy - xx), 2zz +- c), Y is 2 units, Z is 2 (doubling) or 3 (addition); the g-side is Y or the tightened T.
 BSX_HD ge_p3 ge_p1p1_to_p3(const ge_p1p1 &p, bool with_t) {
-    ge_p3 r; r.X = fe_mul(p.X, p.T); r.Y = fe_mul(p.Y, p.Z); r.Z = fe_mul(p.Z, p.T);
+    const fe tt = fe_tighten(p.T);
+    ge_p3 r; r.X = fe_mul(p.X, tt); r.Y = fe_mul(p.Z, p.Y); r.Z = fe_mul(p.Z, tt);
     r.T = with_t ? fe_mul(p.X, p.Y) : fe_zero();
     return r;
 }
@@ -334,16 +399,37 @@ BSX_HD bool ge_decompress(const uint8_t *in, fe &x, fe &y, uint8_t x_bytes[32], 
 // ---------------------------------------------------------------------------------------------
 // scalar multiplication
 // ---------------------------------------------------------------------------------------------
-#define BSX_ED_BASE_WINDOWS 64
-#define BSX_ED_BASE_ENTRIES 15
-// table[w*15 + (d-1)] = d * 16^w * G   (d = 1..15), affine precomputed form
-BSX_HD ge_p3 ge_scalarmult_base(const uint8_t s[32], const ge_niels *table) {
+#define BSX_ED_BASE_WINDOWS 32
+#define BSX_ED_BASE_ENTRIES 255
+// table[w*255 + (d-1)] = d * 256^w * G   (d = 1..255), affine precomputed form: 8-bit windows, so s*G is at most
+// 32 mixed additions (7M each) and no doubling.  8160 entries x 128 B = 1 MB, resident in L2; each lane gathers
+// its own entry with eight 16-byte loads.
+struct alignas(16) ge_niels_slot { int32_t v[32]; };   // ypx[10] ymx[10] xy2d[10] pad[2]
+BSX_HD ge_niels ge_niels_load(const ge_niels_slot *slot) {
+    ge_niels q;
+#if defined(__CUDA_ARCH__)
+    int32_t v[32];
+    const int4 *p = reinterpret_cast<const int4 *>(slot);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const int4 t = __ldg(p + i); v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+#else
+    const int32_t *v = slot->v;
+#endif
+#pragma unroll
+    for (int i = 0; i < 10; i++) { q.ypx.v[i] = v[i]; q.ymx.v[i] = v[10 + i]; q.xy2d.v[i] = v[20 + i]; }
+    return q;
+}
+BSX_HD void ge_niels_store(ge_niels_slot *slot, const ge_niels &q) {
+    for (int i = 0; i < 10; i++) { slot->v[i] = q.ypx.v[i]; slot->v[10 + i] = q.ymx.v[i]; slot->v[20 + i] = q.xy2d.v[i]; }
+    slot->v[30] = 0; slot->v[31] = 0;
+}
+BSX_HD ge_p3 ge_scalarmult_base(const uint8_t s[32], const ge_niels_slot *table) {
     ge_p3 acc = ge_identity();
 #pragma unroll 1
     for (int w = 0; w < BSX_ED_BASE_WINDOWS; w++) {
-        const uint32_t dgt = (s[w >> 1] >> ((w & 1) * 4)) & 15;
+        const uint32_t dgt = s[w];
         if (dgt) {
-            const ge_niels q = table[w * BSX_ED_BASE_ENTRIES + (dgt - 1)];
+            const ge_niels q = ge_niels_load(table + w * BSX_ED_BASE_ENTRIES + (dgt - 1));
             acc = ge_p1p1_to_p3(ge_add_niels(acc, q), true);
         }
     }
@@ -377,13 +463,14 @@ BSX_HD ge_p3 ge_scalarmult(const uint8_t s[32], const ge_p3 &P) {
     return acc;
 }
 
-// one entry of the s*G table: d * 16^w * G in affine precomputed form (run once per context)
+// one entry of the s*G table: d * 256^w * G in affine precomputed form (run once per context)
 BSX_HD ge_niels ge_base_table_entry(int w, int d) {
     const int32_t gx[10] = BSX_FE_GX, gy[10] = BSX_FE_GY, d2[10] = BSX_FE_2D;
     uint8_t s[32];
     for (int i = 0; i < 32; i++) s[i] = 0;
-    s[w >> 1] = (uint8_t)(d << ((w & 1) * 4));
-    ge_p3 r = ge_scalarmult(s, ge_from_affine(fe_const(gx), fe_const(gy)));
+    s[w] = (uint8_t)d;
+    // canonical constants are one-sided 2-unit values; balance them so that Y + X stays a legal g operand
+    ge_p3 r = ge_scalarmult(s, ge_from_affine(fe_reduce(fe_const(gx)), fe_reduce(fe_const(gy))));
     fe zi = fe_invert(r.Z);
     fe x = fe_mul(r.X, zi), y = fe_mul(r.Y, zi);
     ge_niels n;
@@ -481,7 +568,7 @@ BSX_HD bool sc_lt_l(const uint8_t s[32]) {
 // flags: 1 s<l, 2 A decompressed, 4 R decompressed, 8 sG == Rp+hA
 // ---------------------------------------------------------------------------------------------
 BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], const uint8_t digest[64],
-                                 const ge_niels *base_table, uint8_t *out) {
+                                 const ge_niels_slot *base_table, uint8_t *out) {
     for (int i = 0; i < 64; i++) out[i] = digest[i];
     sc_divrem_l(digest, out + 64, out + 96);
     uint32_t flags = sc_lt_l(sig + 32) ? 1u : 0u;

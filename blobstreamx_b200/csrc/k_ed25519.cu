@@ -21,10 +21,10 @@ __device__ __constant__ uint8_t DUMMY_SIG[64] = {55, 20, 104, 158, 84, 120, 194,
                                                   1, 41, 22, 121, 249, 46, 198, 145, 155, 102, 3, 210, 168, 135, 173, 55,
                                                   252, 72, 45, 126, 169, 178, 191, 7, 153, 67, 112, 90, 150, 33, 140, 7};
 
-__global__ void __launch_bounds__(64) ed25519_base_table_kernel(ge_niels *table) {
+__global__ void __launch_bounds__(64) ed25519_base_table_kernel(ge_niels_slot *table) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES) return;
-    table[i] = ge_base_table_entry(i / BSX_ED_BASE_ENTRIES, i % BSX_ED_BASE_ENTRIES + 1);
+    ge_niels_store(table + i, ge_base_table_entry(i / BSX_ED_BASE_ENTRIES, i % BSX_ED_BASE_ENTRIES + 1));
 }
 
 struct EdIn {
@@ -33,7 +33,7 @@ struct EdIn {
 };
 
 template <int MIN_CTAS>
-__global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels *__restrict__ table,
+__global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
                                                            uint8_t *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -74,8 +74,8 @@ using namespace bsx;
 static int ensure_base_table(bsx_ctx *ctx, cudaStream_t st) {
     if (ctx->ed_table) return BSX_OK;
     const int entries = BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES;
-    BSX_CUDA(ctx, cudaMalloc(&ctx->ed_table, sizeof(ed::ge_niels) * entries));
-    ed25519_base_table_kernel<<<(entries + 63) / 64, 64, 0, st>>>(reinterpret_cast<ed::ge_niels *>(ctx->ed_table));
+    BSX_CUDA(ctx, cudaMalloc(&ctx->ed_table, sizeof(ed::ge_niels_slot) * entries));
+    ed25519_base_table_kernel<<<(entries + 63) / 64, 64, 0, st>>>(reinterpret_cast<ed::ge_niels_slot *>(ctx->ed_table));
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }
@@ -93,7 +93,8 @@ extern "C" int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, c
     EdIn in{pks, sigs, msgs, msg_lens, active, pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride};
     // register budget per thread: 4 CTAs/SM -> 202 registers, 6 -> 168, 8 -> 128 (with spills); BSX_ED_OCC selects (A/B)
     static const int occ = [] { const char *e = getenv("BSX_ED_OCC"); return e ? atoi(e) : 4; }();
-    const ed::ge_niels *tab = reinterpret_cast<const ed::ge_niels *>(ctx->ed_table);
+    const ed::ge_niels_slot *tab = reinterpret_cast<const ed::ge_niels_slot *>(ctx->ed_table);
+    BSX_PIN_CARVEOUT(ed25519_batch_kernel<8>); BSX_PIN_CARVEOUT(ed25519_batch_kernel<6>); BSX_PIN_CARVEOUT(ed25519_batch_kernel<4>);
     if (occ >= 8) ed25519_batch_kernel<8><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (occ >= 6) ed25519_batch_kernel<6><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else ed25519_batch_kernel<4><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);

@@ -472,11 +472,13 @@ template <int B>
 static int launch_subchain_split(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const SubchainArgs &a) {
     const size_t total = (size_t)n_jobs * 2 * B;
     static const int occ = [] { const char *e = getenv("BSX_PROOFS_OCC"); return e ? atoi(e) : 8; }();
+    BSX_PIN_CARVEOUT(subchain_proofs_kernel<8>); BSX_PIN_CARVEOUT(subchain_proofs_kernel<6>);
     if (occ >= 8) subchain_proofs_kernel<8><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, B, n_jobs);   // 64 registers
     else subchain_proofs_kernel<6><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, B, n_jobs);             // 80 registers
     BSX_LAUNCHED(ctx);
     constexpr int G = B >= 128 ? 1 : 128 / B;
     constexpr int T = B * G < 32 ? 32 : B * G;
+    BSX_PIN_CARVEOUT((subchain_commit_kernel<B, G>));
     subchain_commit_kernel<B, G><<<(n_jobs + G - 1) / G, T, 0, st>>>(a, n_jobs);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
@@ -574,6 +576,7 @@ extern "C" int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_r
     size_t smem = 4 * (32 * (size_t)n_jobs + 16 * (size_t)n_jobs);
     if (smem > 48 * 1024)
         BSX_CUDA(ctx, cudaFuncSetAttribute(reduce_subchains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem <= 48 * 1024) BSX_PIN_CARVEOUT(reduce_subchains_kernel);
     reduce_subchains_kernel<<<n_ranges, threads, smem, (cudaStream_t)stream>>>(
         n_jobs, B, map_subchains, start_blocks, start_header, end_blocks, end_header, reduce_digests, reduce_nodes,
         data_commitments, fail);

@@ -288,9 +288,9 @@ static int launch_verify(bsx_ctx *ctx, cudaStream_t st, int mode, uint32_t n, Ve
     const size_t smem = 4 * (8 * (size_t)P + 4 * (size_t)P + 16);
     const uint32_t threads = P < 64 ? 64 : (P > 256 ? 256 : P);
     switch (mode) {
-        case MODE_HEADER: verify_kernel<MODE_HEADER><<<n, threads, smem, st>>>(a); break;
-        case MODE_SKIP: verify_kernel<MODE_SKIP><<<n, threads, smem, st>>>(a); break;
-        default: verify_kernel<MODE_STEP><<<n, threads, smem, st>>>(a); break;
+        case MODE_HEADER: BSX_PIN_CARVEOUT(verify_kernel<MODE_HEADER>); verify_kernel<MODE_HEADER><<<n, threads, smem, st>>>(a); break;
+        case MODE_SKIP: BSX_PIN_CARVEOUT(verify_kernel<MODE_SKIP>); verify_kernel<MODE_SKIP><<<n, threads, smem, st>>>(a); break;
+        default: BSX_PIN_CARVEOUT(verify_kernel<MODE_STEP>); verify_kernel<MODE_STEP><<<n, threads, smem, st>>>(a); break;
     }
     BSX_LAUNCHED(ctx);
     return BSX_OK;

@@ -8,13 +8,13 @@
 
 using namespace bsx::ed;
 
-static ge_niels *g_table = nullptr;
+static ge_niels_slot *g_table = nullptr;
 
 static void build_table() {
     if (g_table) return;
-    g_table = (ge_niels *)malloc(sizeof(ge_niels) * BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES);
+    g_table = (ge_niels_slot *)aligned_alloc(16, sizeof(ge_niels_slot) * BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES);
     for (int w = 0; w < BSX_ED_BASE_WINDOWS; w++)
-        for (int d = 1; d <= BSX_ED_BASE_ENTRIES; d++) g_table[w * BSX_ED_BASE_ENTRIES + d - 1] = ge_base_table_entry(w, d);
+        for (int d = 1; d <= BSX_ED_BASE_ENTRIES; d++) ge_niels_store(g_table + w * BSX_ED_BASE_ENTRIES + d - 1, ge_base_table_entry(w, d));
 }
 
 extern "C" {
@@ -26,6 +26,23 @@ void hc_fe_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) { fe_tobytes(ou
 void hc_fe_sq(const uint8_t *a, uint8_t *out, int twice) {
     fe f = fe_frombytes(a);
     fe_tobytes(out, twice ? fe_sq2(f) : fe_sq(f));
+}
+// raw-limb entry points: operands at the extreme limb bounds the point formulas produce
+void hc_fe_mul_limbs(const int32_t *f, const int32_t *g, uint8_t *out) {
+    fe a, b;
+    for (int i = 0; i < 10; i++) { a.v[i] = f[i]; b.v[i] = g[i]; }
+    fe_tobytes(out, fe_mul(a, b));
+}
+void hc_fe_sq_limbs(const int32_t *f, uint8_t *out, int twice) {
+    fe a;
+    for (int i = 0; i < 10; i++) a.v[i] = f[i];
+    fe_tobytes(out, twice ? fe_sq2(a) : fe_sq(a));
+}
+void hc_fe_tighten_limbs(const int32_t *f, int32_t *out) {
+    fe a;
+    for (int i = 0; i < 10; i++) a.v[i] = f[i];
+    a = fe_tighten(a);
+    for (int i = 0; i < 10; i++) out[i] = a.v[i];
 }
 void hc_fe_invert(const uint8_t *a, uint8_t *out) { fe_tobytes(out, fe_invert(fe_frombytes(a))); }
 void hc_fe_addsub_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) {

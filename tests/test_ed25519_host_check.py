@@ -57,6 +57,45 @@ def test_field_ops(hc):
         assert int.from_bytes(bytes(o), "little") == pow(a, P - 2, P)
 
 
+OFF = [0, 26, 51, 77, 102, 128, 153, 179, 204, 230]
+
+
+def _limb_value(v):
+    return sum(int(x) << o for x, o in zip(v, OFF))
+
+
+def test_field_ops_at_limb_bounds(hc):
+    """fe_mul takes f up to 3 units and g up to 2 units (1 unit = a carried value: |even| <= 1.01*2^25,
+    |odd| <= 1.01*2^24), fe_sq up to 2 units, fe_tighten brings 3 units back under 2 -- exercised at the extremes
+    (all-max, all-min, alternating, random signs), where a 32-bit overflow in the 19x terms would show."""
+    rng = np.random.default_rng(11)
+    unit = np.array([int(1.01 * 2**25) if i % 2 == 0 else int(1.01 * 2**24) for i in range(10)], np.int64)
+    pats = [np.ones(10, np.int64), -np.ones(10, np.int64), np.array([1, -1] * 5), np.array([-1, 1] * 5),
+            np.array([1, 1, -1, -1, 1, 1, -1, -1, 1, 1]), np.array([-1, -1, -1, -1, -1, 1, 1, 1, 1, 1])]
+    pats += [rng.choice([-1, 1], 10) for _ in range(60)]
+    i32 = C.c_int32 * 10
+    for k, pf in enumerate(pats):
+        for pg in (pats[(k + 1) % len(pats)], pats[(k * 7 + 3) % len(pats)], pf):
+            frac_f = 1.0 if k < 12 else rng.uniform(0.5, 1.0, 10)
+            frac_g = 1.0 if k < 12 else rng.uniform(0.5, 1.0, 10)
+            f = (pf * unit * 3 * frac_f).astype(np.int64)
+            g = (pg * unit * 2 * frac_g).astype(np.int64)
+            o = _out(32)
+            hc.hc_fe_mul_limbs(i32(*f.tolist()), i32(*g.tolist()), o)
+            assert int.from_bytes(bytes(o), "little") == (_limb_value(f) * _limb_value(g)) % P
+            for tw in (0, 1):
+                hc.hc_fe_sq_limbs(i32(*g.tolist()), o, tw)
+                assert int.from_bytes(bytes(o), "little") == ((1 + tw) * _limb_value(g) ** 2) % P
+            t = i32()
+            hc.hc_fe_tighten_limbs(i32(*f.tolist()), t)
+            t = np.array(list(t), np.int64)
+            assert _limb_value(t) % P == _limb_value(f) % P
+            assert all(-38 <= t[i] <= (2**26 + 19 if i % 2 == 0 else 2**25 + 1) for i in range(10))
+            # a tightened value is a legal g operand
+            hc.hc_fe_mul_limbs(i32(*f.tolist()), i32(*t.tolist()), o)
+            assert int.from_bytes(bytes(o), "little") == (_limb_value(f) * _limb_value(t)) % P
+
+
 def test_divrem_l(hc):
     rng = np.random.default_rng(6)
     cases = [0, 1, L - 1, L, L + 1, 2 * L - 1, 2 * L, 2**512 - 1, 2**511, L * L, L * L - 1, (2**260 - 1) * L, (2**260 - 1) * L + L - 1,
@@ -142,3 +181,33 @@ def test_witness_records(hc):
             assert want == po.ed_witness_bytes(pk, sig, msg)
         seen.add(want[520])
     assert 0xF in seen and 0x7 in seen and any(not (f & 1) for f in seen) and any(not (f & 2) for f in seen)
+
+
+def test_no_limb_overflow_under_ubsan():
+    """Runs the witness core in a child process against a -fsanitize=signed-integer-overflow build: a limb bound
+    violated anywhere in the point formulas (19x terms, pair sums, 64-bit accumulators) aborts the child."""
+    import sys
+    import textwrap
+    subprocess.check_call(["make", "-C", HERE, "-s", "libed_host_check_ubsan.so"], stderr=subprocess.DEVNULL)
+    code = textwrap.dedent(f"""
+        import ctypes as C, hashlib, sys
+        import numpy as np
+        sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+        from oracle import cbind as orc
+        from nacl.signing import SigningKey
+        hc = C.CDLL({os.path.join(HERE, "libed_host_check_ubsan.so")!r})
+        buf = lambda b: (C.c_uint8 * len(b)).from_buffer_copy(bytes(b))
+        rng = np.random.default_rng(3)
+        for i in range(120):
+            sk = SigningKey(hashlib.sha256(b"u%d" % i).digest())
+            msg = rng.bytes(int(rng.integers(0, 124)))
+            pk, sig = bytes(sk.verify_key), sk.sign(msg).signature
+            if i % 5 == 4:
+                pk, sig, msg = rng.bytes(32), rng.bytes(64), rng.bytes(40)
+            out = (C.c_uint8 * 576)()
+            hc.hc_ed25519_witness(buf(pk), buf(sig), buf(hashlib.sha512(sig[:32] + pk + msg).digest()), out)
+            assert bytes(out) == orc.ed25519_witness(pk, sig, msg)
+        print("clean")
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-2000:]

@@ -134,3 +134,28 @@ def test_header_range_combined(ctx, orc):
         assert (got["map_digests"][r] == wm["map_digests"]).all() and (got["reduce_nodes"][r] == wm["reduce_nodes"]).all()
         assert got["data_commitments"][r].tobytes() == wm["data_commitment"]
         assert k["target"]["header"].tobytes() == mm.end_header.tobytes()   # circuit wiring: skip output = range end header
+
+
+def test_header_range_chunked_pipeline(ctx, orc):
+    """bsx_header_range with more ranges than one pipeline chunk (chunks of 4 rotate over three copy/compute streams,
+    the last chunk ragged): every range's map/reduce witness and skip digests still land in the caller's arrays."""
+    import bench
+    from blobstreamx_b200 import synthetic as S
+    vs = S.ValidatorSet.make()
+    J, B = 2, 4
+    fills = (None, 5, 2, None, 7, 3, None, 3, 8, 6, None, 4, 2)          # 13 ranges -> chunks 4,4,4,1
+    sets = [S.header_range_inputs(J, B, nb, start=4_000_000 + 100 * r, seed=S.SEED + 7 * r, valset=vs) for r, nb in enumerate(fills)]
+    ms, skips = [x[0] for x in sets], [x[1] for x in sets]
+    m = bench.tile_ranges(ms, len(ms))
+    m["n_jobs"], m["batch"] = J, B
+    got = ctx.header_range(skips, m)
+    assert not got["fail"].any() and not got["skip"]["fail"].any()
+    for r, (mm, k) in enumerate(zip(ms, skips)):
+        wm = orc.prove_data_commitment(J, B, mm.dh_leaf, mm.dh_aunts, mm.lb_leaf, mm.lb_aunts, mm.start_headers, mm.end_headers,
+                                       mm.start_block, mm.start_header, mm.end_block, mm.end_header)
+        assert (got["map_digests"][r] == wm["map_digests"]).all() and (got["map_subchains"][r] == wm["map_subchains"]).all(), r
+        assert (got["reduce_digests"][r] == wm["reduce_digests"]).all() and (got["reduce_nodes"][r] == wm["reduce_nodes"]).all(), r
+        assert got["data_commitments"][r].tobytes() == wm["data_commitment"], r
+    for r in (0, 5, 12):
+        ws = orc.verify_skip(skips[r], threads=8)
+        assert (got["skip"]["sha256_digests"][r] == ws["sha256_digests"]).all() and (got["skip"]["ed"][r] == ws["ed"]).all()
