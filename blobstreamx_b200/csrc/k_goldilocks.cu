@@ -11,6 +11,7 @@
 // the traffic is streamed (ld.global.cs / st.global.cs, nothing is reused).  ~1.8 KB of traffic against
 // ~400 field multiplications per row puts the arithmetic gate near the HBM/ALU balance point.
 #include "common.cuh"
+#include "goldilocks.cuh"
 #include "poseidon_constants.cuh"
 
 namespace bsx {
@@ -99,73 +100,107 @@ struct RowIO {
     uint64_t *__restrict__ out;
     size_t rows, r;
     uint32_t c;
-    __device__ __forceinline__ uint64_t w(uint32_t col) const { return gl_canon(__ldcs(wires + (size_t)col * rows + r)); }
+    __device__ __forceinline__ uint64_t raw(uint32_t col) const { return __ldcs(wires + (size_t)col * rows + r); }
+    __device__ __forceinline__ uint64_t w(uint32_t col) const { return glf::canon(raw(col)); }
     __device__ __forceinline__ void put(uint64_t v) { __stcs(out + (size_t)(c++) * rows + r, v); }
+    __device__ __forceinline__ void put_at(uint32_t col, uint64_t v) const { __stcs(out + (size_t)col * rows + r, v); }
 };
 
+// N 2-bit limbs (wires w0 .. w0+N-1, least significant first): their range-check products go to constraints
+// c_top, c_top+1, ... in order of DECREASING significance (the reference iterates the limbs in reverse), and the
+// return value is sum_t limb_t 4^t as a Radix4Sum.  All N loads are issued before the arithmetic.  The callers loop
+// over groups of <= 8 limbs WITHOUT unrolling, so the hot code is one copy of this body (~600 instructions): fully
+// unrolled the arithmetic gate was 58 KB of SASS and a quarter of its issue stalls were instruction-cache misses
+// (profiles/r01i_gl_gate_eval_ncu_full.csv).
+template <int N>
+__device__ __forceinline__ glf::Radix4Sum limb_group(const RowIO &io, uint32_t w0, uint32_t c_top) {
+    // column pointers advance by one row stride per limb (no per-access 64-bit multiply)
+    const uint64_t *wp = io.wires + (size_t)w0 * io.rows + io.r;
+    uint64_t *cp = io.out + (size_t)(c_top + N - 1) * io.rows + io.r;
+    uint64_t limb[N];
+#pragma unroll
+    for (int t = 0; t < N; t++) limb[t] = __ldcs(wp + (size_t)t * io.rows);   // raw: limb_product4 and the sum take any representative
+    glf::Radix4Sum s;
+#pragma unroll
+    for (int t = 0; t < N; t++) {
+        __stcs(cp - (size_t)t * io.rows, glf::limb_product4(limb[t]));
+        s.add(limb[t], t);
+    }
+    return s;
+}
+
+// arithmetic_u32.rs:280-349: per op  [hi_not_max * out_lo, out_hi 2^32 + out_lo - (m0 m1 + addend),
+//   32 limb products (limb 31 first), low16 - out_lo, high16 - out_hi]
 __device__ __forceinline__ void eval_arithmetic(RowIO &io, uint32_t num_ops) {
+#pragma unroll 1
     for (uint32_t i = 0; i < num_ops; i++) {
+        const uint32_t cb = 36 * i, wl = 6 * num_ops + 32 * i;
         const uint64_t m0 = io.w(6 * i), m1 = io.w(6 * i + 1), addend = io.w(6 * i + 2);
         const uint64_t out_lo = io.w(6 * i + 3), out_hi = io.w(6 * i + 4), inverse = io.w(6 * i + 5);
-        const uint64_t computed = gl_add(gl_mul(m0, m1), addend);
-        const uint64_t hi_not_max = gl_sub(gl_mul(inverse, gl_sub(GL_EPS, out_hi)), 1);
-        io.put(gl_mul(hi_not_max, out_lo));
-        io.put(gl_sub(gl_add(gl_mul(out_hi, 1ULL << 32), out_lo), computed));
-        Horner4 lo, hi;
-#pragma unroll
-        for (int h = 1; h >= 0; h--) {            // 16 limbs at a time: all loads issued before the arithmetic (memory-level parallelism)
-            uint64_t limb[16];
-#pragma unroll
-            for (int j = 0; j < 16; j++) limb[j] = io.w(6 * num_ops + 32 * i + 16 * h + j);
-#pragma unroll
-            for (int j = 15; j >= 0; j--) {
-                io.put(limb_product4(limb[j]));
-                if (h == 0) lo.push(limb[j]);
-                else hi.push(limb[j]);
+        const uint64_t computed = glf::add(glf::mul(m0, m1), addend);
+        const uint64_t hi_not_max = glf::sub(glf::mul(inverse, glf::sub(GL_EPS, out_hi)), 1);
+        io.put_at(cb, glf::mul(hi_not_max, out_lo));
+        io.put_at(cb + 1, glf::sub(glf::add(glf::mul(out_hi, 1ULL << 32), out_lo), computed));
+        glf::Radix4Sum top;
+#pragma unroll 1
+        for (int g = 3; g >= 0; g--) {               // limbs 8g .. 8g+7; g = 3, 2 build the high word, g = 1, 0 the low word
+            glf::Radix4Sum s = limb_group<8>(io, wl + 8 * g, cb + 2 + 8 * (3 - g));
+            if (g & 1) top = s;
+            else {
+                s.append_high8(top);
+                io.put_at(cb + 34 + (g >> 1), glf::sub(s.value(), g ? out_hi : out_lo));
             }
         }
-        io.put(gl_sub(lo.value(), out_lo));
-        io.put(gl_sub(hi.value(), out_hi));
     }
 }
 
+// add_many_u32.rs:107-146: per op  [out_carry 2^32 + out_res - sum(addends, carry_in),
+//   19 limb products (limb 18 first: 3 carry limbs, then 16 result limbs), res16 - out_res, carry3 - out_carry]
 __device__ __forceinline__ void eval_add_many(RowIO &io, uint32_t na, uint32_t num_ops) {
+#pragma unroll 1
     for (uint32_t i = 0; i < num_ops; i++) {
-        const uint32_t b = (na + 3) * i;
+        const uint32_t b = (na + 3) * i, cb = 22 * i, wl = (na + 3) * num_ops + 19 * i;
         uint64_t computed = 0;
-        for (uint32_t j = 0; j <= na; j++) computed = gl_add(computed, io.w(b + j));
+#pragma unroll 1
+        for (uint32_t j = 0; j <= na; j++) computed = glf::add(computed, io.w(b + j));
         const uint64_t out_res = io.w(b + na + 1), out_carry = io.w(b + na + 2);
-        io.put(gl_sub(gl_add(gl_mul(out_carry, 1ULL << 32), out_res), computed));
-        Horner4 res, carry;
-#pragma unroll
-        for (int j = 18; j >= 0; j--) {
-            const uint64_t limb = io.w((na + 3) * num_ops + 19 * i + j);
-            io.put(limb_product4(limb));
-            if (j < 16) res.push(limb);
-            else carry.push(limb);
+        io.put_at(cb, glf::sub(glf::add(glf::mul(out_carry, 1ULL << 32), out_res), computed));
+        const glf::Radix4Sum carry = limb_group<3>(io, wl + 16, cb + 1);
+        glf::Radix4Sum top;
+#pragma unroll 1
+        for (int g = 1; g >= 0; g--) {
+            glf::Radix4Sum s = limb_group<8>(io, wl + 8 * g, cb + 4 + 8 * (1 - g));
+            if (g) top = s;
+            else {
+                s.append_high8(top);
+                io.put_at(cb + 20, glf::sub(s.value(), out_res));
+            }
         }
-        io.put(gl_sub(res.value(), out_res));
-        io.put(gl_sub(carry.value(), out_carry));
+        io.put_at(cb + 21, glf::sub(carry.value(), out_carry));
     }
 }
 
+// subtraction_u32.rs:101-135: per op  [out_res - (x - y - borrow_in + 2^32 out_borrow), 16 limb products (limb 15
+//   first), limbs16 - out_res, out_borrow (1 - out_borrow)]
 __device__ __forceinline__ void eval_subtraction(RowIO &io, uint32_t num_ops) {
+#pragma unroll 1
     for (uint32_t i = 0; i < num_ops; i++) {
+        const uint32_t cb = 19 * i, wl = 5 * num_ops + 16 * i;
         const uint64_t x = io.w(5 * i), y = io.w(5 * i + 1), bin = io.w(5 * i + 2), out_res = io.w(5 * i + 3),
                        out_b = io.w(5 * i + 4);
-        const uint64_t initial = gl_sub(gl_sub(x, y), bin);
-        io.put(gl_sub(out_res, gl_add(initial, gl_mul(1ULL << 32, out_b))));
-        Horner4 comb;
-        uint64_t limb[16];
-#pragma unroll
-        for (int j = 0; j < 16; j++) limb[j] = io.w(5 * num_ops + 16 * i + j);
-#pragma unroll
-        for (int j = 15; j >= 0; j--) {
-            io.put(limb_product4(limb[j]));
-            comb.push(limb[j]);
+        const uint64_t initial = glf::sub(glf::sub(x, y), bin);
+        io.put_at(cb, glf::sub(out_res, glf::add(initial, glf::mul(1ULL << 32, out_b))));
+        glf::Radix4Sum top;
+#pragma unroll 1
+        for (int g = 1; g >= 0; g--) {
+            glf::Radix4Sum s = limb_group<8>(io, wl + 8 * g, cb + 1 + 8 * (1 - g));
+            if (g) top = s;
+            else {
+                s.append_high8(top);
+                io.put_at(cb + 17, glf::sub(s.value(), out_res));
+            }
         }
-        io.put(gl_sub(comb.value(), out_res));
-        io.put(gl_mul(out_b, gl_sub(1, out_b)));
+        io.put_at(cb + 18, glf::mul(out_b, glf::sub(1, out_b)));
     }
 }
 
@@ -203,17 +238,27 @@ __device__ __forceinline__ void eval_comparison(RowIO &io, uint32_t num_bits, ui
     io.put(gl_sub(io.w(2), io.w(4 + 5 * nc + cb)));
 }
 
+// range_check_u32.rs:69-91: per value  [aux16 - value, then the 16 limb products in INCREASING limb order]
 __device__ __forceinline__ void eval_range_check(RowIO &io, uint32_t nl) {
+#pragma unroll 1
     for (uint32_t i = 0; i < nl; i++) {
-        Horner4 sum;
-        uint64_t aux[16];
+        const uint32_t cb = 17 * i;
+        glf::Radix4Sum top, sum;
+#pragma unroll 1
+        for (int g = 1; g >= 0; g--) {
+            uint64_t aux[8];
 #pragma unroll
-        for (int j = 0; j < 16; j++) aux[j] = io.w(nl + 16 * i + j);
+            for (int t = 0; t < 8; t++) aux[t] = io.raw(nl + 16 * i + 8 * g + t);
+            glf::Radix4Sum s;
 #pragma unroll
-        for (int j = 15; j >= 0; j--) sum.push(aux[j]);
-        io.put(gl_sub(sum.value(), io.w(i)));
-#pragma unroll
-        for (int j = 0; j < 16; j++) io.put(limb_product4(aux[j]));
+            for (int t = 0; t < 8; t++) {
+                io.put_at(cb + 1 + 8 * g + t, glf::limb_product4(aux[t]));
+                s.add(aux[t], t);
+            }
+            if (g) top = s;
+            else { s.append_high8(top); sum = s; }
+        }
+        io.put_at(cb, glf::sub(sum.value(), io.w(i)));
     }
 }
 

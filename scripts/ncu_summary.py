@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Condense an .ncu-rep (ncu --set full) into the small `metric,unit,launchN` CSV kept under profiles/.
+usage: python scripts/ncu_summary.py gpurun_out/x/prof.ncu-rep profiles/rNN_kernel_ncu_full.csv"""
+import csv
+import subprocess
+import sys
+
+KEEP = [
+    "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes.sum.per_second",
+    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__t_bytes.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__cycles_active.avg",
+]
+STALL = "smsp__average_warps_issue_stalled_"
+
+
+def main(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, launches = rows[0], rows[1], rows[2:]
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["metric", "unit"] + [f"launch{i}" for i in range(len(launches))])
+        for j, (h, u) in enumerate(zip(hdr, units)):
+            if h in KEEP or (h.startswith(STALL) and h.endswith("_per_issue_active.ratio")):
+                w.writerow([h, u] + [l[j] for l in launches])
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])
