@@ -38,6 +38,12 @@ extern "C" int bsx_init(int device, bsx_ctx **out) {
         delete ctx;
         return BSX_ERR_CUDA;
     }
+    {   // stream-ordered scratch (cudaMallocAsync in k_ed25519.cu) stays cached in the pool across synchronizes
+        cudaMemPool_t pool;
+        uint64_t keep = UINT64_MAX;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     for (int i = 0; i < BSX_PIPE_STREAMS; i++) {
         if (cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming) != cudaSuccess) {

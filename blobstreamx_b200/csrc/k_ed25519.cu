@@ -1,4 +1,19 @@
-// K4+K5: batched Ed25519 witness generation (one thread per signature).
+// K4+K5: batched Ed25519 witness generation.
+// Default path = three kernels, because the parallel width of the work changes along a signature:
+//   ed25519_prep_kernel    one thread per POINT (2 per signature): SHA-512, h = digest div/rem l, s < l, and the
+//                          decompression of A or R (a serial chain of ~265 squarings -- nothing to split)
+//   ed25519_quad_kernel    FOUR lanes per signature, one extended coordinate (X, Y, Z, T) each: the four independent
+//                          field multiplications / squarings of every point doubling, addition and p1p1 -> p3
+//                          conversion run side by side and the operands move between the lanes with warp shuffles;
+//                          s*G (8-bit windows), the 16-entry table of A, h*A and R + h*A
+//   ed25519_finish_kernel  one thread per signature: one inversion for the three Z's, affine bytes, flags
+// The latency of one signature drops from ~3 700 dependent field operations to ~265 + ~750 + ~280, and a batch of
+// 25 600 signatures (256 header ranges) is 3 200 warps instead of 800 -- enough to fill the machine.
+// Measured (profiles/r01l_ed25519_modes.txt): 100 signatures 0.57 ms instead of 1.26, 10 000: 0.96 instead of 1.30,
+// 25 600: 1.67 instead of 1.84 -- but the quad kernel executes ~1.5x the instructions per signature (shuffles,
+// fe_tighten, sign selections), so next to the SHA-256 map kernels of bsx_header_range (256 ranges) the step is slower
+// with it (2.49 vs 2.33 ms).  Batches above BSX_ED_QUAD_MAX (16 384) signatures therefore run the
+// one-thread-per-signature kernel below; BSX_ED_MODE = 1 / 2 forces one path.
 // Replaces, per signature, the CPU hints of curta_eddsa_verify_sigs (PX/frontend/ecc/curve25519/
 // ed25519/eddsa.rs:161-203): HashDigestHint<SHA512> (PX/frontend/hash/sha/sha512/curta.rs:103-111),
 // BigUintDivRemGenerator (PX/frontend/uint/num/biguint/mod.rs:451-488) and the seven EcOpResultHint
@@ -66,6 +81,215 @@ __global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n,
     ed25519_witness_core(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// three-stage path
+// ---------------------------------------------------------------------------------------------------------------
+// scratch per signature between the quad and finish kernels: X, Y, Z of sG, hA, R + hA (9 field elements)
+#define BSX_ED_SCRATCH_WORDS 90
+
+// stage 1: thread 2i handles A of signature i (and the hashing), thread 2i+1 handles R
+template <int DUMMY>
+__global__ void __launch_bounds__(128) ed25519_prep_kernel(uint32_t n, EdIn in, uint8_t *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, i = t >> 1, which = t & 1;
+    if (i >= n) return;
+    uint8_t *rec = out + (size_t)BSX_SIG_OUT_BYTES * i;
+    const bool on = !in.active || in.active[(size_t)in.active_stride * i];
+    uint8_t pt[32];
+    fe x, y;
+    if (which == 0) {
+        uint8_t pk[32], sig[64];
+        const uint8_t *m = in.msgs + (size_t)in.msg_stride * i;
+        uint32_t len = in.msg_max;
+        if (in.lens) {
+            const uint8_t *lp = in.lens + (size_t)in.len_stride * i;
+            len = (uint32_t)lp[0] | ((uint32_t)lp[1] << 8) | ((uint32_t)lp[2] << 16) | ((uint32_t)lp[3] << 24);
+        }
+        if (len > in.msg_max) len = in.msg_max;
+        if (on) {
+            for (int k = 0; k < 32; k++) pk[k] = in.pks[(size_t)in.pk_stride * i + k];
+            for (int k = 0; k < 64; k++) sig[k] = in.sigs[(size_t)in.sig_stride * i + k];
+        } else {
+            for (int k = 0; k < 32; k++) pk[k] = DUMMY_PK[k];
+            for (int k = 0; k < 64; k++) sig[k] = DUMMY_SIG[k];
+            len = 32;  // DUMMY_MSG_LENGTH_BYTES: 32 zero bytes (eddsa.rs:28-30,62-63)
+        }
+        uint64_t st[8];
+        sha512_bytes(
+            [&](uint32_t k) -> uint8_t { return k < 32 ? sig[k] : (k < 64 ? pk[k - 32] : (on ? m[k - 64] : (uint8_t)0)); },
+            64 + len, st);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) rec[8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
+        sc_divrem_l(rec, rec + 64, rec + 96);
+        rec[521] = sc_lt_l(sig + 32) ? 1 : 0;
+        for (int k = 0; k < 32; k++) pt[k] = pk[k];
+        // the scalar s travels to the quad kernel in the (still unused) sG slot
+        for (int k = 0; k < 32; k++) rec[136 + k] = sig[32 + k];
+    } else {
+        for (int k = 0; k < 32; k++) pt[k] = on ? in.sigs[(size_t)in.sig_stride * i + k] : DUMMY_SIG[k];
+    }
+    // A -> [200..296), flag byte 522;  R -> [360..456), flag byte 523
+    uint8_t *dst = rec + (which ? 360 : 200);
+    const bool ok = ge_decompress(pt, x, y, dst, dst + 32, dst + 64);
+    rec[522 + which] = ok ? 1 : 0;
+}
+
+// ---- four lanes per signature: lane k of a quad holds coordinate k of the point (0 X, 1 Y, 2 Z, 3 T) ----
+__device__ __forceinline__ fe fe_quad_get(const fe &a, int src) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src, 4);
+    return r;
+}
+__device__ __forceinline__ fe fe_quad_swap(const fe &a) {     // lanes 0<->1, 2<->3
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], 1, 4);
+    return r;
+}
+__device__ __forceinline__ fe fe_lin(int ca, const fe &a, int cb, const fe &b) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = ca * a.v[i] + cb * b.v[i];
+    return r;
+}
+__device__ __forceinline__ fe fe_small(int32_t c) { fe r = fe_zero(); r.v[0] = c; return r; }
+
+// completed point (one coordinate per lane) -> extended:  X3 = X T, Y3 = Z Y, Z3 = Z T, T3 = X Y.
+// The right-hand factors (T or Y) go through fe_tighten, so a 4-unit T is fine (fe_mul bounds, ed25519.cuh).
+__device__ __forceinline__ fe quad_p3(const fe &c, int k) {
+    const fe t = fe_tighten(c);
+    const fe f = fe_quad_get(c, (k == 1 || k == 2) ? 2 : 0);
+    const fe g = fe_quad_get(t, (k & 1) ? 1 : 3);
+    return fe_mul(f, g);
+}
+// doubling: lanes square X, Y, Z, X + Y;  X' = A - YY - XX, Y' = YY + XX, Z' = YY - XX, T' = 2 ZZ - YY + XX
+__device__ __forceinline__ fe quad_dbl(const fe &c, int k) {
+    const fe x = fe_quad_get(c, 0), y = fe_quad_get(c, 1);
+    const fe s = fe_sq(k == 3 ? fe_add(x, y) : c);
+    const fe xx = fe_quad_get(s, 0), yy = fe_quad_get(s, 1);
+    const fe o = fe_quad_get(s, k == 0 ? 3 : 2);          // lane 0 takes A, lane 3 takes ZZ
+    const int co = (k == 0) ? 1 : (k == 3 ? 2 : 0), cy = (k == 0 || k == 3) ? -1 : 1, cx = (k == 0 || k == 2) ? -1 : 1;
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = co * o.v[i] + cy * yy.v[i] + cx * xx.v[i];
+    return r;
+}
+// addition of a precomputed point whose components sit one per lane: g = (Y+X, Y-X, 2Z, 2dT) of the addend
+// (2Z = the constant 2 for an affine table entry).  Lanes multiply (Y+X) g0, (Y-X) g1, Z g2, T g3, then
+// X' = a - b, Y' = a + b, Z' = zz2 + c, T' = zz2 - c with one exchange between neighbouring lanes.
+__device__ __forceinline__ fe quad_add(const fe &c, const fe &g, int k) {
+    const fe o = fe_quad_swap(c);
+    const fe m = fe_mul(fe_lin(1, c, k == 0 ? 1 : (k == 1 ? -1 : 0), o), g);
+    const fe o2 = fe_quad_swap(m);
+    return fe_lin(k == 3 ? -1 : 1, m, k == 0 ? -1 : 1, o2);
+}
+// extended point -> its addend form, one component per lane
+__device__ __forceinline__ fe quad_to_cached(const fe &c, int k) {
+    const int32_t d2[10] = BSX_FE_2D;
+    const fe o = fe_quad_swap(c);
+    const fe v = fe_lin(k == 2 ? 2 : 1, c, k == 0 ? 1 : (k == 1 ? -1 : 0), o);
+    return fe_mul(v, k == 3 ? fe_const(d2) : fe_one());
+}
+
+__global__ void __launch_bounds__(64) ed25519_quad_kernel(uint32_t n, const ge_niels_slot *__restrict__ table,
+                                                           const uint8_t *__restrict__ out, int32_t *__restrict__ scratch) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = t & 3;
+    uint32_t i = t >> 2;
+    const bool live = i < n;
+    if (!live) i = n - 1;                     // keep whole warps in the shuffles; no stores
+    const uint8_t *rec = out + (size_t)BSX_SIG_OUT_BYTES * i;
+    int32_t *scr = scratch + (size_t)BSX_ED_SCRATCH_WORDS * i;
+    const fe ident = fe_small((k == 1 || k == 2) ? 1 : 0);            // (0, 1, 1, 0)
+    const fe ident_addend = fe_small(k == 3 ? 0 : (k == 2 ? 2 : 1));  // (1, 1, 2, 0)
+    const int32_t d2[10] = BSX_FE_2D;
+
+    // ---- s*G: 32 windows of 8 bits over the affine table ----
+    fe acc = ident;
+#pragma unroll 1
+    for (int w = 0; w < BSX_ED_BASE_WINDOWS; w++) {
+        const uint32_t dgt = rec[136 + w];
+        fe g = ident_addend;
+        if (dgt && k != 2) {
+            const int32_t *q = table[w * BSX_ED_BASE_ENTRIES + (dgt - 1)].v + (k == 3 ? 20 : 10 * k);
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const int2 v = __ldg(reinterpret_cast<const int2 *>(q) + j);
+                g.v[2 * j] = v.x; g.v[2 * j + 1] = v.y;
+            }
+        }
+        acc = quad_p3(quad_add(acc, g, k), k);
+    }
+    if (live && k < 3)
+#pragma unroll
+        for (int j = 0; j < 10; j++) scr[10 * k + j] = acc.v[j];
+
+    // ---- table of A: tab[d] = addend form of d*A, d = 0..15 ----
+    const fe ax = fe_frombytes(rec + 200), ay = fe_frombytes(rec + 232);
+    const fe axy = fe_mul(ax, ay);
+    fe cur = k == 0 ? ax : (k == 1 ? ay : (k == 2 ? fe_one() : axy));
+    fe tab[16];
+    tab[0] = ident_addend;
+    tab[1] = quad_to_cached(cur, k);
+#pragma unroll 1
+    for (int d = 2; d < 16; d++) {
+        cur = quad_p3(quad_add(cur, tab[1], k), k);
+        tab[d] = quad_to_cached(cur, k);
+    }
+    // ---- h*A: 64 windows of 4 bits, most significant first ----
+    acc = ident;
+#pragma unroll 1
+    for (int w = 63; w >= 0; w--) {
+        if (w != 63) {
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) acc = quad_p3(quad_dbl(acc, k), k);
+        }
+        const uint32_t dgt = (rec[64 + (w >> 1)] >> ((w & 1) * 4)) & 15;
+        acc = quad_p3(quad_add(acc, tab[dgt], k), k);
+    }
+    if (live && k < 3)
+#pragma unroll
+        for (int j = 0; j < 10; j++) scr[30 + 10 * k + j] = acc.v[j];
+
+    // ---- R + h*A ----
+    const fe rx = fe_frombytes(rec + 360), ry = fe_frombytes(rec + 392);
+    const fe rt = fe_mul(fe_mul(rx, ry), fe_const(d2));
+    const fe gr = k == 0 ? fe_add(ry, rx) : (k == 1 ? fe_sub(ry, rx) : (k == 2 ? fe_small(2) : rt));
+    acc = quad_p3(quad_add(acc, gr, k), k);
+    if (live && k < 3)
+#pragma unroll
+        for (int j = 0; j < 10; j++) scr[60 + 10 * k + j] = acc.v[j];
+}
+
+// stage 3: the three projective results share one inversion; affine bytes and the flags word
+__global__ void __launch_bounds__(128) ed25519_finish_kernel(uint32_t n, const int32_t *__restrict__ scratch, uint8_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t *rec = out + (size_t)BSX_SIG_OUT_BYTES * i;
+    const int32_t *scr = scratch + (size_t)BSX_ED_SCRATCH_WORDS * i;
+    fe c[9];
+#pragma unroll
+    for (int p = 0; p < 9; p++)
+#pragma unroll
+        for (int j = 0; j < 10; j++) c[p].v[j] = scr[10 * p + j];
+    const fe &sgX = c[0], &sgY = c[1], &sgZ = c[2], &haX = c[3], &haY = c[4], &haZ = c[5], &smX = c[6], &smY = c[7], &smZ = c[8];
+    const fe z12 = fe_mul(sgZ, haZ);
+    const fe inv = fe_invert(fe_mul(z12, smZ));
+    const fe isum = fe_mul(inv, z12);
+    const fe i12 = fe_mul(inv, smZ);
+    const fe isg = fe_mul(i12, haZ), iha = fe_mul(i12, sgZ);
+    fe_tobytes(rec + 136, fe_mul(sgX, isg)); fe_tobytes(rec + 168, fe_mul(sgY, isg));
+    fe_tobytes(rec + 296, fe_mul(haX, iha)); fe_tobytes(rec + 328, fe_mul(haY, iha));
+    fe_tobytes(rec + 456, fe_mul(smX, isum)); fe_tobytes(rec + 488, fe_mul(smY, isum));
+    uint32_t flags = (rec[521] ? 1u : 0u) | (rec[522] ? 2u : 0u) | (rec[523] ? 4u : 0u);
+    if (bytes_eq32(rec + 136, rec + 456) && bytes_eq32(rec + 168, rec + 488)) flags |= 8u;
+    rec[520] = (uint8_t)flags; rec[521] = 0; rec[522] = 0; rec[523] = 0;
+    for (int j = 524; j < 576; j++) rec[j] = 0;
+}
+
 }  // namespace bsx
 
 using namespace bsx;
@@ -91,9 +315,27 @@ extern "C" int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, c
     int rc = ensure_base_table(ctx, st);
     if (rc) return rc;
     EdIn in{pks, sigs, msgs, msg_lens, active, pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride};
-    // register budget per thread: 4 CTAs/SM -> 202 registers, 6 -> 168, 8 -> 128 (with spills); BSX_ED_OCC selects (A/B)
-    static const int occ = [] { const char *e = getenv("BSX_ED_OCC"); return e ? atoi(e) : 4; }();
     const ed::ge_niels_slot *tab = reinterpret_cast<const ed::ge_niels_slot *>(ctx->ed_table);
+    // BSX_ED_MODE: 1 = three-stage quad-lane path, 2 = one thread per signature, unset = by batch size
+    static const int forced = [] { const char *e = getenv("BSX_ED_MODE"); return e ? atoi(e) : 0; }();
+    static const uint32_t quad_max = [] { const char *e = getenv("BSX_ED_QUAD_MAX"); return e ? (uint32_t)atoi(e) : 16384u; }();
+    const bool quad = forced ? forced == 1 : n <= quad_max;
+    if (quad) {
+        // three-stage path; the 360-byte-per-signature scratch is stream-ordered (pool allocation, no ctx state)
+        int32_t *scratch = nullptr;
+        BSX_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(int32_t) * BSX_ED_SCRATCH_WORDS * (size_t)n, st));
+        BSX_PIN_CARVEOUT(ed25519_prep_kernel<0>); BSX_PIN_CARVEOUT(ed25519_quad_kernel); BSX_PIN_CARVEOUT(ed25519_finish_kernel);
+        ed25519_prep_kernel<0><<<(2 * n + 127) / 128, 128, 0, st>>>(n, in, out);
+        BSX_LAUNCHED(ctx);
+        ed25519_quad_kernel<<<(4 * n + 63) / 64, 64, 0, st>>>(n, tab, out, scratch);
+        BSX_LAUNCHED(ctx);
+        ed25519_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, scratch, out);
+        BSX_LAUNCHED(ctx);
+        BSX_CUDA(ctx, cudaFreeAsync(scratch, st));
+        return BSX_OK;
+    }
+    // one thread per signature.  Register budget: 4 CTAs/SM -> 214 registers, 6 -> 168, 8 -> 128 (with spills)
+    static const int occ = [] { const char *e = getenv("BSX_ED_OCC"); return e ? atoi(e) : 4; }();
     BSX_PIN_CARVEOUT(ed25519_batch_kernel<8>); BSX_PIN_CARVEOUT(ed25519_batch_kernel<6>); BSX_PIN_CARVEOUT(ed25519_batch_kernel<4>);
     if (occ >= 8) ed25519_batch_kernel<8><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (occ >= 6) ed25519_batch_kernel<6><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);

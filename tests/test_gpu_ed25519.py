@@ -37,6 +37,25 @@ def test_ed25519_batch_synthetic(ctx, orc, n):
     assert (got2 == want2).all()
 
 
+def test_ed25519_large_batch_one_thread_per_signature_path(ctx, orc):
+    """Above 16 384 signatures bsx_ed25519_batch switches from the three-stage quad-lane kernels to the
+    one-thread-per-signature kernel (k_ed25519.cu); both must produce the oracle's records, including DUMMY lanes
+    and a corrupted signature in the middle of the batch."""
+    from blobstreamx_b200 import synthetic as S
+    base = S.ed25519_batch_inputs(700, inactive_every=9)
+    n = 16384 + 516
+    idx = np.arange(n) % 700
+    pks, sigs, msgs, lens, active = (np.ascontiguousarray(a[idx]) for a in base)
+    sigs[9000, 3] ^= 0x10
+    got = ctx.ed25519_batch(pks, sigs, msgs, lens, active)
+    want = orc.ed25519_batch(pks, sigs, msgs, lens, active, threads=8)
+    assert (got == want).all()
+    assert (np.delete(got[:, 520], 9000) == 0xF).all() and got[9000, 520] & 8 == 0
+    # the same inputs cut below the threshold run on the quad-lane path and must agree record for record
+    small = ctx.ed25519_batch(pks[:9100], sigs[:9100], msgs[:9100], lens[:9100], active[:9100])
+    assert (small == got[:9100]).all()
+
+
 def test_ed25519_negative_and_edge_cases(ctx, orc):
     """Flipped bits must not verify (eddsa.rs:344-386 must-panic test); s >= l; undecodable points;
     random garbage -- flags and every intermediate value equal the oracle's."""
