@@ -345,11 +345,33 @@ __global__ void __launch_bounds__(128) gl_gate_witness_kernel(uint32_t gate, uin
 }
 
 // ---- Poseidon (width 12, x^7, 4 + 22 + 4 rounds) ----
+// The state is kept as arbitrary 64-bit representatives (weak reductions, glf::): every step below is correct for
+// any representative, and only the four squeezed words are made canonical at the end.
+__device__ __forceinline__ uint64_t gl_mul_weak(uint64_t a, uint64_t b) {
+    uint64_t hi, lo;
+    glf::mul128(a, b, 0, hi, lo);
+    return glf::reduce128_weak(hi, lo);
+}
 __device__ __forceinline__ uint64_t gl_pow7(uint64_t x) {
-    const uint64_t x2 = gl_mul(x, x), x4 = gl_mul(x2, x2);
-    return gl_mul(gl_mul(x4, x2), x);
+    const uint64_t x2 = gl_mul_weak(x, x), x4 = gl_mul_weak(x2, x2);
+    return gl_mul_weak(gl_mul_weak(x4, x2), x);
+}
+// s + c for any 64-bit s and canonical c: wrapped + eps on carry (cannot carry twice because c < p)
+__device__ __forceinline__ uint64_t gl_add_const_weak(uint64_t s, uint64_t c) {
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 cy;\n\t"
+        "add.cc.u64 %0, %1, %2;\n\t"
+        "addc.u32 cy, 0, 0;\n\t"
+        "mad.wide.u32 %0, cy, 0xFFFFFFFF, %0;\n\t"
+        "}"
+        : "=&l"(r)
+        : "l"(s), "l"(c));
+    return r;
 }
 
+// MDS = circulant(CIRC) + diag(8, 0, ...): the constants are below 2^6, so each output is two sums of 32-bit halves
+// times immediates (IMAD.WIDE.U32, < 2^42) folded into one 128-bit value and reduced once
 __device__ __forceinline__ void poseidon_mds(uint64_t s[12]) {
     constexpr uint32_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     uint32_t lo[12], hi[12];
@@ -357,16 +379,19 @@ __device__ __forceinline__ void poseidon_mds(uint64_t s[12]) {
     for (int i = 0; i < 12; i++) { lo[i] = (uint32_t)s[i]; hi[i] = (uint32_t)(s[i] >> 32); }
 #pragma unroll
     for (int k = 0; k < 12; k++) {
-        uint64_t al = 0, ah = 0;  // sums of 32-bit halves times 6-bit constants: < 2^42
+        uint64_t al = 0, ah = 0;
 #pragma unroll
         for (int i = 0; i < 12; i++) {
             al += (uint64_t)lo[(i + k) % 12] * CIRC[i];
             ah += (uint64_t)hi[(i + k) % 12] * CIRC[i];
         }
         if (k == 0) { al += (uint64_t)lo[0] * 8; ah += (uint64_t)hi[0] * 8; }  // MDS_MATRIX_DIAG = [8, 0, ...]
-        const uint64_t l = al + (ah << 32);
-        const uint64_t h = (ah >> 32) + (l < al ? 1 : 0);
-        s[k] = gl_reduce128(h, l);
+        uint64_t l = al, h = ah >> 32;
+        asm("add.cc.u64 %0, %0, %2;\n\t"
+            "addc.u64 %1, %1, 0;"
+            : "+l"(l), "+l"(h)
+            : "l"(ah << 32));
+        s[k] = glf::reduce128_weak(h, l);
     }
 }
 
@@ -374,7 +399,7 @@ __device__ __forceinline__ void poseidon_permute(uint64_t s[12]) {
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], BSX_POSEIDON_RC[12 * r + i]);
+        for (int i = 0; i < 12; i++) s[i] = gl_add_const_weak(s[i], BSX_POSEIDON_RC[12 * r + i]);
         if (r < 4 || r >= 26) {
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
@@ -398,11 +423,11 @@ __global__ void __launch_bounds__(128) gl_poseidon_batch_kernel(const uint64_t *
     for (uint32_t p = b; p < e; p += 8) {
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            if (p + k < e) s[k] = gl_canon(in[p + k]);
+            if (p + k < e) s[k] = in[p + k];          // any representative
         poseidon_permute(s);
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) out[4 * (size_t)i + k] = s[k];
+    for (int k = 0; k < 4; k++) out[4 * (size_t)i + k] = glf::canon(s[k]);
 }
 
 }  // namespace bsx
