@@ -618,6 +618,81 @@ def run_poseidon(args):
                       "cpu_baseline": cpu}))
 
 
+def run_shape(args):
+    """Input shaping on the device: --ranges header ranges of 32 x 32 + 1 encoded headers -> the proofs and
+    job headers the map circuits consume (27 SHA-256 calls = 41 compressions per header)."""
+    import torch
+    from blobstreamx_b200 import inputs as I, lib, synthetic as S
+    from blobstreamx_b200.lib import ptr, u32
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = lib.Context(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    R, J, B = args.ranges, N_JOBS, BATCH
+    per = J * B + 1
+    base = []
+    for r in range(min(R, args.distinct)):
+        m, _, chain = S.header_range_inputs(J, B, None, start=1_000_000 + 2000 * r, seed=S.SEED + r, with_skip=False)
+        base.append((I.pack_range_headers(chain.trees, m.start_block, J, B), m))
+    rec = np.stack([base[r % len(base)][0] for r in range(R)])
+    sb = np.array([base[r % len(base)][1].start_block for r in range(R)], np.uint64)
+    eb = np.array([base[r % len(base)][1].end_block for r in range(R)], np.uint64)
+    dt = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    d_rec, d_sb, d_eb = dt(rec), dt(sb), dt(eb)
+    shapes = dict(dh_leaf=R * J * B * 34, dh_aunts=R * J * B * 128, lb_leaf=R * J * B * 72, lb_aunts=R * J * B * 128,
+                  start_headers=R * J * 32, end_headers=R * J * 32, start_header=R * 32, end_header=R * 32, fail=R * 4)
+    d_out = {k: torch.zeros(v, dtype=torch.uint8, device=dev) for k, v in shapes.items()}
+    P = lambda t: ptr(t.data_ptr())
+
+    def step():
+        ctx.call_dev("bsx_header_range_inputs_dev", stream, u32(R), u32(J), u32(B), P(d_rec), P(d_sb), P(d_eb),
+                     *[P(d_out[k]) for k in shapes])
+
+    step()
+    torch.cuda.synchronize()
+    assert int(d_out["fail"].view(torch.int32).abs().sum().item()) == 0
+    m0 = base[0][1]
+    for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers"):
+        want = getattr(m0, k).reshape(-1)
+        assert (d_out[k][: want.size].cpu().numpy() == want).all(), k
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with ClockSampler(0) as clk:
+        ev[0].record()
+        for _ in range(args.steps):
+            step()
+        ev[1].record()
+        torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / args.steps
+    headers = R * per
+    alg = headers * (41 * 64 + 27 * 32) + sum(shapes.values())    # SHA-256 algorithmic bytes + the shaped outputs
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cbind as orc
+        t0 = time.perf_counter()
+        orc.header_range_inputs(J, B, base[0][0], int(sb[0]), int(eb[0]))
+        cpu = {"value": per / (time.perf_counter() - t0), "unit": "headers/s", "cores": 1, "kind": "port", "sample": "1 range (1025 headers)"}
+    print(json.dumps({"metric": "headers/sec, header_range_1024 input shaping (header trees + map-circuit proofs)", "value": headers / (ms * 1e-3),
+                      "unit": "headers/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "dtype": "u32", "data": "synthetic",
+                      "config": {"workload": f"{R} ranges x {per} encoded headers (512-byte records) -> dh/lb proofs, job and range headers",
+                                 "l2": f"{(d_rec.numel() + sum(shapes.values())) / 1e6:.0f} MB per step > 126 MB L2"},
+                      "gpu_launches": args.steps, "clocks": clk.summary(),
+                      "roofline": {"kernel": "range_inputs_kernel", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                                   "note": "SHA-256 ALU-bound like the map stage"},
+                      "cpu_baseline": cpu}))
+
+
 def run_tree(args):
     """Config 4: data_commitment Merkle over 2048 data roots, T independent trees per step; SHA-256 GB/s
     (algorithmic bytes = 64 B per compression + 32 B per digest: 4095 digests / 8190 compressions per tree)."""
@@ -691,7 +766,7 @@ def run_tree(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon"])
+    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon", "shape"])
     ap.add_argument("--trees", type=int, default=4096)
     ap.add_argument("--hashes", type=int, default=1 << 20)
     ap.add_argument("--hash-len", type=int, default=8)
@@ -719,6 +794,8 @@ def main():
         run_tree(args)
     elif args.mode == "poseidon":
         run_poseidon(args)
+    elif args.mode == "shape":
+        run_shape(args)
     else:
         run_gpu(args)
 

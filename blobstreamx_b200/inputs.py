@@ -133,6 +133,32 @@ class HeaderTree:
         return [l0[index ^ 1], l1[(index >> 1) ^ 1], l2[(index >> 2) ^ 1], l3[(index >> 3) ^ 1]]
 
 
+HEADER_LEAVES_BYTES = 512   # include/bsx.h BSX_HEADER_LEAVES_BYTES
+
+
+def pack_header_record(leaves: Sequence[bytes]) -> np.ndarray:
+    """The 14 encoded header fields as the record bsx_header_trees / bsx_header_range_inputs take:
+    bytes [0,14) = field lengths, bytes [16, 16+sum) = the fields back to back."""
+    assert len(leaves) == 14 and all(len(x) < 256 for x in leaves)
+    body = b"".join(leaves)
+    if 16 + len(body) > HEADER_LEAVES_BYTES:
+        raise ValueError(f"encoded header fields are {len(body)} bytes, the record holds {HEADER_LEAVES_BYTES - 16}")
+    rec = np.zeros(HEADER_LEAVES_BYTES, np.uint8)
+    rec[:14] = [len(x) for x in leaves]
+    rec[16:16 + len(body)] = np.frombuffer(body, np.uint8)
+    return rec
+
+
+def pack_range_headers(trees: Dict[int, "HeaderTree"], start: int, n_jobs: int, batch_size: int) -> np.ndarray:
+    """Records of blocks start .. start + n_jobs*batch_size (missing blocks beyond the chain tip stay zero)."""
+    out = np.zeros((n_jobs * batch_size + 1, HEADER_LEAVES_BYTES), np.uint8)
+    for o in range(n_jobs * batch_size + 1):
+        t = trees.get(start + o)
+        if t is not None:
+            out[o] = pack_header_record(t.leaves)
+    return out
+
+
 def header_hash(h: dict) -> bytes:
     return HeaderTree.build(header_leaves(h)).root
 

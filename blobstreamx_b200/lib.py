@@ -225,6 +225,32 @@ class Context:
         self._call("bsx_gl_poseidon_batch", _ptr(_in(inputs, np.uint64)), _ptr(offsets), C.c_uint32(n), _ptr(out))
         return out
 
+    # -- input shaping on the device --
+    def header_trees(self, records, levels: bool = False):
+        """Header hashes (and optionally all 27 tree digests) of n header records (inputs.pack_header_record)."""
+        rec = _in(records).reshape(-1, 512)
+        n = len(rec)
+        roots = np.zeros((n, 32), np.uint8)
+        lv = np.zeros((n, 27, 32), np.uint8) if levels else None
+        self._call("bsx_header_trees", _ptr(rec), C.c_uint32(n), _ptr(roots), _ptr(lv))
+        return (roots, lv) if levels else roots
+
+    def header_range_inputs(self, records, start_blocks, end_blocks, n_jobs: int, batch_size: int) -> dict:
+        """Map-circuit inputs of n ranges from their header records [n, n_jobs*B+1, 512] -> the input arrays of
+        header_range / prove_data_commitment (dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers,
+        start_header, end_header) + fail[n]."""
+        sb, eb = _in(start_blocks, np.uint64).reshape(-1), _in(end_blocks, np.uint64).reshape(-1)
+        n, J, B = len(sb), n_jobs, batch_size
+        rec = _in(records).reshape(n, J * B + 1, 512)
+        out = dict(dh_leaf=np.zeros((n, J * B, 34), np.uint8), dh_aunts=np.zeros((n, J * B, 128), np.uint8),
+                   lb_leaf=np.zeros((n, J * B, 72), np.uint8), lb_aunts=np.zeros((n, J * B, 128), np.uint8),
+                   start_headers=np.zeros((n, J, 32), np.uint8), end_headers=np.zeros((n, J, 32), np.uint8),
+                   start_header=np.zeros((n, 32), np.uint8), end_header=np.zeros((n, 32), np.uint8), fail=np.zeros(n, np.uint32))
+        self._call("bsx_header_range_inputs", C.c_uint32(n), C.c_uint32(J), C.c_uint32(B), _ptr(rec), _ptr(sb), _ptr(eb),
+                   *[_ptr(out[k]) for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers",
+                                            "start_header", "end_header", "fail")])
+        return out
+
     # -- witness data formats --
     def hash_input_data(self, bufs, buf_offsets, lens, kinds, sha512: bool = False):
         """HashInputData of one SHA accelerator -> dict(padded_chunks [chunks,16], end_bits, digest_bits, digest_indices)."""

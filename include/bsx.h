@@ -128,6 +128,7 @@ int bsx_data_commitment_batch_dev(bsx_ctx *ctx, void *stream, const uint8_t *dat
 #define BSX_FAIL_REDUCE_LINK 32u      /* :349-355 */
 #define BSX_FAIL_RANGE 64u            /* :291-297 */
 #define BSX_FAIL_RESULT 128u          /* :398-406 */
+#define BSX_FAIL_INPUT_LEAF 256u      /* input shaping: a proven header field does not have the circuit's fixed size */
 int bsx_prove_subchain_batch(bsx_ctx *ctx, uint32_t B, uint32_t n_jobs, const uint8_t *dh_leaf,
                              const uint8_t *dh_aunts, const uint8_t *lb_leaf, const uint8_t *lb_aunts,
                              const uint8_t *start_headers, const uint8_t *end_headers, const uint64_t *batch_start,
@@ -354,6 +355,37 @@ int bsx_header_range(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n_jobs, uint
                      const bsx_range_batch *range);
 int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, uint32_t n_jobs, uint32_t B,
                          const bsx_skip_batch *skip, const bsx_range_batch *range);
+
+/* ------------------------------------------------------------------------------------------
+ * Input shaping on the device
+ * The 14-leaf Tendermint tree of every header of a range and the inclusion proofs the map circuits consume.
+ * Replaces the per-header host work of generate_proofs_from_header / compute_hash_from_aunts
+ * (TX/input/tendermint_utils.rs:214-224,276-336,374-393), DataCommitmentInputs::get_data_commitment_inputs
+ * (BX/circuits/input.rs:149-271) and the DataCommitmentOffchainInputs hints of a range (BX/circuits/builder.rs:316-333):
+ * 27 SHA-256 calls per header.  The protobuf field encoders stay on the host.
+ *
+ * header record (BSX_HEADER_LEAVES_BYTES): bytes [0,14) = lengths of the 14 encoded fields in header order
+ *   (version, chain_id, height, time, last_block_id, last_commit_hash, data_hash, validators_hash,
+ *   next_validators_hash, consensus_hash, app_hash, last_results_hash, evidence_hash, proposer_address),
+ *   bytes [16, 16+sum) = the fields back to back; sum <= 496.
+ * bsx_header_trees: roots[n*32] = header hashes; levels (optional) n*27*32 = l0[14] l1[7] l2[4] l3[2].
+ * bsx_header_range_inputs: headers = n_ranges * (n_jobs*B + 1) records, record o of range r = block
+ *   start_blocks[r] + o (records beyond end_blocks[r] are ignored); outputs are exactly the input arrays of
+ *   bsx_range_batch (slots beyond the range end zero); fail[r] = BSX_FAIL_INPUT_LEAF if a data_hash /
+ *   last_block_id field is not 34 / 72 bytes (the host shaper returns an error there).
+ * ------------------------------------------------------------------------------------------ */
+#define BSX_HEADER_LEAVES_BYTES 512
+int bsx_header_trees(bsx_ctx *ctx, const uint8_t *headers, uint32_t n, uint8_t *roots, uint8_t *levels);
+int bsx_header_trees_dev(bsx_ctx *ctx, void *stream, const uint8_t *headers, uint32_t n, uint8_t *roots, uint8_t *levels);
+int bsx_header_range_inputs(bsx_ctx *ctx, uint32_t n_ranges, uint32_t n_jobs, uint32_t B, const uint8_t *headers,
+                            const uint64_t *start_blocks, const uint64_t *end_blocks, uint8_t *dh_leaf, uint8_t *dh_aunts,
+                            uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers, uint8_t *end_headers,
+                            uint8_t *start_header, uint8_t *end_header, uint32_t *fail);
+int bsx_header_range_inputs_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs, uint32_t B,
+                                const uint8_t *headers, const uint64_t *start_blocks, const uint64_t *end_blocks,
+                                uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts,
+                                uint8_t *start_headers, uint8_t *end_headers, uint8_t *start_header, uint8_t *end_header,
+                                uint32_t *fail);
 
 /* ------------------------------------------------------------------------------------------
  * Witness data formats

@@ -43,6 +43,13 @@ void orc_leaf_hash(const uint8_t *leaf, size_t len, uint8_t out[32]);
 void orc_inner_hash(const uint8_t l[32], const uint8_t r[32], uint8_t out[32]);
 /* variable-shape tree root (TX/input/tendermint_utils.rs:276-349) over n byte-slices */
 void orc_tm_root_from_slices(const uint8_t *items, const uint32_t *offsets, uint32_t n, uint8_t out[32]);
+/* aunts (leaf side first) of leaf `index` in the same tree (TX/input/tendermint_utils.rs:276-336); returns the depth */
+uint32_t orc_tm_aunts_from_slices(const uint8_t *items, const uint32_t *offsets, uint32_t n, uint32_t index, uint8_t *aunts,
+                                  uint8_t root[32]);
+/* inputs of the map circuits of one range from its encoded headers (BX/circuits/input.rs:149-271, builder.rs:316-333) */
+int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers, uint64_t start, uint64_t end,
+                            uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers,
+                            uint8_t *end_headers, uint8_t start_header[32], uint8_t end_header[32]);
 /* fixed-shape proof: digests = [leaf?] + (left,right) per level, schedule order.
  * path_bits bit i = path_indices[i].  hashed_leaf!=0 => `leaf` is the 32-byte digest. */
 void orc_tm_merkle_proof(const uint8_t *leaf, uint32_t leaf_len, const uint8_t *aunts, uint32_t depth,

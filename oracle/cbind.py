@@ -95,6 +95,32 @@ def tm_root_from_slices(items) -> bytes:
     return out.tobytes()
 
 
+def tm_aunts_from_slices(items, index: int):
+    """(aunts [depth,32], root) of leaf `index` of the variable-shape Tendermint tree over `items`."""
+    flat = _u8(b"".join(items))
+    offs = np.zeros(len(items) + 1, np.uint32)
+    offs[1:] = np.cumsum([len(i) for i in items])
+    aunts, root = np.zeros((32, 32), np.uint8), np.zeros(32, np.uint8)
+    lib().orc_tm_aunts_from_slices.restype = C.c_uint32
+    d = lib().orc_tm_aunts_from_slices(_p(flat), _p(offs), C.c_uint32(len(items)), C.c_uint32(index), _p(aunts), _p(root))
+    return aunts[:d].copy(), root.tobytes()
+
+
+def header_range_inputs(n_jobs: int, B: int, headers, start: int, end: int):
+    """Map-circuit inputs of one range from its header records (n_jobs*B + 1 records of 512 bytes)."""
+    h = _u8(headers)
+    assert h.size == (n_jobs * B + 1) * 512
+    slots = n_jobs * B
+    out = dict(dh_leaf=np.zeros((slots, 34), np.uint8), dh_aunts=np.zeros((slots, 128), np.uint8),
+               lb_leaf=np.zeros((slots, 72), np.uint8), lb_aunts=np.zeros((slots, 128), np.uint8),
+               start_headers=np.zeros((n_jobs, 32), np.uint8), end_headers=np.zeros((n_jobs, 32), np.uint8),
+               start_header=np.zeros(32, np.uint8), end_header=np.zeros(32, np.uint8))
+    out["bad"] = lib().orc_header_range_inputs(C.c_uint32(n_jobs), C.c_uint32(B), _p(h), C.c_uint64(start), C.c_uint64(end),
+                                               *[_p(out[k]) for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers",
+                                                                      "end_headers", "start_header", "end_header")])
+    return out
+
+
 def tm_merkle_proof(leaf: bytes, aunts: bytes, depth: int, path_bits: int, hashed_leaf: bool = False):
     l, a = _u8(leaf), _u8(aunts)
     nd = 2 * depth + (0 if hashed_leaf else 1)

@@ -60,6 +60,92 @@ void orc_tm_root_from_slices(const uint8_t *items, const uint32_t *offsets, uint
     root_rec(items, offsets, 0, n, out);
 }
 
+/* TX/input/tendermint_utils.rs:276-336 (proofs_from_byte_slices / trails_from_byte_slices, flatten_aunts): the aunts of
+ * leaf `index` in the variable-shape tree over items [lo, hi), leaf-side first.  Returns the subtree root in `out` and
+ * appends to aunts[*depth].  Generic in n -- the product hard-codes the 14-leaf shape, this does not. */
+static void aunts_rec(const uint8_t *items, const uint32_t *offsets, uint32_t lo, uint32_t hi, uint32_t index,
+                      uint8_t *aunts, uint32_t *depth, uint8_t out[32]) {
+    if (hi - lo == 1) {
+        orc_leaf_hash(items + offsets[lo], offsets[lo + 1] - offsets[lo], out);
+        return;
+    }
+    uint32_t n = hi - lo, k = 1;
+    while (k * 2 < n) k *= 2; /* get_split_point: largest power of two strictly below n (:338-349) */
+    uint8_t l[32], r[32];
+    if (index < lo + k) {
+        aunts_rec(items, offsets, lo, lo + k, index, aunts, depth, l);
+        root_rec(items, offsets, lo + k, hi, r);
+        memcpy(aunts + 32 * (*depth)++, r, 32);
+    } else {
+        root_rec(items, offsets, lo, lo + k, l);
+        aunts_rec(items, offsets, lo + k, hi, index, aunts, depth, r);
+        memcpy(aunts + 32 * (*depth)++, l, 32);
+    }
+    orc_inner_hash(l, r, out);
+}
+uint32_t orc_tm_aunts_from_slices(const uint8_t *items, const uint32_t *offsets, uint32_t n, uint32_t index, uint8_t *aunts,
+                                  uint8_t root[32]) {
+    uint32_t depth = 0;
+    aunts_rec(items, offsets, 0, n, index, aunts, &depth, root);
+    return depth;
+}
+
+/* BX/circuits/input.rs:149-271 + BX/circuits/builder.rs:316-333: the inputs of the n_jobs map circuits of one range from
+ * the encoded headers of blocks start .. start + n_jobs*B (records as include/bsx.h BSX_HEADER_LEAVES_BYTES: 14 lengths,
+ * then at byte 16 the fields).  Job j covers [start + jB, start + (j+1)B) clamped to `end`; data_hash proofs (leaf 6)
+ * for blocks [bs, req_end), last_block_id proofs (leaf 4) for (bs, req_end]; unused slots and dummy jobs are zero.
+ * Returns 0, or 1 if a proven field does not have the circuit's fixed size (the reference errors out). */
+int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers, uint64_t start, uint64_t end,
+                            uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers,
+                            uint8_t *end_headers, uint8_t start_header[32], uint8_t end_header[32]) {
+    const size_t slots = (size_t)n_jobs * B;
+    int bad = 0;
+    memset(dh_leaf, 0, slots * 34); memset(dh_aunts, 0, slots * 128);
+    memset(lb_leaf, 0, slots * 72); memset(lb_aunts, 0, slots * 128);
+    memset(start_headers, 0, (size_t)n_jobs * 32); memset(end_headers, 0, (size_t)n_jobs * 32);
+    memset(start_header, 0, 32); memset(end_header, 0, 32);
+    if (end <= start) return 0;
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        const uint64_t bs = start + (uint64_t)j * B, be = bs + B;
+        if (bs >= end) continue; /* dummy job */
+        const uint64_t req_end = be < end ? be : end;
+        uint32_t k_dh = 0, k_lb = 0;
+        for (uint64_t i = bs; i <= req_end; i++) {
+            const uint8_t *rec = headers + (size_t)(i - start) * 512;
+            uint32_t offs[15];
+            offs[0] = 0;
+            for (int f = 0; f < 14; f++) offs[f + 1] = offs[f] + rec[f];
+            uint8_t aunts[8 * 32], root[32];
+            if (i < req_end) {
+                uint8_t *slot = dh_leaf + ((size_t)j * B + k_dh) * 34;
+                if (rec[6] != 34) bad = 1;
+                memcpy(slot, rec + 16 + offs[6], rec[6] < 34 ? rec[6] : 34);
+                uint32_t d = orc_tm_aunts_from_slices(rec + 16, offs, 14, 6, aunts, root);
+                if (d != 4) bad = 1;
+                memcpy(dh_aunts + ((size_t)j * B + k_dh) * 128, aunts, 128);
+                k_dh++;
+            }
+            if (i > bs) {
+                uint8_t *slot = lb_leaf + ((size_t)j * B + k_lb) * 72;
+                if (rec[4] != 72) bad = 1;
+                memcpy(slot, rec + 16 + offs[4], rec[4] < 72 ? rec[4] : 72);
+                uint32_t d = orc_tm_aunts_from_slices(rec + 16, offs, 14, 4, aunts, root);
+                if (d != 4) bad = 1;
+                memcpy(lb_aunts + ((size_t)j * B + k_lb) * 128, aunts, 128);
+                k_lb++;
+            }
+            if (i == bs || i == req_end) {
+                orc_tm_root_from_slices(rec + 16, offs, 14, root);
+                if (i == bs) memcpy(start_headers + 32 * (size_t)j, root, 32);
+                if (i == req_end) memcpy(end_headers + 32 * (size_t)j, root, 32);
+                if (i == start) memcpy(start_header, root, 32);
+                if (i == end) memcpy(end_header, root, 32);
+            }
+        }
+    }
+    return bad;
+}
+
 /* PX/frontend/merkle/tendermint.rs:62-93: leaf hash, then per level BOTH inner(h,aunt) and
  * inner(aunt,h) are requested (left form first) and the path bit selects. */
 void orc_tm_merkle_proof(const uint8_t *leaf, uint32_t leaf_len, const uint8_t *aunts, uint32_t depth,

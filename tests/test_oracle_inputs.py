@@ -1,0 +1,65 @@
+"""Input shaping on the CPU: the oracle's generic Tendermint proof generator and range-input restatement
+against the reference's fixtures (header hash chain of mocha-4 10000-10004, data commitments) and against the host
+shaper (blobstreamx_b200/inputs.py, the mirror of BX/circuits/input.rs)."""
+import numpy as np
+import pytest
+
+from blobstreamx_b200 import inputs as I
+from blobstreamx_b200 import synthetic as S
+from oracle import cbind as orc
+
+FIELDS = ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers", "start_header", "end_header")
+
+
+def _same(o, m):
+    for k in FIELDS:
+        assert (o[k].reshape(-1) == getattr(m, k).reshape(-1)).all(), k
+
+
+def test_aunts_match_fixture_header_hashes(golden):
+    """Every leaf's aunts rebuild the header hash the NEXT header commits to (last_block_id.hash), with the path of
+    compute_hash_from_aunts (TX/input/tendermint_utils.rs:225-273)."""
+    for h in ("10000", "10001", "10002", "10003"):
+        leaves = I.header_leaves(golden["headers"][h])
+        want = bytes.fromhex(golden["headers"][str(int(h) + 1)]["last_block_id"]["hash"])
+        assert orc.tm_root_from_slices(leaves) == want
+        for idx in range(14):
+            aunts, root = orc.tm_aunts_from_slices(leaves, idx)
+            assert root == want and len(aunts) == (4 if idx < 12 else 3)
+            if idx < 12:
+                dig, r2 = orc.tm_merkle_proof(leaves[idx], aunts.tobytes(), 4, idx)
+                assert r2 == want
+
+
+def test_range_inputs_fixture(golden):
+    """10000 -> 10004 in the shapes of the reference's small test circuits (BX/circuits/header_range.rs:193-214)."""
+    trees = {int(k): I.HeaderTree.build(I.header_leaves(v)) for k, v in golden["headers"].items()}
+    for (a, b, J, B) in ((10000, 10004, 2, 4), (10000, 10004, 4, 2), (10002, 10004, 2, 2), (10000, 10001, 2, 4)):
+        m = I.get_header_range_map_inputs(trees, a, b, J, B)
+        o = orc.header_range_inputs(J, B, I.pack_range_headers(trees, a, J, B), a, b)
+        assert o["bad"] == 0
+        _same(o, m)
+        w = orc.prove_data_commitment(J, B, *[o[k] for k in FIELDS[:6]], a, o["start_header"], b, o["end_header"])
+        assert w["fail"] == 0
+    # the shaped inputs of 10000 -> 10004 prove the fixture's data commitment
+    assert w is not None
+    o = orc.header_range_inputs(2, 4, I.pack_range_headers(trees, 10000, 2, 4), 10000, 10004)
+    w = orc.prove_data_commitment(2, 4, *[o[k] for k in FIELDS[:6]], 10000, o["start_header"], 10004, o["end_header"])
+    assert w["data_commitment"].hex().upper().startswith("5F1B8536")
+
+
+@pytest.mark.parametrize("J,B,nb", [(4, 8, None), (4, 8, 19), (2, 4, 1), (8, 4, 32), (4, 4, 5)])
+def test_range_inputs_synthetic(J, B, nb):
+    m, _, chain = S.header_range_inputs(J, B, nb, with_skip=False)
+    o = orc.header_range_inputs(J, B, I.pack_range_headers(chain.trees, m.start_block, J, B), m.start_block, m.end_block)
+    assert o["bad"] == 0
+    _same(o, m)
+
+
+def test_range_inputs_wrong_leaf_size():
+    m, _, chain = S.header_range_inputs(2, 4, None, with_skip=False)
+    rec = I.pack_range_headers(chain.trees, m.start_block, 2, 4)
+    leaves = list(chain.trees[m.start_block + 2].leaves)
+    leaves[6] = leaves[6][:-1]                       # a 33-byte data_hash field
+    rec[2] = I.pack_header_record(leaves)
+    assert orc.header_range_inputs(2, 4, rec, m.start_block, m.end_block)["bad"] == 1
