@@ -7,6 +7,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "sha256_tail_table.cuh"
+
 namespace bsx {
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
@@ -60,19 +62,66 @@ __device__ __forceinline__ void sha256_rounds(uint32_t st[8], uint32_t w[16]) {
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
+// The same compression as a loop: rounds 0..15 unrolled, then three passes of 16 schedule steps + 16 rounds (after 16
+// rounds both the a..h rotation and the rolling schedule index are back where they started, so a pass is a loop body
+// with no register shuffling).  ~10 KB of SASS instead of 22 KB; the round constants of the looped part come from
+// constant memory, indexed by the pass.
+__device__ __constant__ uint32_t BSX_SHA256_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+    0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174,
+    0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da,
+    0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967,
+    0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
+    0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
+    0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+#define BSX_SHA_ROUND(wk)                                                                              \
+    {                                                                                                  \
+        const uint32_t t1 = h + xor3(rotr32(e, 6), rotr32(e, 11), rotr32(e, 25)) + ch32(e, f, g) + (wk); \
+        const uint32_t t2 = xor3(rotr32(a, 2), rotr32(a, 13), rotr32(a, 22)) + maj32(a, b, c);           \
+        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;                             \
+    }
+__device__ __forceinline__ void sha256_rounds_looped(uint32_t st[8], uint32_t w[16]) {
+    constexpr uint32_t K0[16] = {0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+                                 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174};
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 16; i++) BSX_SHA_ROUND(K0[i] + w[i])
+#pragma unroll 1
+    for (int p = 1; p < 4; p++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            const uint32_t s0 = xor3(rotr32(w15, 7), rotr32(w15, 18), w15 >> 3);
+            const uint32_t s1 = xor3(rotr32(w2, 17), rotr32(w2, 19), w2 >> 10);
+            w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
+            BSX_SHA_ROUND(BSX_SHA256_K[16 * p + i] + w[i])
+        }
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
 // The 64 unrolled rounds are ~1500 instructions (24 KB).  Inlined at every hash site a kernel grows
 // to hundreds of KB and stalls on instruction fetch (r01a profile: 52 % of samples `no_instructions`),
 // so the compression is ONE real function per module; state and block travel by value in registers.
 //   BSX_SHA_VARIANT 0: inline everywhere (the r01a build)   1: one generic function
 //                   2: generic + a function specialised for the constant tail block of 65-byte messages
+//                   3: generic + a tail function whose schedule comes from a 256-row table (below)
+//                   4: 3 with both functions looped (16 rounds unrolled + loop): 15 KB of SASS instead of 37 KB --
+//                      with two fully unrolled functions the proofs kernel lost its gain to instruction-cache misses
+//                      (ncu r01m: no_instruction 5.3 stall cycles per issue against 0.09)
 #ifndef BSX_SHA_VARIANT
-#define BSX_SHA_VARIANT 1  // measured on B200 (profiles/r01b): 0 -> 1.68 ms, 1 -> 1.13 ms, 2 -> 1.15 ms per 8192 map jobs
+#define BSX_SHA_VARIANT 4  // measured on B200 (profiles/r01b): 0 -> 1.68 ms, 1 -> 1.13 ms, 2 -> 1.15 ms per 8192 map jobs; 3: r01m
 #endif
 struct sha256_state { uint32_t s[8]; };
 struct sha256_block { uint32_t w[16]; };
 #if BSX_SHA_VARIANT >= 1
 static __device__ __noinline__ sha256_state sha256_compress_fn(sha256_state st, sha256_block blk) {
+#if BSX_SHA_VARIANT >= 4
+    sha256_rounds_looped(st.s, blk.w);
+#else
     sha256_rounds(st.s, blk.w);
+#endif
     return st;
 }
 __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) {
@@ -89,7 +138,46 @@ __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) 
 __device__ __forceinline__ void sha256_compress(uint32_t st[8], uint32_t w[16]) { sha256_rounds(st, w); }
 #endif
 // second block of a 65-byte message (inner nodes, data-root tuples): byte 64, 0x80, zeros, bit length 520
-#if BSX_SHA_VARIANT >= 2
+#if BSX_SHA_VARIANT >= 3
+// Only schedule word 0 of this block depends on the data, so W[16..63] + K[16..63] is one of 256 precomputed rows
+// (sha256_tail_table.cuh, 48 KB, L1-resident): the 48 schedule steps (~480 ALU-pipe instructions of ~1390) become
+// twelve 16-byte loads on the otherwise idle load pipe.  18 of the 39 compressions per header in the map stage are
+// such tail blocks.
+static __device__ __noinline__ sha256_state sha256_tail65_fn(sha256_state st, uint32_t last_byte) {
+    constexpr uint32_t K0[16] = {0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
+                                 0xd807aa98, 0x12835b01, 0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174};
+    uint32_t a = st.s[0], b = st.s[1], c = st.s[2], d = st.s[3], e = st.s[4], f = st.s[5], g = st.s[6], h = st.s[7];
+    BSX_SHA_ROUND(K0[0] + ((last_byte << 24) | 0x00800000u))
+#pragma unroll
+    for (int i = 1; i < 15; i++) BSX_SHA_ROUND(K0[i])
+    BSX_SHA_ROUND(K0[15] + 65u * 8u)
+    const uint4 *row = BSX_SHA_TAIL_WK + 12 * last_byte;
+#if BSX_SHA_VARIANT >= 4
+#pragma unroll 1
+    for (int q = 0; q < 12; q += 2) {          // 8 rounds per pass: the a..h rotation is back in place
+        const uint4 wk = __ldg(row + q), wl = __ldg(row + q + 1);
+        BSX_SHA_ROUND(wk.x) BSX_SHA_ROUND(wk.y) BSX_SHA_ROUND(wk.z) BSX_SHA_ROUND(wk.w)
+        BSX_SHA_ROUND(wl.x) BSX_SHA_ROUND(wl.y) BSX_SHA_ROUND(wl.z) BSX_SHA_ROUND(wl.w)
+    }
+#else
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+        const uint4 wk = __ldg(row + q);
+        BSX_SHA_ROUND(wk.x) BSX_SHA_ROUND(wk.y) BSX_SHA_ROUND(wk.z) BSX_SHA_ROUND(wk.w)
+    }
+#endif
+    st.s[0] += a; st.s[1] += b; st.s[2] += c; st.s[3] += d; st.s[4] += e; st.s[5] += f; st.s[6] += g; st.s[7] += h;
+    return st;
+}
+__device__ __forceinline__ void sha256_tail65(uint32_t st[8], uint32_t last_byte) {
+    sha256_state s;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s.s[i] = st[i];
+    s = sha256_tail65_fn(s, last_byte);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = s.s[i];
+}
+#elif BSX_SHA_VARIANT >= 2
 static __device__ __noinline__ sha256_state sha256_tail65_fn(sha256_state st, uint32_t last_byte) {
     uint32_t w[16];
     w[0] = (last_byte << 24) | 0x00800000u;
