@@ -188,6 +188,28 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(torch, local: int):
+    """Pin this rank to the CPUs next to its GPU before any pinned host buffer is allocated (first touch then places
+    the buffers on the GPU's NUMA node), so that every rank's H2D/D2H copies stay on its own socket.  Returns the cpulist
+    used, or None when the topology is not readable (then nothing changes)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -203,6 +225,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     R = args.ranges                      # ranges this rank reduces / verifies per step
@@ -408,7 +431,7 @@ def run_gpu(args):
                                          "pipe, 73 % busy (profiles/r01b); the HBM fraction is <<1 % by construction"},
             "kernels_alone_ms": {"map stage (proofs + commit kernels)": k_ms, "verify_skip (ed25519_batch_kernel beside verify_kernel<1>)": skip_ms},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ranges_per_step": Re},
+                    "ranges_per_step": Re, "host_cpus": numa},
             "cpu_baseline": cpu,
         }
         print(json.dumps(out))
