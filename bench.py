@@ -526,8 +526,18 @@ def run_ed25519(args):
                       "gpu_launches": args.steps, "clocks": clk.summary(), "cpu_baseline": cpu}))
 
 
+GATE_CONFIGS = {   # name -> (gate id, p0, p1, description)   (standard_recursion_config: 135 wires, 80 routed)
+    "arithmetic": (0, 3, 0, "U32ArithmeticGate num_ops=3"),
+    "add_many": (1, 2, 5, "U32AddManyGate 2 addends, num_ops=5"),
+    "subtraction": (2, 6, 0, "U32SubtractionGate num_ops=6"),
+    "comparison": (3, 32, 16, "ComparisonGate 32 bits in 16 chunks"),
+    "range_check": (4, 7, 0, "U32RangeCheckGate 7 values"),
+}
+
+
 def run_gates(args):
-    """constraints/sec: U32ArithmeticGate (3 ops/row, 114 wires, 108 constraints) over 2^k rows, HBM roofline."""
+    """constraints/sec of Gate::eval_unfiltered_base_batch for one of the five u32 gates over 2^k rows (default:
+    U32ArithmeticGate, 3 ops/row, 114 wires, 108 constraints), against the HBM roofline."""
     import torch
     from blobstreamx_b200 import lib
     from blobstreamx_b200.lib import ptr, u32
@@ -535,31 +545,34 @@ def run_gates(args):
     dev = torch.device("cuda", 0)
     ctx = lib.Context(0)
     stream = torch.cuda.current_stream().cuda_stream
-    rows, gate, p0, p1 = args.rows, 0, 3, 0
+    gate, p0, p1, desc = GATE_CONFIGS[args.gate]
+    rows = args.rows
     nw, ncn = ctx.gate_num_wires(gate, p0, p1), ctx.gate_num_constraints(gate, p0, p1)
     g = torch.Generator(device=dev)
     g.manual_seed(1)
-    wires = torch.zeros(nw * rows, dtype=torch.int64, device=dev)
-    wv = wires.view(nw, rows)
-    for i in range(p0):   # random u32 inputs of valid operations; the generator kernel fills the rest
-        wv[6 * i:6 * i + 3] = torch.randint(0, 2**32, (3, rows), generator=g, device=dev, dtype=torch.int64)
     cons = torch.zeros(ncn * rows, dtype=torch.int64, device=dev)
     P = lambda t: ptr(t.data_ptr())
-    ctx.call_dev("bsx_gl_gate_witness_dev", stream, u32(gate), u32(p0), u32(p1), P(wires), u32(rows))
+    wires = None
 
-    def step(w=None):
-        ctx.call_dev("bsx_gl_gate_eval_dev", stream, u32(gate), u32(p0), u32(p1), P(wires if w is None else w), u32(rows), P(cons))
+    def step():
+        ctx.call_dev("bsx_gl_gate_eval_dev", stream, u32(gate), u32(p0), u32(p1), P(wires), u32(rows), P(cons))
 
-    step()
-    torch.cuda.synchronize()
-    assert int(cons.abs().max().item()) == 0, "valid witness must satisfy every constraint"
+    if gate == 0:
+        # valid witnesses first: random u32 inputs of valid operations, the generator kernel fills the rest -> all zero
+        wires = torch.zeros(nw * rows, dtype=torch.int64, device=dev)
+        wv = wires.view(nw, rows)
+        for i in range(p0):
+            wv[6 * i:6 * i + 3] = torch.randint(0, 2**32, (3, rows), generator=g, device=dev, dtype=torch.int64)
+        ctx.call_dev("bsx_gl_gate_witness_dev", stream, u32(gate), u32(p0), u32(p1), P(wires), u32(rows))
+        step()
+        torch.cuda.synchronize()
+        assert int(cons.abs().max().item()) == 0, "valid witness must satisfy every constraint"
     # timed input: uniform random canonical field elements on every wire -- what the gate sees on the points of the
     # low-degree extension inside the quotient computation (no constraint is zero there)
     rnd = (torch.randint(0, 2**62, (nw * rows,), generator=g, device=dev, dtype=torch.int64) * 4 +
            torch.randint(0, 4, (nw * rows,), generator=g, device=dev, dtype=torch.int64))
     pm = torch.tensor(-(2**32) + 1, dtype=torch.int64, device=dev)   # p as a signed 64-bit pattern = 0xFFFFFFFF00000001
-    rnd = torch.where((rnd < 0) & (rnd >= pm), rnd - pm, rnd)        # values >= p (unsigned) wrapped into [0, p)
-    wires_valid, wires = wires, rnd
+    wires = torch.where((rnd < 0) & (rnd >= pm), rnd - pm, rnd)      # values >= p (unsigned) wrapped into [0, p)
     if not args.no_check:
         from oracle import cbind as orc
         k = 512
@@ -593,13 +606,13 @@ def run_gates(args):
         t0 = time.perf_counter()
         orc.gate_eval(gate, p0, p1, sub, threads=1)
         cpu = {"value": ncn * k / (time.perf_counter() - t0), "unit": "constraints/s", "cores": 1, "kind": "port", "sample": f"{k} rows"}
-    print(json.dumps({"metric": "constraints/sec, U32ArithmeticGate eval_unfiltered_base_batch", "value": ncn * rows / (ms * 1e-3),
+    print(json.dumps({"metric": f"constraints/sec, {desc.split()[0]} eval_unfiltered_base_batch", "value": ncn * rows / (ms * 1e-3),
                       "unit": "constraints/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                       "higher_is_better": True, "dtype": "u64 mod 2^64-2^32+1", "data": "synthetic",
-                      "config": {"workload": f"U32ArithmeticGate num_ops=3, {rows} rows x 114 wires (uniform random field elements) -> 108 constraints/row",
+                      "config": {"workload": f"{desc}, {rows} rows x {nw} wires (uniform random field elements) -> {ncn} constraints/row",
                                  "l2": f"{alg / 1e6:.0f} MB per step > 126 MB L2"},
                       "gpu_launches": args.steps, "clocks": clk.summary(),
-                      "roofline": {"kernel": "gl_gate_eval_kernel<0>", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+                      "roofline": {"kernel": f"gl_gate_eval_kernel<{gate}>", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
                                    "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                                    "algorithmic_bytes_per_launch": alg},
                       "cpu_baseline": cpu}))
@@ -828,6 +841,7 @@ def main():
     ap.add_argument("--hashes", type=int, default=1 << 20)
     ap.add_argument("--hash-len", type=int, default=8)
     ap.add_argument("--rows", type=int, default=1 << 20)
+    ap.add_argument("--gate", default="arithmetic", choices=["arithmetic", "add_many", "subtraction", "comparison", "range_check"])
     ap.add_argument("--sigs", type=int, default=100000)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
