@@ -455,13 +455,14 @@ def run_gpu(args):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-                         "note": "SHA-256 is ~23 int ops/byte: the int32 ALU pipe (93 % busy in the proofs kernel, profiles/r01e), not HBM, "
-                                 "is the physical bound"},
+                         "note": "SHA-256 is ~20 int ops/byte: the int32 ALU pipe (91 % busy in the proofs kernel, "
+                                 "profiles/r01n_subchain_proofs_kernel_R256_ncu_full.csv), not HBM, is the physical bound"},
             "roofline_ed25519": {"kernel": "ed25519_batch_kernel (+ verify_kernel<1> beside it)", "bound": "hbm",
                                  "achieved": 704 * R * N_VAL / (skip_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": 704 * R * N_VAL / (skip_ms * 1e-3) / 1e9 / peak, "traffic": None,
-                                 "note": "704 B/signature against ~3700 field multiplications: bound by the integer-multiply (fmaheavy) "
-                                         "pipe, 73 % busy (profiles/r01b); the HBM fraction is <<1 % by construction"},
+                                 "note": "704 B/signature against ~3700 field operations: bound by the integer-multiply (fmaheavy) pipe and, at "
+                                         "25 600 signatures (one wave, 1.3 warps per sub-partition), by per-thread latency "
+                                         "(profiles/r01k_ed25519_batch_25600_ncu_full.csv); the HBM fraction is <<1 % by construction"},
             "kernels_alone_ms": {"map stage (proofs + commit kernels)": k_ms, "verify_skip (ed25519_batch_kernel beside verify_kernel<1>)": skip_ms},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ranges_per_step": Re, "host_cpus": numa, "host_threads": n_thr, "single_call": e2e_single,
