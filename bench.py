@@ -281,6 +281,15 @@ def run_gpu(args):
     fails = d_sout["fail"].view(torch.int32).abs().sum() + (eng.fail if eng else d_out["fail"]).view(torch.int32).abs().sum()
     if int(fails.item()) != 0:
         raise SystemExit("bench.py: circuit assertions failed on the synthetic workload")
+    # every range of the step, not only the first: the R ranges tile `distinct` different chains, so range r must
+    # reproduce range r - distinct bit for bit (all digests, Ed25519 records, commitments) -- checked on the device
+    D_ = min(args.distinct, len(ms))
+    if R > D_ and world == 1:
+        for name, t in (("map_digests", d_out["map_digests"]), ("data_commitments", d_out["data_commitments"]),
+                        ("reduce_nodes", d_out["reduce_nodes"]), ("skip digests", d_sout["digests"]), ("ed_out", d_sout["ed_out"])):
+            v = t.view(R, -1)
+            if not torch.equal(v[D_:], v[:-D_]):
+                raise SystemExit(f"bench.py: {name} differ between ranges built from the same chain")
     if not args.no_check:
         from oracle import cbind as orc
         w = orc.verify_skip(own[0], threads=8)
@@ -298,6 +307,17 @@ def run_gpu(args):
             g = d_out["map_digests"][: N_JOBS * (20 * BATCH - 1) * 32].cpu().numpy().reshape(N_JOBS, 20 * BATCH - 1, 32)
             assert (g == w["map_digests"]).all(), "GPU map digests differ from the oracle"
             assert d_out["data_commitments"][:32].cpu().numpy().tobytes() == w["data_commitment"]
+            # the other distinct chains too (with the tile check above this covers every range of the step)
+            per_d = N_JOBS * (20 * BATCH - 1) * 32
+            for r in range(1, min(D_, R)):
+                m = ms[r]
+                w = orc.prove_data_commitment(N_JOBS, BATCH, m.dh_leaf, m.dh_aunts, m.lb_leaf, m.lb_aunts, m.start_headers,
+                                              m.end_headers, m.start_block, m.start_header, m.end_block, m.end_header, threads=8)
+                g = d_out["map_digests"][r * per_d:(r + 1) * per_d].cpu().numpy().reshape(N_JOBS, 20 * BATCH - 1, 32)
+                assert (g == w["map_digests"]).all() and d_out["data_commitments"][32 * r:32 * r + 32].cpu().numpy().tobytes() == w["data_commitment"]
+                ws = orc.verify_skip(own[r], threads=8)
+                assert (d_sout["digests"][r * 490 * 32:(r + 1) * 490 * 32].cpu().numpy().reshape(490, 32) == ws["sha256_digests"]).all()
+                assert (d_sout["ed_out"][r * N_VAL * 576:(r + 1) * N_VAL * 576].cpu().numpy().reshape(N_VAL, 576) == ws["ed"]).all()
 
     # ---- device-resident timing ----
     for _ in range(args.warmup):
