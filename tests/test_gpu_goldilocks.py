@@ -36,6 +36,31 @@ def test_gate_eval_random_wires(ctx, orc, gate, p0, p1, rows):
 
 
 @pytest.mark.parametrize("gate,p0,p1", GATES)
+def test_gate_eval_edge_values(ctx, orc, gate, p0, p1):
+    """Wires drawn from the corners of the field and of the 64-bit range (0, 1, 2, 3, 4, p-1, p, p+1, 2^32-1, 2^32,
+    2^32+1, 2^63, 2^64-2^32, 2^64-1, ...) mixed with random values: every carry / borrow branch of the weak reductions."""
+    rng = np.random.default_rng(900 + gate * 10 + p0)
+    nw = orc.gate_num_wires(gate, p0, p1)
+    corners = np.array([0, 1, 2, 3, 4, 5, P - 1, P - 2, P - 3, P, P + 1, P + 2, 2**32 - 1, 2**32, 2**32 + 1, 2**33 - 1, 2**63, 2**63 - 1,
+                        2**64 - 2**32, 2**64 - 2**32 - 1, 2**64 - 2**32 + 2, 2**64 - 1, 2**64 - 2, 2**64 - 4, 0xFFFFFFFE00000001,
+                        0xFFFFFFFF, 0xFFFFFFFF00000000, 0x00000001FFFFFFFF, 0x8000000080000000], dtype=np.uint64)
+    rows = 4096
+    w = corners[rng.integers(0, len(corners), (nw, rows))]
+    mix = rng.random((nw, rows)) < 0.25
+    w[mix] = rng.integers(0, 2**64, int(mix.sum()), dtype=np.uint64)
+    assert (ctx.gl_gate_eval(gate, p0, p1, w) == orc.gate_eval(gate, p0, p1, w, threads=8)).all()
+
+
+def test_poseidon_edge_values(ctx, orc):
+    rng = np.random.default_rng(77)
+    corners = np.array([0, 1, P - 1, P, P + 1, 2**32 - 1, 2**32, 2**64 - 2**32, 2**64 - 1, 2**63, 0xFFFFFFFF00000000], dtype=np.uint64)
+    n, L_ = 3000, 12
+    x = corners[rng.integers(0, len(corners), n * L_)]
+    offs = (np.arange(n + 1) * L_).astype(np.uint32)
+    assert (ctx.gl_poseidon_batch(x, offs) == orc.poseidon_batch(x, offs, threads=8)).all()
+
+
+@pytest.mark.parametrize("gate,p0,p1", GATES)
 def test_gate_witness_and_zero_constraints(ctx, orc, gate, p0, p1):
     """test_gate_constraint analogue on the GPU: generator kernel output == oracle generator, and it satisfies
     every constraint; a corrupted wire breaks at least one (test_canonicity)."""
