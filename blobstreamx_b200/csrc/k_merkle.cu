@@ -106,6 +106,70 @@ __global__ void data_commitment_kernel(const uint8_t *__restrict__ data_hashes, 
     }
 }
 
+// Attestation proofs: the Merkle inclusion proof of one data-root tuple in a data commitment, in the
+// form BlobstreamX.verifyAttestation consumes (BX/contracts/src/BlobstreamX.sol, BinaryMerkleProof: sideNodes leaf side
+// first, key = height - start, numLeaves = end - start) -- the aunts of compute_hash_from_aunts
+// (TX/input/tendermint_utils.rs:225-273).  A pure gather over the digests data_commitment_kernel already wrote:
+//   sel_s[j], the value the fixed-shape tree moves up for node j of level s, is the raw inner hash of the first
+//   node on j's leftmost path whose two children are both enabled, or the leaf digest if there is none;
+//   level s contributes the aunt sel_s[(i >> s) ^ 1] unless that sibling subtree is entirely beyond the last leaf
+//   (then the variable-shape Tendermint tree has no node at that level: the value passes up unchanged).
+// One thread per (query, level).
+__global__ void __launch_bounds__(128) attestation_proofs_kernel(const uint8_t *__restrict__ digests, uint32_t N, uint32_t P, uint32_t logP,
+                                                                 const uint64_t *__restrict__ start_blocks,
+                                                                 const uint64_t *__restrict__ end_blocks, uint32_t n_q,
+                                                                 const uint32_t *__restrict__ q_tree, const uint64_t *__restrict__ q_height,
+                                                                 uint8_t *__restrict__ side_nodes, uint32_t *__restrict__ depth,
+                                                                 uint32_t *__restrict__ key, uint32_t *__restrict__ num_leaves) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = t / (logP ? logP : 1), s = t % (logP ? logP : 1);
+    if (q >= n_q) return;
+    const uint32_t tr = q_tree[q];
+    const uint64_t start = start_blocks[tr], end = end_blocks[tr], h = q_height[q];
+    const uint64_t span = end > start ? end - start : 0;
+    const uint32_t n = span < (uint64_t)N ? (uint32_t)span : N;
+    const bool valid = h >= start && h - start < (uint64_t)n;
+    const uint32_t i = valid ? (uint32_t)(h - start) : 0;
+    if (s == 0) {
+        key[q] = valid ? i : 0xFFFFFFFFu;
+        num_leaves[q] = n;
+    }
+    uint8_t *out = side_nodes + (size_t)q * logP * 32;
+    // position of level s among the levels that contribute an aunt, and the total
+    uint32_t pos = 0, total = 0;
+    bool mine = false;
+    for (uint32_t l = 0; l < logP; l++) {
+        const uint32_t sib = (i >> l) ^ 1u;
+        const bool has = valid && (((uint64_t)sib << l) < (uint64_t)n);
+        if (l == s) { mine = has; pos = total; }
+        total += has ? 1u : 0u;
+    }
+    if (s == 0) depth[q] = total;
+    if (logP == 0) return;
+    uint4 *o = reinterpret_cast<uint4 *>(out + 32 * (size_t)(mine ? pos : 0));
+    if (!mine) {
+        // zero the unused tail slots: slot (total + k) for the k-th level without an aunt
+        uint32_t k = 0;
+        for (uint32_t l = 0; l < s; l++) {
+            const uint32_t sib = (i >> l) ^ 1u;
+            k += (valid && (((uint64_t)sib << l) < (uint64_t)n)) ? 0u : 1u;
+        }
+        o = reinterpret_cast<uint4 *>(out + 32 * (size_t)(total + k));
+        o[0] = make_uint4(0, 0, 0, 0);
+        o[1] = make_uint4(0, 0, 0, 0);
+        return;
+    }
+    // descend from node j of level s along left children until a node with both children enabled (or a leaf)
+    const uint8_t *base = digests + 32 * (size_t)(N + P - 1) * tr;
+    uint32_t j = (i >> s) ^ 1u, lvl = s;
+    while (lvl > 0 && !((((uint64_t)(2 * j + 1)) << (lvl - 1)) < (uint64_t)n)) { j <<= 1; lvl--; }
+    // layer-major offsets: inner hashes of level 1 (P/2 nodes) start at N, level l at N + P - (P >> (l - 1))
+    const size_t idx = lvl == 0 ? (size_t)j : (size_t)N + (size_t)P - (size_t)(P >> (lvl - 1)) + j;
+    const uint4 *src = reinterpret_cast<const uint4 *>(base + 32 * idx);
+    o[0] = src[0];
+    o[1] = src[1];
+}
+
 static inline uint32_t pow2_ceil(uint32_t n) {
     uint32_t p = 1;
     while (p < n) p <<= 1;
@@ -238,5 +302,69 @@ extern "C" int bsx_data_commitment_batch(bsx_ctx *ctx, const uint8_t *data_hashe
     BSX_CUDA(ctx, cudaMemcpyAsync(roots, d_root, s_root, cudaMemcpyDeviceToHost, ctx->stream));
     if (fail) BSX_CUDA(ctx, cudaMemcpyAsync(fail, d_fail, 4 * (size_t)t, cudaMemcpyDeviceToHost, ctx->stream));
     BSX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BSX_OK;
+}
+
+// ---- attestation proofs ----
+extern "C" int bsx_attestation_proofs_dev(bsx_ctx *ctx, void *stream, const uint8_t *digests, uint32_t N,
+                                          const uint64_t *start_blocks, const uint64_t *end_blocks, uint32_t n_q,
+                                          const uint32_t *q_tree, const uint64_t *q_height, uint8_t *side_nodes, uint32_t *depth,
+                                          uint32_t *key, uint32_t *num_leaves) {
+    BSX_REQUIRE(ctx, ctx && digests && start_blocks && end_blocks && q_tree && q_height && side_nodes && depth && key && num_leaves);
+    BSX_REQUIRE(ctx, N >= 1 && N <= 4096);
+    BSX_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(digests) | reinterpret_cast<uintptr_t>(side_nodes)) & 15) == 0);
+    if (n_q == 0) return BSX_OK;
+    const uint32_t P = pow2_ceil(N);
+    uint32_t logP = 0;
+    while ((1u << logP) < P) logP++;
+    const size_t threads = (size_t)n_q * (logP ? logP : 1);
+    attestation_proofs_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        digests, N, P, logP, start_blocks, end_blocks, n_q, q_tree, q_height, side_nodes, depth, key, num_leaves);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+extern "C" uint32_t bsx_attestation_max_depth(uint32_t N) {
+    uint32_t logP = 0;
+    while ((1u << logP) < N) logP++;
+    return logP;
+}
+
+extern "C" int bsx_attestation_proofs(bsx_ctx *ctx, const uint8_t *data_hashes, uint32_t N, uint32_t t, const uint64_t *start_blocks,
+                                      const uint64_t *end_blocks, uint32_t n_q, const uint32_t *q_tree, const uint64_t *q_height,
+                                      uint8_t *side_nodes, uint32_t *depth, uint32_t *key, uint32_t *num_leaves, uint8_t *roots) {
+    BSX_REQUIRE(ctx, ctx && data_hashes && start_blocks && end_blocks && q_tree && q_height && side_nodes && depth && key && num_leaves);
+    BSX_REQUIRE(ctx, N >= 1 && N <= 4096 && t >= 1);
+    for (uint32_t q = 0; q < n_q; q++) BSX_REQUIRE(ctx, q_tree[q] < t);
+    if (n_q == 0) return BSX_OK;
+    BSX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t P = pow2_ceil(N), logP = bsx_attestation_max_depth(N);
+    const size_t T = t, Q = n_q, s_in = T * N * 32, s_dig = T * (N + P - 1) * 32, s_side = Q * (logP ? logP : 1) * 32;
+    int rc = ws_begin(ctx, ws_size(s_in) + 2 * ws_size(8 * T) + ws_size(s_dig) + ws_size(32 * T) + ws_size(4 * T) + ws_size(4 * Q) + ws_size(8 * Q) +
+                               ws_size(s_side) + 3 * ws_size(4 * Q));
+    if (rc) return rc;
+    uint8_t *d_in = ws_take<uint8_t>(ctx, s_in);
+    uint64_t *d_s = ws_take<uint64_t>(ctx, T), *d_e = ws_take<uint64_t>(ctx, T);
+    uint8_t *d_dig = ws_take<uint8_t>(ctx, s_dig), *d_root = ws_take<uint8_t>(ctx, 32 * T);
+    uint32_t *d_fail = ws_take<uint32_t>(ctx, T), *d_qt = ws_take<uint32_t>(ctx, Q);
+    uint64_t *d_qh = ws_take<uint64_t>(ctx, Q);
+    uint8_t *d_side = ws_take<uint8_t>(ctx, s_side);
+    uint32_t *d_depth = ws_take<uint32_t>(ctx, Q), *d_key = ws_take<uint32_t>(ctx, Q), *d_nl = ws_take<uint32_t>(ctx, Q);
+    cudaStream_t st = ctx->stream;
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_in, data_hashes, s_in, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_s, start_blocks, 8 * T, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_e, end_blocks, 8 * T, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_qt, q_tree, 4 * Q, cudaMemcpyHostToDevice, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(d_qh, q_height, 8 * Q, cudaMemcpyHostToDevice, st));
+    rc = bsx_data_commitment_batch_dev(ctx, st, d_in, N, t, d_s, d_e, d_dig, d_root, d_fail);
+    if (rc) return rc;
+    rc = bsx_attestation_proofs_dev(ctx, st, d_dig, N, d_s, d_e, n_q, d_qt, d_qh, d_side, d_depth, d_key, d_nl);
+    if (rc) return rc;
+    BSX_CUDA(ctx, cudaMemcpyAsync(side_nodes, d_side, s_side, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(depth, d_depth, 4 * Q, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(key, d_key, 4 * Q, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaMemcpyAsync(num_leaves, d_nl, 4 * Q, cudaMemcpyDeviceToHost, st));
+    if (roots) BSX_CUDA(ctx, cudaMemcpyAsync(roots, d_root, 32 * T, cudaMemcpyDeviceToHost, st));
+    BSX_CUDA(ctx, cudaStreamSynchronize(st));
     return BSX_OK;
 }

@@ -154,6 +154,20 @@ class Context:
                    _ptr(end_blocks), _ptr(dig), _ptr(roots), _ptr(fail))
         return dig, roots, fail
 
+    def attestation_proofs(self, data_hashes, N: int, start_blocks, end_blocks, q_tree, q_height):
+        """Inclusion proofs of data-root tuples (BlobstreamX.verifyAttestation): per query (tree, height) ->
+        dict(side_nodes [nq, max_depth, 32], depth, key, num_leaves, roots [t, 32])."""
+        start_blocks, end_blocks = _in(start_blocks, np.uint64), _in(end_blocks, np.uint64)
+        q_tree, q_height = _in(q_tree, np.uint32), _in(q_height, np.uint64)
+        t, nq = len(start_blocks), len(q_tree)
+        md = int(self._lib.bsx_attestation_max_depth(C.c_uint32(N)))
+        out = dict(side_nodes=np.zeros((nq, max(md, 1), 32), np.uint8), depth=np.zeros(nq, np.uint32), key=np.zeros(nq, np.uint32),
+                   num_leaves=np.zeros(nq, np.uint32), roots=np.zeros((t, 32), np.uint8))
+        self._call("bsx_attestation_proofs", _ptr(_in(data_hashes)), C.c_uint32(N), C.c_uint32(t), _ptr(start_blocks), _ptr(end_blocks),
+                   C.c_uint32(nq), _ptr(q_tree), _ptr(q_height), _ptr(out["side_nodes"]), _ptr(out["depth"]), _ptr(out["key"]),
+                   _ptr(out["num_leaves"]), _ptr(out["roots"]))
+        return out
+
     # -- map circuit --
     def prove_subchain_batch(self, B: int, dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, batch_start,
                              batch_end, global_end, global_end_header):

@@ -106,6 +106,24 @@ int bsx_data_commitment_batch_dev(bsx_ctx *ctx, void *stream, const uint8_t *dat
                                   uint8_t *roots, uint32_t *fail);
 
 /* ------------------------------------------------------------------------------------------
+ * Attestation proofs: Merkle inclusion proofs of data-root tuples in a data commitment, as
+ * BlobstreamX.verifyAttestation consumes them (BX/contracts/src/BlobstreamX.sol: BinaryMerkleProof{sideNodes, key,
+ * numLeaves} over DataRootTuple{height, dataRoot}); sideNodes = the aunts of compute_hash_from_aunts
+ * (TX/input/tendermint_utils.rs:225-273), leaf side first.
+ * Query q asks for block q_height[q] of tree q_tree[q].  side_nodes: n_q * bsx_attestation_max_depth(N) * 32, the
+ * first depth[q] entries are the proof, the rest zero; key[q] = height - start (0xFFFFFFFF if the height is outside
+ * [start, end)); num_leaves[q] = end - start.  The _dev form gathers from the `digests` array of
+ * bsx_data_commitment_batch_dev; the host form computes the commitments first (roots optional).
+ * ------------------------------------------------------------------------------------------ */
+uint32_t bsx_attestation_max_depth(uint32_t N);
+int bsx_attestation_proofs(bsx_ctx *ctx, const uint8_t *data_hashes, uint32_t N, uint32_t t, const uint64_t *start_blocks,
+                           const uint64_t *end_blocks, uint32_t n_q, const uint32_t *q_tree, const uint64_t *q_height,
+                           uint8_t *side_nodes, uint32_t *depth, uint32_t *key, uint32_t *num_leaves, uint8_t *roots);
+int bsx_attestation_proofs_dev(bsx_ctx *ctx, void *stream, const uint8_t *digests, uint32_t N, const uint64_t *start_blocks,
+                               const uint64_t *end_blocks, uint32_t n_q, const uint32_t *q_tree, const uint64_t *q_height,
+                               uint8_t *side_nodes, uint32_t *depth, uint32_t *key, uint32_t *num_leaves);
+
+/* ------------------------------------------------------------------------------------------
  * prove_subchain<B>  -- the map circuit of header_range (BX/circuits/builder.rs:150-271)
  * n_jobs independent map jobs of B headers each (B in {1,2,4,...,256}).
  *   dh_leaf  n_jobs*B*34   protobuf data_hash leaves        dh_aunts n_jobs*B*4*32
