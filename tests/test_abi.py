@@ -48,3 +48,18 @@ def test_product_does_not_import_oracle():
                 assert "oracle" not in txt.replace("the oracle", "").lower() or "import oracle" not in txt, f
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "bsx_oracle" not in txt, f
+
+
+def test_rust_ffi_crate_matches_header():
+    """bindings/rust/bsx-sys/src/lib.rs is generated from include/bsx.h: the committed file is up to date and declares
+    every entry point the header does."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(ROOT, "scripts", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text, n = gen.main()
+    assert open(gen.PATH).read() == text, "run scripts/gen_rust_ffi.py"
+    syms = _declared_symbols()
+    assert n == len(syms)
+    for s_ in syms:
+        assert f"pub fn {s_}(" in text, s_
