@@ -96,7 +96,7 @@ BSX_HD fe fe_tighten(const fe &f) {
 //   h[2n+1] = SS_n - LL_n - HH_n;  h[2n] = LL_n + 2 HH_{n-1};  h[0] = LL_0 + 38 HH_4
 // Bounds: g at most 2 units (|g_even| <= 2.02*2^25, |g_odd| <= 2.02*2^24: one add/sub of carried values, or a
 // fe_tighten output) so that 19 (c_m + d_m) < 2^31; f at most 3 units.  Sums stay below 2^61.
-BSX_CALL fe fe_mul(const fe f, const fe g) {
+BSX_HD fe fe_mul_inl(const fe &f, const fe &g) {
     int32_t fs[5], gs[5], c19[5], d19[5], gs19[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) {
@@ -130,7 +130,7 @@ BSX_CALL fe fe_mul(const fe f, const fe g) {
 }
 
 #else
-BSX_CALL fe fe_mul(const fe f, const fe g) {
+BSX_HD fe fe_mul_inl(const fe &f, const fe &g) {
     int32_t g19[10], f2[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) { g19[i] = 19 * g.v[i]; f2[i] = 2 * f.v[i]; }
@@ -150,6 +150,11 @@ BSX_CALL fe fe_mul(const fe f, const fe g) {
 }
 
 #endif
+BSX_CALL fe fe_mul(const fe f, const fe g) { return fe_mul_inl(f, g); }
+// INL selects the inlined body (hot loops of the scalar multiplications: the independent multiplications of one point
+// operation are then scheduled together, and no registers are shuffled into a call) or the shared function (everything
+// else: keeps the kernel small)
+template <bool INL> BSX_HD fe fe_mul_x(const fe &f, const fe &g) { if (INL) return fe_mul_inl(f, g); return fe_mul(f, g); }
 
 // h = f*f (times 2 when `twice`), using the symmetry of the product: 55 IMAD.WIDE.  (The pair-Karatsuba form of the
 // squaring is 45 IMAD.WIDE but measured slower on B200 at every occupancy -- 376 vs 341 cycles per squaring per SM
@@ -182,6 +187,8 @@ BSX_HD fe fe_sq_impl(const fe &f) {
 }
 BSX_CALL fe fe_sq(const fe f) { return fe_sq_impl<false>(f); }
 BSX_CALL fe fe_sq2(const fe f) { return fe_sq_impl<true>(f); }
+template <bool INL> BSX_HD fe fe_sq_x(const fe &f) { if (INL) return fe_sq_impl<false>(f); return fe_sq(f); }
+template <bool INL> BSX_HD fe fe_sq2_x(const fe &f) { if (INL) return fe_sq_impl<true>(f); return fe_sq2(f); }
 // n >= 1 successive squarings (one call for the long chains of inversion / square roots)
 BSX_CALL fe fe_sqn(fe f, int n) {
 #pragma unroll 1
@@ -325,34 +332,38 @@ BSX_HD ge_cached ge_to_cached(const ge_p3 &p) {
 // completed -> extended (4M); with_t=false skips T (3M) when the next operation is a doubling
 // Operand order follows fe_mul's bounds: X and T of a completed point are 3-unit values (a - (yy + xx),
 // 2zz - (yy - xx), 2zz +- c), Y is 2 units, Z is 2 (doubling) or 3 (addition); the g-side is Y or the tightened T.
+template <bool INL = false>
 BSX_HD ge_p3 ge_p1p1_to_p3(const ge_p1p1 &p, bool with_t) {
     const fe tt = fe_tighten(p.T);
-    ge_p3 r; r.X = fe_mul(p.X, tt); r.Y = fe_mul(p.Z, p.Y); r.Z = fe_mul(p.Z, tt);
-    r.T = with_t ? fe_mul(p.X, p.Y) : fe_zero();
+    ge_p3 r; r.X = fe_mul_x<INL>(p.X, tt); r.Y = fe_mul_x<INL>(p.Z, p.Y); r.Z = fe_mul_x<INL>(p.Z, tt);
+    r.T = with_t ? fe_mul_x<INL>(p.X, p.Y) : fe_zero();
     return r;
 }
 // doubling (uses X, Y, Z only): 3S + 1 S2
+template <bool INL = false>
 BSX_HD ge_p1p1 ge_dbl(const ge_p3 &p) {
     ge_p1p1 r;
-    fe xx = fe_sq(p.X), yy = fe_sq(p.Y), zz2 = fe_sq2(p.Z);
-    fe a = fe_sq(fe_add(p.X, p.Y));
+    fe xx = fe_sq_x<INL>(p.X), yy = fe_sq_x<INL>(p.Y), zz2 = fe_sq2_x<INL>(p.Z);
+    fe a = fe_sq_x<INL>(fe_add(p.X, p.Y));
     r.Y = fe_add(yy, xx); r.Z = fe_sub(yy, xx); r.X = fe_sub(a, r.Y); r.T = fe_sub(zz2, r.Z);
     return r;
 }
 // p + q, q cached: 4M
+template <bool INL = false>
 BSX_HD ge_p1p1 ge_add_cached(const ge_p3 &p, const ge_cached &q) {
     ge_p1p1 r;
-    fe a = fe_mul(fe_add(p.Y, p.X), q.YpX), b = fe_mul(fe_sub(p.Y, p.X), q.YmX);
-    fe c = fe_mul(q.T2d, p.T), zz = fe_mul(p.Z, q.Z);
+    fe a = fe_mul_x<INL>(fe_add(p.Y, p.X), q.YpX), b = fe_mul_x<INL>(fe_sub(p.Y, p.X), q.YmX);
+    fe c = fe_mul_x<INL>(q.T2d, p.T), zz = fe_mul_x<INL>(p.Z, q.Z);
     fe d = fe_add(zz, zz);
     r.X = fe_sub(a, b); r.Y = fe_add(a, b); r.Z = fe_add(d, c); r.T = fe_sub(d, c);
     return r;
 }
 // p + q, q affine precomputed: 3M
+template <bool INL = false>
 BSX_HD ge_p1p1 ge_add_niels(const ge_p3 &p, const ge_niels &q) {
     ge_p1p1 r;
-    fe a = fe_mul(fe_add(p.Y, p.X), q.ypx), b = fe_mul(fe_sub(p.Y, p.X), q.ymx);
-    fe c = fe_mul(q.xy2d, p.T);
+    fe a = fe_mul_x<INL>(fe_add(p.Y, p.X), q.ypx), b = fe_mul_x<INL>(fe_sub(p.Y, p.X), q.ymx);
+    fe c = fe_mul_x<INL>(q.xy2d, p.T);
     fe d = fe_add(p.Z, p.Z);
     r.X = fe_sub(a, b); r.Y = fe_add(a, b); r.Z = fe_add(d, c); r.T = fe_sub(d, c);
     return r;
@@ -423,6 +434,7 @@ BSX_HD void ge_niels_store(ge_niels_slot *slot, const ge_niels &q) {
     for (int i = 0; i < 10; i++) { slot->v[i] = q.ypx.v[i]; slot->v[10 + i] = q.ymx.v[i]; slot->v[20 + i] = q.xy2d.v[i]; }
     slot->v[30] = 0; slot->v[31] = 0;
 }
+template <bool INL = false>
 BSX_HD ge_p3 ge_scalarmult_base(const uint8_t s[32], const ge_niels_slot *table) {
     ge_p3 acc = ge_identity();
 #pragma unroll 1
@@ -430,13 +442,14 @@ BSX_HD ge_p3 ge_scalarmult_base(const uint8_t s[32], const ge_niels_slot *table)
         const uint32_t dgt = s[w];
         if (dgt) {
             const ge_niels q = ge_niels_load(table + w * BSX_ED_BASE_ENTRIES + (dgt - 1));
-            acc = ge_p1p1_to_p3(ge_add_niels(acc, q), true);
+            acc = ge_p1p1_to_p3<INL>(ge_add_niels<INL>(acc, q), true);
         }
     }
     return acc;
 }
 
 // scalar * P for an arbitrary 256-bit scalar (EcOpResultHint::ScalarMul takes the U256 unreduced)
+template <bool INL = false>
 BSX_HD ge_p3 ge_scalarmult(const uint8_t s[32], const ge_p3 &P) {
     ge_cached tab[15];                       // tab[d-1] = d*P
     {
@@ -453,12 +466,12 @@ BSX_HD ge_p3 ge_scalarmult(const uint8_t s[32], const ge_p3 &P) {
     for (int w = 63; w >= 0; w--) {
         if (w != 63) {
 #pragma unroll 1
-            for (int k = 0; k < 4; k++) acc = ge_p1p1_to_p3(ge_dbl(acc), k == 3);
+            for (int k = 0; k < 4; k++) acc = ge_p1p1_to_p3<INL>(ge_dbl<INL>(acc), k == 3);
         }
         const uint32_t dgt = (s[w >> 1] >> ((w & 1) * 4)) & 15;
         // T is consumed only by additions: the 4th doubling of a window produces it, an addition
         // drops it again (the next step is a doubling) except in the last window.
-        if (dgt) acc = ge_p1p1_to_p3(ge_add_cached(acc, tab[dgt - 1]), w == 0);
+        if (dgt) acc = ge_p1p1_to_p3<INL>(ge_add_cached<INL>(acc, tab[dgt - 1]), w == 0);
     }
     return acc;
 }
@@ -567,6 +580,10 @@ BSX_HD bool sc_lt_l(const uint8_t s[32]) {
 //   [296..360) hA  [360..424) Rp  [424..456) R_root  [456..520) Rp+hA  [520..524) flags
 // flags: 1 s<l, 2 A decompressed, 4 R decompressed, 8 sG == Rp+hA
 // ---------------------------------------------------------------------------------------------
+// INL: inline the field arithmetic of the scalar-multiplication loops (+10 % when the kernel has the SMs to itself:
+// independent multiplications of a point operation are scheduled together and nothing is shuffled into calls; next to
+// the SHA-256 kernels of bsx_header_range the larger loop bodies cost more than they save -- measured r01o).
+template <bool INL = false>
 BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], const uint8_t digest[64],
                                  const ge_niels_slot *base_table, uint8_t *out) {
     for (int i = 0; i < 64; i++) out[i] = digest[i];
@@ -577,8 +594,8 @@ BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], co
     if (ge_decompress(pk, ax, ay, out + 200, out + 232, out + 264)) flags |= 2u;
     if (ge_decompress(sig, rx, ry, out + 360, out + 392, out + 424)) flags |= 4u;
     // sG, hA, Rp + hA in projective form
-    ge_p3 sg = ge_scalarmult_base(sig + 32, base_table);
-    ge_p3 ha = ge_scalarmult(out + 64, ge_from_affine(ax, ay));
+    ge_p3 sg = ge_scalarmult_base<INL>(sig + 32, base_table);
+    ge_p3 ha = ge_scalarmult<INL>(out + 64, ge_from_affine(ax, ay));
     ge_p3 sum = ge_p1p1_to_p3(ge_add_cached(ha, ge_to_cached(ge_from_affine(rx, ry))), false);
     // one inversion for the three Z's
     fe z12 = fe_mul(sg.Z, ha.Z);

@@ -47,7 +47,7 @@ struct EdIn {
     uint32_t pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride;
 };
 
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool INL>
 __global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
                                                            uint8_t *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n,
     for (int k = 0; k < 8; k++)
 #pragma unroll
         for (int j = 0; j < 8; j++) digest[8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
-    ed25519_witness_core(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
+    ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
 }
 
 
@@ -319,22 +319,27 @@ static int launch_quad(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     return BSX_OK;
 }
 
-// one thread per signature.  Register budget: 4 CTAs/SM -> 214 registers, 6 -> 168, 8 -> 128 (with spills)
-static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in, const ed::ge_niels_slot *tab, uint8_t *out) {
+// one thread per signature.  Register budget: 4 CTAs/SM -> 214 registers, 6 -> 168, 8 -> 128 (with spills).
+// `alone`: the batch is not issued next to SHA-256 kernels (bsx_ed25519_batch*), so the build with inlined point
+// arithmetic is used; the verify_* / header_range paths share the SMs with the hash kernels and use the compact build.
+static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in, const ed::ge_niels_slot *tab, uint8_t *out, bool alone) {
     static const int occ = [] { const char *e = getenv("BSX_ED_OCC"); return e ? atoi(e) : 4; }();
-    BSX_PIN_CARVEOUT(ed25519_batch_kernel<8>); BSX_PIN_CARVEOUT(ed25519_batch_kernel<6>); BSX_PIN_CARVEOUT(ed25519_batch_kernel<4>);
-    if (occ >= 8) ed25519_batch_kernel<8><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
-    else if (occ >= 6) ed25519_batch_kernel<6><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
-    else ed25519_batch_kernel<4><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+    static const int inl = [] { const char *e = getenv("BSX_ED_INLINE"); return e ? atoi(e) : -1; }();   // -1: by call site
+    BSX_PIN_CARVEOUT((ed25519_batch_kernel<8, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<6, false>));
+    BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, true>));
+    const bool use_inl = inl < 0 ? alone : inl != 0;
+    if (occ >= 8) ed25519_batch_kernel<8, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+    else if (occ >= 6) ed25519_batch_kernel<6, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+    else if (use_inl) ed25519_batch_kernel<4, true><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+    else ed25519_batch_kernel<4, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }
 
-// strided form: used by the verify_* entry points to run straight over validator records
-extern "C" int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, uint32_t pk_stride,
-                                       const uint8_t *sigs, uint32_t sig_stride, const uint8_t *msgs, uint32_t msg_stride,
-                                       uint32_t msg_max, const uint8_t *msg_lens, uint32_t len_stride, const uint8_t *active,
-                                       uint32_t active_stride, uint8_t *out) {
+static int ed25519_strided(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, uint32_t pk_stride,
+                           const uint8_t *sigs, uint32_t sig_stride, const uint8_t *msgs, uint32_t msg_stride,
+                           uint32_t msg_max, const uint8_t *msg_lens, uint32_t len_stride, const uint8_t *active,
+                           uint32_t active_stride, uint8_t *out, bool alone) {
     BSX_REQUIRE(ctx, ctx && pks && sigs && (msgs || msg_max == 0) && out);
     if (n == 0) return BSX_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -348,14 +353,23 @@ extern "C" int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, c
     // (A split of one large batch over both paths at once was measured: 25 600 signatures alone 1.84 -> 1.72 ms at a
     // 35 % quad share, but the header_range step next to the map kernels gets slower beyond 20 % -- not kept.)
     const bool quad = forced ? forced == 1 : n <= quad_max;
-    return quad ? launch_quad(ctx, st, n, in, tab, out) : launch_mono(ctx, st, n, in, tab, out);
+    return quad ? launch_quad(ctx, st, n, in, tab, out) : launch_mono(ctx, st, n, in, tab, out, alone);
+}
+
+// strided form: used by the verify_* entry points to run straight over validator records, next to their SHA-256 kernels
+extern "C" int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, uint32_t pk_stride,
+                                       const uint8_t *sigs, uint32_t sig_stride, const uint8_t *msgs, uint32_t msg_stride,
+                                       uint32_t msg_max, const uint8_t *msg_lens, uint32_t len_stride, const uint8_t *active,
+                                       uint32_t active_stride, uint8_t *out) {
+    return ed25519_strided(ctx, stream, n, pks, pk_stride, sigs, sig_stride, msgs, msg_stride, msg_max, msg_lens, len_stride, active,
+                           active_stride, out, false);
 }
 
 extern "C" int bsx_ed25519_batch_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, const uint8_t *sigs,
                                      const uint8_t *msgs, uint32_t msg_stride, const uint32_t *msg_lens,
                                      const uint8_t *active, uint8_t *out) {
-    return bsx_ed25519_strided_dev(ctx, stream, n, pks, 32, sigs, 64, msgs, msg_stride, msg_stride,
-                                   reinterpret_cast<const uint8_t *>(msg_lens), 4, active, 1, out);
+    return ed25519_strided(ctx, stream, n, pks, 32, sigs, 64, msgs, msg_stride, msg_stride,
+                           reinterpret_cast<const uint8_t *>(msg_lens), 4, active, 1, out, true);
 }
 
 extern "C" int bsx_ed25519_batch(bsx_ctx *ctx, uint32_t n, const uint8_t *pks, const uint8_t *sigs, const uint8_t *msgs,
