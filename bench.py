@@ -791,6 +791,66 @@ def run_shape(args):
                       "cpu_baseline": cpu}))
 
 
+def run_pack(args):
+    """Witness bit expansion (ByteVariable = 8 field elements per byte, PX/frontend/vars/byte.rs:49-57): --pack-bytes payload
+    bytes -> 64x as many bytes of u64 elements, and back.  A pure HBM stream: reported against the copy-bandwidth peak."""
+    import torch
+    from blobstreamx_b200 import lib
+    from blobstreamx_b200.lib import ptr
+    import ctypes as C
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = lib.Context(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    n = args.pack_bytes
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    b = torch.randint(0, 256, (n,), generator=g, device=dev, dtype=torch.uint8)
+    el = torch.zeros(8 * n, dtype=torch.int64, device=dev)
+    back = torch.zeros(n, dtype=torch.uint8, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    P = lambda t: ptr(t.data_ptr())
+    pack = lambda: ctx.call_dev("bsx_witness_pack_bytes_dev", stream, P(b), C.c_size_t(n), P(el))
+    unpack = lambda: ctx.call_dev("bsx_witness_unpack_bytes_dev", stream, P(el), C.c_size_t(n), P(back), P(bad))
+    pack(); unpack()
+    torch.cuda.synchronize()
+    assert torch.equal(back, b) and int(bad.item()) == 0
+    k = min(n, 4096)
+    bits = ((b[:k].to(torch.int64).unsqueeze(1) >> torch.arange(7, -1, -1, device=dev)) & 1).reshape(-1)   # MSB first
+    assert torch.equal(el[: 8 * k], bits), "bit elements differ from ByteVariable's big-endian order"
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    res = {}
+    with ClockSampler(0) as clk:
+        for name, fn in (("pack", pack), ("unpack", unpack)):
+            for _ in range(args.warmup):
+                fn()
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            for _ in range(args.steps):
+                fn()
+            ev[1].record()
+            torch.cuda.synchronize()
+            res[name] = ev[0].elapsed_time(ev[1]) / args.steps
+    alg = 65 * n
+    print(json.dumps({"metric": "payload bytes/sec, witness bit expansion (bytes -> 8 big-endian bit elements)", "value": n / (res["pack"] * 1e-3),
+                      "unit": "bytes/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["pack"], "higher_is_better": True,
+                      "dtype": "u8 -> u64", "data": "synthetic",
+                      "config": {"workload": f"{n} payload bytes -> {8 * n} u64 elements ({64 * n / 1e9:.2f} GB)", "unpack_ms": res["unpack"],
+                                 "unpack_GBps": alg / (res["unpack"] * 1e-3) / 1e9, "l2": f"{alg / 1e6:.0f} MB per step > 126 MB L2"},
+                      "gpu_launches": 2 * args.steps, "clocks": clk.summary(),
+                      "roofline": {"kernel": "pack_bytes_kernel", "bound": "hbm", "achieved": alg / (res["pack"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": alg / (res["pack"] * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                                   "note": "peak = measured copy bandwidth (read + write); this kernel is almost write-only"},
+                      "cpu_baseline": None}))
+
+
 def run_tree(args):
     """Config 4: data_commitment Merkle over 2048 data roots, T independent trees per step; SHA-256 GB/s
     (algorithmic bytes = 64 B per compression + 32 B per digest: 4095 digests / 8190 compressions per tree)."""
@@ -864,9 +924,10 @@ def run_tree(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon", "shape"])
+    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon", "shape", "pack"])
     ap.add_argument("--trees", type=int, default=4096)
     ap.add_argument("--hashes", type=int, default=1 << 20)
+    ap.add_argument("--pack-bytes", type=int, default=1 << 25)
     ap.add_argument("--hash-len", type=int, default=8)
     ap.add_argument("--rows", type=int, default=1 << 20)
     ap.add_argument("--gate", default="arithmetic", choices=["arithmetic", "add_many", "subtraction", "comparison", "range_check"])
@@ -898,6 +959,8 @@ def main():
         run_poseidon(args)
     elif args.mode == "shape":
         run_shape(args)
+    elif args.mode == "pack":
+        run_pack(args)
     else:
         run_gpu(args)
 

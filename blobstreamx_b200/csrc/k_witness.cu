@@ -54,29 +54,31 @@ __global__ void __launch_bounds__(256) hash_input_data_kernel(uint32_t n_req, co
     }
 }
 
-// bytes -> 8 big-endian bit elements each (ByteVariable)
+// bytes -> 8 big-endian bit elements each (ByteVariable): the witness is 64x the payload, a pure HBM-write stream.
+// One thread per PAIR of elements (16 bytes): consecutive lanes write consecutive 16-byte pieces, so every store
+// instruction of a warp is one contiguous 512-byte segment; the four lanes of a byte read it once through L1.
 __global__ void __launch_bounds__(256) pack_bytes_kernel(const uint8_t *__restrict__ bytes, size_t n, uint64_t *__restrict__ el) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t b = bytes[i];
-    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(el + 8 * i);
-#pragma unroll
-    for (int k = 0; k < 4; k++) __stcs(o + k, make_ulonglong2((b >> (7 - 2 * k)) & 1, (b >> (6 - 2 * k)) & 1));
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // pair index: byte t / 4, bits 7-2k and 6-2k, k = t % 4
+    if (t >= 4 * n) return;
+    const uint32_t b = __ldg(bytes + (t >> 2)), k = (uint32_t)t & 3u;
+    __stcs(reinterpret_cast<ulonglong2 *>(el) + t, make_ulonglong2((b >> (7 - 2 * k)) & 1, (b >> (6 - 2 * k)) & 1));
 }
-// inverse; ok[0] is set to 1 when some element is not a bit
+// inverse; bad[0] is set to 1 when some element is not a bit.  Same mapping: a lane loads 16 contiguous bytes, the four
+// lanes of a byte combine their two bits with shuffles.
 __global__ void __launch_bounds__(256) unpack_bytes_kernel(const uint64_t *__restrict__ el, size_t n, uint8_t *__restrict__ bytes,
                                                            uint32_t *__restrict__ bad) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t b = 0, nb = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const uint64_t e = __ldcs(el + 8 * i + k);
-        nb |= e > 1;
-        b = (b << 1) | (uint32_t)(e & 1);
-    }
-    bytes[i] = (uint8_t)b;
-    if (nb && bad) atomicOr(bad, 1u);
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < 4 * n;
+    ulonglong2 e = make_ulonglong2(0, 0);
+    if (live) e = __ldcs(reinterpret_cast<const ulonglong2 *>(el) + t);
+    const uint32_t k = (uint32_t)t & 3u;
+    uint32_t v = ((uint32_t)(e.x & 1) << (7 - 2 * k)) | ((uint32_t)(e.y & 1) << (6 - 2 * k));
+    uint32_t nb = (e.x > 1 || e.y > 1) ? 1u : 0u;
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    if (live && k == 0) bytes[t >> 2] = (uint8_t)v;
+    nb = __any_sync(0xffffffffu, nb);
+    if (nb && bad && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
 }
 // big-endian 4-byte (8-byte) groups -> one element each ([U32Variable; 8] digests; u64 state words as (lo, hi) u32 limbs)
 __global__ void __launch_bounds__(256) pack_u32_be_kernel(const uint8_t *__restrict__ bytes, size_t n_words, uint64_t *__restrict__ el) {
@@ -169,15 +171,15 @@ extern "C" int bsx_hash_input_data(bsx_ctx *ctx, int sha512, uint32_t n_req, con
 extern "C" int bsx_witness_pack_bytes_dev(bsx_ctx *ctx, void *stream, const uint8_t *bytes, size_t n, uint64_t *elements) {
     BSX_REQUIRE(ctx, ctx && (n == 0 || (bytes && elements)) && (reinterpret_cast<uintptr_t>(elements) & 15) == 0);
     if (n == 0) return BSX_OK;
-    pack_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bytes, n, elements);
+    pack_bytes_kernel<<<(unsigned)((4 * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bytes, n, elements);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }
 extern "C" int bsx_witness_unpack_bytes_dev(bsx_ctx *ctx, void *stream, const uint64_t *elements, size_t n, uint8_t *bytes,
                                             uint32_t *not_bits) {
-    BSX_REQUIRE(ctx, ctx && (n == 0 || (bytes && elements)));
+    BSX_REQUIRE(ctx, ctx && (n == 0 || (bytes && elements)) && (reinterpret_cast<uintptr_t>(elements) & 15) == 0);
     if (n == 0) return BSX_OK;
-    unpack_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(elements, n, bytes, not_bits);
+    unpack_bytes_kernel<<<(unsigned)((4 * n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(elements, n, bytes, not_bits);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }
