@@ -384,7 +384,8 @@ def run_gpu(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("prove_subchain (subchain_proofs_kernel<8>)", {}).get("dram_bytes_per_launch_R256")
+            per_range = json.load(f).get("prove_subchain (subchain_proofs_kernel<8>)", {}).get("dram_bytes_per_range")
+            traffic = int(per_range * R) if per_range else None     # ncu capture of the proofs kernel, scaled to this launch's ranges
     except Exception:
         pass
 
