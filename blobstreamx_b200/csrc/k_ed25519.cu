@@ -264,30 +264,57 @@ __global__ void __launch_bounds__(64) ed25519_quad_kernel(uint32_t n, const ge_n
         for (int j = 0; j < 10; j++) scr[60 + 10 * k + j] = acc.v[j];
 }
 
-// stage 3: the three projective results share one inversion; affine bytes and the flags word
+__device__ __forceinline__ fe scr_load(const int32_t *scr, int p) {
+    fe r;
+#pragma unroll
+    for (int j = 0; j < 10; j++) r.v[j] = scr[10 * p + j];
+    return r;
+}
+
+// stage 3: K signatures per thread.  The three projective results of a signature share one inversion, and the K
+// signatures of a thread share it too (Montgomery's trick: prefix products, ONE field inversion, back-substitution):
+// (265 + 3K) instead of 265 K field operations.  The quad-lane path uses K = 1 (more threads, lower latency).
+// Z is never zero (complete addition law; undecodable inputs were replaced by the identity), so the product is invertible.
+template <int K>
 __global__ void __launch_bounds__(128) ed25519_finish_kernel(uint32_t n, const int32_t *__restrict__ scratch, uint8_t *__restrict__ out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint8_t *rec = out + (size_t)BSX_SIG_OUT_BYTES * i;
-    const int32_t *scr = scratch + (size_t)BSX_ED_SCRATCH_WORDS * i;
-    fe c[9];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, i0 = t * K;
+    if (i0 >= n) return;
+    const uint32_t cnt = (n - i0 < (uint32_t)K) ? n - i0 : (uint32_t)K;
+    fe z12[K], pre[K];                 // z12_j = Z_sg Z_ha;  pre_j = prod_{l <= j} z12_l Z_sum_l
 #pragma unroll
-    for (int p = 0; p < 9; p++)
+    for (int j = 0; j < K; j++) {
+        if ((uint32_t)j < cnt) {
+            const int32_t *scr = scratch + (size_t)BSX_ED_SCRATCH_WORDS * (i0 + j);
+            z12[j] = fe_mul(scr_load(scr, 2), scr_load(scr, 5));
+            const fe z = fe_mul(z12[j], scr_load(scr, 8));
+            pre[j] = j ? fe_mul(pre[j - 1], z) : z;
+        }
+    }
+    fe run = fe_invert(pre[cnt - 1]);  // 1 / (z_0 ... z_{cnt-1})
 #pragma unroll
-        for (int j = 0; j < 10; j++) c[p].v[j] = scr[10 * p + j];
-    const fe &sgX = c[0], &sgY = c[1], &sgZ = c[2], &haX = c[3], &haY = c[4], &haZ = c[5], &smX = c[6], &smY = c[7], &smZ = c[8];
-    const fe z12 = fe_mul(sgZ, haZ);
-    const fe inv = fe_invert(fe_mul(z12, smZ));
-    const fe isum = fe_mul(inv, z12);
-    const fe i12 = fe_mul(inv, smZ);
-    const fe isg = fe_mul(i12, haZ), iha = fe_mul(i12, sgZ);
-    fe_tobytes(rec + 136, fe_mul(sgX, isg)); fe_tobytes(rec + 168, fe_mul(sgY, isg));
-    fe_tobytes(rec + 296, fe_mul(haX, iha)); fe_tobytes(rec + 328, fe_mul(haY, iha));
-    fe_tobytes(rec + 456, fe_mul(smX, isum)); fe_tobytes(rec + 488, fe_mul(smY, isum));
-    uint32_t flags = (rec[521] ? 1u : 0u) | (rec[522] ? 2u : 0u) | (rec[523] ? 4u : 0u);
-    if (bytes_eq32(rec + 136, rec + 456) && bytes_eq32(rec + 168, rec + 488)) flags |= 8u;
-    rec[520] = (uint8_t)flags; rec[521] = 0; rec[522] = 0; rec[523] = 0;
-    for (int j = 524; j < 576; j++) rec[j] = 0;
+    for (int j = K - 1; j >= 0; j--) {
+        if ((uint32_t)j >= cnt) continue;
+        const uint32_t i = i0 + j;
+        uint8_t *rec = out + (size_t)BSX_SIG_OUT_BYTES * i;
+        const int32_t *scr = scratch + (size_t)BSX_ED_SCRATCH_WORDS * i;
+        const fe smZ = scr_load(scr, 8);
+        fe inv = run;                                          // 1 / (z_0 ... z_j)
+        if (j) {
+            inv = fe_mul(run, pre[j - 1]);                     // 1 / z_j
+            run = fe_mul(run, fe_mul(z12[j], smZ));            // 1 / (z_0 ... z_{j-1})
+        }
+        const fe sgZ = scr_load(scr, 2), haZ = scr_load(scr, 5);
+        const fe isum = fe_mul(inv, z12[j]);
+        const fe i12 = fe_mul(inv, smZ);
+        const fe isg = fe_mul(i12, haZ), iha = fe_mul(i12, sgZ);
+        fe_tobytes(rec + 136, fe_mul(scr_load(scr, 0), isg)); fe_tobytes(rec + 168, fe_mul(scr_load(scr, 1), isg));
+        fe_tobytes(rec + 296, fe_mul(scr_load(scr, 3), iha)); fe_tobytes(rec + 328, fe_mul(scr_load(scr, 4), iha));
+        fe_tobytes(rec + 456, fe_mul(scr_load(scr, 6), isum)); fe_tobytes(rec + 488, fe_mul(scr_load(scr, 7), isum));
+        uint32_t flags = (rec[521] ? 1u : 0u) | (rec[522] ? 2u : 0u) | (rec[523] ? 4u : 0u);
+        if (bytes_eq32(rec + 136, rec + 456) && bytes_eq32(rec + 168, rec + 488)) flags |= 8u;
+        rec[520] = (uint8_t)flags; rec[521] = 0; rec[522] = 0; rec[523] = 0;
+        for (int q = 524; q < 576; q++) rec[q] = 0;
+    }
 }
 
 }  // namespace bsx
@@ -308,12 +335,12 @@ static int ensure_base_table(bsx_ctx *ctx, cudaStream_t st) {
 static int launch_quad(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in, const ed::ge_niels_slot *tab, uint8_t *out) {
     int32_t *scratch = nullptr;
     BSX_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(int32_t) * BSX_ED_SCRATCH_WORDS * (size_t)n, st));
-    BSX_PIN_CARVEOUT(ed25519_prep_kernel<0>); BSX_PIN_CARVEOUT(ed25519_quad_kernel); BSX_PIN_CARVEOUT(ed25519_finish_kernel);
+    BSX_PIN_CARVEOUT(ed25519_prep_kernel<0>); BSX_PIN_CARVEOUT(ed25519_quad_kernel); BSX_PIN_CARVEOUT(ed25519_finish_kernel<1>);
     ed25519_prep_kernel<0><<<(2 * n + 127) / 128, 128, 0, st>>>(n, in, out);
     BSX_LAUNCHED(ctx);
     ed25519_quad_kernel<<<(4 * n + 63) / 64, 64, 0, st>>>(n, tab, out, scratch);
     BSX_LAUNCHED(ctx);
-    ed25519_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, scratch, out);
+    ed25519_finish_kernel<1><<<(n + 127) / 128, 128, 0, st>>>(n, scratch, out);
     BSX_LAUNCHED(ctx);
     BSX_CUDA(ctx, cudaFreeAsync(scratch, st));
     return BSX_OK;
@@ -328,6 +355,8 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     BSX_PIN_CARVEOUT((ed25519_batch_kernel<8, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<6, false>));
     BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, true>));
     const bool use_inl = inl < 0 ? alone : inl != 0;
+    // (Splitting this path into prep / main / finish kernels with a 4-way batched inversion was measured slower:
+    // 19.3 vs 21.4 M sig/s at 37 800 signatures, 2.98 vs 2.91 ms for the header_range step -- not kept.)
     if (occ >= 8) ed25519_batch_kernel<8, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (occ >= 6) ed25519_batch_kernel<6, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (use_inl) ed25519_batch_kernel<4, true><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
