@@ -71,7 +71,7 @@ def _worker(rank, world, port, R, J, B, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,R,J,B", [(2, 4, 4, 8), (4, 4, 8, 4), (2, 2, 2, 16)])
+@pytest.mark.parametrize("world,R,J,B", [(2, 4, 4, 8), (4, 4, 8, 4), (2, 2, 2, 16), (8, 8, 8, 2)])
 def test_sharded_header_range_gloo(world, R, J, B):
     from oracle import cbind as orc
     with socket.socket() as s:
