@@ -474,8 +474,9 @@ def run_gpu(args):
                                    f"{N_JOBS * (20 * BATCH - 1) + N_JOBS - 1 + 490} SHA-256 digests and 100 Ed25519 records per range written",
                        "ranges_per_step_per_gpu": R, "distinct_chains": args.distinct,
                        "sharding": "single GPU: bsx_header_range_dev" if not eng else
-                                   f"map jobs of {Rt} ranges sharded {N_JOBS // world} per range per rank, one all-gather of "
-                                   f"{Rt * N_JOBS * 128} B subchain records, reduce + skip of {R} ranges per rank",
+                                   f"map jobs of {Rt} ranges sharded {N_JOBS // world} per range per rank; {Rt * N_JOBS * 128} B of subchain "
+                                   f"records exchanged by {'peer-memory stores from the map kernel + one device barrier' if eng.exchange == 'peer stores' else 'one all_gather_into_tensor'}; "
+                                   f"reduce + skip of {R} ranges per rank",
                        "l2": f"inputs+outputs per step per GPU = {resident / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),

@@ -22,7 +22,21 @@ struct SubchainArgs {
     const uint64_t *start_blocks, *end_blocks;
     const uint8_t *range_end_header;
     uint8_t *digests, *subchains;
+    // peer placement of the subchain records (multi-GPU, bsx_prove_subchain_batch_p2p_dev): with n_peers > 0 the record
+    // of local job j2 = (range r, local job jl) is stored straight into the gathered [ranges, total_jobs] array of the
+    // rank that reduces range r -- peers[r / ranges_per_owner] + ((r % ranges_per_owner) * total_jobs + rank * per + jl) * 128
+    // -- over NVLink peer memory; the exchange step of the map/reduce needs no collective kernel.
+    uint8_t *peers[BSX_MAX_PEERS];
+    uint32_t n_peers, p2p_rank, p2p_per, p2p_total_jobs, p2p_ranges_per_owner;
 };
+#define BSX_SUBCHAIN_ARGS_NO_P2P {nullptr}, 0u, 0u, 0u, 0u, 0u
+
+__device__ __forceinline__ uint32_t *subchain_record(const SubchainArgs &a, size_t j2) {
+    if (a.n_peers == 0) return reinterpret_cast<uint32_t *>(a.subchains + j2 * BSX_SUBCHAIN_BYTES);
+    const size_t r = j2 / a.p2p_per, jl = j2 % a.p2p_per;
+    const size_t owner = r / a.p2p_ranges_per_owner, rl = r % a.p2p_ranges_per_owner;
+    return reinterpret_cast<uint32_t *>(a.peers[owner] + (rl * a.p2p_total_jobs + (size_t)a.p2p_rank * a.p2p_per + jl) * BSX_SUBCHAIN_BYTES);
+}
 
 __device__ __forceinline__ void load_words_be(const uint8_t *p, uint32_t d[8]) {  // any alignment
 #pragma unroll
@@ -187,7 +201,7 @@ __global__ void __launch_bounds__((2 * B < 32) ? 32 : 2 * B) prove_subchain_kern
         const bool e_B = batch_enabled && (uint64_t)B <= kk;
         load_words_be(a.end_headers + 32 * job, eh);
         if (e_B && !digest_eq(cur, eh)) f |= BSX_FAIL_BATCH_END_HEADER;
-        uint32_t *rec = reinterpret_cast<uint32_t *>(a.subchains + job * BSX_SUBCHAIN_BYTES);
+        uint32_t *rec = subchain_record(a, job);
         rec[0] = batch_enabled ? 1u : 0u;
         rec[1] = f;
         rec[2] = (uint32_t)batch_start; rec[3] = (uint32_t)(batch_start >> 32);
@@ -452,7 +466,7 @@ __global__ void __launch_bounds__(B * G < 32 ? 32 : B * G) subchain_commit_kerne
         const bool e_B = en && (uint64_t)B <= k2;
         load_words_be(a.end_headers + 32 * j2, eh);
         if (e_B && !digest_eq(cur, eh)) f |= BSX_FAIL_BATCH_END_HEADER;
-        uint32_t *rec = reinterpret_cast<uint32_t *>(a.subchains + j2 * BSX_SUBCHAIN_BYTES);
+        uint32_t *rec = subchain_record(a, j2);
         rec[0] = en ? 1u : 0u;
         rec[1] = f;
         rec[2] = (uint32_t)bs; rec[3] = (uint32_t)(bs >> 32);
@@ -556,7 +570,35 @@ extern "C" int bsx_prove_subchain_batch_dev(bsx_ctx *ctx, void *stream, uint32_t
                          (reinterpret_cast<uintptr_t>(start_headers) & 3) == 0);
     if (n_jobs == 0) return BSX_OK;
     SubchainArgs a{dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, batch_start, batch_end, global_end,
-                   global_end_header, 0, nullptr, nullptr, nullptr, digests, subchains};
+                   global_end_header, 0, nullptr, nullptr, nullptr, digests, subchains, BSX_SUBCHAIN_ARGS_NO_P2P};
+    return dispatch_subchain(ctx, (cudaStream_t)stream, B, n_jobs, a);
+}
+
+// multi-GPU form: the same map jobs, but every subchain record is stored into the reducing rank's gathered array through
+// peer memory (pointers from torch symmetric memory / CUDA IPC; NVLink).  peer_bases[w] = base of rank w's
+// [ranges_per_owner, total_jobs, 128] array as mapped in THIS process.  The caller runs a cross-rank barrier before the reduce.
+extern "C" int bsx_prove_subchain_batch_p2p_dev(bsx_ctx *ctx, void *stream, uint32_t B, uint32_t n_jobs,
+                                                const uint8_t *dh_leaf, const uint8_t *dh_aunts, const uint8_t *lb_leaf,
+                                                const uint8_t *lb_aunts, const uint8_t *start_headers,
+                                                const uint8_t *end_headers, const uint64_t *batch_start,
+                                                const uint64_t *batch_end, const uint64_t *global_end,
+                                                const uint8_t *global_end_header, uint8_t *digests,
+                                                const uint64_t *peer_bases, uint32_t n_peers, uint32_t rank,
+                                                uint32_t jobs_per_rank, uint32_t total_jobs, uint32_t ranges_per_owner) {
+    BSX_REQUIRE(ctx, ctx && dh_leaf && dh_aunts && lb_leaf && lb_aunts && start_headers && end_headers && batch_start &&
+                         batch_end && global_end && global_end_header && digests && peer_bases);
+    BSX_REQUIRE(ctx, n_peers >= 1 && n_peers <= BSX_MAX_PEERS && rank < n_peers && jobs_per_rank >= 1 && ranges_per_owner >= 1 &&
+                         total_jobs == jobs_per_rank * n_peers && n_jobs % jobs_per_rank == 0 &&
+                         (n_jobs / jobs_per_rank) == ranges_per_owner * n_peers);
+    BSX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(digests) & 15) == 0 && (reinterpret_cast<uintptr_t>(start_headers) & 3) == 0);
+    if (n_jobs == 0) return BSX_OK;
+    SubchainArgs a{dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, batch_start, batch_end, global_end,
+                   global_end_header, 0, nullptr, nullptr, nullptr, digests, nullptr, {nullptr}, n_peers, rank, jobs_per_rank,
+                   total_jobs, ranges_per_owner};
+    for (uint32_t w = 0; w < n_peers; w++) {
+        BSX_REQUIRE(ctx, peer_bases[w] != 0 && (peer_bases[w] & 15) == 0);
+        a.peers[w] = reinterpret_cast<uint8_t *>(peer_bases[w]);
+    }
     return dispatch_subchain(ctx, (cudaStream_t)stream, B, n_jobs, a);
 }
 
@@ -599,7 +641,7 @@ extern "C" int bsx_prove_data_commitment_dev(bsx_ctx *ctx, void *stream, uint32_
     BSX_REQUIRE(ctx, n_jobs >= 1 && (n_jobs & (n_jobs - 1)) == 0);
     if (n_ranges == 0) return BSX_OK;
     SubchainArgs a{dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, nullptr, nullptr, nullptr, nullptr,
-                   n_jobs, start_blocks, end_blocks, end_header, map_digests, map_subchains};
+                   n_jobs, start_blocks, end_blocks, end_header, map_digests, map_subchains, BSX_SUBCHAIN_ARGS_NO_P2P};
     int rc = dispatch_subchain(ctx, (cudaStream_t)stream, B, n_ranges * n_jobs, a);
     if (rc) return rc;
     return bsx_reduce_subchains_dev(ctx, stream, n_ranges, n_jobs, map_subchains, start_blocks, start_header, end_blocks,

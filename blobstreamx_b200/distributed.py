@@ -6,14 +6,20 @@ Reference shape (SURVEY 8e): `MapReduceGenerator::run_once` proves the NB_MAP_JO
 own BATCH_SIZE headers -- and then log2(jobs) reduce layers (generator.rs:113-151, closure BX/circuits/builder.rs:
 337-395).  The reference's only multi-worker story is `PROVER=remote` (HTTP, PX/backend/prover/remote.rs:98-153).
 Here rank r of W owns jobs [r*J/W, (r+1)*J/W) of EVERY range in flight (contiguous job slice = contiguous header
-range), the 128-byte subchain records are exchanged with one `all_gather_into_tensor` (NCCL over NVLink on GPUs,
-gloo in the CPU tests), and rank r reduces ranges [r*R/W, (r+1)*R/W).  No other collective is on the data path.
+range) and reduces ranges [r*R/W, (r+1)*R/W).  The exchange between the two is 128 bytes per job:
+  * on GPUs the map kernels store each record straight into the reducing rank's gathered array through NVLink peer
+    memory (torch symmetric memory gives every rank the peers' buffer addresses; `bsx_prove_subchain_batch_p2p_dev`),
+    followed by one device-side barrier -- compute and exchange are ONE kernel, no collective kernel competes with the
+    Ed25519 CTAs for an SM (the NCCL all-gather could only start once an SM had drained: 8 GPUs 3.20 ms per step);
+  * if symmetric memory cannot be set up, and in the CPU tests (gloo), one `all_gather_into_tensor`.
+No other collective is on the data path.
 
 The compute backend is injected: `CudaBackend` (below) drives libbsx through device pointers on torch's current
 stream; the CPU tests pass an oracle-backed stand-in that lives under tests/ (the product has no CPU path).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -78,6 +84,17 @@ class CudaBackend:
                           P(t["end_headers"]), P(t["batch_start"]), P(t["batch_end"]), P(t["global_end"]),
                           P(t["global_end_header"]), P(digests), P(subchains))
 
+    def map_p2p(self, B, n_jobs, t, digests, peer_ptrs, rank, per, total_jobs, ranges_per_owner):
+        """The map stage with every subchain record stored into its reducing rank's array (peer memory)."""
+        P = lambda x: self.lib.ptr(x.data_ptr())
+        bases = np.asarray(peer_ptrs, np.uint64)
+        u32 = self.lib.u32
+        self.ctx.call_dev("bsx_prove_subchain_batch_p2p_dev", torch.cuda.current_stream().cuda_stream, u32(B), u32(n_jobs),
+                          P(t["dh_leaf"]), P(t["dh_aunts"]), P(t["lb_leaf"]), P(t["lb_aunts"]), P(t["start_headers"]),
+                          P(t["end_headers"]), P(t["batch_start"]), P(t["batch_end"]), P(t["global_end"]),
+                          P(t["global_end_header"]), P(digests), self.lib.ptr(bases.ctypes.data), u32(len(bases)), u32(rank),
+                          u32(per), u32(total_jobs), u32(ranges_per_owner))
+
     def reduce(self, n_ranges, n_jobs, B, subchains, t, reduce_digests, reduce_nodes, dcs, fail):
         P = lambda x: self.lib.ptr(x.data_ptr())
         self.ctx.call_dev("bsx_reduce_subchains_dev", torch.cuda.current_stream().cuda_stream, self.lib.u32(n_ranges), self.lib.u32(n_jobs),
@@ -98,14 +115,41 @@ class ShardedHeaderRange:
         e = backend.empty
         self.map_digests = e(R * per * (20 * B - 1) * 32)
         self.local_sub = e(R * per * SUBCHAIN_BYTES)
-        self.gathered = e(world * R * per * SUBCHAIN_BYTES) if world > 1 else None
-        self.all_sub = e(R * n_jobs * SUBCHAIN_BYTES) if world > 1 else self.local_sub
         Ro = R // world
+        self.p2p = None          # (handles, buffers, peer pointer lists) of the two alternating gathered arrays
+        self.exchange = "none" if world == 1 else "all_gather"
+        if world > 1 and hasattr(backend, "map_p2p") and os.environ.get("BSX_EXCHANGE", "p2p") == "p2p":
+            self.p2p = self._setup_peer_memory(Ro * n_jobs * SUBCHAIN_BYTES)
+            if self.p2p:
+                self.exchange = "peer stores"
+        self.gathered = e(world * R * per * SUBCHAIN_BYTES) if world > 1 and not self.p2p else None
+        self.all_sub = (e(R * n_jobs * SUBCHAIN_BYTES) if not self.p2p else None) if world > 1 else self.local_sub
+        self._flip = 0
         self.reduce_digests = e(Ro * max(n_jobs - 1, 1) * 32)
         self.reduce_nodes = e(Ro * max(n_jobs - 1, 1) * SUBCHAIN_BYTES)
         self.data_commitments = e(Ro * 32)
         self.fail = e(Ro * 4)
         self.t: Optional[dict] = None
+
+    def _setup_peer_memory(self, nbytes: int):
+        """Two [R/W, J, 128] arrays per rank in symmetric memory (alternating per step, so one barrier per step is enough:
+        when the barrier of step k+1 completes every rank has finished the reduce of step k, whose array step k+2 reuses)."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group or dist.group.WORLD
+            out = []
+            for _ in range(2):
+                buf = symm.empty(nbytes, dtype=torch.uint8, device=self.be.device)
+                buf.zero_()
+                hdl = symm.rendezvous(buf, group)
+                out.append((hdl, buf, [int(p) for p in hdl.buffer_ptrs]))
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            return out
+        except Exception as exc:   # no peer access / no fabric handles in this environment: NCCL all-gather instead
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({type(exc).__name__}: {exc}); using all_gather_into_tensor")
+            return None
 
     def load(self, host: Dict[str, np.ndarray]):
         """host arrays of ALL ranges -> device-resident shard + this rank's public inputs for the reduce."""
@@ -120,6 +164,14 @@ class ShardedHeaderRange:
 
     def step(self):
         R, J, per, W = self.R, self.J, self.per, self.world
+        if self.p2p:
+            hdl, buf, ptrs = self.p2p[self._flip]
+            self._flip ^= 1
+            self.be.map_p2p(self.B, R * per, self.t, self.map_digests, ptrs, self.rank, per, J, R // W)
+            hdl.barrier(channel=0)          # device-side, on the current stream: every rank's records have landed
+            self._last = buf
+            self.be.reduce(R // W, J, self.B, buf, self.t, self.reduce_digests, self.reduce_nodes, self.data_commitments, self.fail)
+            return
         self.be.map(self.B, R * per, self.t, self.map_digests, self.local_sub)
         if W > 1:
             dist.all_gather_into_tensor(self.gathered, self.local_sub, group=self.group)
@@ -135,5 +187,6 @@ class ShardedHeaderRange:
         return dict(data_commitments=self.data_commitments.cpu().numpy().reshape(Ro, 32),
                     fail=self.fail.cpu().numpy().view(np.uint32).reshape(Ro),
                     reduce_nodes=self.reduce_nodes.cpu().numpy().reshape(Ro, max(self.J - 1, 1), SUBCHAIN_BYTES),
-                    map_subchains=self.all_sub.cpu().numpy().reshape(self.R, self.J, SUBCHAIN_BYTES)[self.own],
+                    map_subchains=(self._last.cpu().numpy().reshape(Ro, self.J, SUBCHAIN_BYTES) if self.p2p else
+                                   self.all_sub.cpu().numpy().reshape(self.R, self.J, SUBCHAIN_BYTES)[self.own]),
                     local_map_digests=self.map_digests.cpu().numpy().reshape(self.R, self.per, 20 * self.B - 1, 32))

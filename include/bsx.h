@@ -182,6 +182,20 @@ int bsx_prove_data_commitment_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges,
                                   uint8_t *data_commitments, uint32_t *fail);
 /* reduce stage alone over already-computed map outputs (used after the multi-GPU all-gather):
  * map_subchains n_ranges*n_jobs*128 -> reduce_* / data_commitments / fail as above. */
+/* Multi-GPU map stage: as bsx_prove_subchain_batch_dev, but each 128-byte subchain record is stored through
+ * peer memory (NVLink) straight into the gathered [ranges_per_owner, total_jobs, 128] array of the rank that reduces its
+ * range, so the exchange step of the map/reduce needs no collective kernel -- only a cross-rank barrier before
+ * bsx_reduce_subchains_dev.  This rank holds `jobs_per_rank` jobs (global jobs rank*jobs_per_rank ...) of every range
+ * in flight, n_jobs = jobs_per_rank * ranges_per_owner * n_peers, range r is reduced by rank r / ranges_per_owner.
+ * peer_bases: host array of n_peers device addresses (rank w's array as mapped in this process, e.g. the buffer_ptrs of
+ * torch symmetric memory or cudaIpcOpenMemHandle results); n_peers <= BSX_MAX_PEERS. */
+#define BSX_MAX_PEERS 16
+int bsx_prove_subchain_batch_p2p_dev(bsx_ctx *ctx, void *stream, uint32_t B, uint32_t n_jobs, const uint8_t *dh_leaf,
+                                     const uint8_t *dh_aunts, const uint8_t *lb_leaf, const uint8_t *lb_aunts,
+                                     const uint8_t *start_headers, const uint8_t *end_headers, const uint64_t *batch_start,
+                                     const uint64_t *batch_end, const uint64_t *global_end, const uint8_t *global_end_header,
+                                     uint8_t *digests, const uint64_t *peer_bases, uint32_t n_peers, uint32_t rank,
+                                     uint32_t jobs_per_rank, uint32_t total_jobs, uint32_t ranges_per_owner);
 int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs,
                              const uint8_t *map_subchains, const uint64_t *start_blocks, const uint8_t *start_header,
                              const uint64_t *end_blocks, const uint8_t *end_header, uint32_t B, uint8_t *reduce_digests,
