@@ -47,3 +47,36 @@ def test_bench_two_ranks_nccl():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     assert '"n_gpus": 2' in out.stdout
+
+
+def test_peer_store_map_emulated_two_ranks():
+    """bsx_prove_subchain_batch_p2p_dev on ONE GPU: two "ranks" run one after the other, each storing its jobs' subchain
+    records into the array of the rank that reduces the range (both arrays local here).  The gathered arrays must equal the
+    records of the plain map stage, and the reduce over them the oracle's."""
+    import bench
+    import torch
+    from blobstreamx_b200 import synthetic as S
+    from blobstreamx_b200.distributed import SUBCHAIN_BYTES, CudaBackend, shard_map_inputs
+    from oracle import cbind as orc
+    R, J, B, W = 4, 8, 4, 2
+    ms = [S.header_range_inputs(J, B, nb, start=6_000_000 + 1000 * r, seed=S.SEED + r, with_skip=False)[0]
+          for r, nb in enumerate((None, 13, 5, 32))]
+    host = bench.tile_ranges(ms, R)
+    be = CudaBackend(0)
+    per, Ro = J // W, R // W
+    bufs = [be.empty(Ro * J * SUBCHAIN_BYTES) for _ in range(W)]
+    ptrs = [int(b.data_ptr()) for b in bufs]
+    for rank in range(W):
+        t = {k: be.tensor(v) for k, v in shard_map_inputs(host, R, J, B, rank, W).items()}
+        dig = be.empty(R * per * (20 * B - 1) * 32)
+        be.map_p2p(B, R * per, t, dig, ptrs, rank, per, J, Ro)
+        plain = be.empty(R * per * SUBCHAIN_BYTES)
+        be.map(B, R * per, t, dig, plain)
+        torch.cuda.synchronize()
+        got = torch.cat(bufs).cpu().numpy().reshape(R, J, SUBCHAIN_BYTES)[:, rank * per:(rank + 1) * per]
+        assert (got == plain.cpu().numpy().reshape(R, per, SUBCHAIN_BYTES)).all()
+    gathered = torch.cat(bufs).cpu().numpy().reshape(R, J, SUBCHAIN_BYTES)
+    for r, m in enumerate(ms):
+        w = orc.prove_data_commitment(J, B, m.dh_leaf, m.dh_aunts, m.lb_leaf, m.lb_aunts, m.start_headers, m.end_headers,
+                                      m.start_block, m.start_header, m.end_block, m.end_header)
+        assert (gathered[r] == w["map_subchains"]).all()
