@@ -20,6 +20,7 @@ struct bsx_ctx {
     size_t ws_cap;
     size_t ws_off;
     void *ed_table;            // s*G window table (k_ed25519.cu), built on first use
+    int ed_corun;              // set by the pipelined host path: Ed25519 in its 128-register build (see launch_mono)
     cudaStream_t stream2;      // second stream + events: bsx_header_range runs its two halves concurrently
     cudaEvent_t ev_fork, ev_join;     // bsx_header_range (host path: two copy+compute pipelines)
     cudaEvent_t ev_fork2, ev_join2;   // verify_*: Ed25519 kernel on stream2 beside the SHA-256 schedule

@@ -448,30 +448,57 @@ BSX_HD ge_p3 ge_scalarmult_base(const uint8_t s[32], const ge_niels_slot *table)
     return acc;
 }
 
-// scalar * P for an arbitrary 256-bit scalar (EcOpResultHint::ScalarMul takes the U256 unreduced)
+// -q for an addend in cached form: swap Y+X and Y-X, negate 2dT
+BSX_HD ge_cached ge_cached_cneg(const ge_cached &q, bool neg) {
+    ge_cached r;
+    r.YpX = fe_select(neg, q.YmX, q.YpX); r.YmX = fe_select(neg, q.YpX, q.YmX); r.Z = q.Z;
+    r.T2d = fe_select(neg, fe_neg(q.T2d), q.T2d);
+    return r;
+}
+
+// scalar * P for an arbitrary 256-bit scalar (EcOpResultHint::ScalarMul takes the U256 unreduced).
+// Signed radix-16 digits e_w in [-8, 8) (w = 0..63, carry-out e_64 in {0, 1}): the table holds 1P..8P only -- 7
+// additions to build instead of 14 and 1.25 KB of local memory per thread instead of 2.4 KB (the table is read from
+// L1/L2 on every window; halving it matters once four CTAs share an SM's L1).  Doublings start at the first non-zero digit.
 template <bool INL = false>
 BSX_HD ge_p3 ge_scalarmult(const uint8_t s[32], const ge_p3 &P) {
-    ge_cached tab[15];                       // tab[d-1] = d*P
+    ge_cached tab[8];                        // tab[d-1] = d*P
     {
         ge_p3 cur = P;
         tab[0] = ge_to_cached(cur);
 #pragma unroll 1
-        for (int d = 2; d <= 15; d++) {
+        for (int d = 2; d <= 8; d++) {
             cur = ge_p1p1_to_p3(ge_add_cached(cur, tab[0]), true);
             tab[d - 1] = ge_to_cached(cur);
         }
     }
-    ge_p3 acc = ge_identity();
+    int8_t e[65];
+    {
+        int carry = 0;
 #pragma unroll 1
-    for (int w = 63; w >= 0; w--) {
-        if (w != 63) {
+        for (int w = 0; w < 64; w++) {
+            int d = (int)((s[w >> 1] >> ((w & 1) * 4)) & 15) + carry;
+            carry = d >= 8;
+            e[w] = (int8_t)(d - 16 * carry);
+        }
+        e[64] = (int8_t)carry;
+    }
+    ge_p3 acc = ge_identity();
+    bool started = false;
+#pragma unroll 1
+    for (int w = 64; w >= 0; w--) {
+        if (started) {
 #pragma unroll 1
             for (int k = 0; k < 4; k++) acc = ge_p1p1_to_p3<INL>(ge_dbl<INL>(acc), k == 3);
         }
-        const uint32_t dgt = (s[w >> 1] >> ((w & 1) * 4)) & 15;
+        const int d = e[w];
         // T is consumed only by additions: the 4th doubling of a window produces it, an addition
         // drops it again (the next step is a doubling) except in the last window.
-        if (dgt) acc = ge_p1p1_to_p3<INL>(ge_add_cached<INL>(acc, tab[dgt - 1]), w == 0);
+        if (d) {
+            const ge_cached q = ge_cached_cneg(tab[(d < 0 ? -d : d) - 1], d < 0);
+            acc = ge_p1p1_to_p3<INL>(ge_add_cached<INL>(acc, q), w == 0);
+            started = true;
+        }
     }
     return acc;
 }

@@ -346,11 +346,16 @@ static int launch_quad(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     return BSX_OK;
 }
 
-// one thread per signature.  Register budget: 4 CTAs/SM -> 214 registers, 6 -> 168, 8 -> 128 (with spills).
+// one thread per signature.  The register file is per SM sub-partition (16 K registers): 2 warps of this kernel per
+// sub-partition (4 CTAs/SM) -> 216 registers, 3 (6 CTAs) -> 168, 4 (8 CTAs) -> 128 with spills.
 // `alone`: the batch is not issued next to SHA-256 kernels (bsx_ed25519_batch*), so the build with inlined point
 // arithmetic is used; the verify_* / header_range paths share the SMs with the hash kernels and use the compact build.
+// ctx->ed_corun (pipelined host path): the 128-register build.  One wave of the 216-register build leaves room for a
+// single 80-register warp per sub-partition, so the map kernels of the first chunks -- whose digests the D2H engine is
+// waiting for -- queue behind it; the 128-register build leaves half the register file (single call 6.9 -> 6.35 ms).
 static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in, const ed::ge_niels_slot *tab, uint8_t *out, bool alone) {
-    static const int occ = [] { const char *e = getenv("BSX_ED_OCC"); return e ? atoi(e) : 4; }();
+    static const int env_occ = [] { const char *e = getenv("BSX_ED_OCC"); return e ? atoi(e) : 0; }();
+    const int occ = env_occ ? env_occ : ctx->ed_corun ? 8 : 4;
     static const int inl = [] { const char *e = getenv("BSX_ED_INLINE"); return e ? atoi(e) : -1; }();   // -1: by call site
     BSX_PIN_CARVEOUT((ed25519_batch_kernel<8, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<6, false>));
     BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, true>));

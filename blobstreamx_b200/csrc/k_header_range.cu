@@ -162,7 +162,9 @@ extern "C" int bsx_header_range(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n
     auto *d_sfail = a.out<uint32_t>(R);
     if (a.rc) return a.rc;
     auto run_skip = [&]() -> int {
+        ctx->ed_corun = 1;   // the chunks' map kernels must get onto the SMs while the Ed25519 wave is resident
         int r = bsx_verify_skip_dev(ctx, ctx->stream2, n, N, d_hdr, d_val, d_skip, d_tpk, d_tpw, d_tbl, d_sdig, d_ed, d_sfail);
+        ctx->ed_corun = 0;
         if (r) return r;
         a.back(s->digests, d_sdig, R * D * 32);
         a.back(s->ed_out, d_ed, nN * BSX_SIG_OUT_BYTES);
