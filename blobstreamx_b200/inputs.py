@@ -159,6 +159,92 @@ def pack_range_headers(trees: Dict[int, "HeaderTree"], start: int, n_jobs: int, 
     return out
 
 
+# fixed-layout inputs of the device-side encoders (include/bsx.h: bsx_header_fields, bsx_commit_in, bsx_commit_sig_in)
+HEADER_FIELDS_DTYPE = np.dtype([
+    ("version_block", "<u8"), ("version_app", "<u8"), ("height", "<u8"), ("time_seconds", "<i8"), ("time_nanos", "<u4"),
+    ("chain_id_len", "<u4"), ("chain_id", "u1", 56), ("parts_total", "<u4"), ("has_last_block_id", "u1"), ("hash_len", "u1", 9),
+    ("_pad", "u1", 2), ("last_block_hash", "u1", 32), ("parts_hash", "u1", 32), ("hashes", "u1", (9, 32))])
+COMMIT_DTYPE = np.dtype([
+    ("height", "<u8"), ("round", "<u4"), ("n_signatures", "<u4"), ("block_hash", "u1", 32), ("parts_hash", "u1", 32),
+    ("parts_total", "<u4"), ("chain_id_len", "<u4"), ("chain_id", "u1", 56), ("has_block_id", "u1"), ("_pad", "u1", 7)])
+COMMIT_SIG_DTYPE = np.dtype([
+    ("pubkey", "u1", 32), ("signature", "u1", 64), ("voting_power", "<u8"), ("ts_seconds", "<i8"), ("ts_nanos", "<u4"),
+    ("block_id_flag", "u1"), ("_pad", "u1", 3), ("address", "u1", 20), ("sig_address", "u1", 20)])
+assert HEADER_FIELDS_DTYPE.itemsize == 464 and COMMIT_DTYPE.itemsize == 152 and COMMIT_SIG_DTYPE.itemsize == 160
+
+_HEADER_HASH_KEYS = ("last_commit_hash", "data_hash", "validators_hash", "next_validators_hash", "consensus_hash", "app_hash",
+                     "last_results_hash", "evidence_hash", "proposer_address")
+
+
+def parse_time(ts) -> Tuple[int, int]:
+    """RFC 3339 (as in the RPC's JSON) or (seconds, nanos) -> (seconds, nanos)."""
+    if isinstance(ts, tuple):
+        return int(ts[0]), int(ts[1])
+    m = _TS.match(ts)
+    if not m:
+        raise ValueError(f"bad RFC3339 time {ts!r}")
+    y, mo, d, hh, mm, ss = (int(x) for x in m.groups()[:6])
+    return calendar.timegm((y, mo, d, hh, mm, ss)), int((m.group(7) or "").ljust(9, "0")[:9] or 0)
+
+
+def _put(dst: np.ndarray, b: bytes) -> int:
+    dst[: len(b)] = np.frombuffer(b, np.uint8)
+    return len(b)
+
+
+def pack_header_fields(headers: Sequence[dict]) -> np.ndarray:
+    """Decoded headers (the RPC's JSON dicts) -> bsx_header_fields records for `encode_headers`."""
+    out = np.zeros(len(headers), HEADER_FIELDS_DTYPE)
+    for r, h in zip(out, headers):
+        r["version_block"], r["version_app"] = int(h["version"]["block"]), int(h["version"].get("app") or 0)
+        r["height"] = int(h["height"])
+        r["time_seconds"], r["time_nanos"] = parse_time(h["time"])
+        r["chain_id_len"] = _put(r["chain_id"], h["chain_id"].encode())
+        bid = h.get("last_block_id")
+        if bid and bid.get("hash"):
+            r["has_last_block_id"], r["parts_total"] = 1, int(bid["parts"]["total"])
+            _put(r["last_block_hash"], bytes.fromhex(bid["hash"]))
+            _put(r["parts_hash"], bytes.fromhex(bid["parts"]["hash"]))
+        for k, key in enumerate(_HEADER_HASH_KEYS):
+            r["hash_len"][k] = _put(r["hashes"][k], bytes.fromhex(h.get(key) or ""))
+    return out
+
+
+def _b64(x) -> bytes:
+    return bytes(x) if isinstance(x, (bytes, bytearray)) else base64.b64decode(x)
+
+
+def pack_commit(header: dict, commit: dict, validators: Sequence[dict], n_max: int = VALIDATOR_SET_SIZE_MAX):
+    """One commit and its validator set -> (bsx_commit_in record, n_max bsx_commit_sig_in slots) for
+    `validator_records` / `present_on_trusted`.  validators: [{pub_key, voting_power, address (hex)}] in set order."""
+    cm = np.zeros((), COMMIT_DTYPE)
+    cm["height"], cm["round"], cm["n_signatures"] = int(commit["height"]), int(commit["round"]), len(commit["signatures"])
+    cm["chain_id_len"] = _put(cm["chain_id"], header["chain_id"].encode())
+    bid = commit.get("block_id")
+    if bid and bid.get("hash"):
+        cm["has_block_id"], cm["parts_total"] = 1, int(bid["parts"]["total"])
+        _put(cm["block_hash"], bytes.fromhex(bid["hash"]))
+        _put(cm["parts_hash"], bytes.fromhex(bid["parts"]["hash"]))
+    sg = np.zeros(n_max, COMMIT_SIG_DTYPE)
+    for i, (v, cs) in enumerate(zip(validators, commit["signatures"])):
+        if i >= n_max:
+            break
+        s = sg[i]
+        _put(s["pubkey"], _b64(v["pub_key"]))
+        s["voting_power"] = int(v["voting_power"])
+        s["block_id_flag"] = int(cs["block_id_flag"])
+        if v.get("address"):
+            _put(s["address"], bytes.fromhex(v["address"]) if isinstance(v["address"], str) else bytes(v["address"]))
+        if cs.get("validator_address"):
+            a = cs["validator_address"]
+            _put(s["sig_address"], bytes.fromhex(a) if isinstance(a, str) else bytes(a))
+        if cs.get("signature"):
+            _put(s["signature"], _b64(cs["signature"]))
+        if cs.get("timestamp") and int(cs["block_id_flag"]) != 1:
+            s["ts_seconds"], s["ts_nanos"] = parse_time(cs["timestamp"])
+    return cm, sg
+
+
 def header_hash(h: dict) -> bytes:
     return HeaderTree.build(header_leaves(h)).root
 

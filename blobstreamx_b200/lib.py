@@ -265,6 +265,41 @@ class Context:
                                             "start_header", "end_header", "fail")])
         return out
 
+    def encode_headers(self, fields) -> np.ndarray:
+        """bsx_header_fields records (inputs.pack_header_fields) -> header records [n, 512]."""
+        f = np.ascontiguousarray(fields)
+        assert f.dtype.itemsize == 464
+        out = np.zeros((f.size, 512), np.uint8)
+        self._call("bsx_encode_headers", C.c_uint32(f.size), _ptr(f), _ptr(out))
+        return out
+
+    def validator_records(self, commits, sigs, n_validators: int, records: bool = True, hash_fields: bool = False) -> dict:
+        """commits [n] (bsx_commit_in) + sigs [n, N] (bsx_commit_sig_in), from inputs.pack_commit ->
+        validators [n, N, 240] and/or pubkeys [n, N, 32], powers [n, N], byte_lengths [n, N]; fail [n]."""
+        cm, sg = np.ascontiguousarray(commits).reshape(-1), np.ascontiguousarray(sigs)
+        n, N = cm.size, n_validators
+        assert cm.dtype.itemsize == 152 and sg.dtype.itemsize == 160 and sg.size == n * N
+        out = dict(fail=np.zeros(n, np.uint32))
+        if records:
+            out["validators"] = np.zeros((n, N, 240), np.uint8)
+        if hash_fields:
+            out.update(pubkeys=np.zeros((n, N, 32), np.uint8), powers=np.zeros((n, N), np.uint64), byte_lengths=np.zeros((n, N), np.uint32))
+        self._call("bsx_validator_records", C.c_uint32(n), C.c_uint32(N), _ptr(cm), _ptr(sg), _ptr(out.get("validators")),
+                   _ptr(out.get("pubkeys")), _ptr(out.get("powers")), _ptr(out.get("byte_lengths")), _ptr(out["fail"]))
+        return out
+
+    def present_on_trusted(self, target_sigs, n_target, trusted_sigs, n_trusted, validators):
+        """Sets present_on_trusted_header in validators [n, N, 240] (in place) -> fail [n]."""
+        val = validators
+        assert val.dtype == np.uint8 and val.flags.c_contiguous and val.ndim == 3
+        n, N = val.shape[0], val.shape[1]
+        tg, tr = np.ascontiguousarray(target_sigs), np.ascontiguousarray(trusted_sigs)
+        assert tg.size == n * N and tr.size == n * N and tg.dtype.itemsize == 160
+        nt, ns = _in(n_target, np.uint32).reshape(-1), _in(n_trusted, np.uint32).reshape(-1)
+        fail = np.zeros(n, np.uint32)
+        self._call("bsx_present_on_trusted", C.c_uint32(n), C.c_uint32(N), _ptr(tg), _ptr(nt), _ptr(tr), _ptr(ns), _ptr(val), _ptr(fail))
+        return fail
+
     # -- witness data formats --
     def hash_input_data(self, bufs, buf_offsets, lens, kinds, sha512: bool = False):
         """HashInputData of one SHA accelerator -> dict(padded_chunks [chunks,16], end_bits, digest_bits, digest_indices)."""

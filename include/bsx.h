@@ -420,6 +420,81 @@ int bsx_header_range_inputs_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, u
                                 uint32_t *fail);
 
 /* ------------------------------------------------------------------------------------------
+ * Input shaping on the device, continued: protobuf field encoders, sign-bytes, validator records
+ *
+ * bsx_encode_headers: decoded headers -> the header records bsx_header_trees / bsx_header_range_inputs take.
+ *   replaces the 14 `encode_vec` calls of generate_proofs_from_header (TX/input/tendermint_utils.rs:374-393).
+ *   proto3 rules: zero varints and empty byte strings are omitted; last_block_id encodes to nothing when absent.
+ * bsx_validator_records: one commit + its validator set -> N ValidatorVariable records (BSX_VAL_IN_BYTES, above)
+ *   and/or the ValidatorHashField arrays of verify_skip's trusted set.
+ *   replaces get_signed_message_data / get_validator_data_from_block (TX/input/conversion.rs:20-140): slot i <
+ *   n_signatures with block_id_flag = commit carries the validator's signature and the CanonicalVote sign-bytes
+ *   (length-delimited, zero padded to 124; precommit, the commit's height / round / block id, the signature's own
+ *   timestamp, chain id); other slots of the set carry DUMMY_SIGNATURE, a zero message and length 32; slots beyond
+ *   the set carry DUMMY_PUBLIC_KEY, power 0 and validator_byte_length 46 -- and validator_hash_field_from_block
+ *   (:142-184).  Validators are passed in the set's canonical order (as the RPC returns them).  The reference also
+ *   re-verifies every signature on the host (:49-50); here that is the witness kernel's job.
+ *   fail[c] = BSX_FAIL_INPUT_SIGN_BYTES when a message exceeds 124 bytes or the set exceeds N (the reference panics).
+ * bsx_present_on_trusted: sets present_on_trusted_header (record byte 237) of the target records.
+ *   replaces update_present_on_trusted_header (:186-240): the trusted set is walked in order while
+ *   total_power * (1/3) > shared (f64 arithmetic, as there); a trusted validator found in the target set (by address)
+ *   whose address appears in the target commit's signatures (commit or nil votes) is marked and its power added once
+ *   per matching signature.  fail[c] = BSX_FAIL_INPUT_THRESHOLD when a third is not reached (the reference asserts).
+ * ------------------------------------------------------------------------------------------ */
+#define BSX_FAIL_INPUT_SIGN_BYTES 512u
+#define BSX_FAIL_INPUT_THRESHOLD 1024u
+typedef struct bsx_header_fields {    /* a decoded tendermint Header; 464 bytes, 8-byte aligned */
+    uint64_t version_block, version_app, height;
+    int64_t time_seconds;
+    uint32_t time_nanos;
+    uint32_t chain_id_len;            /* <= 50 */
+    uint8_t chain_id[56];
+    uint32_t parts_total;             /* last_block_id.part_set_header.total */
+    uint8_t has_last_block_id;        /* 0: the field encodes to nothing (first block) */
+    uint8_t hash_len[9];              /* lengths of `hashes` (0 = absent / empty; proposer_address 20) */
+    uint8_t _pad[2];
+    uint8_t last_block_hash[32], parts_hash[32];
+    uint8_t hashes[9][32];            /* last_commit_hash, data_hash, validators_hash, next_validators_hash, consensus_hash,
+                                         app_hash, last_results_hash, evidence_hash, proposer_address */
+} bsx_header_fields;
+typedef struct bsx_commit_in {        /* Commit + chain id; 152 bytes, 8-byte aligned */
+    uint64_t height;
+    uint32_t round;
+    uint32_t n_signatures;            /* commit.signatures.len() = validators in the set */
+    uint8_t block_hash[32], parts_hash[32];   /* commit.block_id */
+    uint32_t parts_total;
+    uint32_t chain_id_len;            /* <= 50 */
+    uint8_t chain_id[56];
+    uint8_t has_block_id;             /* 0: block id omitted from the vote (nil) */
+    uint8_t _pad[7];
+} bsx_commit_in;
+typedef struct bsx_commit_sig_in {    /* validator i of the set + commit.signatures[i]; 160 bytes, 8-byte aligned */
+    uint8_t pubkey[32];
+    uint8_t signature[64];
+    uint64_t voting_power;
+    int64_t ts_seconds;               /* the signature's timestamp */
+    uint32_t ts_nanos;
+    uint8_t block_id_flag;            /* 1 absent, 2 commit, 3 nil */
+    uint8_t _pad[3];
+    uint8_t address[20];              /* the validator's address */
+    uint8_t sig_address[20];          /* commit.signatures[i].validator_address (ignored when absent) */
+} bsx_commit_sig_in;
+int bsx_encode_headers(bsx_ctx *ctx, uint32_t n, const bsx_header_fields *fields, uint8_t *headers /* n*512 */);
+int bsx_encode_headers_dev(bsx_ctx *ctx, void *stream, uint32_t n, const bsx_header_fields *fields, uint8_t *headers);
+/* validators (n*N*240), and pubkeys (n*N*32) / powers (n*N) / byte_lengths (n*N) may each be NULL (all three or none) */
+int bsx_validator_records(bsx_ctx *ctx, uint32_t n, uint32_t N, const bsx_commit_in *commits, const bsx_commit_sig_in *sigs,
+                          uint8_t *validators, uint8_t *pubkeys, uint64_t *powers, uint32_t *byte_lengths, uint32_t *fail);
+int bsx_validator_records_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const bsx_commit_in *commits,
+                              const bsx_commit_sig_in *sigs, uint8_t *validators, uint8_t *pubkeys, uint64_t *powers,
+                              uint32_t *byte_lengths, uint32_t *fail);
+/* target_sigs / trusted_sigs: n*N slots; n_target[c] / n_trusted[c] validators in each set; validators: in/out */
+int bsx_present_on_trusted(bsx_ctx *ctx, uint32_t n, uint32_t N, const bsx_commit_sig_in *target_sigs, const uint32_t *n_target,
+                           const bsx_commit_sig_in *trusted_sigs, const uint32_t *n_trusted, uint8_t *validators, uint32_t *fail);
+int bsx_present_on_trusted_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const bsx_commit_sig_in *target_sigs,
+                               const uint32_t *n_target, const bsx_commit_sig_in *trusted_sigs, const uint32_t *n_trusted,
+                               uint8_t *validators, uint32_t *fail);
+
+/* ------------------------------------------------------------------------------------------
  * Witness data formats
  * HashInputData: the STARK public-input layout of one SHA accelerator, built from its request list
  *   replaces get_hash_data (PX/frontend/hash/curta/mod.rs:95-192; stream order PX/frontend/hash/curta/data.rs:63-78)

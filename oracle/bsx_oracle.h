@@ -50,6 +50,22 @@ uint32_t orc_tm_aunts_from_slices(const uint8_t *items, const uint32_t *offsets,
 int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers, uint64_t start, uint64_t end,
                             uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers,
                             uint8_t *end_headers, uint8_t start_header[32], uint8_t end_header[32]);
+/* off-chain input shaping: the 14 protobuf field encoders of a header (TX/input/tendermint_utils.rs:374-393),
+ * CanonicalVote sign-bytes (TX/input/conversion.rs:34-39), validator records (:59-184), trusted-set walk (:186-240) */
+uint32_t orc_encode_header_fields(uint64_t version_block, uint64_t version_app, const uint8_t *chain_id, uint32_t chain_id_len,
+                                  uint64_t height, int64_t time_secs, uint32_t time_nanos, int has_last_block_id,
+                                  const uint8_t last_block_hash[32], uint32_t parts_total, const uint8_t parts_hash[32],
+                                  const uint8_t *hashes, const uint8_t hash_len[9], uint8_t lens[14], uint8_t *out);
+uint32_t orc_vote_sign_bytes(const uint8_t *chain_id, uint32_t chain_id_len, uint64_t height, uint64_t round, int has_block_id,
+                             const uint8_t block_hash[32], uint32_t parts_total, const uint8_t parts_hash[32], int64_t ts_secs,
+                             uint32_t ts_nanos, uint8_t *out);
+int orc_validator_records(uint32_t N, uint32_t n_sigs, const uint8_t *chain_id, uint32_t chain_id_len, uint64_t height, uint64_t round,
+                          int has_block_id, const uint8_t block_hash[32], uint32_t parts_total, const uint8_t parts_hash[32],
+                          const uint8_t *pubkeys, const uint8_t *signatures, const uint64_t *powers, const int64_t *ts_secs,
+                          const uint32_t *ts_nanos, const uint8_t *flags, uint8_t *records, uint8_t *hf_pubkeys, uint64_t *hf_powers,
+                          uint32_t *hf_lens);
+int orc_present_on_trusted(uint32_t n_target, const uint8_t *tg_addr, const uint8_t *tg_sig_addr, const uint8_t *tg_flags,
+                           const uint64_t *tg_powers, uint32_t n_trusted, const uint8_t *tr_addr, uint8_t *records);
 /* fixed-shape proof: digests = [leaf?] + (left,right) per level, schedule order.
  * path_bits bit i = path_indices[i].  hashed_leaf!=0 => `leaf` is the 32-byte digest. */
 void orc_tm_merkle_proof(const uint8_t *leaf, uint32_t leaf_len, const uint8_t *aunts, uint32_t depth,

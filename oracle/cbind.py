@@ -121,6 +121,62 @@ def header_range_inputs(n_jobs: int, B: int, headers, start: int, end: int):
     return out
 
 
+def _field(rec, name) -> np.ndarray:
+    return np.ascontiguousarray(rec[name])
+
+
+def encode_header_fields(rec):
+    """One decoded header (a record with the fields of include/bsx.h bsx_header_fields) -> (lens[14], fields back to back)."""
+    lens, out = np.zeros(14, np.uint8), np.zeros(512, np.uint8)
+    cid, lb, ph, hs, hl = (_field(rec, k) for k in ("chain_id", "last_block_hash", "parts_hash", "hashes", "hash_len"))
+    f = lib().orc_encode_header_fields
+    f.restype = C.c_uint32
+    n = f(C.c_uint64(int(rec["version_block"])), C.c_uint64(int(rec["version_app"])), _p(cid), C.c_uint32(int(rec["chain_id_len"])),
+          C.c_uint64(int(rec["height"])), C.c_int64(int(rec["time_seconds"])), C.c_uint32(int(rec["time_nanos"])),
+          C.c_int(int(rec["has_last_block_id"])), _p(lb), C.c_uint32(int(rec["parts_total"])), _p(ph), _p(hs), _p(hl), _p(lens), _p(out))
+    return lens, out[:n].tobytes()
+
+
+def vote_sign_bytes(chain_id: bytes, height: int, round_: int, block_hash, parts_total: int, parts_hash, ts_secs: int,
+                    ts_nanos: int) -> bytes:
+    cid, out = _u8(chain_id), np.zeros(256, np.uint8)
+    has = block_hash is not None
+    bh, ph = _u8(block_hash if has else bytes(32)), _u8(parts_hash if has else bytes(32))
+    f = lib().orc_vote_sign_bytes
+    f.restype = C.c_uint32
+    n = f(_p(cid), C.c_uint32(len(cid)), C.c_uint64(height), C.c_uint64(round_), C.c_int(int(has)), _p(bh), C.c_uint32(parts_total),
+          _p(ph), C.c_int64(ts_secs), C.c_uint32(ts_nanos), _p(out))
+    return out[:n].tobytes()
+
+
+def validator_records(cm, sg, N: int):
+    """One commit (bsx_commit_in fields) + its N signature slots (bsx_commit_sig_in fields) ->
+    dict(validators [N,240], pubkeys [N,32], powers [N], byte_lengths [N], bad)."""
+    n_sigs = int(cm["n_signatures"])
+    k = min(n_sigs, len(sg))
+    cols = {name: np.ascontiguousarray(sg[name][:k]) for name in ("pubkey", "signature", "voting_power", "ts_seconds", "ts_nanos", "block_id_flag")}
+    out = dict(validators=np.zeros((N, 240), np.uint8), pubkeys=np.zeros((N, 32), np.uint8), powers=np.zeros(N, np.uint64),
+               byte_lengths=np.zeros(N, np.uint32))
+    cid, bh, ph = _field(cm, "chain_id"), _field(cm, "block_hash"), _field(cm, "parts_hash")
+    f = lib().orc_validator_records
+    f.restype = C.c_int
+    out["bad"] = f(C.c_uint32(N), C.c_uint32(n_sigs), _p(cid), C.c_uint32(int(cm["chain_id_len"])), C.c_uint64(int(cm["height"])),
+                   C.c_uint64(int(cm["round"])), C.c_int(int(cm["has_block_id"])), _p(bh), C.c_uint32(int(cm["parts_total"])), _p(ph),
+                   _p(cols["pubkey"]), _p(cols["signature"]), _p(cols["voting_power"]), _p(cols["ts_seconds"]), _p(cols["ts_nanos"]),
+                   _p(cols["block_id_flag"]), _p(out["validators"]), _p(out["pubkeys"]), _p(out["powers"]), _p(out["byte_lengths"]))
+    return out
+
+
+def present_on_trusted(tg, n_target: int, tr, n_trusted: int, validators: np.ndarray) -> int:
+    """Marks present_on_trusted_header in validators [N,240] (in place); returns non-zero below the 1/3 threshold."""
+    assert validators.dtype == np.uint8 and validators.flags.c_contiguous
+    cols = [np.ascontiguousarray(tg[name][:n_target]) for name in ("address", "sig_address", "block_id_flag", "voting_power")]
+    tra = np.ascontiguousarray(tr["address"][:n_trusted])
+    f = lib().orc_present_on_trusted
+    f.restype = C.c_int
+    return f(C.c_uint32(n_target), _p(cols[0]), _p(cols[1]), _p(cols[2]), _p(cols[3]), C.c_uint32(n_trusted), _p(tra), _p(validators))
+
+
 def tm_merkle_proof(leaf: bytes, aunts: bytes, depth: int, path_bits: int, hashed_leaf: bool = False):
     l, a = _u8(leaf), _u8(aunts)
     nd = 2 * depth + (0 if hashed_leaf else 1)

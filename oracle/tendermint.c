@@ -385,3 +385,171 @@ void orc_hash_validator_set(uint32_t N, const uint8_t *pubkeys, const uint64_t *
     }
     orc_tm_merkle_tree(digests, N, nb_enabled, digests + 32 * (size_t)N, root);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Off-chain input shaping: protobuf encoders, sign-bytes, validator records
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { uint8_t *p; uint32_t n; } pbw;
+static void pb_byte(pbw *w, uint8_t b) { w->p[w->n++] = b; }
+static void pb_uvarint(pbw *w, uint64_t v) {
+    while (v >= 0x80) { pb_byte(w, (uint8_t)(v | 0x80)); v >>= 7; }
+    pb_byte(w, (uint8_t)v);
+}
+static void pb_varint_field(pbw *w, uint8_t tag, uint64_t v) {      /* proto3: default value omitted */
+    if (!v) return;
+    pb_byte(w, tag); pb_uvarint(w, v);
+}
+static void pb_bytes_field(pbw *w, uint8_t tag, const uint8_t *s, uint32_t len) {
+    if (!len) return;
+    pb_byte(w, tag); pb_uvarint(w, len);
+    memcpy(w->p + w->n, s, len); w->n += len;
+}
+/* BlockId {hash = 1, part_set_header = 2 {total = 1, hash = 2}}; CanonicalBlockId uses the same numbers */
+static uint32_t enc_block_id(const uint8_t hash[32], uint32_t parts_total, const uint8_t parts_hash[32], uint8_t *out) {
+    uint8_t psh[48];
+    pbw p = {psh, 0};
+    pb_varint_field(&p, 0x08, parts_total);
+    pb_bytes_field(&p, 0x12, parts_hash, 32);
+    pbw w = {out, 0};
+    pb_bytes_field(&w, 0x0A, hash, 32);
+    pb_bytes_field(&w, 0x12, psh, p.n);
+    return w.n;
+}
+static uint32_t enc_timestamp(int64_t secs, uint32_t nanos, uint8_t *out) {
+    pbw w = {out, 0};
+    pb_varint_field(&w, 0x08, (uint64_t)secs);
+    pb_varint_field(&w, 0x10, nanos);
+    return w.n;
+}
+
+/* the 14 encode_vec calls of generate_proofs_from_header (TX/input/tendermint_utils.rs:374-393); fields back to back
+ * into out (<= 496 bytes), their lengths into lens; hashes = last_commit_hash, data_hash, validators_hash,
+ * next_validators_hash, consensus_hash, app_hash, last_results_hash, evidence_hash, proposer_address */
+uint32_t orc_encode_header_fields(uint64_t version_block, uint64_t version_app, const uint8_t *chain_id, uint32_t chain_id_len,
+                                  uint64_t height, int64_t time_secs, uint32_t time_nanos, int has_last_block_id,
+                                  const uint8_t last_block_hash[32], uint32_t parts_total, const uint8_t parts_hash[32],
+                                  const uint8_t *hashes, const uint8_t hash_len[9], uint8_t lens[14], uint8_t *out) {
+    pbw w = {out, 0};
+    uint32_t at = 0;
+#define ORC_CLOSE(f) do { lens[f] = (uint8_t)(w.n - at); at = w.n; } while (0)
+    pb_varint_field(&w, 0x08, version_block);
+    pb_varint_field(&w, 0x10, version_app);
+    ORC_CLOSE(0);
+    pb_bytes_field(&w, 0x0A, chain_id, chain_id_len);
+    ORC_CLOSE(1);
+    pb_varint_field(&w, 0x08, height);
+    ORC_CLOSE(2);
+    w.n += enc_timestamp(time_secs, time_nanos, w.p + w.n);
+    ORC_CLOSE(3);
+    if (has_last_block_id) w.n += enc_block_id(last_block_hash, parts_total, parts_hash, w.p + w.n);
+    ORC_CLOSE(4);
+    for (int k = 0; k < 9; k++) {
+        pb_bytes_field(&w, 0x0A, hashes + 32 * k, hash_len[k]);
+        ORC_CLOSE(5 + k);
+    }
+#undef ORC_CLOSE
+    return w.n;
+}
+
+/* SignedVote::sign_bytes of a precommit (TX/input/conversion.rs:34-39): length-delimited CanonicalVote
+ * {type = 1, height = 2 sfixed64, round = 3 sfixed64, block_id = 4, timestamp = 5, chain_id = 6}; out >= 192 bytes */
+uint32_t orc_vote_sign_bytes(const uint8_t *chain_id, uint32_t chain_id_len, uint64_t height, uint64_t round, int has_block_id,
+                             const uint8_t block_hash[32], uint32_t parts_total, const uint8_t parts_hash[32], int64_t ts_secs,
+                             uint32_t ts_nanos, uint8_t *out) {
+    uint8_t body[192], tmp[96];
+    pbw b = {body, 0};
+    pb_varint_field(&b, 0x08, 2);
+    if (height) { pb_byte(&b, 0x11); put64(b.p + b.n, height); b.n += 8; }
+    if (round) { pb_byte(&b, 0x19); put64(b.p + b.n, round); b.n += 8; }
+    if (has_block_id) pb_bytes_field(&b, 0x22, tmp, enc_block_id(block_hash, parts_total, parts_hash, tmp));
+    uint32_t tl = enc_timestamp(ts_secs, ts_nanos, tmp);
+    pb_byte(&b, 0x2A); pb_uvarint(&b, tl);            /* Some(timestamp): written even when empty */
+    memcpy(b.p + b.n, tmp, tl); b.n += tl;
+    pb_bytes_field(&b, 0x32, chain_id, chain_id_len);
+    pbw w = {out, 0};
+    pb_uvarint(&w, b.n);
+    memcpy(w.p + w.n, body, b.n);
+    return w.n + b.n;
+}
+
+static const uint8_t ORC_DUMMY_PK[32] = {138, 136, 227, 221, 116, 9, 241, 149, 253, 82, 219, 45, 60, 186, 93, 114,
+                                         202, 103, 9, 191, 29, 148, 18, 27, 243, 116, 136, 1, 180, 15, 111, 92};
+static const uint8_t ORC_DUMMY_SIG[64] = {55, 20, 104, 158, 84, 120, 194, 17, 6, 237, 157, 164, 85, 88, 158, 137,
+                                          187, 119, 187, 240, 159, 73, 80, 63, 133, 162, 74, 91, 48, 53, 6, 138,
+                                          1, 41, 22, 121, 249, 46, 198, 145, 155, 102, 3, 210, 168, 135, 173, 55,
+                                          252, 72, 45, 126, 169, 178, 191, 7, 153, 67, 112, 90, 150, 33, 140, 7};
+
+/* get_validator_data_from_block (TX/input/conversion.rs:59-140) + validator_hash_field_from_block (:142-184) for one
+ * commit.  records: N * 240 bytes in the layout of include/bsx.h (ValidatorVariable); hf_*: N entries each.
+ * Either output group may be NULL.  Returns non-zero when a message exceeds 124 bytes or n_sigs > N (panics there). */
+int orc_validator_records(uint32_t N, uint32_t n_sigs, const uint8_t *chain_id, uint32_t chain_id_len, uint64_t height, uint64_t round,
+                          int has_block_id, const uint8_t block_hash[32], uint32_t parts_total, const uint8_t parts_hash[32],
+                          const uint8_t *pubkeys, const uint8_t *signatures, const uint64_t *powers, const int64_t *ts_secs,
+                          const uint32_t *ts_nanos, const uint8_t *flags, uint8_t *records, uint8_t *hf_pubkeys, uint64_t *hf_powers,
+                          uint32_t *hf_lens) {
+    int bad = n_sigs > N;
+    for (uint32_t i = 0; i < N; i++) {
+        const int in_set = i < n_sigs, is_commit = in_set && flags[i] == 2;
+        const uint8_t *pk = in_set ? pubkeys + 32 * (size_t)i : ORC_DUMMY_PK;
+        const uint64_t power = in_set ? powers[i] : 0;
+        uint8_t vb[48];
+        uint32_t vlen = 46;                                       /* VALIDATOR_BYTE_LENGTH_MAX */
+        if (in_set) {                                             /* validator.hash_bytes(): 0a 22 0a 20 pk 10 varint */
+            pbw v = {vb, 0};
+            pb_byte(&v, 0x0A); pb_byte(&v, 0x22); pb_byte(&v, 0x0A); pb_byte(&v, 0x20);
+            memcpy(v.p + v.n, pk, 32); v.n += 32;
+            pb_byte(&v, 0x10); pb_uvarint(&v, power);
+            vlen = v.n;
+        }
+        if (hf_pubkeys) {
+            memcpy(hf_pubkeys + 32 * (size_t)i, pk, 32);
+            hf_powers[i] = power;
+            hf_lens[i] = vlen;
+        }
+        if (!records) continue;
+        uint8_t *r = records + 240 * (size_t)i;
+        memset(r, 0, 240);
+        memcpy(r, pk, 32);
+        uint32_t msg_len = 32;
+        if (is_commit) {
+            uint8_t msg[200];
+            memcpy(r + 32, signatures + 64 * (size_t)i, 64);
+            msg_len = orc_vote_sign_bytes(chain_id, chain_id_len, height, round, has_block_id, block_hash, parts_total, parts_hash,
+                                          ts_secs[i], ts_nanos[i], msg);
+            if (msg_len > 124) { bad = 1; msg_len = 0; }
+            memcpy(r + 96, msg, msg_len);
+        } else {
+            memcpy(r + 32, ORC_DUMMY_SIG, 64);
+        }
+        put32(r + 220, msg_len);
+        put64(r + 224, power);
+        put32(r + 232, vlen);
+        r[236] = (uint8_t)is_commit;
+    }
+    return bad;
+}
+
+/* update_present_on_trusted_header (TX/input/conversion.rs:186-240) for one commit; addresses are 20 bytes.
+ * Sets records[i*240 + 237]; returns non-zero when a third of the target power is not reached (asserts there). */
+int orc_present_on_trusted(uint32_t n_target, const uint8_t *tg_addr, const uint8_t *tg_sig_addr, const uint8_t *tg_flags,
+                           const uint64_t *tg_powers, uint32_t n_trusted, const uint8_t *tr_addr, uint8_t *records) {
+    uint64_t total = 0, shared = 0;
+    for (uint32_t i = 0; i < n_target; i++) total += tg_powers[i];
+    const double threshold = 1.0 / 3.0;
+    uint32_t s = 0;
+    while ((double)total * threshold > (double)shared && s < n_trusted) {
+        const uint8_t *a = tr_addr + 20 * (size_t)s;
+        for (uint32_t i = 0; i < n_target; i++) {
+            if (memcmp(tg_addr + 20 * (size_t)i, a, 20)) continue;
+            for (uint32_t j = 0; j < n_target; j++) {             /* sig.validator_address(): Some for commit and nil votes */
+                if ((tg_flags[j] == 2 || tg_flags[j] == 3) && !memcmp(tg_sig_addr + 20 * (size_t)j, a, 20)) {
+                    shared += tg_powers[i];
+                    records[240 * (size_t)i + 237] = 1;
+                }
+            }
+            break;
+        }
+        s++;
+    }
+    return (double)total * threshold > (double)shared;
+}
