@@ -793,6 +793,98 @@ def run_shape(args):
                       "cpu_baseline": cpu}))
 
 
+def run_encode(args):
+    """Device-side encoders: --ranges x 1025 decoded headers -> header records (14 protobuf fields each), and
+    --ranges commits x 100 validators -> ValidatorVariable records with CanonicalVote sign-bytes.  Byte shuffling only:
+    reported against the copy-bandwidth peak."""
+    import torch
+    from blobstreamx_b200 import inputs as I, lib
+    from blobstreamx_b200.lib import ptr, u32
+    from tests._encode_cases import chain_header_fields, random_commits, random_header_fields
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = lib.Context(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    R = args.ranges if args.ranges > 0 else 256
+    n_hdr, N = R * (N_JOBS * BATCH + 1), N_VAL
+    f0 = random_header_fields(256, seed=3)                   # every proto3 default and length: the parity sample
+    fields_rand = np.tile(f0, (n_hdr + 255) // 256)[:n_hdr]
+    fields = chain_header_fields(n_hdr)                      # the timed workload: headers as a live chain has them
+    cm0, tg0, _, _, _ = random_commits(16, N, seed=4)
+    cm, tg = np.tile(cm0, (R + 15) // 16)[:R], np.tile(tg0, ((R + 15) // 16, 1))[:R]
+    dt = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    d_f, d_fr, d_cm, d_tg = dt(fields), dt(fields_rand), dt(cm), dt(tg)
+    d_rec = torch.zeros(n_hdr * 512, dtype=torch.uint8, device=dev)
+    d_val = torch.zeros(R * N * 240, dtype=torch.uint8, device=dev)
+    d_fail = torch.zeros(R * 4, dtype=torch.uint8, device=dev)
+    P = lambda t: ptr(t.data_ptr())
+
+    def step_headers():
+        ctx.call_dev("bsx_encode_headers_dev", stream, u32(n_hdr), P(d_f), P(d_rec))
+
+    def step_headers_rand():
+        ctx.call_dev("bsx_encode_headers_dev", stream, u32(n_hdr), P(d_fr), P(d_rec))
+
+    def step_vals():
+        ctx.call_dev("bsx_validator_records_dev", stream, u32(R), u32(N), P(d_cm), P(d_tg), P(d_val), ptr(0), ptr(0), ptr(0), P(d_fail))
+
+    from oracle import cbind as orc
+    for fn, src in ((step_headers_rand, f0), (step_headers, fields)):
+        fn()
+        torch.cuda.synchronize()
+        got = d_rec[: 256 * 512].cpu().numpy().reshape(256, 512)
+        for i in range(0, 256, 17):
+            lens, body = orc.encode_header_fields(src[i])
+            assert got[i, :14].tolist() == lens.tolist() and got[i, 16:16 + len(body)].tobytes() == body, "header records differ from the oracle"
+    step_vals()
+    torch.cuda.synchronize()
+    gv = d_val[: 16 * N * 240].cpu().numpy().reshape(16, N, 240)
+    for c in range(16):
+        assert (gv[c] == orc.validator_records(cm0[c], tg0[c], N)["validators"]).all(), "validator records differ from the oracle"
+    res = {}
+    with ClockSampler(0) as clk:
+        for name, fn in (("headers", step_headers), ("headers_rand", step_headers_rand), ("validators", step_vals)):
+            for _ in range(args.warmup):
+                fn()
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            for _ in range(args.steps):
+                fn()
+            ev[1].record()
+            torch.cuda.synchronize()
+            res[name] = ev[0].elapsed_time(ev[1]) / args.steps
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_h, alg_v = n_hdr * (464 + 512), R * N * (160 + 240) + R * 152
+    ms = res["headers"]
+    cpu = None
+    if not args.no_cpu:
+        t0 = time.perf_counter()
+        for i in range(2000):
+            orc.encode_header_fields(f0[i % 256])
+        cpu = {"value": 2000 / (time.perf_counter() - t0), "unit": "headers/s", "cores": 1, "kind": "port",
+               "sample": "2000 headers through oracle/tendermint.c (ctypes call per header)"}
+    print(json.dumps({"metric": "headers/sec, protobuf field encoding of decoded headers", "value": n_hdr / (ms * 1e-3), "unit": "headers/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "u8",
+                      "data": "synthetic",
+                      "config": {"workload": f"{n_hdr} decoded headers of a synthetic chain (464 B) -> 512-byte header records; {R} commits x {N} validators -> 240-byte records",
+                                 "l2": f"{alg_h / 1e6:.0f} MB per step > 126 MB L2"},
+                      "gpu_launches": 3 * args.steps, "clocks": clk.summary(),
+                      "random_field_lengths": {"ms_per_step": res["headers_rand"], "headers_per_s": n_hdr / (res["headers_rand"] * 1e-3),
+                                               "note": "every thread of a warp at a different output offset (the parity sample, tiled)"},
+                      "validator_records": {"ms_per_step": res["validators"], "records_per_s": R * N / (res["validators"] * 1e-3),
+                                            "achieved_gbs": alg_v / (res["validators"] * 1e-3) / 1e9},
+                      "roofline": {"kernel": "encode_headers_kernel", "bound": "hbm", "achieved": alg_h / (ms * 1e-3) / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": alg_h / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_h},
+                      "cpu_baseline": cpu}))
+
+
 def run_pack(args):
     """Witness bit expansion (ByteVariable = 8 field elements per byte, PX/frontend/vars/byte.rs:49-57): --pack-bytes payload
     bytes -> 64x as many bytes of u64 elements, and back.  A pure HBM stream: reported against the copy-bandwidth peak."""
@@ -926,7 +1018,7 @@ def run_tree(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon", "shape", "pack"])
+    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon", "shape", "encode", "pack"])
     ap.add_argument("--trees", type=int, default=4096)
     ap.add_argument("--hashes", type=int, default=1 << 20)
     ap.add_argument("--pack-bytes", type=int, default=1 << 25)
@@ -961,6 +1053,8 @@ def main():
         run_poseidon(args)
     elif args.mode == "shape":
         run_shape(args)
+    elif args.mode == "encode":
+        run_encode(args)
     elif args.mode == "pack":
         run_pack(args)
     else:

@@ -6,8 +6,11 @@
 //   get_validator_data_from_block       TX/input/conversion.rs:59-140
 //   validator_hash_field_from_block     TX/input/conversion.rs:142-184
 //   update_present_on_trusted_header    TX/input/conversion.rs:186-240
-// All byte-serial work on a few hundred bytes per item: one thread per header / validator slot builds its record in
-// local memory and stores it with 16-byte writes; the trusted-set walk is sequential per commit and takes one warp.
+// All byte-serial work on a few hundred bytes per item: one thread per header / validator slot; the header records are
+// staged through shared memory on both sides, the (smaller) validator records are built in local memory and stored with
+// 16-byte writes; the trusted-set walk is sequential per commit and takes one warp.
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace bsx {
@@ -20,11 +23,16 @@ __constant__ uint8_t DUMMY_SIGN[64] = {55,  20,  104, 158, 84,  120, 194, 17,  6
                                        1,   41,  22,  121, 249, 46,  198, 145, 155, 102, 3,   210, 168, 135, 173, 55,
                                        252, 72,  45,  126, 169, 178, 191, 7,   153, 67,  112, 90,  150, 33,  140, 7};
 
-// proto3 writer over a byte buffer in local memory
-struct Pb {
+// proto3 writer over a byte buffer: W = 1 a linear buffer (local memory); W > 1 a buffer whose 32-bit words are interleaved
+// with those of W - 1 other writers (word w of this writer at word index w * W), the layout of the header kernel's stage
+template <int W>
+struct PbW {
     uint8_t *p;
     uint32_t n;
-    __device__ void byte(uint32_t b) { p[n++] = (uint8_t)b; }
+    __device__ void byte(uint32_t b) {
+        p[W == 1 ? n : (n >> 2) * (4 * W) + (n & 3)] = (uint8_t)b;
+        n++;
+    }
     __device__ void varint(uint64_t v) {
         while (v >= 0x80) {
             byte((uint32_t)(v & 0x7F) | 0x80);
@@ -53,6 +61,7 @@ struct Pb {
         }
     }
 };
+using Pb = PbW<1>;
 __device__ __forceinline__ uint32_t varint_len(uint64_t v) {
     uint32_t n = 1;
     while (v >= 0x80) {
@@ -62,7 +71,8 @@ __device__ __forceinline__ uint32_t varint_len(uint64_t v) {
     return n;
 }
 // BlockId / CanonicalBlockId (same field numbers): hash = 1, part_set_header = 2 {total = 1, hash = 2}
-__device__ void pb_block_id(Pb &o, const uint8_t *hash, uint32_t parts_total, const uint8_t *parts_hash) {
+template <class O>
+__device__ void pb_block_id(O &o, const uint8_t *hash, uint32_t parts_total, const uint8_t *parts_hash) {
     o.ld(0x0A, hash, 32);
     o.byte(0x12);
     o.varint((parts_total ? 1 + varint_len(parts_total) : 0) + 34);
@@ -70,7 +80,8 @@ __device__ void pb_block_id(Pb &o, const uint8_t *hash, uint32_t parts_total, co
     o.ld(0x12, parts_hash, 32);
 }
 __device__ __forceinline__ uint32_t block_id_len(uint32_t parts_total) { return 34 + 2 + (parts_total ? 1 + varint_len(parts_total) : 0) + 34; }
-__device__ void pb_timestamp(Pb &o, int64_t seconds, uint32_t nanos) {
+template <class O>
+__device__ void pb_timestamp(O &o, int64_t seconds, uint32_t nanos) {
     o.vi(0x08, (uint64_t)seconds);
     o.vi(0x10, nanos);
 }
@@ -78,36 +89,70 @@ __device__ __forceinline__ uint32_t timestamp_len(int64_t seconds, uint32_t nano
     return (seconds ? 1 + varint_len((uint64_t)seconds) : 0) + (nanos ? 1 + varint_len(nanos) : 0);
 }
 
-// header record: lengths of the 14 fields in bytes [0,14), the fields back to back from byte 16 (bsx.h)
-__global__ void __launch_bounds__(128) encode_headers_kernel(uint32_t n, const bsx_header_fields *__restrict__ fields, uint8_t *__restrict__ headers) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const bsx_header_fields &h = fields[t];
-    __align__(16) uint8_t rec[BSX_HEADER_LEAVES_BYTES];
-    for (int i = 0; i < BSX_HEADER_LEAVES_BYTES / 4; i++) reinterpret_cast<uint32_t *>(rec)[i] = 0;
-    Pb o{rec, 16};
-    uint32_t at = o.n;
-    auto close = [&](int f) {
-        rec[f] = (uint8_t)(o.n - at);
-        at = o.n;
-    };
-    o.vi(0x08, h.version_block);
-    o.vi(0x10, h.version_app);
-    close(0);
-    o.ld(0x0A, h.chain_id, h.chain_id_len > 50 ? 50 : h.chain_id_len);
-    close(1);
-    o.vi(0x08, h.height);
-    close(2);
-    pb_timestamp(o, h.time_seconds, h.time_nanos);
-    close(3);
-    if (h.has_last_block_id) pb_block_id(o, h.last_block_hash, h.parts_total, h.parts_hash);
-    close(4);
-    for (int k = 0; k < 9; k++) {
-        o.ld(0x0A, h.hashes[k], h.hash_len[k] > 32 ? 32 : h.hash_len[k]);
-        close(5 + k);
+// header record: lengths of the 14 fields in bytes [0,14), the fields back to back from byte 16 (bsx.h).
+// One thread encodes one header, one warp per CTA, and neither side touches global or local memory byte-wise: the 32
+// input structs come in with coalesced 16-byte loads into shared memory (stride padded to 117 words: a thread's byte reads
+// stay in its own bank), and the record is written byte by byte into a second shared buffer with the threads' words
+// interleaved (word w of thread t at w*33 + t: conflict-free while the threads are at the same offset, a few-way conflict
+// once their field lengths differ), from which the warp stores each record as four 128-byte rows.
+// (First version -- fields read from global, record built in local memory: 32 sectors per byte access, 0.68 ms for 262 k
+// headers = 6 % of the copy bandwidth.)
+constexpr int ENC_T = 32, ENC_IN_WORDS = sizeof(bsx_header_fields) / 4, ENC_IN_STRIDE = ENC_IN_WORDS + 1, ENC_OUT_WORDS = BSX_HEADER_LEAVES_BYTES / 4;
+static_assert(sizeof(bsx_header_fields) % 16 == 0, "bulk loads of the input structs");
+
+__global__ void __launch_bounds__(ENC_T) encode_headers_kernel(uint32_t n, const bsx_header_fields *__restrict__ fields, uint8_t *__restrict__ headers) {
+    __shared__ __align__(16) uint32_t sm_in[ENC_T * ENC_IN_STRIDE];
+    __shared__ __align__(16) uint32_t sm_out[ENC_OUT_WORDS * (ENC_T + 1)];
+    const uint32_t base = blockIdx.x * ENC_T, t = threadIdx.x, cnt = n - base < (uint32_t)ENC_T ? n - base : (uint32_t)ENC_T;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(fields + base);
+        for (uint32_t q = t; q < cnt * (ENC_IN_WORDS / 4); q += ENC_T) {
+            const uint4 v = __ldg(src + q);
+            const uint32_t s = q / (ENC_IN_WORDS / 4), w = 4 * (q % (ENC_IN_WORDS / 4));
+            uint32_t *d = sm_in + s * ENC_IN_STRIDE + w;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        for (int w = 0; w < ENC_OUT_WORDS; w++) sm_out[w * (ENC_T + 1) + t] = 0;
     }
-    uint4 *dst = reinterpret_cast<uint4 *>(headers + (size_t)BSX_HEADER_LEAVES_BYTES * t);
-    for (int i = 0; i < BSX_HEADER_LEAVES_BYTES / 16; i++) dst[i] = reinterpret_cast<const uint4 *>(rec)[i];
+    __syncwarp();
+    if (t < cnt) {
+        // field offsets as in bsx_header_fields; the struct sits at a 4-byte aligned shared address
+        const uint8_t *hb = reinterpret_cast<const uint8_t *>(sm_in + t * ENC_IN_STRIDE);
+        auto u32at = [&](int off) { return *reinterpret_cast<const uint32_t *>(hb + off); };
+        auto u64at = [&](int off) { return (uint64_t)u32at(off) | ((uint64_t)u32at(off + 4) << 32); };
+        const uint64_t version_block = u64at(offsetof(bsx_header_fields, version_block)), version_app = u64at(offsetof(bsx_header_fields, version_app)),
+                       height = u64at(offsetof(bsx_header_fields, height));
+        const int64_t time_seconds = (int64_t)u64at(offsetof(bsx_header_fields, time_seconds));
+        const uint32_t time_nanos = u32at(offsetof(bsx_header_fields, time_nanos)), chain_id_len = u32at(offsetof(bsx_header_fields, chain_id_len)),
+                       parts_total = u32at(offsetof(bsx_header_fields, parts_total));
+        const uint8_t *hash_len = hb + offsetof(bsx_header_fields, hash_len);
+        PbW<ENC_T + 1> o{reinterpret_cast<uint8_t *>(sm_out + t), 16};
+        uint32_t at = o.n;
+        auto close = [&](uint32_t f) {
+            o.p[(f >> 2) * (4 * (ENC_T + 1)) + (f & 3)] = (uint8_t)(o.n - at);
+            at = o.n;
+        };
+        o.vi(0x08, version_block);
+        o.vi(0x10, version_app);
+        close(0);
+        o.ld(0x0A, hb + offsetof(bsx_header_fields, chain_id), chain_id_len > 50 ? 50 : chain_id_len);
+        close(1);
+        o.vi(0x08, height);
+        close(2);
+        pb_timestamp(o, time_seconds, time_nanos);
+        close(3);
+        if (hb[offsetof(bsx_header_fields, has_last_block_id)])
+            pb_block_id(o, hb + offsetof(bsx_header_fields, last_block_hash), parts_total, hb + offsetof(bsx_header_fields, parts_hash));
+        close(4);
+        for (int k = 0; k < 9; k++) {
+            o.ld(0x0A, hb + offsetof(bsx_header_fields, hashes) + 32 * k, hash_len[k] > 32 ? 32 : hash_len[k]);
+            close(5 + k);
+        }
+    }
+    __syncwarp();
+    uint32_t *dst = reinterpret_cast<uint32_t *>(headers) + (size_t)base * ENC_OUT_WORDS;
+    for (uint32_t j = 0; j < cnt; j++)
+        for (int k = 0; k < ENC_OUT_WORDS / 32; k++) dst[(size_t)j * ENC_OUT_WORDS + 32 * k + t] = sm_out[(32 * k + t) * (ENC_T + 1) + j];
 }
 
 // one thread per validator slot
@@ -224,10 +269,12 @@ __global__ void __launch_bounds__(128) present_on_trusted_kernel(uint32_t n, uin
 
 extern "C" int bsx_encode_headers_dev(bsx_ctx *ctx, void *stream, uint32_t n, const bsx_header_fields *fields, uint8_t *headers) {
     BSX_REQUIRE(ctx, ctx && fields && headers);
-    BSX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(fields) & 7) == 0 && (reinterpret_cast<uintptr_t>(headers) & 15) == 0);
+    BSX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(fields) & 15) == 0 && (reinterpret_cast<uintptr_t>(headers) & 15) == 0);
     if (n == 0) return BSX_OK;
-    BSX_PIN_CARVEOUT(bsx::encode_headers_kernel);
-    bsx::encode_headers_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, fields, headers);
+    // not part of the witness pipeline (never beside the Ed25519 wave): takes the largest shared-memory carveout, 7 CTAs per SM
+    static const bool carve = (cudaFuncSetAttribute(bsx::encode_headers_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100), true);
+    (void)carve;
+    bsx::encode_headers_kernel<<<(n + bsx::ENC_T - 1) / bsx::ENC_T, bsx::ENC_T, 0, (cudaStream_t)stream>>>(n, fields, headers);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }

@@ -28,6 +28,26 @@ def random_header_fields(n: int, seed: int = 11) -> np.ndarray:
     return f
 
 
+def chain_header_fields(n: int, seed: int = 13) -> np.ndarray:
+    """Headers as a live chain has them: one chain id, consecutive heights, 12 s block time, every hash present."""
+    rng = np.random.default_rng(seed)
+    f = np.zeros(n, I.HEADER_FIELDS_DTYPE)
+    f["version_block"], f["version_app"] = 11, 1
+    f["height"] = 1_000_000 + np.arange(n)
+    f["time_seconds"] = 1_700_000_000 + 12 * np.arange(n)
+    f["time_nanos"] = rng.integers(0, 10**9, n)
+    cid = b"celestia"
+    f["chain_id_len"] = len(cid)
+    f["chain_id"][:, : len(cid)] = np.frombuffer(cid, np.uint8)
+    f["has_last_block_id"], f["parts_total"] = 1, 1
+    f["last_block_hash"] = rng.integers(0, 256, (n, 32))
+    f["parts_hash"] = rng.integers(0, 256, (n, 32))
+    f["hash_len"][:, :8], f["hash_len"][:, 8] = 32, 20
+    f["hashes"] = rng.integers(0, 256, (n, 9, 32))
+    f["hashes"][:, 8, 20:] = 0
+    return f
+
+
 def random_commits(n: int, N: int, seed: int = 12):
     """-> commits [n], target slots [n, N], trusted slots [n, N], n_target [n], n_trusted [n]"""
     rng = np.random.default_rng(seed)
