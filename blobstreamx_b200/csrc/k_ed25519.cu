@@ -47,9 +47,24 @@ struct EdIn {
     uint32_t pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride;
 };
 
+template <bool INL>
+__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out);
+
 template <int MIN_CTAS, bool INL>
 __global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
                                                            uint8_t *__restrict__ out) {
+    ed25519_batch_body<INL>(n, in, table, out);
+}
+// the same kernel under an explicit register cap (64-thread CTAs): still 2 warps per SM sub-partition, but more of the
+// register file left to the SHA-256 warps that run beside it
+template <int REGS>
+__global__ void __maxnreg__(REGS) ed25519_batch_kernel_capped(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
+                                                               uint8_t *__restrict__ out) {
+    ed25519_batch_body<false>(n, in, table, out);
+}
+
+template <bool INL>
+__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t pk[32], sig[64];
@@ -362,7 +377,16 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     const bool use_inl = inl < 0 ? alone : inl != 0;
     // (Splitting this path into prep / main / finish kernels with a 4-way batched inversion was measured slower:
     // 19.3 vs 21.4 M sig/s at 37 800 signatures, 2.98 vs 2.91 ms for the header_range step -- not kept.)
-    if (occ >= 8) ed25519_batch_kernel<8, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+    // beside the SHA-256 kernels the build capped at 192 registers (no spills) is used: each sub-partition keeps room for two
+    // 64-register hash warps instead of one (header_range step 2.81 -> 2.77 ms).  BSX_ED_REGS: 0 = uncapped, 176 / 160 for A/B.
+    static const int cap = [] { const char *e = getenv("BSX_ED_REGS"); return e ? atoi(e) : 192; }();
+    if (cap && !alone && !env_occ && !ctx->ed_corun && inl <= 0) {
+        BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<192>); BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<176>);
+        BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<160>);
+        if (cap >= 192) ed25519_batch_kernel_capped<192><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+        else if (cap >= 176) ed25519_batch_kernel_capped<176><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+        else ed25519_batch_kernel_capped<160><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+    } else if (occ >= 8) ed25519_batch_kernel<8, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (occ >= 6) ed25519_batch_kernel<6, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (use_inl) ed25519_batch_kernel<4, true><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else ed25519_batch_kernel<4, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);

@@ -9,14 +9,18 @@
 #include <algorithm>
 #include <vector>
 
+// side streams of the device-resident step: stream2 (high priority) and pipe[0]
 static int fork_join_begin(bsx_ctx *ctx, cudaStream_t main) {
     BSX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
     BSX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    BSX_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe[0], ctx->ev_fork, 0));
     return BSX_OK;
 }
 static int fork_join_end(bsx_ctx *ctx, cudaStream_t main) {
     BSX_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
     BSX_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join, 0));
+    BSX_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[0], ctx->pipe[0]));
+    BSX_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_pipe[0], 0));
     return BSX_OK;
 }
 
@@ -27,23 +31,45 @@ extern "C" int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint
                          s->digests && s->ed_out && s->fail);
     if (n == 0) return BSX_OK;
     cudaStream_t main = (cudaStream_t)stream;
+    // BSX_HR_TRACE=1 (diagnostic, synchronises): when each half of the step finishes, on stderr
+    static const bool trace = getenv("BSX_HR_TRACE") != nullptr;
+    cudaEvent_t tev[4] = {};
+    if (trace) {
+        for (cudaEvent_t &e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], main);
+    }
     int rc = fork_join_begin(ctx, main);
     if (rc) return rc;
     // high-priority stream: the Ed25519 kernel only (few fat CTAs, latency-bound)
     rc = bsx_verify_launch_ed(ctx, ctx->stream2, n, N, s->validators, s->ed_out);
     if (rc) return rc;
-    // caller's stream: every SHA-256 kernel -- the skip schedule, then map and reduce
-    rc = bsx_verify_launch_hash(ctx, main, 1, n, N, s->hdr, s->validators, s->skip, s->trusted_pubkeys, s->trusted_powers,
+    if (trace) cudaEventRecord(tev[1], ctx->stream2);
+    // third stream: the skip schedule's SHA-256 kernel (one CTA per range, 490 dependent digests: latency-bound).  On the
+    // caller's stream it held the map kernels back until it had squeezed past the Ed25519 wave (1.7 ms instead of 0.19).
+    static const int hash_side = [] { const char *e = getenv("BSX_HR_HASH_STREAM"); return e ? atoi(e) : 1; }();   // 0: caller's stream, first
+    cudaStream_t hs = hash_side ? ctx->pipe[0] : main;
+    rc = bsx_verify_launch_hash(ctx, hs, 1, n, N, s->hdr, s->validators, s->skip, s->trusted_pubkeys, s->trusted_powers,
                                 s->trusted_byte_lengths, nullptr, s->digests, nullptr, s->fail);
     if (rc) return rc;
+    if (trace) cudaEventRecord(tev[2], hs);
+    // caller's stream: map and reduce
     rc = bsx_prove_data_commitment_dev(ctx, main, n, n_jobs, B, m->dh_leaf, m->dh_aunts, m->lb_leaf, m->lb_aunts,
                                        m->start_headers, m->end_headers, m->start_blocks, m->start_header, m->end_blocks,
                                        m->end_header, m->map_digests, m->map_subchains, m->reduce_digests, m->reduce_nodes,
                                        m->data_commitments, m->fail);
     if (rc) return rc;
+    if (trace) cudaEventRecord(tev[3], main);
     rc = fork_join_end(ctx, main);
     if (rc) return rc;
-    return bsx_verify_launch_flags(ctx, main, n, N, s->ed_out, s->fail);
+    rc = bsx_verify_launch_flags(ctx, main, n, N, s->ed_out, s->fail);
+    if (trace) {
+        cudaStreamSynchronize(main);
+        float t[3];
+        for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], tev[0], tev[i + 1]);
+        fprintf(stderr, "[bsx header_range] Ed25519 done %.3f ms, skip hashes done %.3f ms, map + reduce done %.3f ms\n", t[0], t[1], t[2]);
+        for (cudaEvent_t &e : tev) cudaEventDestroy(e);
+    }
+    return rc;
 }
 
 namespace {
