@@ -33,6 +33,15 @@ struct bsx_ctx {
     uint32_t n_ev_chunk;
 };
 
+// Does a batch of n signatures fill whole waves of the thread-per-signature Ed25519 kernel (4 CTAs of 64 per SM)?  Then
+// every SM's register file is full for the kernel's whole run, and the step is arranged to leave room for the SHA-256
+// kernels beside it (192-register build, skip hashes on their own stream: +1..2.6 % at 378 / 756 / 1134 ranges per step).
+// With a partly filled last wave the SMs have room anyway and the same arrangement costs 2..4 % (256 / 512 ranges).
+static inline bool bsx_ed_fills_waves(const bsx_ctx *ctx, uint64_t n) {
+    const uint64_t wave = (uint64_t)ctx->sm_count * 4, ctas = (n + 63) / 64, tail = ctas % wave;
+    return ctas >= wave && (tail == 0 || tail * 10 >= wave * 9);
+}
+
 // stages of verify_* (k_verify.cu), reused by bsx_header_range_dev
 int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out);
 int bsx_verify_launch_hash(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t N, const bsx_header_in *hdr,

@@ -377,9 +377,11 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     const bool use_inl = inl < 0 ? alone : inl != 0;
     // (Splitting this path into prep / main / finish kernels with a 4-way batched inversion was measured slower:
     // 19.3 vs 21.4 M sig/s at 37 800 signatures, 2.98 vs 2.91 ms for the header_range step -- not kept.)
-    // beside the SHA-256 kernels the build capped at 192 registers (no spills) is used: each sub-partition keeps room for two
-    // 64-register hash warps instead of one (header_range step 2.81 -> 2.77 ms).  BSX_ED_REGS: 0 = uncapped, 176 / 160 for A/B.
-    static const int cap = [] { const char *e = getenv("BSX_ED_REGS"); return e ? atoi(e) : 192; }();
+    // beside the SHA-256 kernels, for batches that fill whole waves, the build capped at 192 registers (no spills) is used:
+    // each sub-partition keeps room for two 64-register hash warps instead of one (header_range step 2.81 -> 2.77 ms).
+    // BSX_ED_REGS: 0 = never, 192 / 176 / 160 = always that cap (A/B).
+    static const int env_cap = [] { const char *e = getenv("BSX_ED_REGS"); return e ? atoi(e) : -1; }();
+    const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves(ctx, n) ? 192 : 0);
     if (cap && !alone && !env_occ && !ctx->ed_corun && inl <= 0) {
         BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<192>); BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<176>);
         BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<160>);

@@ -46,8 +46,9 @@ extern "C" int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint
     if (trace) cudaEventRecord(tev[1], ctx->stream2);
     // third stream: the skip schedule's SHA-256 kernel (one CTA per range, 490 dependent digests: latency-bound).  On the
     // caller's stream it held the map kernels back until it had squeezed past the Ed25519 wave (1.7 ms instead of 0.19).
-    static const int hash_side = [] { const char *e = getenv("BSX_HR_HASH_STREAM"); return e ? atoi(e) : 1; }();   // 0: caller's stream, first
-    cudaStream_t hs = hash_side ? ctx->pipe[0] : main;
+    // Only when the Ed25519 batch fills whole waves (common.cuh); otherwise it stays first on the caller's stream.
+    static const int hash_side = [] { const char *e = getenv("BSX_HR_HASH_STREAM"); return e ? atoi(e) : -1; }();   // 0 caller's stream, 1 own
+    cudaStream_t hs = (hash_side >= 0 ? hash_side != 0 : bsx_ed_fills_waves(ctx, (uint64_t)n * N)) ? ctx->pipe[0] : main;
     rc = bsx_verify_launch_hash(ctx, hs, 1, n, N, s->hdr, s->validators, s->skip, s->trusted_pubkeys, s->trusted_powers,
                                 s->trusted_byte_lengths, nullptr, s->digests, nullptr, s->fail);
     if (rc) return rc;
