@@ -379,15 +379,13 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     // 19.3 vs 21.4 M sig/s at 37 800 signatures, 2.98 vs 2.91 ms for the header_range step -- not kept.)
     // beside the SHA-256 kernels, for batches that fill whole waves, the build capped at 192 registers (no spills) is used:
     // each sub-partition keeps room for two 64-register hash warps instead of one (header_range step 2.81 -> 2.77 ms).
-    // BSX_ED_REGS: 0 = never, 192 / 176 / 160 = always that cap (A/B).
+    // BSX_ED_REGS: 0 = never, non-zero = always (A/B).
     static const int env_cap = [] { const char *e = getenv("BSX_ED_REGS"); return e ? atoi(e) : -1; }();
     const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves(ctx, n) ? 192 : 0);
     if (cap && !alone && !env_occ && !ctx->ed_corun && inl <= 0) {
-        BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<192>); BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<176>);
-        BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<160>);
-        if (cap >= 192) ed25519_batch_kernel_capped<192><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
-        else if (cap >= 176) ed25519_batch_kernel_capped<176><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
-        else ed25519_batch_kernel_capped<160><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+        // (caps of 176 and 160 registers spill and were slower: profiles/r01p_step_ab.txt)
+        BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<192>);
+        ed25519_batch_kernel_capped<192><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     } else if (occ >= 8) ed25519_batch_kernel<8, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (occ >= 6) ed25519_batch_kernel<6, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (use_inl) ed25519_batch_kernel<4, true><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
