@@ -56,6 +56,30 @@ def make_ranges(n_distinct: int, n_jobs: int = N_JOBS, batch: int = BATCH, with_
 FIELDS = ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers")
 
 
+def cpu_library_baseline():
+    """SURVEY 8d baseline (B): what tuned CPU libraries do with one range's hashing and signature checks on all host cores
+    (baseline/cpu_library.c: OpenSSL SHA-256 with SHA extensions + EVP Ed25519 verification, OpenMP).  Digests and
+    accept / reject only -- no witness -- so it is reported beside `cpu_baseline`, not instead of it.  None if not built."""
+    import ctypes
+    path = os.path.join(ROOT, "baseline", "_cpulib", "libbsx_cpulib.so")
+    if not os.path.exists(path):
+        return None
+    try:
+        lib_ = ctypes.CDLL(path)
+    except OSError:
+        return None
+    lib_.cpulib_header_range.restype = ctypes.c_double
+    cores = len(os.sched_getaffinity(0))
+    n, sink = 24 * cores, ctypes.c_uint32(0)
+    lib_.cpulib_header_range(cores, cores, ctypes.byref(sink))          # threads up, caches warm
+    dt = lib_.cpulib_header_range(n, cores, ctypes.byref(sink))
+    if dt <= 0:
+        return None
+    return {"value": n * HEADERS_PER_RANGE / dt, "unit": UNIT, "cores": cores, "kind": "library",
+            "sample": f"{n} ranges x (20 969 OpenSSL SHA-256 digests of the schedule's message sizes + 100 EVP Ed25519 verifications), {dt:.2f} s",
+            "note": "digests and accept/reject only: none of the EC intermediates, quotients or request-order layout of the witness"}
+
+
 def tile_ranges(ms, R):
     """Concatenate R ranges (cycling over the distinct chains) into the flat arrays of the C ABI."""
     pick = [ms[r % len(ms)] for r in range(R)]
@@ -461,6 +485,8 @@ def run_gpu(args):
         cpu = {"value": rps * HEADERS_PER_RANGE, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{args.cpu_ranges} ranges x 1024 headers (same generator), single thread like the reference's witness loop"}
 
+    cpu_lib = cpu_library_baseline() if (rank == 0 and world == 1 and not args.no_cpu) else None
+
     if rank == 0:
         resident = sum(t.numel() for t in d_skip.values()) + sum(t.numel() for t in d_sout.values()) + \
             (sum(t.numel() for t in d_in.values()) + sum(t.numel() for t in d_out.values()) if not eng else
@@ -497,6 +523,7 @@ def run_gpu(args):
                     "ranges_per_step": Re, "host_cpus": numa, "host_threads": n_thr, "single_call": e2e_single,
                     "note": "one ctx + pinned buffers per host thread, calls dealt round-robin; every call copies its inputs up and its witness down"},
             "cpu_baseline": cpu,
+            "cpu_library_baseline": cpu_lib,
         }
         print(json.dumps(out))
     if world > 1:

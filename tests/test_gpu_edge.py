@@ -26,6 +26,11 @@ def test_empty_batches_are_noops(ctx):
     assert ctx.header_trees(np.zeros((0, 512), np.uint8)).shape == (0, 32)
     nw = orc.gate_num_wires(orc.GATE_U32_ARITHMETIC, 3, 0)
     assert ctx.gl_gate_eval(orc.GATE_U32_ARITHMETIC, 3, 0, np.zeros((nw, 0), np.uint64)).size == 0
+    from blobstreamx_b200 import inputs as I
+    assert ctx.encode_headers(np.zeros(0, I.HEADER_FIELDS_DTYPE)).shape == (0, 512)
+    assert ctx.validator_records(np.zeros(0, I.COMMIT_DTYPE), np.zeros((0, 100), I.COMMIT_SIG_DTYPE), 100)["validators"].shape == (0, 100, 240)
+    assert ctx.present_on_trusted(np.zeros((0, 100), I.COMMIT_SIG_DTYPE), [], np.zeros((0, 100), I.COMMIT_SIG_DTYPE), [],
+                                  np.zeros((0, 100, 240), np.uint8)).size == 0
     assert ctx.launch_count == l0          # nothing was launched
     # a zero-length message and a zero-length hash input are real work, not empty batches
     assert ctx.sha256_batch(np.zeros(0, np.uint8), np.array([0, 0], np.uint32))[0].tobytes().hex().startswith("e3b0c442")
@@ -47,6 +52,14 @@ def test_invalid_arguments_are_refused(ctx):
         w, c = np.zeros((4, 4), np.uint64), np.zeros((4, 4), np.uint64)
         ctx._call("bsx_gl_gate_eval", C.c_uint32(99), C.c_uint32(3), C.c_uint32(0), w.ctypes.data_as(C.c_void_p), C.c_uint32(4),
                   c.ctypes.data_as(C.c_void_p))                       # unknown gate
+    with pytest.raises(lib.BsxError, match="invalid argument"):    # neither records nor hash fields requested
+        ctx._call("bsx_validator_records", C.c_uint32(1), C.c_uint32(4), w.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                  C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), c.ctypes.data_as(C.c_void_p))
+    with pytest.raises(lib.BsxError, match="invalid argument"):    # hash fields come as a group of three arrays
+        ctx._call("bsx_validator_records", C.c_uint32(1), C.c_uint32(4), w.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                  C.c_void_p(0), c.ctypes.data_as(C.c_void_p), C.c_void_p(0), C.c_void_p(0), c.ctypes.data_as(C.c_void_p))
+    with pytest.raises(lib.BsxError, match="invalid argument"):
+        ctx._call("bsx_encode_headers", C.c_uint32(3), C.c_void_p(0), C.c_void_p(0))
     # the ctx stays usable after an error
     got = ctx.prove_data_commitment(1, 2, 4, *a)
     assert got["fail"][0] == 0
