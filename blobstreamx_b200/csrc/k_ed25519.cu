@@ -382,7 +382,7 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     // BSX_ED_REGS: 0 = never, non-zero = always (A/B).
     static const int env_cap = [] { const char *e = getenv("BSX_ED_REGS"); return e ? atoi(e) : -1; }();
     const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves(ctx, n) ? 192 : 0);
-    if (cap && !alone && !env_occ && !ctx->ed_corun && inl <= 0) {
+    if (cap && (!alone || env_cap > 0) && !env_occ && !ctx->ed_corun && inl <= 0) {
         // (caps of 176 and 160 registers spill and were slower: profiles/r01p_step_ab.txt)
         BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<192>);
         ed25519_batch_kernel_capped<192><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
