@@ -487,6 +487,49 @@ def run_gpu(args):
 
     cpu_lib = cpu_library_baseline() if (rank == 0 and world == 1 and not args.no_cpu) else None
 
+    # ---- the metric's second half: constraints/sec (U32ArithmeticGate over 2^20 trace rows per GPU, every rank its own rows) ----
+    def gate_constraints():
+        gate, p0, p1, desc = GATE_CONFIGS["arithmetic"]
+        rows = 1 << 20
+        nw, ncn = ctx.gate_num_wires(gate, p0, p1), ctx.gate_num_constraints(gate, p0, p1)
+        g = torch.Generator(device=dev)
+        g.manual_seed(1 + rank)
+        rnd = (torch.randint(0, 2**62, (nw * rows,), generator=g, device=dev, dtype=torch.int64) * 4 +
+               torch.randint(0, 4, (nw * rows,), generator=g, device=dev, dtype=torch.int64))
+        pm = torch.tensor(-(2**32) + 1, dtype=torch.int64, device=dev)
+        wires = torch.where((rnd < 0) & (rnd >= pm), rnd - pm, rnd)         # uniform canonical field elements
+        del rnd
+        cons = torch.zeros(ncn * rows, dtype=torch.int64, device=dev)
+
+        def gstep():
+            ctx.call_dev("bsx_gl_gate_eval_dev", stream, u32(gate), u32(p0), u32(p1), ptr(wires.data_ptr()), u32(rows), ptr(cons.data_ptr()))
+        if rank == 0 and not args.no_check:
+            from oracle import cbind as orc
+            sub = wires.view(nw, rows)[:, :256].contiguous().cpu().numpy().view(np.uint64)
+            assert (ctx.gl_gate_eval(gate, p0, p1, sub) == orc.gate_eval(gate, p0, p1, sub, threads=4)).all(), "gate constraints differ from the oracle"
+        for _ in range(max(3, args.warmup)):
+            gstep()
+        barrier()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record()
+        for _ in range(args.steps):
+            gstep()
+        e[1].record()
+        barrier()
+        gms = e[0].elapsed_time(e[1]) / args.steps
+        if world > 1:
+            t = torch.tensor([gms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gms = float(t.item())
+        alg_g = 8 * (nw + ncn) * rows
+        return {"metric": "constraints/sec, U32ArithmeticGate eval_unfiltered_base_batch", "value": world * ncn * rows / (gms * 1e-3),
+                "unit": "constraints/s", "ms_per_step": gms, "rows_per_gpu": rows, "constraints_per_row": ncn, "scaling": "weak",
+                "roofline": {"bound": "hbm", "achieved": alg_g / (gms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg_g / (gms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg_g},
+                "note": f"{alg_g / 1e6:.0f} MB per launch > 126 MB L2; other gates and the CPU port: bench.py --mode gates"}
+
+    constraints = gate_constraints()
+
     if rank == 0:
         resident = sum(t.numel() for t in d_skip.values()) + sum(t.numel() for t in d_sout.values()) + \
             (sum(t.numel() for t in d_in.values()) + sum(t.numel() for t in d_out.values()) if not eng else
@@ -522,6 +565,7 @@ def run_gpu(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ranges_per_step": Re, "host_cpus": numa, "host_threads": n_thr, "single_call": e2e_single,
                     "note": "one ctx + pinned buffers per host thread, calls dealt round-robin; every call copies its inputs up and its witness down"},
+            "constraints": constraints,
             "cpu_baseline": cpu,
             "cpu_library_baseline": cpu_lib,
         }
