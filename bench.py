@@ -251,6 +251,8 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa(torch, local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if args.ranges <= 0:
         # wave-aligned batch: the Ed25519 kernel keeps 4 CTAs x 64 signatures resident per SM; a step whose signatures
