@@ -57,10 +57,10 @@ __global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n,
 }
 // the same kernel under an explicit register cap (64-thread CTAs): still 2 warps per SM sub-partition, but more of the
 // register file left to the SHA-256 warps that run beside it
-template <int REGS>
+template <int REGS, bool INL>
 __global__ void __maxnreg__(REGS) ed25519_batch_kernel_capped(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
                                                                uint8_t *__restrict__ out) {
-    ed25519_batch_body<false>(n, in, table, out);
+    ed25519_batch_body<INL>(n, in, table, out);
 }
 
 template <bool INL>
@@ -384,8 +384,9 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves(ctx, n) ? 192 : 0);
     if (cap && (!alone || env_cap > 0) && !env_occ && !ctx->ed_corun && inl <= 0) {
         // (caps of 176 and 160 registers spill and were slower: profiles/r01p_step_ab.txt)
-        BSX_PIN_CARVEOUT(ed25519_batch_kernel_capped<192>);
-        ed25519_batch_kernel_capped<192><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+        // (the same cap with inlined point arithmetic: 378 ranges per step 2.768 -> 2.818 ms, 756 ranges 5.595 -> 5.530 ms -- not kept)
+        BSX_PIN_CARVEOUT((ed25519_batch_kernel_capped<192, false>));
+        ed25519_batch_kernel_capped<192, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     } else if (occ >= 8) ed25519_batch_kernel<8, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (occ >= 6) ed25519_batch_kernel<6, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
     else if (use_inl) ed25519_batch_kernel<4, true><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
