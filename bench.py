@@ -250,9 +250,13 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa(torch, local)
+    json_out = sys.stdout
     if world > 1:
-        # NCCL writes its version / debug lines to stdout by default; stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version banner (and any NCCL_DEBUG output) on file descriptor 1; stdout must carry exactly one
+        # JSON line, so fd 1 is pointed at stderr for the libraries and the line goes to a private copy of the real stdout
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     if args.ranges <= 0:
         # wave-aligned batch: the Ed25519 kernel keeps 4 CTAs x 64 signatures resident per SM; a step whose signatures
@@ -571,7 +575,7 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "cpu_library_baseline": cpu_lib,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
