@@ -9,7 +9,8 @@ digests + Ed25519 records of the target header).
 
   value      whole-job headers/s, inputs resident in HBM, CUDA events, max over ranks
   e2e        same metric through the host-buffer C-ABI entry point (pinned host buffers, H2D + D2H inside)
-  roofline   the dominant kernel (prove_subchain_kernel<32>) against the measured HBM peak
+  roofline   the map stage (subchain_proofs_kernel + subchain_commit_kernel) against the measured HBM peak
+  constraints  constraints/sec of the U32Arithmetic gate over 2^20 trace rows per GPU (the metric's second half)
   cpu_baseline  the CPU oracle ("port" of the reference's witness path) on a bounded sample, 1 thread
 
 `--impl reference` times the CPU restatement of the reference's path on all host cores

@@ -10,9 +10,10 @@
 //   * fe_mul / fe_sq / fe_sqn are real calls (by-value structs travel in registers), so the whole
 //     kernel stays a few thousand instructions and lives in the instruction cache -- fully inlined
 //     it would be >1 MB of SASS.
-//   * s*G: 64 unsigned 4-bit windows over a precomputed affine table ((y+x, y-x, 2dxy) entries, built
-//     once per context on the device); h*A: 16-entry cached table in local memory, 4 doublings + 1
-//     addition per window, extended coordinates; all three projective results share ONE inversion.
+//   * s*G: 32 unsigned 8-bit windows over a precomputed affine table ((y+x, y-x, 2dxy) entries, 1 MB, built
+//     once per context on the device); h*A: signed 4-bit windows over an 8-entry cached table (1A..8A) in
+//     local memory, 4 doublings + 1 addition per window, extended coordinates (the quad-lane kernel keeps
+//     its own unsigned 16-entry table, one component per lane); all three projective results share ONE inversion.
 //   * h, div: Barrett division of the 512-bit digest by l with a 264-bit reciprocal.
 // Affine results in canonical form are unique, so parity with the reference's BigUint affine
 // arithmetic (starkyx, un-vendored) is exact; `decompress` returns the EVEN root.
