@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(ENC_T) encode_headers_kernel(uint32_t n, const
         o.vi(0x08, version_block);
         o.vi(0x10, version_app);
         close(0);
-        o.ld(0x0A, hb + offsetof(bsx_header_fields, chain_id), chain_id_len > 50 ? 50 : chain_id_len);
+        o.ld(0x0A, hb + offsetof(bsx_header_fields, chain_id), chain_id_len > 56 ? 56 : chain_id_len);
         close(1);
         o.vi(0x08, height);
         close(2);
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(128) validator_records_kernel(uint32_t n, uint
     if (is_signed) {
         // CanonicalVote: type = 1 (precommit = 2), height = 2 sfixed64, round = 3 sfixed64, block_id = 4, timestamp = 5,
         // chain_id = 6; SignedVote::sign_bytes is the length-delimited encoding
-        const uint32_t cid = cm.chain_id_len > 50 ? 50 : cm.chain_id_len, bid = cm.has_block_id ? block_id_len(cm.parts_total) : 0,
+        const uint32_t cid = cm.chain_id_len > 56 ? 56 : cm.chain_id_len, bid = cm.has_block_id ? block_id_len(cm.parts_total) : 0,
                        ts = timestamp_len(sg.ts_seconds, sg.ts_nanos);
         const uint32_t body = 2 + (cm.height ? 9 : 0) + (cm.round ? 9 : 0) + (bid ? 1 + varint_len(bid) + bid : 0) + 2 + ts + (cid ? 2 + cid : 0);
         msg_len = varint_len(body) + body;

@@ -447,7 +447,7 @@ typedef struct bsx_header_fields {    /* a decoded tendermint Header; 464 bytes,
     uint64_t version_block, version_app, height;
     int64_t time_seconds;
     uint32_t time_nanos;
-    uint32_t chain_id_len;            /* <= 50 */
+    uint32_t chain_id_len;            /* <= 56 (larger values are read as 56; tendermint allows 50) */
     uint8_t chain_id[56];
     uint32_t parts_total;             /* last_block_id.part_set_header.total */
     uint8_t has_last_block_id;        /* 0: the field encodes to nothing (first block) */
@@ -463,7 +463,7 @@ typedef struct bsx_commit_in {        /* Commit + chain id; 152 bytes, 8-byte al
     uint32_t n_signatures;            /* commit.signatures.len() = validators in the set */
     uint8_t block_hash[32], parts_hash[32];   /* commit.block_id */
     uint32_t parts_total;
-    uint32_t chain_id_len;            /* <= 50 */
+    uint32_t chain_id_len;            /* <= 56 (larger values are read as 56; tendermint allows 50) */
     uint8_t chain_id[56];
     uint8_t has_block_id;             /* 0: block id omitted from the vote (nil) */
     uint8_t _pad[7];

@@ -14,7 +14,7 @@ def random_header_fields(n: int, seed: int = 11) -> np.ndarray:
         r["height"] = 0 if i == 0 else int(rng.integers(1, 1 << int(rng.integers(1, 63))))
         r["time_seconds"] = 0 if i == 1 else int(rng.integers(1, 1 << 33))
         r["time_nanos"] = 0 if i % 5 == 2 else int(rng.integers(1, 10**9))
-        cl = int(rng.integers(0, 51))
+        cl = 56 if i == 4 else int(rng.integers(0, 51))       # 56 = the whole array
         r["chain_id_len"] = cl
         r["chain_id"][:cl] = rng.integers(97, 123, cl)
         r["has_last_block_id"] = int(i % 7 != 3)
