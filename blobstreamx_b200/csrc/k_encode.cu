@@ -13,6 +13,14 @@
 
 #include "common.cuh"
 
+// the layouts the Python binding (blobstreamx_b200/inputs.py) and the Rust FFI crate mirror
+static_assert(sizeof(bsx_header_fields) == 464 && offsetof(bsx_header_fields, chain_id) == 40 && offsetof(bsx_header_fields, hash_len) == 101 &&
+                  offsetof(bsx_header_fields, last_block_hash) == 112 && offsetof(bsx_header_fields, hashes) == 176,
+              "bsx_header_fields layout");
+static_assert(sizeof(bsx_commit_in) == 152 && offsetof(bsx_commit_in, block_hash) == 16 && offsetof(bsx_commit_in, chain_id) == 88, "bsx_commit_in layout");
+static_assert(sizeof(bsx_commit_sig_in) == 160 && offsetof(bsx_commit_sig_in, voting_power) == 96 && offsetof(bsx_commit_sig_in, address) == 120,
+              "bsx_commit_sig_in layout");
+
 namespace bsx {
 namespace {
 
