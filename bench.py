@@ -1105,8 +1105,8 @@ def main():
     ap.add_argument("--gate", default="arithmetic", choices=["arithmetic", "add_many", "subtraction", "comparison", "range_check"])
     ap.add_argument("--sigs", type=int, default=100000)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)     # 50 x 2.8 ms: a multi-millisecond hiccup on one of 8 ranks stays below 2 %
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ranges", type=int, default=0,
                     help="independent header ranges per step per GPU; 0 = one full wave of the Ed25519 kernel "
