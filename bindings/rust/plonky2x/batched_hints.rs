@@ -33,7 +33,7 @@ thread_local! {
     static CTX: RefCell<*mut bsx_ctx> = RefCell::new(std::ptr::null_mut());
 }
 
-fn with_ctx<T>(f: impl FnOnce(*mut bsx_ctx) -> T) -> T {
+pub(crate) fn with_ctx<T>(f: impl FnOnce(*mut bsx_ctx) -> T) -> T {
     CTX.with(|c| {
         let mut c = c.borrow_mut();
         if c.is_null() {
@@ -45,7 +45,7 @@ fn with_ctx<T>(f: impl FnOnce(*mut bsx_ctx) -> T) -> T {
     })
 }
 
-fn check(ctx: *mut bsx_ctx, rc: i32, what: &str) {
+pub(crate) fn check(ctx: *mut bsx_ctx, rc: i32, what: &str) {
     if rc != BSX_OK {
         let msg = unsafe { std::ffi::CStr::from_ptr(bsx_last_error(ctx)) }.to_string_lossy().into_owned();
         panic!("{what} failed ({rc}): {msg}"); // hints report failure by panicking (simple/generator.rs:74-79)
