@@ -63,3 +63,40 @@ def test_rust_ffi_crate_matches_header():
     assert n == len(syms)
     for s_ in syms:
         assert f"pub fn {s_}(" in text, s_
+
+
+def test_struct_layouts_match_the_bindings(tmp_path):
+    """sizeof / offsetof of every struct of include/bsx.h as gcc lays them out == the numpy dtypes and ctypes structures
+    the Python binding fills (a drifted field would silently shift every input that follows it)."""
+    import subprocess
+    import numpy as np
+    from blobstreamx_b200 import inputs as I, lib
+
+    structs = {"bsx_header_in": lib.HEADER_IN, "bsx_skip_in": lib.SKIP_IN, "bsx_step_in": lib.STEP_IN,
+               "bsx_header_fields": I.HEADER_FIELDS_DTYPE, "bsx_commit_in": I.COMMIT_DTYPE, "bsx_commit_sig_in": I.COMMIT_SIG_DTYPE}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bsx.h"', "int main(void) {"]
+    for name, dt in structs.items():
+        lines.append(f'printf("{name} size %zu\\n", sizeof({name}));')
+        for f in dt.names:
+            lines.append(f'printf("{name} {f} %zu\\n", offsetof({name}, {f}));')
+    for name, cls in (("bsx_skip_batch", lib.SkipBatch), ("bsx_range_batch", lib.RangeBatch)):
+        lines.append(f'printf("{name} size %zu\\n", sizeof({name}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{name} {f} %zu\\n", offsetof({name}, {f}));')
+    lines += ["return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        s, f, v = ln.split()
+        got[(s, f)] = int(v)
+    for name, dt in structs.items():
+        assert got[(name, "size")] == np.dtype(dt).itemsize, name
+        for f in dt.names:
+            assert got[(name, f)] == dt.fields[f][1], (name, f)
+    for name, cls in (("bsx_skip_batch", lib.SkipBatch), ("bsx_range_batch", lib.RangeBatch)):
+        assert got[(name, "size")] == ctypes.sizeof(cls), name
+        for f, _ in cls._fields_:
+            assert got[(name, f)] == getattr(cls, f).offset, (name, f)
