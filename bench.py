@@ -235,6 +235,43 @@ def bind_to_gpu_numa(torch, local: int):
     return None
 
 
+def csrc_sha16() -> str:
+    """Hash of the CUDA sources the loaded library was built from: ties profiles/ncu_summary.json to THIS build."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "blobstreamx_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_capture(kernel_key: str):
+    """Entry of profiles/ncu_summary.json (written by scripts/ncu_capture.py from `ncu --set full` captures of the bench
+    command) for one kernel, or None; `stale` when the capture was taken from other sources than the ones built here."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            d = json.load(f)
+        k = d["kernels"].get(kernel_key)
+        if not k:
+            return None
+        k = dict(k)
+        k["stale"] = d.get("csrc_sha16") != csrc_sha16()
+        k["file"] = "profiles/ncu_summary.json <- " + k.get("source", "?")
+        return k
+    except Exception:
+        return None
+
+
+def step_stats(torch, events):
+    """Per-step durations from the events recorded after every step: median / p95 / max in ms."""
+    d = sorted(events[i].elapsed_time(events[i + 1]) for i in range(len(events) - 1))
+    if not d:
+        return None
+    return {"median": d[len(d) // 2], "p95": d[min(len(d) - 1, int(0.95 * len(d)))], "max": d[-1], "min": d[0]}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -268,7 +305,6 @@ def run_gpu(args):
         args.e2e_ranges = args.ranges
     R = args.ranges                      # ranges this rank reduces / verifies per step
     Rt = R * world                       # ranges in flight per step over all ranks
-    ms, skips = make_ranges(args.distinct)
     be = CudaBackend(local)
     ctx = be.ctx
     main = torch.cuda.current_stream()
@@ -277,109 +313,20 @@ def run_gpu(args):
     dt = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
     zeros = lambda shape: torch.zeros(int(np.prod(shape)), dtype=torch.uint8, device=dev)
 
-    # ---- skip half: this rank's R instances, device resident ----
-    own = [skips[(rank * R + r) % len(skips)] for r in range(R)]
-    h_skip = tile_skips(own, R)
-    d_skip = {k: dt(v) for k, v in h_skip.items()}
-    d_sout = {k: zeros(sh) for k, sh in skip_out_shapes(R).items()}
-    sb = fill_struct(SkipBatch(), **{k: P(v) for k, v in d_skip.items()}, **{k: P(v) for k, v in d_sout.items()})
-
-    # ---- map/reduce half ----
-    host = tile_ranges(ms, Rt)
-    if world == 1:
-        d_in = {k: dt(v) for k, v in host.items()}
-        d_out = {k: zeros(sh) for k, sh in out_shapes(R).items()}
-        rb = fill_struct(RangeBatch(), **{k: P(v) for k, v in d_in.items()}, **{k: P(v) for k, v in d_out.items()})
-
-        def step_dev():
-            ctx.call_dev("bsx_header_range_dev", stream, u32(R), u32(N_VAL), u32(N_JOBS), u32(BATCH), C.byref(sb), C.byref(rb))
-        eng = None
-    else:
-        eng = ShardedHeaderRange(be, Rt, N_JOBS, BATCH, rank, world)
-        eng.load(host)
-        side = torch.cuda.Stream()
-
-        def step_dev():
-            # skip of this rank's ranges on a side stream, map -> all-gather -> reduce on the main stream
-            side.wait_stream(main)
-            ctx.call_dev("bsx_verify_skip_dev", side.cuda_stream, u32(R), u32(N_VAL), ptr(P(d_skip["hdr"])), ptr(P(d_skip["validators"])),
-                         ptr(P(d_skip["skip"])), ptr(P(d_skip["trusted_pubkeys"])), ptr(P(d_skip["trusted_powers"])),
-                         ptr(P(d_skip["trusted_byte_lengths"])), ptr(P(d_sout["digests"])), ptr(P(d_sout["ed_out"])), ptr(P(d_sout["fail"])))
-            eng.step()
-            main.wait_stream(side)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness gate before timing: range 0 / skip 0 of this rank against the oracle ----
-    step_dev()
-    torch.cuda.synchronize()
-    fails = d_sout["fail"].view(torch.int32).abs().sum() + (eng.fail if eng else d_out["fail"]).view(torch.int32).abs().sum()
-    if int(fails.item()) != 0:
-        raise SystemExit("bench.py: circuit assertions failed on the synthetic workload")
-    # every range of the step, not only the first: the R ranges tile `distinct` different chains, so range r must
-    # reproduce range r - distinct bit for bit (all digests, Ed25519 records, commitments) -- checked on the device
-    D_ = min(args.distinct, len(ms))
-    if R > D_ and world == 1:
-        for name, t in (("map_digests", d_out["map_digests"]), ("data_commitments", d_out["data_commitments"]),
-                        ("reduce_nodes", d_out["reduce_nodes"]), ("skip digests", d_sout["digests"]), ("ed_out", d_sout["ed_out"])):
-            v = t.view(R, -1)
-            if not torch.equal(v[D_:], v[:-D_]):
-                raise SystemExit(f"bench.py: {name} differ between ranges built from the same chain")
-    if not args.no_check:
-        from oracle import cbind as orc
-        w = orc.verify_skip(own[0], threads=8)
-        assert (d_sout["digests"][: 490 * 32].cpu().numpy().reshape(490, 32) == w["sha256_digests"]).all(), "skip digests differ"
-        assert (d_sout["ed_out"][: N_VAL * 576].cpu().numpy().reshape(N_VAL, 576) == w["ed"]).all(), "Ed25519 records differ"
-        m = ms[(rank * R) % len(ms)]
-        w = orc.prove_data_commitment(N_JOBS, BATCH, m.dh_leaf, m.dh_aunts, m.lb_leaf, m.lb_aunts, m.start_headers,
-                                      m.end_headers, m.start_block, m.start_header, m.end_block, m.end_header, threads=8)
-        if eng:
-            res = eng.results()
-            assert res["data_commitments"][0].tobytes() == w["data_commitment"] and (res["reduce_nodes"][0] == w["reduce_nodes"]).all()
-            js = slice(rank * eng.per, (rank + 1) * eng.per)
-            assert (res["local_map_digests"][rank * R] == w["map_digests"][js]).all(), "GPU map digests differ from the oracle"
-        else:
-            g = d_out["map_digests"][: N_JOBS * (20 * BATCH - 1) * 32].cpu().numpy().reshape(N_JOBS, 20 * BATCH - 1, 32)
-            assert (g == w["map_digests"]).all(), "GPU map digests differ from the oracle"
-            assert d_out["data_commitments"][:32].cpu().numpy().tobytes() == w["data_commitment"]
-            # the other distinct chains too (with the tile check above this covers every range of the step)
-            per_d = N_JOBS * (20 * BATCH - 1) * 32
-            for r in range(1, min(D_, R)):
-                m = ms[r]
-                w = orc.prove_data_commitment(N_JOBS, BATCH, m.dh_leaf, m.dh_aunts, m.lb_leaf, m.lb_aunts, m.start_headers,
-                                              m.end_headers, m.start_block, m.start_header, m.end_block, m.end_header, threads=8)
-                g = d_out["map_digests"][r * per_d:(r + 1) * per_d].cpu().numpy().reshape(N_JOBS, 20 * BATCH - 1, 32)
-                assert (g == w["map_digests"]).all() and d_out["data_commitments"][32 * r:32 * r + 32].cpu().numpy().tobytes() == w["data_commitment"]
-                ws = orc.verify_skip(own[r], threads=8)
-                assert (d_sout["digests"][r * 490 * 32:(r + 1) * 490 * 32].cpu().numpy().reshape(490, 32) == ws["sha256_digests"]).all()
-                assert (d_sout["ed_out"][r * N_VAL * 576:(r + 1) * N_VAL * 576].cpu().numpy().reshape(N_VAL, 576) == ws["ed"]).all()
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
 
-    # ---- device-resident timing ----
-    for _ in range(args.warmup):
-        step_dev()
-    barrier()
-    l0 = ctx.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    with ClockSampler(local) as clk:
-        ev[0].record()
-        for _ in range(args.steps):
-            step_dev()
-        ev[1].record()
-        barrier()
-    launches = ctx.launch_count - l0
-    ms_total = ev[0].elapsed_time(ev[1])
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * R * HEADERS_PER_RANGE / (ms_step * 1e-3)
-
-    # ---- the kernels alone (same launches, CUDA events on the launching stream) ----
     def timed(fn, reps):
+        """One launch sequence alone: CUDA events on the launching stream, after warm-up, synchronised on both sides."""
         fn(); fn()
         torch.cuda.synchronize()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -390,19 +337,166 @@ def run_gpu(args):
         torch.cuda.synchronize()
         return e[0].elapsed_time(e[1]) / reps
 
-    if eng:
-        map_fn = lambda: be.map(BATCH, Rt * eng.per, eng.t, eng.map_digests, eng.local_sub)
-    else:
-        jb = (host["start_blocks"][:, None] + np.arange(N_JOBS, dtype=np.uint64)[None, :] * np.uint64(BATCH)).reshape(-1)
-        tm = dict(d_in, batch_start=dt(jb), batch_end=dt(jb + np.uint64(BATCH)), global_end=dt(np.repeat(host["end_blocks"], N_JOBS)),
-                  global_end_header=dt(np.repeat(host["end_header"], N_JOBS, axis=0)))
-        map_fn = lambda: be.map(BATCH, R * N_JOBS, tm, d_out["map_digests"], d_out["map_subchains"])
-    skip_fn = lambda: ctx.call_dev("bsx_verify_skip_dev", stream, u32(R), u32(N_VAL), ptr(P(d_skip["hdr"])), ptr(P(d_skip["validators"])),
-                                   ptr(P(d_skip["skip"])), ptr(P(d_skip["trusted_pubkeys"])), ptr(P(d_skip["trusted_powers"])),
-                                   ptr(P(d_skip["trusted_byte_lengths"])), ptr(P(d_sout["digests"])), ptr(P(d_sout["ed_out"])),
-                                   ptr(P(d_sout["fail"])))
-    k_ms = timed(map_fn, args.steps)
-    skip_ms = timed(skip_fn, max(3, args.steps // 2))
+    class Leg:
+        """The device-resident header_range step of this rank for one circuit size (32 map jobs x B headers): inputs in
+        HBM, one call of step() = skip + map + (exchange) + reduce of R ranges per rank."""
+
+        def __init__(self, B):
+            self.B, self.J = B, N_JOBS
+            self.ms, self.skips = make_ranges(args.distinct, N_JOBS, B)
+            self.own = [self.skips[(rank * R + r) % len(self.skips)] for r in range(R)]
+            self.h_skip = tile_skips(self.own, R)
+            self.d_skip = {k: dt(v) for k, v in self.h_skip.items()}
+            self.d_sout = {k: zeros(sh) for k, sh in skip_out_shapes(R).items()}
+            self.sb = fill_struct(SkipBatch(), **{k: P(v) for k, v in self.d_skip.items()}, **{k: P(v) for k, v in self.d_sout.items()})
+            self.host = tile_ranges(self.ms, Rt)
+            self.eng = None
+            if world == 1:
+                self.d_in = {k: dt(v) for k, v in self.host.items()}
+                self.d_out = {k: zeros(sh) for k, sh in out_shapes(R, N_JOBS, B).items()}
+                self.rb = fill_struct(RangeBatch(), **{k: P(v) for k, v in self.d_in.items()}, **{k: P(v) for k, v in self.d_out.items()})
+            else:
+                self.eng = ShardedHeaderRange(be, Rt, N_JOBS, B, rank, world)
+                self.eng.load(self.host)
+                self.side = torch.cuda.Stream()
+            self._omap, self._oskip = {}, {}
+
+        def skip_only(self):
+            d, o = self.d_skip, self.d_sout
+            ctx.call_dev("bsx_verify_skip_dev", torch.cuda.current_stream().cuda_stream, u32(R), u32(N_VAL), ptr(P(d["hdr"])), ptr(P(d["validators"])),
+                         ptr(P(d["skip"])), ptr(P(d["trusted_pubkeys"])), ptr(P(d["trusted_powers"])), ptr(P(d["trusted_byte_lengths"])),
+                         ptr(P(o["digests"])), ptr(P(o["ed_out"])), ptr(P(o["fail"])))
+
+        def step(self):
+            if not self.eng:
+                ctx.call_dev("bsx_header_range_dev", stream, u32(R), u32(N_VAL), u32(N_JOBS), u32(self.B), C.byref(self.sb), C.byref(self.rb))
+                return
+            # skip of this rank's ranges on a side stream, map -> exchange -> reduce on the main stream
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.skip_only()
+            self.eng.step()
+            main.wait_stream(self.side)
+
+        def map_only(self):
+            if self.eng:
+                be.map(self.B, Rt * self.eng.per, self.eng.t, self.eng.map_digests, self.eng.local_sub)
+                return
+            if not hasattr(self, "tm"):
+                jb = (self.host["start_blocks"][:, None] + np.arange(N_JOBS, dtype=np.uint64)[None, :] * np.uint64(self.B)).reshape(-1)
+                self.tm = dict(self.d_in, batch_start=dt(jb), batch_end=dt(jb + np.uint64(self.B)),
+                               global_end=dt(np.repeat(self.host["end_blocks"], N_JOBS)),
+                               global_end_header=dt(np.repeat(self.host["end_header"], N_JOBS, axis=0)))
+            be.map(self.B, R * N_JOBS, self.tm, self.d_out["map_digests"], self.d_out["map_subchains"])
+
+        # oracle results per distinct chain, computed once and used by the device gate and by the end-to-end gate
+        def oracle_map(self, d):
+            from oracle import cbind as orc
+            if d not in self._omap:
+                m = self.ms[d]
+                self._omap[d] = orc.prove_data_commitment(N_JOBS, self.B, m.dh_leaf, m.dh_aunts, m.lb_leaf, m.lb_aunts, m.start_headers,
+                                                          m.end_headers, m.start_block, m.start_header, m.end_block, m.end_header, threads=8)
+            return self._omap[d]
+
+        def oracle_skip(self, d):
+            from oracle import cbind as orc
+            if d not in self._oskip:
+                self._oskip[d] = orc.verify_skip(self.skips[d], threads=8)
+            return self._oskip[d]
+
+        def gate(self):
+            """Correctness gate before timing: every range of the step against the oracle (every distinct chain directly,
+            the tiled repeats by equality with the range they repeat), all circuit assertions satisfied."""
+            B, ms, skips, d_sout = self.B, self.ms, self.skips, self.d_sout
+            self.step()
+            torch.cuda.synchronize()
+            fails = d_sout["fail"].view(torch.int32).abs().sum() + (self.eng.fail if self.eng else self.d_out["fail"]).view(torch.int32).abs().sum()
+            if int(fails.item()) != 0:
+                raise SystemExit("bench.py: circuit assertions failed on the synthetic workload")
+            D_ = min(args.distinct, len(ms))
+            if R > D_ and world == 1:
+                for name, t in (("map_digests", self.d_out["map_digests"]), ("data_commitments", self.d_out["data_commitments"]),
+                                ("reduce_nodes", self.d_out["reduce_nodes"]), ("skip digests", d_sout["digests"]), ("ed_out", d_sout["ed_out"])):
+                    v = t.view(R, -1)
+                    if not torch.equal(v[D_:], v[:-D_]):
+                        raise SystemExit(f"bench.py: {name} differ between ranges built from the same chain")
+            if args.no_check:
+                return 0
+            w = self.oracle_skip((rank * R) % len(skips))
+            assert (d_sout["digests"][: 490 * 32].cpu().numpy().reshape(490, 32) == w["sha256_digests"]).all(), "skip digests differ"
+            assert (d_sout["ed_out"][: N_VAL * 576].cpu().numpy().reshape(N_VAL, 576) == w["ed"]).all(), "Ed25519 records differ"
+            w = self.oracle_map((rank * R) % len(ms))
+            if self.eng:
+                res = self.eng.results()
+                assert res["data_commitments"][0].tobytes() == w["data_commitment"] and (res["reduce_nodes"][0] == w["reduce_nodes"]).all()
+                js = slice(rank * self.eng.per, (rank + 1) * self.eng.per)
+                assert (res["local_map_digests"][rank * R] == w["map_digests"][js]).all(), "GPU map digests differ from the oracle"
+                return 1
+            per_d = N_JOBS * (20 * B - 1) * 32
+            d_out = self.d_out
+            for r in range(min(D_, R)):
+                w, ws = self.oracle_map(r), self.oracle_skip(r)
+                g = d_out["map_digests"][r * per_d:(r + 1) * per_d].cpu().numpy().reshape(N_JOBS, 20 * B - 1, 32)
+                assert (g == w["map_digests"]).all(), "GPU map digests differ from the oracle"
+                assert d_out["data_commitments"][32 * r:32 * r + 32].cpu().numpy().tobytes() == w["data_commitment"]
+                assert (d_out["reduce_nodes"][r * (N_JOBS - 1) * 128:(r + 1) * (N_JOBS - 1) * 128].cpu().numpy().reshape(N_JOBS - 1, 128) == w["reduce_nodes"]).all()
+                assert (d_sout["digests"][r * 490 * 32:(r + 1) * 490 * 32].cpu().numpy().reshape(490, 32) == ws["sha256_digests"]).all()
+                assert (d_sout["ed_out"][r * N_VAL * 576:(r + 1) * N_VAL * 576].cpu().numpy().reshape(N_VAL, 576) == ws["ed"]).all()
+            return R
+
+        def time_steps(self, clocks: bool):
+            """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the launching stream (one
+            after every step for the distribution), max over ranks."""
+            for _ in range(args.warmup):
+                self.step()
+            barrier()
+            l0 = ctx.launch_count
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+            clk = ClockSampler(local) if clocks else None
+            if clk:
+                clk.__enter__()
+            ev[0].record()
+            for i in range(args.steps):
+                self.step()
+                ev[i + 1].record()
+            barrier()
+            if clk:
+                clk.__exit__()
+            ms_step = max_over_ranks(ev[0].elapsed_time(ev[-1])) / args.steps
+            st = step_stats(torch, ev)
+            st["max_over_ranks"] = max_over_ranks(st["max"])
+            st["p95_over_median"] = st["p95"] / st["median"]
+            return ms_step, st, ctx.launch_count - l0, clk
+
+        def resident_bytes(self):
+            n = sum(t.numel() for t in self.d_skip.values()) + sum(t.numel() for t in self.d_sout.values())
+            if self.eng:
+                return n + sum(t.numel() for t in self.eng.t.values()) + self.eng.map_digests.numel() + self.eng.local_sub.numel()
+            return n + sum(t.numel() for t in self.d_in.values()) + sum(t.numel() for t in self.d_out.values())
+
+    def workload_text(B, R_):
+        return (f"header_range_{N_JOBS * B} witness-gen: {R_} independent ranges/step/GPU, each = verify_skip (100 Ed25519 "
+                f"signatures, 490 SHA-256 digests) + 32 map jobs x {B} headers + 31 reduce nodes; all "
+                f"{N_JOBS * (20 * B - 1) + N_JOBS - 1 + 490} SHA-256 digests and 100 Ed25519 records per range written")
+
+    # ---- the headline leg: header_range_1024 (BASELINE config 2) ----
+    leg = Leg(BATCH)
+    ranges_checked = leg.gate()
+    ms_step, st_stats, launches, clk = leg.time_steps(clocks=True)
+    value = world * R * HEADERS_PER_RANGE / (ms_step * 1e-3)
+    ms, skips, h_skip, eng = leg.ms, leg.skips, leg.h_skip, leg.eng
+    D_ = min(args.distinct, len(ms))
+
+    # ---- the kernels alone (same launches, CUDA events on the launching stream) ----
+    k_ms = timed(leg.map_only, args.steps)
+    skip_ms = timed(leg.skip_only, max(3, args.steps // 2))
+    # the Ed25519 batch of the step alone (the time-dominant kernel): the same validators, same kernel build as in the step
+    d_ed_alone = zeros((R, N_VAL, 576))
+    v = leg.d_skip["validators"]
+    ed_fn = lambda: ctx.call_dev("bsx_ed25519_strided_dev", stream, u32(R * N_VAL), ptr(P(v)), u32(240), ptr(P(v) + 32), u32(240),
+                                 ptr(P(v) + 96), u32(240), u32(124), ptr(P(v) + 220), u32(240), ptr(P(v) + 236), u32(240), ptr(P(d_ed_alone)))
+    ed_ms = timed(ed_fn, max(3, args.steps // 2))
+    assert torch.equal(d_ed_alone, leg.d_sout["ed_out"]), "Ed25519 records of the stand-alone launch differ from the step's"
     alg = algorithmic_bytes_map(R)
     peaks = {}
     try:
@@ -412,13 +506,29 @@ def run_gpu(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg / (k_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            per_range = json.load(f).get("prove_subchain (subchain_proofs_kernel<8>)", {}).get("dram_bytes_per_range")
-            traffic = int(per_range * R) if per_range else None     # ncu capture of the proofs kernel, scaled to this launch's ranges
-    except Exception:
-        pass
+    cap_ed, cap_map = ncu_capture("ed25519"), ncu_capture("subchain_proofs")
+
+    def traffic_of(cap, units):
+        """DRAM bytes of one launch from the ncu capture, scaled to this launch's units if the capture had another size."""
+        if not cap or cap.get("stale") or not cap.get("dram_bytes_per_launch"):
+            return None
+        return int(cap["dram_bytes_per_launch"] * units / cap["units_per_launch"])
+
+    # ---- latency of ONE range (the reference's operating point: one proof per request) through the host-buffer entry point ----
+    lat_ms = None
+    if rank == 0:
+        one_m = tile_ranges(ms[:1], 1)
+        one_m["n_jobs"], one_m["batch"] = N_JOBS, BATCH
+        ts = []
+        for i in range(12):
+            t0 = time.perf_counter()
+            g1 = ctx.header_range([skips[0]], one_m)
+            ts.append(time.perf_counter() - t0)
+        lat_ms = 1e3 * statistics.median(ts[2:])
+        if not args.no_check:
+            w1 = leg.oracle_map(0)
+            assert (g1["map_digests"][0] == w1["map_digests"]).all() and g1["data_commitments"][0].tobytes() == w1["data_commitment"]
+            assert (g1["skip"]["ed"][0] == leg.oracle_skip(0)["ed"]).all()
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + kernels + D2H inside every call) ----
     # A ctx belongs to one calling thread (include/bsx.h), so a host that keeps the GPU busy runs one ctx per thread:
@@ -469,21 +579,58 @@ def run_gpu(args):
     def timed_e2e(active):
         run_e2e(active, max(len(active), args.warmup // 2 * len(active)))
         barrier()
-        dt_ = run_e2e(active, args.steps)
-        if world > 1:
-            t = torch.tensor([dt_], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt_ = float(t.item())
+        dt_ = max_over_ranks(run_e2e(active, args.steps))
         return world * Re * HEADERS_PER_RANGE * args.steps / dt_
 
     e2e_single = timed_e2e(lanes[:1])
     e2e = timed_e2e(lanes) if n_thr > 1 else e2e_single
     assert all(l.ok() for l in lanes)
     ref = lanes[0]
+    # the witness the host received (lane 0, the pipelined path with the Ed25519 batch in its co-run build) against the
+    # oracle, for every distinct chain; ranges built from the same chain must then be equal bit for bit
+    e2e_checked = 0
+    if not args.no_check:
+        hm = {k: v.numpy().reshape(out_shapes(Re)[k]) for k, v in ref.hm_out.items() if k != "fail"}
+        hs = {k: v.numpy().reshape(skip_out_shapes(Re)[k]) for k, v in ref.hs_out.items() if k != "fail"}
+        for r in range(min(D_, Re)):
+            w, ws = leg.oracle_map(r % len(ms)), leg.oracle_skip((rank * R + r) % len(skips))
+            assert (hm["map_digests"][r] == w["map_digests"]).all(), "e2e: map digests differ from the oracle"
+            assert (hm["reduce_nodes"][r] == w["reduce_nodes"]).all() and (hm["reduce_digests"][r] == w["reduce_digests"]).all()
+            assert hm["data_commitments"][r].tobytes() == w["data_commitment"], "e2e: data commitment differs from the oracle"
+            assert (hs["digests"][r] == ws["sha256_digests"]).all(), "e2e: skip digests differ from the oracle"
+            assert (hs["ed_out"][r] == ws["ed"]).all(), "e2e: Ed25519 records differ from the oracle"
+            e2e_checked += 1
+        if Re > D_ and D_ == len(ms) == len(skips) and (rank * R) % D_ == 0:
+            for k, v in list(hm.items()) + list(hs.items()):
+                assert (v[D_:] == v[:-D_]).all(), f"e2e: {k} differ between ranges built from the same chain"
+            e2e_checked = Re
     for l in lanes[1:]:      # every lane produced the same witness
         assert torch.equal(l.hm_out["map_digests"], ref.hm_out["map_digests"]) and torch.equal(l.hs_out["ed_out"], ref.hs_out["ed_out"])
     h2d = sum(t.numel() for t in ref.hs_in.values()) + sum(t.numel() for t in ref.hm_in.values())
     d2h = sum(t.numel() for t in ref.hs_out.values()) + sum(t.numel() for t in ref.hm_out.values())
+    resident_1024 = leg.resident_bytes()
+    exchange = eng.exchange if eng else None
+    del lanes, ref
+
+    # ---- BASELINE config 3: header_range_2048 (32 map jobs x 64 headers), same sharding, device-resident ----
+    hr2048 = None
+    if not args.no_2048:
+        R2 = R
+        leg2 = Leg(2 * BATCH)
+        checked2 = leg2.gate()
+        ms2, st2, launches2, _ = leg2.time_steps(clocks=False)
+        k2_ms = timed(leg2.map_only, max(3, args.steps // 2))
+        alg2 = algorithmic_bytes_map(R2, N_JOBS, 2 * BATCH)
+        hr2048 = {"metric": "headers/sec, header_range_2048 witness-gen", "value": world * R2 * N_JOBS * 2 * BATCH / (ms2 * 1e-3), "unit": UNIT,
+                  "n_gpus": world, "ms_per_step": ms2, "step_ms": st2, "gpu_launches": int(launches2), "scaling": "weak",
+                  "config": {"workload": workload_text(2 * BATCH, R2), "ranges_per_step_per_gpu": R2,
+                             "reference": "BX/bin/header_range_2048.rs:7-16 (NB_MAP_JOBS = 32, BATCH_SIZE = 64)",
+                             "sharding": "single GPU: bsx_header_range_dev" if world == 1 else f"as the 1024 line: {N_JOBS // world} map jobs per range per rank"},
+                  "ranges_checked_against_oracle": checked2,
+                  "roofline_map": {"kernel": "map stage: subchain_proofs_kernel<8> + subchain_commit_kernel<64,2>", "bound": "hbm",
+                                   "achieved": alg2 / (k2_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg2 / (k2_ms * 1e-3) / 1e9 / peak,
+                                   "kernel_ms": k2_ms, "algorithmic_bytes_per_launch": alg2}}
+        del leg2
 
     # ---- CPU oracle beside it (rank 0, N=1 only, bounded sample) ----
     cpu = None
@@ -523,11 +670,7 @@ def run_gpu(args):
             gstep()
         e[1].record()
         barrier()
-        gms = e[0].elapsed_time(e[1]) / args.steps
-        if world > 1:
-            t = torch.tensor([gms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            gms = float(t.item())
+        gms = max_over_ranks(e[0].elapsed_time(e[1]) / args.steps)
         alg_g = 8 * (nw + ncn) * rows
         return {"metric": "constraints/sec, U32ArithmeticGate eval_unfiltered_base_batch", "value": world * ncn * rows / (gms * 1e-3),
                 "unit": "constraints/s", "ms_per_step": gms, "rows_per_gpu": rows, "constraints_per_row": ncn, "scaling": "weak",
@@ -538,43 +681,54 @@ def run_gpu(args):
     constraints = gate_constraints()
 
     if rank == 0:
-        resident = sum(t.numel() for t in d_skip.values()) + sum(t.numel() for t in d_sout.values()) + \
-            (sum(t.numel() for t in d_in.values()) + sum(t.numel() for t in d_out.values()) if not eng else
-             sum(t.numel() for t in eng.t.values()) + eng.map_digests.numel() + eng.local_sub.numel())
+        ed_alg = 704 * R * N_VAL
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
-            "config": {"workload": f"header_range_1024 witness-gen: {R} independent ranges/step/GPU, each = verify_skip (100 Ed25519 "
-                                   f"signatures, 490 SHA-256 digests) + 32 map jobs x 32 headers + 31 reduce nodes; all "
-                                   f"{N_JOBS * (20 * BATCH - 1) + N_JOBS - 1 + 490} SHA-256 digests and 100 Ed25519 records per range written",
+            "config": {"workload": workload_text(BATCH, R),
                        "ranges_per_step_per_gpu": R, "distinct_chains": args.distinct,
                        "sharding": "single GPU: bsx_header_range_dev" if not eng else
                                    f"map jobs of {Rt} ranges sharded {N_JOBS // world} per range per rank; {Rt * N_JOBS * 128} B of subchain "
-                                   f"records exchanged by {'peer-memory stores from the map kernel + one device barrier' if eng.exchange == 'peer stores' else 'one all_gather_into_tensor'}; "
-                                   f"reduce + skip of {R} ranges per rank",
-                       "l2": f"inputs+outputs per step per GPU = {resident / 1e6:.0f} MB > 126 MB L2 (no flush needed)"},
+                                   f"records exchanged by {eng.exchange_text()}; reduce + skip of {R} ranges per rank",
+                       "l2": f"inputs+outputs per step per GPU = {resident_1024 / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+                       "also_measured": "header_range_2048 (BASELINE config 3) in the key header_range_2048"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
-            "roofline": {"kernel": "map stage: subchain_proofs_kernel<8> + subchain_commit_kernel<32,4>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-                         "note": "SHA-256 is ~20 int ops/byte: the int32 ALU pipe (91 % busy in the proofs kernel, "
-                                 "profiles/r01n_subchain_proofs_kernel_R256_ncu_full.csv), not HBM, is the physical bound"},
-            "roofline_ed25519": {"kernel": "ed25519_batch_kernel (+ verify_kernel<1> beside it)", "bound": "hbm",
-                                 "achieved": 704 * R * N_VAL / (skip_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": 704 * R * N_VAL / (skip_ms * 1e-3) / 1e9 / peak, "traffic": None,
-                                 "note": "704 B/signature against ~3700 field operations: bound by the integer-multiply (fmaheavy) pipe and, at "
-                                         "25 600 signatures (one wave, 1.3 warps per sub-partition), by per-thread latency "
-                                         "(profiles/r01k_ed25519_batch_25600_ncu_full.csv); the HBM fraction is <<1 % by construction"},
-            "kernels_alone_ms": {"map stage (proofs + commit kernels)": k_ms, "verify_skip (ed25519_batch_kernel beside verify_kernel<1>)": skip_ms},
+            "step_ms": st_stats,
+            "ranges_checked_against_oracle": ranges_checked,
+            "latency_single_range_ms": lat_ms,
+            "latency_note": "ONE header_range_1024 (the reference proves one range per request) through bsx_header_range with host "
+                            "buffers, median of 10 calls: the throughput lines batch hundreds of independent ranges per launch",
+            # the time-dominant kernel of the step: the Ed25519 batch
+            "roofline": {"kernel": "ed25519_batch_kernel (thread per signature; the step's time-dominant kernel)", "bound": "hbm",
+                         "achieved": ed_alg / (ed_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": ed_alg / (ed_ms * 1e-3) / 1e9 / peak,
+                         "traffic": traffic_of(cap_ed, R * N_VAL), "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "algorithmic_bytes_per_launch": ed_alg, "kernel_ms": ed_ms, "signatures_per_s": R * N_VAL / (ed_ms * 1e-3),
+                         "pipe": (cap_ed or {}).get("pipes"), "pipe_source": (cap_ed or {}).get("file"), "capture_stale": (cap_ed or {}).get("stale"),
+                         "note": "704 B/signature against ~3400 field operations: the binding resource is integer/FP64 issue, not HBM "
+                                 "(`pipe` = pct_of_peak_sustained_active of each pipe from the ncu capture of this build); the HBM fraction is <<1 % by construction"},
+            "roofline_map": {"kernel": "map stage: subchain_proofs_kernel<8> + subchain_commit_kernel<32,4>", "bound": "hbm", "achieved": achieved,
+                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_of(cap_map, R),
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "pipe": (cap_map or {}).get("pipes"),
+                             "pipe_source": (cap_map or {}).get("file"), "capture_stale": (cap_map or {}).get("stale"),
+                             "note": "SHA-256 is ~20 int ops/byte: the int32 ALU pipe, not HBM, is the physical bound (the algorithmic-byte "
+                                     "convention of SURVEY 8d counts inner-node blocks that never touch HBM, so traffic < algorithmic bytes)"},
+            "whole_step_hbm": {"algorithmic_bytes": alg + ed_alg + R * (64 * 978 + 32 * 490), "GBps": (alg + ed_alg + R * (64 * 978 + 32 * 490)) / (ms_step * 1e-3) / 1e9},
+            "kernels_alone_ms": {"ed25519 batch": ed_ms, "map stage (proofs + commit kernels)": k_ms,
+                                 "verify_skip (ed25519 batch beside verify_kernel<1>)": skip_ms},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ranges_per_step": Re, "host_cpus": numa, "host_threads": n_thr, "single_call": e2e_single,
+                    "ranges_checked_against_oracle": e2e_checked,
+                    "bound": "PCIe download of the witness (0.74 MB per range)",
                     "note": "one ctx + pinned buffers per host thread, calls dealt round-robin; every call copies its inputs up and its witness down"},
+            "header_range_2048": hr2048,
             "constraints": constraints,
             "cpu_baseline": cpu,
             "cpu_library_baseline": cpu_lib,
+            "parity_notes": "oracle pinned by the reference's fixtures (tests/golden); weak pins: Ed25519 decompress root convention (audit "
+                            "prose only), Poseidon (one KAT), gates (properties only) -- DESIGN.md section 6",
+            "csrc_sha16": csrc_sha16(),
         }
         print(json.dumps(out), file=json_out, flush=True)
     if world > 1:
@@ -1117,6 +1271,7 @@ def main():
     ap.add_argument("--cpu-ranges", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-2048", action="store_true", help="skip the header_range_2048 block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

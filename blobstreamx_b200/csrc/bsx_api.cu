@@ -17,6 +17,35 @@ static cudaError_t create_priority_stream(cudaStream_t *st) {
     return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, hi);
 }
 
+static const struct { const char *name; int dflt; } TUNABLES[BSX_TUN_COUNT] = {
+    {"ED_MODE", 0},      {"ED_QUAD_MAX", 16384}, {"ED_INLINE", -1},  {"ED_OCC", 0},     {"ED_REGS", -1},
+    {"ED_FP64", -1},     {"HR_HASH_STREAM", -1}, {"HR_TRACE", 0},    {"PIPE_CHUNK", 0}, {"PIPE_ED", 0},
+    {"PIPE_TRACE", 0},   {"PROOFS_OCC", 8},      {"SUBCHAIN_FUSED", 0},
+};
+
+static int tunable_index(const char *name) {
+    if (!name) return -1;
+    if (!strncmp(name, "BSX_", 4)) name += 4;
+    for (int i = 0; i < BSX_TUN_COUNT; i++)
+        if (!strcmp(name, TUNABLES[i].name)) return i;
+    return -1;
+}
+
+extern "C" int bsx_set_tunable(bsx_ctx *ctx, const char *name, int value) {
+    BSX_REQUIRE(ctx, ctx != nullptr);
+    const int i = tunable_index(name);
+    if (i < 0) return bsx::fail(ctx, BSX_ERR_INVALID, "unknown tunable %s%s", name ? name : "(null)");
+    ctx->tun[i] = value;
+    return BSX_OK;
+}
+
+extern "C" int bsx_get_tunable(const bsx_ctx *ctx, const char *name, int *value) {
+    const int i = tunable_index(name);
+    if (!ctx || !value || i < 0) return BSX_ERR_INVALID;
+    *value = ctx->tun[i];
+    return BSX_OK;
+}
+
 extern "C" int bsx_init(int device, bsx_ctx **out) {
     if (!out) return BSX_ERR_INVALID;
     *out = nullptr;
@@ -27,6 +56,12 @@ extern "C" int bsx_init(int device, bsx_ctx **out) {
     if (!ctx) return BSX_ERR_NOMEM;
     memset(ctx, 0, sizeof *ctx);
     ctx->device = device;
+    for (int i = 0; i < BSX_TUN_COUNT; i++) {
+        char var[64];
+        snprintf(var, sizeof var, "BSX_%s", TUNABLES[i].name);
+        const char *e = getenv(var);
+        ctx->tun[i] = e ? atoi(e) : TUNABLES[i].dflt;
+    }
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -79,6 +114,7 @@ extern "C" void bsx_destroy(bsx_ctx *ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
     if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
+    if (ctx->ev_table) cudaEventDestroy(ctx->ev_table);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ed_table) cudaFree(ctx->ed_table);
     delete ctx;

@@ -10,6 +10,26 @@
 
 #define BSX_PIPE_STREAMS 3
 
+// Measurement knobs.  Defaults are the measured best; the environment variable BSX_<name> overrides a default when the
+// ctx is created and bsx_set_tunable(ctx, "<name>", v) changes it afterwards (per ctx, so every path can be exercised
+// in one process).  DESIGN.md section 4 lists what each one selects.
+enum bsx_tun_id {
+    BSX_TUN_ED_MODE,         // 0 by batch size, 1 three-stage quad-lane path, 2 one thread per signature
+    BSX_TUN_ED_QUAD_MAX,     // largest batch that takes the quad-lane path (16384)
+    BSX_TUN_ED_INLINE,       // thread-per-signature kernel: -1 by call site, 0 compact, 1 inlined point arithmetic
+    BSX_TUN_ED_OCC,          // 0 default (4 CTAs/SM), 6 -> 168 registers, 8 -> 128 registers
+    BSX_TUN_ED_REGS,         // 192-register build beside the hash kernels: -1 by wave fill, 0 never, >0 always
+    BSX_TUN_ED_FP64,         // field arithmetic of the scalar multiplications on the FP64 pipe: -1 default, 0 off, 1 on
+    BSX_TUN_HR_HASH_STREAM,  // skip hashes: -1 by wave fill, 0 caller's stream, 1 own stream
+    BSX_TUN_HR_TRACE,        // device-resident step: print when each half finishes (synchronises)
+    BSX_TUN_PIPE_CHUNK,      // host path: ranges per chunk (0 = growing chunks)
+    BSX_TUN_PIPE_ED,         // host path: 0/1 skip half first, 2 last
+    BSX_TUN_PIPE_TRACE,      // host path: per-chunk timeline on stderr
+    BSX_TUN_PROOFS_OCC,      // proofs kernel: 8 (64 registers) or 6 (80 registers)
+    BSX_TUN_SUBCHAIN_FUSED,  // 1 = one-CTA-per-job map kernel with TMA-staged inputs (A/B only)
+    BSX_TUN_COUNT
+};
+
 struct bsx_ctx {
     int device;
     int sm_count;
@@ -20,7 +40,9 @@ struct bsx_ctx {
     size_t ws_cap;
     size_t ws_off;
     void *ed_table;            // s*G window table (k_ed25519.cu), built on first use
-    int ed_corun;              // set by the pipelined host path: Ed25519 in its 128-register build (see launch_mono)
+    cudaEvent_t ev_table;      // recorded after the table build: every consumer stream waits on it (the build runs once,
+    int ed_table_pending;      // on whichever stream made the first Ed25519 call); pending until the event has been seen complete
+    int tun[BSX_TUN_COUNT];    // measurement knobs (bsx_set_tunable; defaults from the BSX_* environment at bsx_init)
     cudaStream_t stream2;      // second stream + events: bsx_header_range runs its two halves concurrently
     cudaEvent_t ev_fork, ev_join;     // bsx_header_range (host path: two copy+compute pipelines)
     cudaEvent_t ev_fork2, ev_join2;   // verify_*: Ed25519 kernel on stream2 beside the SHA-256 schedule
@@ -43,7 +65,10 @@ static inline bool bsx_ed_fills_waves(const bsx_ctx *ctx, uint64_t n) {
 }
 
 // stages of verify_* (k_verify.cu), reused by bsx_header_range_dev
-int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out);
+int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out, int ed_corun = 0);
+int bsx_verify_skip_corun_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const bsx_header_in *hdr, const uint8_t *validators,
+                              const bsx_skip_in *skip, const uint8_t *trusted_pubkeys, const uint64_t *trusted_powers,
+                              const uint32_t *trusted_byte_lengths, uint8_t *digests, uint8_t *ed_out, uint32_t *fail);
 int bsx_verify_launch_hash(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t N, const bsx_header_in *hdr,
                            const uint8_t *validators, const bsx_skip_in *skip, const uint8_t *trusted_pubkeys,
                            const uint64_t *trusted_powers, const uint32_t *trusted_byte_lengths, const bsx_step_in *step,

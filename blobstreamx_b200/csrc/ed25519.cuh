@@ -23,6 +23,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "fe51d.cuh"
+
 #if defined(__CUDACC__)
 #define BSX_HD __host__ __device__ __forceinline__
 #define BSX_CALL static __host__ __device__ __noinline__
@@ -640,4 +642,226 @@ BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], co
 }
 
 }  // namespace ed
+
+// ---------------------------------------------------------------------------------------------
+// The same group arithmetic over the FP64-pipe field (fe51d.cuh): 5 x 51-bit limbs in doubles.
+// Unit bookkeeping ("u" = a carried value, |limb| <= 2^50 + 2^14; a product needs |f_i g_j| < 2^103, i.e. units
+// multiplying to at most 7): every multiplication / squaring returns 1u; sums are noted where they arise.
+// ---------------------------------------------------------------------------------------------
+namespace edd {
+using ed::fe;
+
+#define BSX_FED_D {929955233495222.0, 466365720129213.0, -589740348686295.0, -217950738957124.0, -809005158844672.0}
+#define BSX_FED_2D {-391889346694823.0, 932731440258427.0, 1072319116312658.0, -435901477914249.0, 633789495995904.0}
+#define BSX_FED_SQRTM1 {-533094393274192.0, 234908883556510.0, -18285341111200.0, -134597186663265.0, 765476049583134.0}
+BSX_HD fed fed_const(const double c[5]) { fed r; for (int i = 0; i < 5; i++) r.v[i] = c[i]; return r; }
+
+// 10 x 25.5-bit integer limbs <-> 5 x 51-bit double limbs (limb pair 2k, 2k+1 = bits 51k .. 51k+50)
+BSX_HD fed fed_from_fe(const fe &f) {
+    int64_t E[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) E[k] = (int64_t)f.v[2 * k] + ((int64_t)f.v[2 * k + 1] << 26);
+    return fed_carry(E);
+}
+BSX_HD fe fe_from_fed(const fed &f) {
+    int64_t h[10];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int64_t l = fed_limb_i64(f.v[k]);
+        h[2 * k] = l & 0x3ffffff;
+        h[2 * k + 1] = l >> 26;
+    }
+    return ed::fe_carry64(h);
+}
+
+struct ged_p3 { fed X, Y, Z, T; };
+struct ged_p1p1 { fed X, Y, Z, T; };
+struct ged_cached { fed YpX, YmX, Z, T2d; };   // YpX, YmX: 2u;  Z, T2d: 1u
+struct ged_niels { fed ypx, ymx, xy2d; };      // 1u each (converted table entries)
+
+BSX_HD ged_p3 ged_identity() { ged_p3 r; r.X = fed_zero(); r.Y = fed_one(); r.Z = fed_one(); r.T = fed_zero(); return r; }
+BSX_HD ged_p3 ged_from_affine(const fed &x, const fed &y) { ged_p3 r; r.X = x; r.Y = y; r.Z = fed_one(); r.T = fed_mul(x, y); return r; }
+BSX_HD ged_cached ged_to_cached(const ged_p3 &p) {
+    const double d2[5] = BSX_FED_2D;
+    ged_cached c; c.YpX = fed_add(p.Y, p.X); c.YmX = fed_sub(p.Y, p.X); c.Z = p.Z; c.T2d = fed_mul(p.T, fed_const(d2));
+    return c;
+}
+// completed -> extended.  Units of the completed point: after a doubling X 3u, Y 2u, Z 2u, T 1u; after an addition all 2u
+// (T 1u for a table addition) -- every product below stays within 6.
+template <bool INL = false>
+BSX_HD ged_p3 ged_p1p1_to_p3(const ged_p1p1 &p, bool with_t) {
+    ged_p3 r; r.X = fed_mul_x<INL>(p.X, p.T); r.Y = fed_mul_x<INL>(p.Z, p.Y); r.Z = fed_mul_x<INL>(p.Z, p.T);
+    r.T = with_t ? fed_mul_x<INL>(p.X, p.Y) : fed_zero();
+    return r;
+}
+// doubling (X, Y, Z of a 1u point): T' = 2 ZZ - YY + XX is combined on the folded 64-bit columns BEFORE the carry, so it
+// comes out carried (1u) instead of as a 3-unit difference -- X' = A - YY - XX is 3u, and 3u x 3u would exceed the product bound.
+template <bool INL = false>
+BSX_HD ged_p1p1 ged_dbl(const ged_p3 &p) {
+    ged_p1p1 r;
+    const fed_raw exx = fed_sq_raw_x<INL>(p.X), eyy = fed_sq_raw_x<INL>(p.Y), ezz = fed_sq_raw_x<INL>(p.Z);
+    const fed a = fed_sq_x<INL>(fed_add(p.X, p.Y));                    // (2u)^2
+    int64_t et[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) et[k] = 2 * ezz.E[k] - eyy.E[k] + exx.E[k];   // < 4 * 2^59.7
+    const fed xx = fed_carry(exx.E), yy = fed_carry(eyy.E);
+    r.T = fed_carry(et);
+    r.Y = fed_add(yy, xx); r.Z = fed_sub(yy, xx); r.X = fed_sub(a, r.Y);
+    return r;
+}
+// p + q, q cached: 2 Z1 Z2 comes doubled out of the multiplication (1u), so Z' and T' are 2u
+template <bool INL = false>
+BSX_HD ged_p1p1 ged_add_cached(const ged_p3 &p, const ged_cached &q) {
+    ged_p1p1 r;
+    const fed a = fed_mul_x<INL>(fed_add(p.Y, p.X), q.YpX), b = fed_mul_x<INL>(fed_sub(p.Y, p.X), q.YmX);
+    const fed c = fed_mul_x<INL>(q.T2d, p.T), d = fed_mul2_x<INL>(p.Z, q.Z);
+    r.X = fed_sub(a, b); r.Y = fed_add(a, b); r.Z = fed_add(d, c); r.T = fed_sub(d, c);
+    return r;
+}
+// p + q, q affine precomputed: d = 2 Z1 is 2u, so T' = d - c is re-carried (Z' stays 3u: 3u x 2u and 3u x 1u are fine)
+template <bool INL = false>
+BSX_HD ged_p1p1 ged_add_niels(const ged_p3 &p, const ged_niels &q) {
+    ged_p1p1 r;
+    const fed a = fed_mul_x<INL>(fed_add(p.Y, p.X), q.ypx), b = fed_mul_x<INL>(fed_sub(p.Y, p.X), q.ymx);
+    const fed c = fed_mul_x<INL>(q.xy2d, p.T);
+    const fed d = fed_add(p.Z, p.Z);
+    r.X = fed_sub(a, b); r.Y = fed_add(a, b); r.Z = fed_add(d, c); r.T = fed_reduce(fed_sub(d, c));
+    return r;
+}
+
+// decompress: as ed::ge_decompress, the square-root chain on the FP64 pipe
+BSX_HD bool ged_decompress(const uint8_t *in, fed &x, fed &y, uint8_t x_bytes[32], uint8_t y_bytes[32], uint8_t root_bytes[32]) {
+    const double dc[5] = BSX_FED_D, sm1[5] = BSX_FED_SQRTM1;
+    const bool sign = (in[31] >> 7) != 0;
+    const fe yi = ed::fe_frombytes(in);
+    y = fed_from_fe(yi);
+    const fed yy = fed_sq(y);
+    const fed u = fed_sub(yy, fed_one());                       // 1u + 1
+    const fed v = fed_add(fed_mul(yy, fed_const(dc)), fed_one());
+    const fed v3 = fed_mul(fed_sq(v), v);
+    const fed uv7 = fed_mul(fed_mul(fed_sq(v3), v), u);
+    fed r = fed_mul(fed_mul(fed_pow22523(uv7), v3), u);   // u v^3 (u v^7)^((p-5)/8)
+    const fed vxx = fed_mul(fed_sq(r), v);
+    uint8_t a[32], b[32];
+    ed::fe_tobytes(a, fe_from_fed(fed_sub(vxx, u)));      // v r^2 - u
+    bool ok = ed::fe_iszero_bytes(a);
+    if (!ok) {
+        ed::fe_tobytes(b, fe_from_fed(fed_add(vxx, u)));  // v r^2 + u
+        if (ed::fe_iszero_bytes(b)) { r = fed_mul(r, fed_const(sm1)); ok = true; }
+    }
+    if (!ok) {
+        x = fed_zero(); y = fed_one();
+        for (int i = 0; i < 32; i++) { x_bytes[i] = 0; y_bytes[i] = 0; root_bytes[i] = 0; }
+        y_bytes[0] = 1;
+        return false;
+    }
+    ed::fe_tobytes(root_bytes, fe_from_fed(r));
+    if (root_bytes[0] & 1) { r = fed_neg(r); ed::fe_tobytes(root_bytes, fe_from_fed(r)); }
+    x = sign ? fed_neg(r) : r;
+    if (sign) ed::fe_tobytes(x_bytes, fe_from_fed(x)); else for (int i = 0; i < 32; i++) x_bytes[i] = root_bytes[i];
+    ed::fe_tobytes(y_bytes, yi);
+    return true;
+}
+
+// table entry (integer limbs, ed::ge_niels_slot) -> doubles: limb k = v[2k] + 2^26 v[2k+1], exact (|.| < 2^51)
+BSX_HD ged_niels ged_niels_load(const ed::ge_niels_slot *slot) {
+    const ed::ge_niels q = ed::ge_niels_load(slot);
+    ged_niels r;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        r.ypx.v[k] = (double)q.ypx.v[2 * k] + 67108864.0 * (double)q.ypx.v[2 * k + 1];
+        r.ymx.v[k] = (double)q.ymx.v[2 * k] + 67108864.0 * (double)q.ymx.v[2 * k + 1];
+        r.xy2d.v[k] = (double)q.xy2d.v[2 * k] + 67108864.0 * (double)q.xy2d.v[2 * k + 1];
+    }
+    return r;
+}
+template <bool INL = false>
+BSX_HD ged_p3 ged_scalarmult_base(const uint8_t s[32], const ed::ge_niels_slot *table) {
+    ged_p3 acc = ged_identity();
+#pragma unroll 1
+    for (int w = 0; w < BSX_ED_BASE_WINDOWS; w++) {
+        const uint32_t dgt = s[w];
+        if (dgt) {
+            const ged_niels q = ged_niels_load(table + w * BSX_ED_BASE_ENTRIES + (dgt - 1));
+            acc = ged_p1p1_to_p3<INL>(ged_add_niels<INL>(acc, q), true);
+        }
+    }
+    return acc;
+}
+BSX_HD ged_cached ged_cached_cneg(const ged_cached &q, bool neg) {
+    ged_cached r;
+    r.YpX = fed_select(neg, q.YmX, q.YpX); r.YmX = fed_select(neg, q.YpX, q.YmX); r.Z = q.Z;
+    r.T2d = fed_select(neg, fed_neg(q.T2d), q.T2d);
+    return r;
+}
+// scalar * P: signed radix-16 digits over the table 1P..8P, as ed::ge_scalarmult
+template <bool INL = false>
+BSX_HD ged_p3 ged_scalarmult(const uint8_t s[32], const ged_p3 &P) {
+    ged_cached tab[8];
+    {
+        ged_p3 cur = P;
+        tab[0] = ged_to_cached(cur);
+#pragma unroll 1
+        for (int d = 2; d <= 8; d++) {
+            cur = ged_p1p1_to_p3(ged_add_cached(cur, tab[0]), true);
+            tab[d - 1] = ged_to_cached(cur);
+        }
+    }
+    int8_t e[65];
+    {
+        int carry = 0;
+#pragma unroll 1
+        for (int w = 0; w < 64; w++) {
+            int d = (int)((s[w >> 1] >> ((w & 1) * 4)) & 15) + carry;
+            carry = d >= 8;
+            e[w] = (int8_t)(d - 16 * carry);
+        }
+        e[64] = (int8_t)carry;
+    }
+    ged_p3 acc = ged_identity();
+    bool started = false;
+#pragma unroll 1
+    for (int w = 64; w >= 0; w--) {
+        if (started) {
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) acc = ged_p1p1_to_p3<INL>(ged_dbl<INL>(acc), k == 3);
+        }
+        const int d = e[w];
+        if (d) {
+            const ged_cached q = ged_cached_cneg(tab[(d < 0 ? -d : d) - 1], d < 0);
+            acc = ged_p1p1_to_p3<INL>(ged_add_cached<INL>(acc, q), w == 0);
+            started = true;
+        }
+    }
+    return acc;
+}
+
+// one signature on the FP64 pipe: same record as ed::ed25519_witness_core
+template <bool INL = false>
+BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], const uint8_t digest[64],
+                                 const ed::ge_niels_slot *base_table, uint8_t *out) {
+    for (int i = 0; i < 64; i++) out[i] = digest[i];
+    ed::sc_divrem_l(digest, out + 64, out + 96);
+    uint32_t flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
+    fed ax, ay, rx, ry;
+    if (ged_decompress(pk, ax, ay, out + 200, out + 232, out + 264)) flags |= 2u;
+    if (ged_decompress(sig, rx, ry, out + 360, out + 392, out + 424)) flags |= 4u;
+    const ged_p3 sg = ged_scalarmult_base<INL>(sig + 32, base_table);
+    const ged_p3 ha = ged_scalarmult<INL>(out + 64, ged_from_affine(ax, ay));
+    const ged_p3 sum = ged_p1p1_to_p3(ged_add_cached(ha, ged_to_cached(ged_from_affine(rx, ry))), false);
+    // one inversion for the three Z's
+    const fed z12 = fed_mul(sg.Z, ha.Z);
+    const fed inv = fed_invert(fed_mul(z12, sum.Z));
+    const fed isum = fed_mul(inv, z12);
+    const fed i12 = fed_mul(inv, sum.Z);
+    const fed isg = fed_mul(i12, ha.Z), iha = fed_mul(i12, sg.Z);
+    ed::fe_tobytes(out + 136, fe_from_fed(fed_mul(sg.X, isg))); ed::fe_tobytes(out + 168, fe_from_fed(fed_mul(sg.Y, isg)));
+    ed::fe_tobytes(out + 296, fe_from_fed(fed_mul(ha.X, iha))); ed::fe_tobytes(out + 328, fe_from_fed(fed_mul(ha.Y, iha)));
+    ed::fe_tobytes(out + 456, fe_from_fed(fed_mul(sum.X, isum))); ed::fe_tobytes(out + 488, fe_from_fed(fed_mul(sum.Y, isum)));
+    if (ed::bytes_eq32(out + 136, out + 456) && ed::bytes_eq32(out + 168, out + 488)) flags |= 8u;
+    out[520] = (uint8_t)flags; out[521] = 0; out[522] = 0; out[523] = 0;
+    for (int i = 524; i < 576; i++) out[i] = 0;
+}
+
+}  // namespace edd
 }  // namespace bsx

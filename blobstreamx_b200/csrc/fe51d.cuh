@@ -76,12 +76,12 @@ BSX_D_HD double dadd(double a, double b) {
 #define BSX_D_LO_BITS 0x4330000000000000LL   /* 2^52 */
 #define BSX_D_MAGIC_BITS 0x4338000000000000LL /* 1.5 * 2^52 */
 
-struct prod { int64_t hi, lo; };   // bit patterns, constants still inside
+struct prod { uint64_t hi, lo; };   // bit patterns, constants still inside (summed modulo 2^64: unsigned)
 BSX_D_HD prod dmul(double a, double b) {
     const double c1 = bits2d(BSX_D_C1_BITS), c2 = bits2d(BSX_D_C2_BITS);
     const double ph = fma_rz(a, b, c1);
     const double pl = fma_rz(a, b, dsub(c2, ph));
-    prod r; r.hi = d2bits(ph); r.lo = d2bits(pl);
+    prod r; r.hi = (uint64_t)d2bits(ph); r.lo = (uint64_t)d2bits(pl);
     return r;
 }
 
@@ -97,7 +97,7 @@ BSX_D_HD fed fed_select(bool c, const fed &a, const fed &b) { fed r; for (int i 
 BSX_D_HD fed fed_carry(const int64_t E[5]) {
     int64_t c[5], l[5];
 #pragma unroll
-    for (int k = 0; k < 5; k++) { c[k] = (E[k] + ((int64_t)1 << 50)) >> 51; l[k] = E[k] - (c[k] << 51); }
+    for (int k = 0; k < 5; k++) { c[k] = (E[k] + ((int64_t)1 << 50)) >> 51; l[k] = E[k] - c[k] * ((int64_t)1 << 51); }
     fed r;
     const double magic = bits2d(BSX_D_MAGIC_BITS);
 #pragma unroll
@@ -110,12 +110,12 @@ BSX_D_HD fed fed_carry(const int64_t E[5]) {
 
 // column sums of the products -> E[5]
 //   H[k], L[k]: sums of hi / lo bit patterns of column k (k = 0..8) with nh[k] terms each
-BSX_D_HD void fed_fold(const int64_t H[9], const int64_t L[9], const int nterms[9], int64_t E[5]) {
+BSX_D_HD void fed_fold(const uint64_t H[9], const uint64_t L[9], const int nterms[9], int64_t E[5]) {
     int64_t hs[9], ls[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) {
-        hs[k] = H[k] - (int64_t)nterms[k] * BSX_D_C1_BITS;
-        ls[k] = L[k] - (int64_t)nterms[k] * BSX_D_LO_BITS;
+        hs[k] = (int64_t)(H[k] - (uint64_t)nterms[k] * (uint64_t)BSX_D_C1_BITS);
+        ls[k] = (int64_t)(L[k] - (uint64_t)nterms[k] * (uint64_t)BSX_D_LO_BITS);
     }
     // value = sum_k (ls[k] + 2^52 hs[k]) 2^(51k);  2^52 2^(51k) = 2 * 2^(51(k+1));  2^(51*5) = 19
 #pragma unroll
@@ -126,8 +126,10 @@ BSX_D_HD void fed_fold(const int64_t H[9], const int64_t L[9], const int nterms[
     }
 }
 
-BSX_D_HD fed fed_mul_inl(const fed &f, const fed &g) {
-    int64_t H[9], L[9];
+struct fed_raw { int64_t E[5]; };   // folded columns before the carry: weight 2^(51k), |E_k| < 2^59.7
+
+BSX_D_HD fed_raw fed_mul_raw(const fed &f, const fed &g) {
+    uint64_t H[9], L[9];
     const int nt[9] = {1, 2, 3, 4, 5, 4, 3, 2, 1};
 #pragma unroll
     for (int k = 0; k < 9; k++) { H[k] = 0; L[k] = 0; }
@@ -138,15 +140,14 @@ BSX_D_HD fed fed_mul_inl(const fed &f, const fed &g) {
             const prod p = dmul(f.v[i], g.v[j]);
             H[i + j] += p.hi; L[i + j] += p.lo;
         }
-    int64_t E[5];
-    fed_fold(H, L, nt, E);
-    return fed_carry(E);
+    fed_raw r;
+    fed_fold(H, L, nt, r.E);
+    return r;
 }
 
-// f*f (times 2 when TWICE): 15 products, cross terms doubled as integers
-template <bool TWICE>
-BSX_D_HD fed fed_sq_impl(const fed &f) {
-    int64_t Hd[9], Ld[9], Hc[9], Lc[9];
+// f*f: 15 products, cross terms doubled as integers (so that a 2-unit input stays within the product bound)
+BSX_D_HD fed_raw fed_sq_raw(const fed &f) {
+    uint64_t Hd[9], Ld[9], Hc[9], Lc[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) { Hd[k] = 0; Ld[k] = 0; Hc[k] = 0; Lc[k] = 0; }
 #pragma unroll
@@ -157,33 +158,121 @@ BSX_D_HD fed fed_sq_impl(const fed &f) {
             if (i == j) { Hd[i + j] += p.hi; Ld[i + j] += p.lo; }
             else { Hc[i + j] += p.hi; Lc[i + j] += p.lo; }
         }
-    // diagonal terms: columns 0,2,4,6,8 one each; cross terms: column k has floor((k+1)/2) for k<=4 ... counted below
     const int nd[9] = {1, 0, 1, 0, 1, 0, 1, 0, 1};
     const int nc[9] = {0, 1, 1, 2, 2, 2, 1, 1, 0};
-    int64_t H[9], L[9];
-    int nt[9];
+    uint64_t H[9], L[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) {
-        // remove the constants before doubling so that one fold serves both
-        const int64_t hc = Hc[k] - (int64_t)nc[k] * BSX_D_C1_BITS, lc = Lc[k] - (int64_t)nc[k] * BSX_D_LO_BITS;
-        H[k] = Hd[k] + 2 * hc; L[k] = Ld[k] + 2 * lc; nt[k] = nd[k];
+        // the cross sums lose their constants before the doubling, so that one fold serves both kinds
+        const uint64_t hc = Hc[k] - (uint64_t)nc[k] * (uint64_t)BSX_D_C1_BITS, lc = Lc[k] - (uint64_t)nc[k] * (uint64_t)BSX_D_LO_BITS;
+        H[k] = Hd[k] + 2 * hc; L[k] = Ld[k] + 2 * lc;
     }
-    int64_t E[5];
-    fed_fold(H, L, nt, E);
-    if (TWICE) { for (int k = 0; k < 5; k++) E[k] *= 2; }
-    return fed_carry(E);
+    fed_raw r;
+    fed_fold(H, L, nd, r.E);
+    return r;
+}
+
+BSX_D_HD fed fed_mul_inl(const fed &f, const fed &g) { const fed_raw r = fed_mul_raw(f, g); return fed_carry(r.E); }
+BSX_D_HD fed fed_mul2_inl(const fed &f, const fed &g) {
+    fed_raw r = fed_mul_raw(f, g);
+#pragma unroll
+    for (int k = 0; k < 5; k++) r.E[k] *= 2;
+    return fed_carry(r.E);
+}
+template <bool TWICE>
+BSX_D_HD fed fed_sq_impl(const fed &f) {
+    fed_raw r = fed_sq_raw(f);
+    if (TWICE) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) r.E[k] *= 2;
+    }
+    return fed_carry(r.E);
 }
 
 BSX_D_CALL fed fed_mul(const fed f, const fed g) { return fed_mul_inl(f, g); }
+BSX_D_CALL fed fed_mul2(const fed f, const fed g) { return fed_mul2_inl(f, g); }
 BSX_D_CALL fed fed_sq(const fed f) { return fed_sq_impl<false>(f); }
 BSX_D_CALL fed fed_sq2(const fed f) { return fed_sq_impl<true>(f); }
+BSX_D_CALL fed_raw fed_sq_raw_call(const fed f) { return fed_sq_raw(f); }
+template <bool INL> BSX_D_HD fed fed_mul_x(const fed &f, const fed &g) { if (INL) return fed_mul_inl(f, g); return fed_mul(f, g); }
+template <bool INL> BSX_D_HD fed fed_mul2_x(const fed &f, const fed &g) { if (INL) return fed_mul2_inl(f, g); return fed_mul2(f, g); }
+template <bool INL> BSX_D_HD fed fed_sq_x(const fed &f) { if (INL) return fed_sq_impl<false>(f); return fed_sq(f); }
+template <bool INL> BSX_D_HD fed_raw fed_sq_raw_x(const fed &f) { if (INL) return fed_sq_raw(f); return fed_sq_raw_call(f); }
+// n >= 1 successive squarings (the long chains of the inversion and the square roots)
+BSX_D_CALL fed fed_sqn(fed f, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) f = fed_sq_impl<false>(f);
+    return f;
+}
 
+// integer-valued limbs below 2^62 in magnitude -> carried (same value mod p)
+BSX_D_HD fed fed_from_i64(const int64_t l[5]) { return fed_carry(l); }
+// exact integer value of a limb (|v| < 2^62)
+BSX_D_HD int64_t fed_limb_i64(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2ll_rn(v);
+#else
+    return (int64_t)v;
+#endif
+}
 // re-carry a sum/difference of carried values (same value mod p)
 BSX_D_HD fed fed_reduce(const fed &f) {
     int64_t E[5];
 #pragma unroll
-    for (int k = 0; k < 5; k++) E[k] = d2bits(dadd(f.v[k], bits2d(BSX_D_MAGIC_BITS))) - BSX_D_MAGIC_BITS;
+    for (int k = 0; k < 5; k++) E[k] = fed_limb_i64(f.v[k]);
     return fed_carry(E);
+}
+
+// z^(2^252 - 3) = z^((p-5)/8)
+BSX_D_HD fed fed_pow22523(const fed &z) {
+    fed t0 = fed_sq(z);
+    fed t1 = fed_sqn(t0, 2);
+    t1 = fed_mul(z, t1);
+    t0 = fed_mul(t0, t1);
+    t0 = fed_sq(t0);
+    t0 = fed_mul(t1, t0);
+    t1 = fed_sqn(t0, 5);
+    t0 = fed_mul(t1, t0);
+    t1 = fed_sqn(t0, 10);
+    t1 = fed_mul(t1, t0);
+    fed t2 = fed_sqn(t1, 20);
+    t1 = fed_mul(t2, t1);
+    t1 = fed_sqn(t1, 10);
+    t0 = fed_mul(t1, t0);
+    t1 = fed_sqn(t0, 50);
+    t1 = fed_mul(t1, t0);
+    t2 = fed_sqn(t1, 100);
+    t1 = fed_mul(t2, t1);
+    t1 = fed_sqn(t1, 50);
+    t0 = fed_mul(t1, t0);
+    t0 = fed_sqn(t0, 2);
+    return fed_mul(t0, z);
+}
+
+// z^(p-2)
+BSX_D_HD fed fed_invert(const fed &z) {
+    fed t0 = fed_sq(z);
+    fed t1 = fed_sqn(t0, 2);
+    t1 = fed_mul(z, t1);
+    t0 = fed_mul(t0, t1);
+    fed t2 = fed_sq(t0);
+    t1 = fed_mul(t1, t2);
+    t2 = fed_sqn(t1, 5);
+    t1 = fed_mul(t2, t1);
+    t2 = fed_sqn(t1, 10);
+    t2 = fed_mul(t2, t1);
+    fed t3 = fed_sqn(t2, 20);
+    t2 = fed_mul(t3, t2);
+    t2 = fed_sqn(t2, 10);
+    t1 = fed_mul(t2, t1);
+    t2 = fed_sqn(t1, 50);
+    t2 = fed_mul(t2, t1);
+    t3 = fed_sqn(t2, 100);
+    t2 = fed_mul(t3, t2);
+    t2 = fed_sqn(t2, 50);
+    t1 = fed_mul(t2, t1);
+    t1 = fed_sqn(t1, 5);
+    return fed_mul(t1, t0);
 }
 
 }  // namespace edd

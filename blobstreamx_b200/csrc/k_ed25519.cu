@@ -336,13 +336,33 @@ __global__ void __launch_bounds__(128) ed25519_finish_kernel(uint32_t n, const i
 
 using namespace bsx;
 
-// the s*G table lives in the ctx (built on first use)
+// the s*G table lives in the ctx (built on first use, on the stream of that first call).  A later call on another stream
+// must not read it before the build kernel has finished: every consumer stream waits on ev_table until the event has
+// been seen complete once.
 static int ensure_base_table(bsx_ctx *ctx, cudaStream_t st) {
-    if (ctx->ed_table) return BSX_OK;
-    const int entries = BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES;
-    BSX_CUDA(ctx, cudaMalloc(&ctx->ed_table, sizeof(ed::ge_niels_slot) * entries));
-    ed25519_base_table_kernel<<<(entries + 63) / 64, 64, 0, st>>>(reinterpret_cast<ed::ge_niels_slot *>(ctx->ed_table));
-    BSX_LAUNCHED(ctx);
+    if (!ctx->ed_table) {
+        const int entries = BSX_ED_BASE_WINDOWS * BSX_ED_BASE_ENTRIES;
+        void *tab = nullptr;
+        BSX_CUDA(ctx, cudaMalloc(&tab, sizeof(ed::ge_niels_slot) * entries));
+        if (!ctx->ev_table && cudaEventCreateWithFlags(&ctx->ev_table, cudaEventDisableTiming) != cudaSuccess) {
+            cudaFree(tab);
+            return bsx::fail(ctx, BSX_ERR_CUDA, "cudaEventCreate (s*G table)%s%s");
+        }
+        ed25519_base_table_kernel<<<(entries + 63) / 64, 64, 0, st>>>(reinterpret_cast<ed::ge_niels_slot *>(tab));
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->ev_table, st) != cudaSuccess) {
+            cudaStreamSynchronize(st);
+            cudaFree(tab);
+            return bsx::fail(ctx, BSX_ERR_CUDA, "s*G table build failed%s%s");
+        }
+        ctx->ed_table = tab;
+        ctx->ed_table_pending = 1;
+        return BSX_OK;
+    }
+    if (ctx->ed_table_pending) {
+        if (cudaEventQuery(ctx->ev_table) == cudaSuccess) ctx->ed_table_pending = 0;
+        else BSX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_table, 0));
+    }
     return BSX_OK;
 }
 
@@ -351,13 +371,22 @@ static int launch_quad(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     int32_t *scratch = nullptr;
     BSX_CUDA(ctx, cudaMallocAsync(&scratch, sizeof(int32_t) * BSX_ED_SCRATCH_WORDS * (size_t)n, st));
     BSX_PIN_CARVEOUT(ed25519_prep_kernel<0>); BSX_PIN_CARVEOUT(ed25519_quad_kernel); BSX_PIN_CARVEOUT(ed25519_finish_kernel<1>);
+    cudaError_t e = cudaSuccess;
     ed25519_prep_kernel<0><<<(2 * n + 127) / 128, 128, 0, st>>>(n, in, out);
-    BSX_LAUNCHED(ctx);
-    ed25519_quad_kernel<<<(4 * n + 63) / 64, 64, 0, st>>>(n, tab, out, scratch);
-    BSX_LAUNCHED(ctx);
-    ed25519_finish_kernel<1><<<(n + 127) / 128, 128, 0, st>>>(n, scratch, out);
-    BSX_LAUNCHED(ctx);
-    BSX_CUDA(ctx, cudaFreeAsync(scratch, st));
+    ctx->launches++;
+    if ((e = cudaGetLastError()) == cudaSuccess) {
+        ed25519_quad_kernel<<<(4 * n + 63) / 64, 64, 0, st>>>(n, tab, out, scratch);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) {
+        ed25519_finish_kernel<1><<<(n + 127) / 128, 128, 0, st>>>(n, scratch, out);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    const cudaError_t ef = cudaFreeAsync(scratch, st);   // stream-ordered: also on the error paths
+    if (e != cudaSuccess) return bsx::fail(ctx, BSX_ERR_CUDA, "kernel launch: %s%s", cudaGetErrorString(e));
+    if (ef != cudaSuccess) return bsx::fail(ctx, BSX_ERR_CUDA, "cudaFreeAsync: %s%s", cudaGetErrorString(ef));
     return BSX_OK;
 }
 
@@ -365,13 +394,14 @@ static int launch_quad(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
 // sub-partition (4 CTAs/SM) -> 216 registers, 3 (6 CTAs) -> 168, 4 (8 CTAs) -> 128 with spills.
 // `alone`: the batch is not issued next to SHA-256 kernels (bsx_ed25519_batch*), so the build with inlined point
 // arithmetic is used; the verify_* / header_range paths share the SMs with the hash kernels and use the compact build.
-// ctx->ed_corun (pipelined host path): the 128-register build.  One wave of the 216-register build leaves room for a
+// `corun` (pipelined host path): the 128-register build.  One wave of the 216-register build leaves room for a
 // single 80-register warp per sub-partition, so the map kernels of the first chunks -- whose digests the D2H engine is
 // waiting for -- queue behind it; the 128-register build leaves half the register file (single call 6.9 -> 6.35 ms).
-static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in, const ed::ge_niels_slot *tab, uint8_t *out, bool alone) {
-    static const int env_occ = [] { const char *e = getenv("BSX_ED_OCC"); return e ? atoi(e) : 0; }();
-    const int occ = env_occ ? env_occ : ctx->ed_corun ? 8 : 4;
-    static const int inl = [] { const char *e = getenv("BSX_ED_INLINE"); return e ? atoi(e) : -1; }();   // -1: by call site
+static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in, const ed::ge_niels_slot *tab, uint8_t *out, bool alone,
+                       bool corun) {
+    const int env_occ = ctx->tun[BSX_TUN_ED_OCC];
+    const int occ = env_occ ? env_occ : corun ? 8 : 4;
+    const int inl = ctx->tun[BSX_TUN_ED_INLINE];   // -1: by call site
     BSX_PIN_CARVEOUT((ed25519_batch_kernel<8, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<6, false>));
     BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, true>));
     const bool use_inl = inl < 0 ? alone : inl != 0;
@@ -380,9 +410,9 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     // beside the SHA-256 kernels, for batches that fill whole waves, the build capped at 192 registers (no spills) is used:
     // each sub-partition keeps room for two 64-register hash warps instead of one (header_range step 2.81 -> 2.77 ms).
     // BSX_ED_REGS: 0 = never, non-zero = always (A/B).
-    static const int env_cap = [] { const char *e = getenv("BSX_ED_REGS"); return e ? atoi(e) : -1; }();
+    const int env_cap = ctx->tun[BSX_TUN_ED_REGS];
     const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves(ctx, n) ? 192 : 0);
-    if (cap && (!alone || env_cap > 0) && !env_occ && !ctx->ed_corun && inl <= 0) {
+    if (cap && (!alone || env_cap > 0) && !env_occ && !corun && inl <= 0) {
         // (caps of 176 and 160 registers spill and were slower: profiles/r01p_step_ab.txt)
         // (the same cap with inlined point arithmetic: 378 ranges per step 2.768 -> 2.818 ms, 756 ranges 5.595 -> 5.530 ms -- not kept)
         BSX_PIN_CARVEOUT((ed25519_batch_kernel_capped<192, false>));
@@ -398,7 +428,7 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
 static int ed25519_strided(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, uint32_t pk_stride,
                            const uint8_t *sigs, uint32_t sig_stride, const uint8_t *msgs, uint32_t msg_stride,
                            uint32_t msg_max, const uint8_t *msg_lens, uint32_t len_stride, const uint8_t *active,
-                           uint32_t active_stride, uint8_t *out, bool alone) {
+                           uint32_t active_stride, uint8_t *out, bool alone, bool corun = false) {
     BSX_REQUIRE(ctx, ctx && pks && sigs && (msgs || msg_max == 0) && out);
     if (n == 0) return BSX_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -407,12 +437,12 @@ static int ed25519_strided(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t
     EdIn in{pks, sigs, msgs, msg_lens, active, pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride};
     const ed::ge_niels_slot *tab = reinterpret_cast<const ed::ge_niels_slot *>(ctx->ed_table);
     // BSX_ED_MODE: 1 = three-stage quad-lane path, 2 = one thread per signature, unset = by batch size
-    static const int forced = [] { const char *e = getenv("BSX_ED_MODE"); return e ? atoi(e) : 0; }();
-    static const uint32_t quad_max = [] { const char *e = getenv("BSX_ED_QUAD_MAX"); return e ? (uint32_t)atoi(e) : 16384u; }();
+    const int forced = ctx->tun[BSX_TUN_ED_MODE];
+    const uint32_t quad_max = (uint32_t)ctx->tun[BSX_TUN_ED_QUAD_MAX];
     // (A split of one large batch over both paths at once was measured: 25 600 signatures alone 1.84 -> 1.72 ms at a
     // 35 % quad share, but the header_range step next to the map kernels gets slower beyond 20 % -- not kept.)
     const bool quad = forced ? forced == 1 : n <= quad_max;
-    return quad ? launch_quad(ctx, st, n, in, tab, out) : launch_mono(ctx, st, n, in, tab, out, alone);
+    return quad ? launch_quad(ctx, st, n, in, tab, out) : launch_mono(ctx, st, n, in, tab, out, alone, corun);
 }
 
 // strided form: used by the verify_* entry points to run straight over validator records, next to their SHA-256 kernels
@@ -422,6 +452,14 @@ extern "C" int bsx_ed25519_strided_dev(bsx_ctx *ctx, void *stream, uint32_t n, c
                                        uint32_t active_stride, uint8_t *out) {
     return ed25519_strided(ctx, stream, n, pks, pk_stride, sigs, sig_stride, msgs, msg_stride, msg_max, msg_lens, len_stride, active,
                            active_stride, out, false);
+}
+
+// internal: the strided form with the co-run register budget of the pipelined host path (k_header_range.cu)
+int bsx_ed25519_strided_corun(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, uint32_t pk_stride, const uint8_t *sigs,
+                              uint32_t sig_stride, const uint8_t *msgs, uint32_t msg_stride, uint32_t msg_max, const uint8_t *msg_lens,
+                              uint32_t len_stride, const uint8_t *active, uint32_t active_stride, uint8_t *out, int corun) {
+    return ed25519_strided(ctx, stream, n, pks, pk_stride, sigs, sig_stride, msgs, msg_stride, msg_max, msg_lens, len_stride, active,
+                           active_stride, out, false, corun != 0);
 }
 
 extern "C" int bsx_ed25519_batch_dev(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, const uint8_t *sigs,

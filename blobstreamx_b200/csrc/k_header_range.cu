@@ -32,7 +32,7 @@ extern "C" int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint
     if (n == 0) return BSX_OK;
     cudaStream_t main = (cudaStream_t)stream;
     // BSX_HR_TRACE=1 (diagnostic, synchronises): when each half of the step finishes, on stderr
-    static const bool trace = getenv("BSX_HR_TRACE") != nullptr;
+    const bool trace = ctx->tun[BSX_TUN_HR_TRACE] != 0;
     cudaEvent_t tev[4] = {};
     if (trace) {
         for (cudaEvent_t &e : tev) cudaEventCreate(&e);
@@ -47,7 +47,7 @@ extern "C" int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint
     // third stream: the skip schedule's SHA-256 kernel (one CTA per range, 490 dependent digests: latency-bound).  On the
     // caller's stream it held the map kernels back until it had squeezed past the Ed25519 wave (1.7 ms instead of 0.19).
     // Only when the Ed25519 batch fills whole waves (common.cuh); otherwise it stays first on the caller's stream.
-    static const int hash_side = [] { const char *e = getenv("BSX_HR_HASH_STREAM"); return e ? atoi(e) : -1; }();   // 0 caller's stream, 1 own
+    const int hash_side = ctx->tun[BSX_TUN_HR_HASH_STREAM];   // -1 by wave fill, 0 caller's stream, 1 own
     cudaStream_t hs = (hash_side >= 0 ? hash_side != 0 : bsx_ed_fills_waves(ctx, (uint64_t)n * N)) ? ctx->pipe[0] : main;
     rc = bsx_verify_launch_hash(ctx, hs, 1, n, N, s->hdr, s->validators, s->skip, s->trusted_pubkeys, s->trusted_powers,
                                 s->trusted_byte_lengths, nullptr, s->digests, nullptr, s->fail);
@@ -108,6 +108,9 @@ static int ensure_chunk_events(bsx_ctx *ctx, uint32_t need) {
     return BSX_OK;
 }
 
+static int header_range_host(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n_jobs, uint32_t B, const bsx_skip_batch *s,
+                             const bsx_range_batch *m);
+
 // host buffers.  The map half is PCIe-bound (371 KB in, 0.66 MB of digests out per range of 1024 headers against ~3 us
 // of kernel time), so it is cut into chunks of ranges that flow through three streams by role -- H2D copies, kernels,
 // D2H copies -- chained with one event per chunk and stage: the upload of chunk k+1, the kernels of chunk k and the
@@ -123,15 +126,29 @@ extern "C" int bsx_header_range(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n
                          s->digests && s->ed_out && s->fail);
     BSX_REQUIRE(ctx, m->dh_leaf && m->dh_aunts && m->lb_leaf && m->lb_aunts && m->start_headers && m->end_headers &&
                          m->start_blocks && m->start_header && m->end_blocks && m->end_header && m->data_commitments && m->fail);
-    BSX_REQUIRE(ctx, n_jobs >= 1 && (n_jobs & (n_jobs - 1)) == 0 && N >= 1);
+    BSX_REQUIRE(ctx, n_jobs >= 1 && (n_jobs & (n_jobs - 1)) == 0 && N >= 1 && N <= 4096);
+    BSX_REQUIRE(ctx, B >= 1 && B <= 256 && (B & (B - 1)) == 0);   // before any size below is derived from it
     if (n == 0) return BSX_OK;
     BSX_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int rc_all = header_range_host(ctx, n, N, n_jobs, B, s, m);
+    if (rc_all != BSX_OK) {
+        // copies against the caller's buffers may still be in flight on any of the five streams: the caller must be free
+        // to release or reuse them once this returns, whatever the status
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream2);
+        for (int i = 0; i < BSX_PIPE_STREAMS; i++) cudaStreamSynchronize(ctx->pipe[i]);
+    }
+    return rc_all;
+}
+
+static int header_range_host(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n_jobs, uint32_t B, const bsx_skip_batch *s,
+                             const bsx_range_batch *m) {
     using bsx::ws_size;
     const size_t R = n, nN = R * N, D = bsx_verify_digest_count(1, N);
     // chunking of the map half: the download of the digests is the longest stage, so the first chunks are small (the
     // D2H engine starts early) and the size doubles up to n/8: for n = 256 the chunks are 8, 16, 32, 32, ... ranges
-    static const uint32_t forced = [] { const char *e = getenv("BSX_PIPE_CHUNK"); return e ? (uint32_t)atoi(e) : 0u; }();
-    static const int ed_order = [] { const char *e = getenv("BSX_PIPE_ED"); return e ? atoi(e) : 0; }();   // 1 first, 2 last
+    const uint32_t forced = (uint32_t)ctx->tun[BSX_TUN_PIPE_CHUNK];
+    const int ed_order = ctx->tun[BSX_TUN_PIPE_ED];   // 1 first, 2 last
     std::vector<uint32_t> chunk_at;   // first range of each chunk, then n
     {
         uint32_t big = forced ? forced : (n + 7) / 8, cur = forced ? forced : (n + 31) / 32;
@@ -166,7 +183,7 @@ extern "C" int bsx_header_range(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n
     BSX_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main));
     BSX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     for (int i = 0; i < BSX_PIPE_STREAMS; i++) BSX_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe[i], ctx->ev_fork, 0));
-    static const bool trace = getenv("BSX_PIPE_TRACE") != nullptr;   // diagnostic: per-chunk timeline on stderr
+    const bool trace = ctx->tun[BSX_TUN_PIPE_TRACE] != 0;   // diagnostic: per-chunk timeline on stderr
     std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) {
         if (!trace) return;
@@ -189,9 +206,8 @@ extern "C" int bsx_header_range(bsx_ctx *ctx, uint32_t n, uint32_t N, uint32_t n
     auto *d_sfail = a.out<uint32_t>(R);
     if (a.rc) return a.rc;
     auto run_skip = [&]() -> int {
-        ctx->ed_corun = 1;   // the chunks' map kernels must get onto the SMs while the Ed25519 wave is resident
-        int r = bsx_verify_skip_dev(ctx, ctx->stream2, n, N, d_hdr, d_val, d_skip, d_tpk, d_tpw, d_tbl, d_sdig, d_ed, d_sfail);
-        ctx->ed_corun = 0;
+        // co-run register budget: the chunks' map kernels must get onto the SMs while the Ed25519 wave is resident
+        int r = bsx_verify_skip_corun_dev(ctx, ctx->stream2, n, N, d_hdr, d_val, d_skip, d_tpk, d_tpw, d_tbl, d_sdig, d_ed, d_sfail);
         if (r) return r;
         a.back(s->digests, d_sdig, R * D * 32);
         a.back(s->ed_out, d_ed, nN * BSX_SIG_OUT_BYTES);

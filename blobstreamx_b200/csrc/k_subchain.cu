@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(B * G < 32 ? 32 : B * G) subchain_commit_kerne
 template <int B>
 static int launch_subchain_split(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const SubchainArgs &a) {
     const size_t total = (size_t)n_jobs * 2 * B;
-    static const int occ = [] { const char *e = getenv("BSX_PROOFS_OCC"); return e ? atoi(e) : 8; }();
+    const int occ = ctx->tun[BSX_TUN_PROOFS_OCC];
     BSX_PIN_CARVEOUT(subchain_proofs_kernel<8>); BSX_PIN_CARVEOUT(subchain_proofs_kernel<6>);
     if (occ >= 8) subchain_proofs_kernel<8><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, B, n_jobs);   // 64 registers
     else subchain_proofs_kernel<6><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, B, n_jobs);             // 80 registers
@@ -517,13 +517,12 @@ static int launch_subchain(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const
     return BSX_OK;
 }
 
-static bool use_fused_map() {  // BSX_SUBCHAIN_FUSED=1 selects the one-CTA-per-job kernel (A/B measurements)
-    static const bool v = [] { const char *e = getenv("BSX_SUBCHAIN_FUSED"); return e && e[0] == '1'; }();
-    return v;
+static bool use_fused_map(const bsx_ctx *ctx) {  // SUBCHAIN_FUSED=1 selects the one-CTA-per-job kernel (A/B measurements)
+    return ctx->tun[BSX_TUN_SUBCHAIN_FUSED] == 1;
 }
 
 static int dispatch_subchain(bsx_ctx *ctx, cudaStream_t st, uint32_t B, uint32_t n_jobs, const SubchainArgs &a) {
-    if (!use_fused_map()) {
+    if (!use_fused_map(ctx)) {
         switch (B) {
             case 1: return launch_subchain_split<1>(ctx, st, n_jobs, a);
             case 2: return launch_subchain_split<2>(ctx, st, n_jobs, a);

@@ -287,6 +287,12 @@ static int launch_verify(bsx_ctx *ctx, cudaStream_t st, int mode, uint32_t n, Ve
     a.P = P;
     const size_t smem = 4 * (8 * (size_t)P + 4 * (size_t)P + 16);
     const uint32_t threads = P < 64 ? 64 : (P > 256 ? 256 : P);
+    if (smem > 48 * 1024) {   // N > 512: above the default dynamic shared-memory limit
+        BSX_CUDA(ctx, cudaFuncSetAttribute(mode == MODE_HEADER ? (const void *)verify_kernel<MODE_HEADER>
+                                           : mode == MODE_SKIP ? (const void *)verify_kernel<MODE_SKIP>
+                                                               : (const void *)verify_kernel<MODE_STEP>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     switch (mode) {
         case MODE_HEADER: BSX_PIN_CARVEOUT(verify_kernel<MODE_HEADER>); verify_kernel<MODE_HEADER><<<n, threads, smem, st>>>(a); break;
         case MODE_SKIP: BSX_PIN_CARVEOUT(verify_kernel<MODE_SKIP>); verify_kernel<MODE_SKIP><<<n, threads, smem, st>>>(a); break;
@@ -300,12 +306,9 @@ static int launch_verify(bsx_ctx *ctx, cudaStream_t st, int mode, uint32_t n, Ve
 
 using namespace bsx;
 
-int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out);
-int bsx_verify_launch_hash(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t N, const bsx_header_in *hdr,
-                           const uint8_t *validators, const bsx_skip_in *skip, const uint8_t *trusted_pubkeys,
-                           const uint64_t *trusted_powers, const uint32_t *trusted_byte_lengths, const bsx_step_in *step,
-                           uint8_t *digests, uint8_t *data_commitments, uint32_t *fail);
-int bsx_verify_launch_flags(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *ed_out, uint32_t *fail);
+int bsx_ed25519_strided_corun(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t *pks, uint32_t pk_stride, const uint8_t *sigs,
+                              uint32_t sig_stride, const uint8_t *msgs, uint32_t msg_stride, uint32_t msg_max, const uint8_t *msg_lens,
+                              uint32_t len_stride, const uint8_t *active, uint32_t active_stride, uint8_t *out, int corun);
 
 extern "C" uint32_t bsx_verify_digest_count(int mode, uint32_t N) {
     uint32_t P = 1;
@@ -317,7 +320,7 @@ extern "C" uint32_t bsx_verify_digest_count(int mode, uint32_t N) {
 static int verify_dev(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t N, const bsx_header_in *hdr,
                       const uint8_t *validators, const bsx_skip_in *skip, const uint8_t *trusted_pubkeys,
                       const uint64_t *trusted_powers, const uint32_t *trusted_byte_lengths, const bsx_step_in *step,
-                      uint8_t *digests, uint8_t *ed_out, uint8_t *data_commitments, uint32_t *fail) {
+                      uint8_t *digests, uint8_t *ed_out, uint8_t *data_commitments, uint32_t *fail, int ed_corun = 0) {
     BSX_REQUIRE(ctx, ctx && hdr && validators && digests && ed_out && fail);
     BSX_REQUIRE(ctx, N >= 1 && N <= 4096);
     BSX_REQUIRE(ctx, mode != MODE_SKIP || (skip && trusted_pubkeys && trusted_powers && trusted_byte_lengths));
@@ -329,7 +332,7 @@ static int verify_dev(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t
     // fork: Ed25519 (FMA pipe, latency-bound) on the high-priority stream, the SHA-256 schedule on the caller's stream
     BSX_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, st));
     BSX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork2, 0));
-    int rc = bsx_verify_launch_ed(ctx, ctx->stream2, n, N, validators, ed_out);
+    int rc = bsx_verify_launch_ed(ctx, ctx->stream2, n, N, validators, ed_out, ed_corun);
     if (rc) return rc;
     rc = bsx_verify_launch_hash(ctx, stream, mode, n, N, hdr, validators, skip, trusted_pubkeys, trusted_powers,
                                 trusted_byte_lengths, step, digests, data_commitments, fail);
@@ -340,11 +343,18 @@ static int verify_dev(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t
 }
 
 // the three stages, also used by bsx_header_range_dev to interleave them with the map/reduce kernels
-int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out) {
+int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out, int ed_corun) {
     // curta_eddsa_verify_sigs_conditional over the validators (is_active = signed), verify.rs:239-251
-    return bsx_ed25519_strided_dev(ctx, stream, n * N, validators, BSX_VAL_IN_BYTES, validators + 32, BSX_VAL_IN_BYTES,
-                                   validators + 96, BSX_VAL_IN_BYTES, 124, validators + 220, BSX_VAL_IN_BYTES,
-                                   validators + 236, BSX_VAL_IN_BYTES, ed_out);
+    return bsx_ed25519_strided_corun(ctx, stream, n * N, validators, BSX_VAL_IN_BYTES, validators + 32, BSX_VAL_IN_BYTES,
+                                     validators + 96, BSX_VAL_IN_BYTES, 124, validators + 220, BSX_VAL_IN_BYTES,
+                                     validators + 236, BSX_VAL_IN_BYTES, ed_out, ed_corun);
+}
+// verify_skip with the Ed25519 batch in its co-run register budget (the pipelined host path of bsx_header_range)
+int bsx_verify_skip_corun_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const bsx_header_in *hdr, const uint8_t *validators,
+                              const bsx_skip_in *skip, const uint8_t *trusted_pubkeys, const uint64_t *trusted_powers,
+                              const uint32_t *trusted_byte_lengths, uint8_t *digests, uint8_t *ed_out, uint32_t *fail) {
+    return verify_dev(ctx, stream, MODE_SKIP, n, N, hdr, validators, skip, trusted_pubkeys, trusted_powers, trusted_byte_lengths,
+                      nullptr, digests, ed_out, nullptr, fail, 1);
 }
 int bsx_verify_launch_hash(bsx_ctx *ctx, void *stream, int mode, uint32_t n, uint32_t N, const bsx_header_in *hdr,
                            const uint8_t *validators, const bsx_skip_in *skip, const uint8_t *trusted_pubkeys,

@@ -182,6 +182,10 @@ class ShardedHeaderRange:
         sub = self.all_sub.view(R, J * SUBCHAIN_BYTES)[o].reshape(-1)
         self.be.reduce(R // W, J, self.B, sub, self.t, self.reduce_digests, self.reduce_nodes, self.data_commitments, self.fail)
 
+    def exchange_text(self) -> str:
+        return {"peer stores": "peer-memory stores from the map kernel + one device barrier",
+                "all_gather": "one all_gather_into_tensor", "none": "nothing (one rank)"}.get(self.exchange, self.exchange)
+
     def results(self):
         Ro = self.R // self.world
         return dict(data_commitments=self.data_commitments.cpu().numpy().reshape(Ro, 32),

@@ -106,6 +106,15 @@ class Context:
     def sync(self):
         self._call("bsx_sync")
 
+    def set_tunable(self, name: str, value: int):
+        """Measurement knob of this ctx (include/bsx.h: bsx_set_tunable), e.g. ("ED_OCC", 8)."""
+        self._call("bsx_set_tunable", C.c_char_p(name.encode()), C.c_int(int(value)))
+
+    def get_tunable(self, name: str) -> int:
+        v = C.c_int(0)
+        self._call("bsx_get_tunable", C.c_char_p(name.encode()), C.byref(v))
+        return int(v.value)
+
     # -- K1 --
     def sha256_batch(self, msgs, offsets) -> np.ndarray:
         offsets = _in(offsets, np.uint32)

@@ -3,6 +3,7 @@
 // GPU.  Never linked into libbsx.so; the product has no CPU path.
 #include "../../blobstreamx_b200/csrc/ed25519.cuh"
 
+#include <fenv.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -61,5 +62,56 @@ void hc_scalarmult(const uint8_t *s, const uint8_t *xy, uint8_t *out, int base) 
 int hc_decompress(const uint8_t *in, uint8_t *xy, uint8_t *root) {
     fe x, y;
     return ge_decompress(in, x, y, xy, xy + 32, root) ? 1 : 0;
+}
+
+// ---- the FP64-pipe field (fe51d.cuh): the host stands in for __fma_rz with fma() under round-toward-zero ----
+struct RoundTowardZero {
+    int old;
+    RoundTowardZero() : old(fegetround()) { fesetround(FE_TOWARDZERO); }
+    ~RoundTowardZero() { fesetround(old); }
+};
+void hc_fp64_ed25519_witness(const uint8_t *pk, const uint8_t *sig, const uint8_t *digest, uint8_t *out) {
+    build_table();
+    RoundTowardZero rz;
+    bsx::edd::ed25519_witness_core(pk, sig, digest, g_table, out);
+}
+// raw limbs (integer-valued doubles) -> product limbs, for the bound tests
+void hc_fed_mul(const double *f, const double *g, double *o, int twice) {
+    RoundTowardZero rz;
+    bsx::edd::fed a, b;
+    for (int i = 0; i < 5; i++) { a.v[i] = f[i]; b.v[i] = g[i]; }
+    const bsx::edd::fed r = twice ? bsx::edd::fed_mul2(a, b) : bsx::edd::fed_mul(a, b);
+    for (int i = 0; i < 5; i++) o[i] = r.v[i];
+}
+void hc_fed_sq(const double *f, double *o, int twice) {
+    RoundTowardZero rz;
+    bsx::edd::fed a;
+    for (int i = 0; i < 5; i++) a.v[i] = f[i];
+    const bsx::edd::fed r = twice ? bsx::edd::fed_sq2(a) : bsx::edd::fed_sq(a);
+    for (int i = 0; i < 5; i++) o[i] = r.v[i];
+}
+// bytes -> integer limbs -> double limbs -> integer limbs -> bytes
+void hc_fed_roundtrip(const uint8_t *a, uint8_t *out) {
+    RoundTowardZero rz;
+    fe_tobytes(out, bsx::edd::fe_from_fed(bsx::edd::fed_from_fe(fe_frombytes(a))));
+}
+void hc_fed_invert(const uint8_t *a, uint8_t *out) {
+    RoundTowardZero rz;
+    fe_tobytes(out, bsx::edd::fe_from_fed(bsx::edd::fed_invert(bsx::edd::fed_from_fe(fe_frombytes(a)))));
+}
+void hc_fp64_scalarmult(const uint8_t *s, const uint8_t *xy, uint8_t *out, int base) {
+    build_table();
+    RoundTowardZero rz;
+    using namespace bsx::edd;
+    ged_p3 r = base ? ged_scalarmult_base(s, g_table)
+                    : ged_scalarmult(s, ged_from_affine(fed_from_fe(fe_frombytes(xy)), fed_from_fe(fe_frombytes(xy + 32))));
+    fed zi = fed_invert(r.Z);
+    fe_tobytes(out, fe_from_fed(fed_mul(r.X, zi)));
+    fe_tobytes(out + 32, fe_from_fed(fed_mul(r.Y, zi)));
+}
+int hc_fp64_decompress(const uint8_t *in, uint8_t *xy, uint8_t *root) {
+    RoundTowardZero rz;
+    bsx::edd::fed x, y;
+    return bsx::edd::ged_decompress(in, x, y, xy, xy + 32, root) ? 1 : 0;
 }
 }

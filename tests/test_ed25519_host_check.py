@@ -207,7 +207,120 @@ def test_no_limb_overflow_under_ubsan():
             out = (C.c_uint8 * 576)()
             hc.hc_ed25519_witness(buf(pk), buf(sig), buf(hashlib.sha512(sig[:32] + pk + msg).digest()), out)
             assert bytes(out) == orc.ed25519_witness(pk, sig, msg)
+            if i % 3 == 0:      # the FP64-pipe build: its 64-bit column arithmetic under the same sanitizer
+                out2 = (C.c_uint8 * 576)()
+                hc.hc_fp64_ed25519_witness(buf(pk), buf(sig), buf(hashlib.sha512(sig[:32] + pk + msg).digest()), out2)
+                assert bytes(out2) == bytes(out)
         print("clean")
     """)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the FP64-pipe field (blobstreamx_b200/csrc/fe51d.cuh): 5 x 51-bit balanced limbs in doubles, products split exactly by
+# two round-toward-zero FMAs.  The host build runs fma() under FE_TOWARDZERO in place of __fma_rz.
+# ---------------------------------------------------------------------------------------------------------------
+def _val51(v):
+    return sum(int(x) << (51 * i) for i, x in enumerate(v))
+
+
+def test_fp64_field_at_limb_bounds(hc):
+    """A product needs |f_i g_j| < 2^103: carried values (|limb| <= 2^50 + 2^14 = 1 unit) in the combinations the point
+    formulas use -- 1x1, 2x2, 3x2, 2x3 and 1x7 units -- at the extremes (all-max, all-min, alternating) and at random;
+    results are integer-valued, carried, and equal the product mod p."""
+    rng = np.random.default_rng(12)
+    D5 = C.c_double * 5
+    U = 2**50 + 2**14
+
+    def limbs(units, mode):
+        m = units * U
+        if mode == 0: return [m] * 5
+        if mode == 1: return [-m] * 5
+        if mode == 2: return [m if i % 2 else -m for i in range(5)]
+        if mode == 3: return [-m if i % 2 else m for i in range(5)]
+        return [int(rng.integers(-m, m + 1)) for _ in range(5)]
+    worst = 0
+    for it in range(6000):
+        uf, ug = [(1, 1), (2, 2), (3, 2), (2, 3), (1, 7)][it % 5]
+        f, g = limbs(uf, it % 7 if it < 200 else 9), limbs(ug, (it // 7) % 7 if it < 200 else 9)
+        o = D5()
+        for tw in (0, 1):
+            hc.hc_fed_mul(D5(*map(float, f)), D5(*map(float, g)), o, tw)
+            assert _val51(o) % P == ((1 + tw) * _val51(f) * _val51(g)) % P, (it, tw)
+            assert all(float(x).is_integer() for x in o)
+            worst = max(worst, max(abs(x) for x in o))
+        if uf <= 2:
+            for tw in (0, 1):
+                hc.hc_fed_sq(D5(*map(float, f)), o, tw)
+                assert _val51(o) % P == ((1 + tw) * _val51(f) ** 2) % P, (it, tw)
+                worst = max(worst, max(abs(x) for x in o))
+    assert worst <= U
+
+
+def test_fp64_field_roundtrip_and_invert(hc):
+    rng = np.random.default_rng(13)
+    for a in _fe_cases(rng, 300):
+        o = _out(32)
+        hc.hc_fed_roundtrip(_buf(a.to_bytes(32, "little")), o)
+        assert int.from_bytes(bytes(o), "little") == (a % 2**255) % P
+    for a in _fe_cases(rng, 40):
+        if (a % 2**255) % P == 0:
+            continue
+        o = _out(32)
+        hc.hc_fed_invert(_buf(a.to_bytes(32, "little")), o)
+        assert int.from_bytes(bytes(o), "little") == pow(a % 2**255, P - 2, P)
+
+
+def test_fp64_decompress_and_scalarmult(hc):
+    from oracle import cbind as orc, pyoracle as po
+    rng = np.random.default_rng(14)
+    pts = []
+    cands = [bytes(32), (1).to_bytes(32, "little"), (P - 1).to_bytes(32, "little"), (2**255 - 1).to_bytes(32, "little"),
+             po.GY.to_bytes(32, "little"), (po.GY | (1 << 255)).to_bytes(32, "little"), (1 | (1 << 255)).to_bytes(32, "little"),
+             (P + 1).to_bytes(32, "little")] + [rng.bytes(32) for _ in range(60)]
+    for c in cands:
+        xy, root = _out(64), _out(32)
+        ok = hc.hc_fp64_decompress(_buf(c), xy, root)
+        wxy, wroot, wok = orc.ed25519_decompress(c)
+        assert bool(ok) == wok and bytes(xy) == wxy and bytes(root) == wroot, c.hex()
+        if ok:
+            pts.append(bytes(xy))
+    scalars = [0, 1, 2, 7, 8, 9, 15, 16, 17, L - 1, L, L + 1, 2**256 - 1, 2**255, 2**252, int("88" * 32, 16), int("77" * 32, 16)] + \
+        [int.from_bytes(rng.bytes(32), "little") for _ in range(12)]
+    g = po.ed_point_bytes(po.G)
+    for i, k in enumerate(scalars):
+        kb = k.to_bytes(32, "little")
+        o = _out(64)
+        hc.hc_fp64_scalarmult(_buf(kb), _buf(g), o, 1)
+        assert bytes(o) == orc.ed25519_scalar_mul(kb, g), k
+        pt = pts[i % len(pts)]
+        hc.hc_fp64_scalarmult(_buf(kb), _buf(pt), o, 0)
+        assert bytes(o) == orc.ed25519_scalar_mul(kb, pt), (k, pt.hex())
+
+
+def test_fp64_witness_records(hc):
+    """The full per-signature record of the FP64 build equals the oracle's: valid signatures, DUMMY, corrupted, garbage."""
+    from nacl.signing import SigningKey
+    from oracle import cbind as orc, pyoracle as po
+    rng = np.random.default_rng(15)
+    cases = [(po.DUMMY_PUBLIC_KEY, po.DUMMY_SIGNATURE, bytes(32))]
+    for i in range(40):
+        sk = SigningKey(hashlib.sha256(b"fp%d" % i).digest())
+        msg = rng.bytes(int(rng.integers(0, 124)))
+        pk, sig = bytes(sk.verify_key), sk.sign(msg).signature
+        if i % 4 == 1:
+            sig = sig[:7] + bytes([sig[7] ^ 2]) + sig[8:]
+        if i % 4 == 2:
+            sig = sig[:32] + (int.from_bytes(sig[32:], "little") + L).to_bytes(32, "little")
+        if i % 8 == 7:
+            pk, sig, msg = rng.bytes(32), rng.bytes(64), rng.bytes(33)
+        cases.append((pk, sig, msg))
+    seen = set()
+    for pk, sig, msg in cases:
+        out = _out(576)
+        hc.hc_fp64_ed25519_witness(_buf(pk), _buf(sig), _buf(hashlib.sha512(sig[:32] + pk + msg).digest()), out)
+        want = orc.ed25519_witness(pk, sig, msg)
+        assert bytes(out) == want, (pk.hex(), sig.hex())
+        seen.add(want[520])
+    assert 0xF in seen and len(seen) >= 3
