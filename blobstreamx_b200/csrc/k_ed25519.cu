@@ -47,23 +47,24 @@ struct EdIn {
     uint32_t pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride;
 };
 
-template <bool INL>
+// FP64: the field arithmetic of the whole signature on the FP64 pipe (fe51d.cuh) instead of IMAD.WIDE
+template <bool INL, bool FP64>
 __device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out);
 
-template <int MIN_CTAS, bool INL>
+template <int MIN_CTAS, bool INL, bool FP64 = false>
 __global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
                                                            uint8_t *__restrict__ out) {
-    ed25519_batch_body<INL>(n, in, table, out);
+    ed25519_batch_body<INL, FP64>(n, in, table, out);
 }
 // the same kernel under an explicit register cap (64-thread CTAs): still 2 warps per SM sub-partition, but more of the
 // register file left to the SHA-256 warps that run beside it
-template <int REGS, bool INL>
+template <int REGS, bool INL, bool FP64 = false>
 __global__ void __maxnreg__(REGS) ed25519_batch_kernel_capped(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
                                                                uint8_t *__restrict__ out) {
-    ed25519_batch_body<INL>(n, in, table, out);
+    ed25519_batch_body<INL, FP64>(n, in, table, out);
 }
 
-template <bool INL>
+template <bool INL, bool FP64>
 __device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -93,7 +94,8 @@ __device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, c
     for (int k = 0; k < 8; k++)
 #pragma unroll
         for (int j = 0; j < 8; j++) digest[8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
-    ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
+    if (FP64) edd::ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
+    else ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
 }
 
 
@@ -102,6 +104,12 @@ __device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, c
 // ---------------------------------------------------------------------------------------------------------------
 // scratch per signature between the quad and finish kernels: X, Y, Z of sG, hA, R + hA (9 field elements)
 #define BSX_ED_SCRATCH_WORDS 90
+// default of the ED_FP64 tunable (-1): set by measurement, see DESIGN.md
+// r02b (profiles/r02b_ab_fp64.txt): 37 888 signatures alone 1.81 -> 1.48 ms (compact), 1.67 -> 1.44 (inlined); header_range step
+// 2.79 -> 2.64 ms.  Beside the SHA-256 kernels the uncapped FP64 build (240 registers) beat the 192-register cap (2.64 vs 2.68 ms).
+#ifndef BSX_ED_FP64_DEFAULT
+#define BSX_ED_FP64_DEFAULT true
+#endif
 
 // stage 1: thread 2i handles A of signature i (and the hashing), thread 2i+1 handles R
 template <int DUMMY>
@@ -402,8 +410,6 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     const int env_occ = ctx->tun[BSX_TUN_ED_OCC];
     const int occ = env_occ ? env_occ : corun ? 8 : 4;
     const int inl = ctx->tun[BSX_TUN_ED_INLINE];   // -1: by call site
-    BSX_PIN_CARVEOUT((ed25519_batch_kernel<8, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<6, false>));
-    BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, false>)); BSX_PIN_CARVEOUT((ed25519_batch_kernel<4, true>));
     const bool use_inl = inl < 0 ? alone : inl != 0;
     // (Splitting this path into prep / main / finish kernels with a 4-way batched inversion was measured slower:
     // 19.3 vs 21.4 M sig/s at 37 800 signatures, 2.98 vs 2.91 ms for the header_range step -- not kept.)
@@ -411,16 +417,34 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     // each sub-partition keeps room for two 64-register hash warps instead of one (header_range step 2.81 -> 2.77 ms).
     // BSX_ED_REGS: 0 = never, non-zero = always (A/B).
     const int env_cap = ctx->tun[BSX_TUN_ED_REGS];
-    const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves(ctx, n) ? 192 : 0);
+    const int fp64_t = ctx->tun[BSX_TUN_ED_FP64];
+    const bool fp64 = fp64_t < 0 ? BSX_ED_FP64_DEFAULT : fp64_t != 0;
+    const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves(ctx, n) && !fp64 ? 192 : 0);
+    const unsigned grid = (n + 63) / 64;
+#define BSX_ED_LAUNCH(K)                                  \
+    do {                                                  \
+        BSX_PIN_CARVEOUT((K));                            \
+        K<<<grid, 64, 0, st>>>(n, in, tab, out);          \
+    } while (0)
     if (cap && (!alone || env_cap > 0) && !env_occ && !corun && inl <= 0) {
         // (caps of 176 and 160 registers spill and were slower: profiles/r01p_step_ab.txt)
         // (the same cap with inlined point arithmetic: 378 ranges per step 2.768 -> 2.818 ms, 756 ranges 5.595 -> 5.530 ms -- not kept)
-        BSX_PIN_CARVEOUT((ed25519_batch_kernel_capped<192, false>));
-        ed25519_batch_kernel_capped<192, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
-    } else if (occ >= 8) ed25519_batch_kernel<8, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
-    else if (occ >= 6) ed25519_batch_kernel<6, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
-    else if (use_inl) ed25519_batch_kernel<4, true><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
-    else ed25519_batch_kernel<4, false><<<(n + 63) / 64, 64, 0, st>>>(n, in, tab, out);
+        if (fp64) BSX_ED_LAUNCH((ed25519_batch_kernel_capped<192, false, true>));
+        else BSX_ED_LAUNCH((ed25519_batch_kernel_capped<192, false, false>));
+    } else if (occ >= 8) {
+        if (fp64) BSX_ED_LAUNCH((ed25519_batch_kernel<8, false, true>));
+        else BSX_ED_LAUNCH((ed25519_batch_kernel<8, false, false>));
+    } else if (occ >= 6) {
+        if (fp64) BSX_ED_LAUNCH((ed25519_batch_kernel<6, false, true>));
+        else BSX_ED_LAUNCH((ed25519_batch_kernel<6, false, false>));
+    } else if (use_inl) {
+        if (fp64) BSX_ED_LAUNCH((ed25519_batch_kernel<4, true, true>));
+        else BSX_ED_LAUNCH((ed25519_batch_kernel<4, true, false>));
+    } else {
+        if (fp64) BSX_ED_LAUNCH((ed25519_batch_kernel<4, false, true>));
+        else BSX_ED_LAUNCH((ed25519_batch_kernel<4, false, false>));
+    }
+#undef BSX_ED_LAUNCH
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }

@@ -28,8 +28,38 @@ struct SubchainArgs {
     // -- over NVLink peer memory; the exchange step of the map/reduce needs no collective kernel.
     uint8_t *peers[BSX_MAX_PEERS];
     uint32_t n_peers, p2p_rank, p2p_per, p2p_total_jobs, p2p_ranges_per_owner;
+    // exchange completion folded into the kernel that writes the records (bsx_shard_step_dev): every CTA counts itself
+    // on `sig_done` after its record stores; the last one publishes `sig_step` into sig_flags[w] of every peer with a
+    // system-scope release store -- the reduce kernel of each rank acquires those flags, so no barrier kernel has to find
+    // an SM slot between the resident Ed25519 CTAs.  sig_done == nullptr: no signalling.
+    uint32_t *sig_done;
+    uint32_t *sig_flags[BSX_MAX_PEERS];
+    uint32_t sig_step;
 };
-#define BSX_SUBCHAIN_ARGS_NO_P2P {nullptr}, 0u, 0u, 0u, 0u, 0u
+#define BSX_SUBCHAIN_ARGS_NO_P2P {nullptr}, 0u, 0u, 0u, 0u, 0u, nullptr, {nullptr}, 0u
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// End of a record-writing kernel.  `wrote`: this thread stored records (peer memory) in this kernel.
+__device__ __forceinline__ void subchain_signal(const SubchainArgs &a, bool wrote) {
+    if (!a.sig_done) return;
+    if (wrote) __threadfence_system();          // this thread's record stores are visible system-wide before the count
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(a.sig_done, 1u);
+        if (prev == gridDim.x - 1) {             // last CTA of the launch: every record of this rank has been stored
+            *a.sig_done = 0;                     // re-armed for the next launch (stream-ordered)
+            __threadfence_system();
+            for (uint32_t w = 0; w < a.n_peers; w++) st_release_sys(a.sig_flags[w], a.sig_step);
+        }
+    }
+}
 
 __device__ __forceinline__ uint32_t *subchain_record(const SubchainArgs &a, size_t j2) {
     if (a.n_peers == 0) return reinterpret_cast<uint32_t *>(a.subchains + j2 * BSX_SUBCHAIN_BYTES);
@@ -215,6 +245,7 @@ __global__ void __launch_bounds__((2 * B < 32) ? 32 : 2 * B) prove_subchain_kern
         for (int k = 0; k < 8; k++) rec[22 + k] = bswap32(root[k]);
         rec[30] = 0; rec[31] = 0;
     }
+    subchain_signal(a, tid == 0);
 }
 
 // ---- reduce stage: one CTA per range, records are 32 little-endian words ----
@@ -224,12 +255,35 @@ __global__ void reduce_subchains_kernel(uint32_t n_jobs, uint32_t B, const uint8
                                         const uint64_t *__restrict__ start_blocks, const uint8_t *__restrict__ start_header,
                                         const uint64_t *__restrict__ end_blocks, const uint8_t *__restrict__ end_header,
                                         uint8_t *__restrict__ reduce_digests, uint8_t *__restrict__ reduce_nodes,
-                                        uint8_t *__restrict__ data_commitments, uint32_t *__restrict__ fail) {
+                                        uint8_t *__restrict__ data_commitments, uint32_t *__restrict__ fail,
+                                        const uint32_t *wait_flags, uint32_t n_wait, uint32_t wait_step) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *src = smem, *dst = smem + 32 * (size_t)n_jobs;
     const size_t r = blockIdx.x;
+    __shared__ uint32_t s_timeout;
+    if (wait_flags) {
+        // the records of this range come from every rank's map kernel (peer stores): acquire each rank's step flag
+        // (subchain_signal) before reading them.  Bounded: a rank that never arrives turns into BSX_FAIL_EXCHANGE_TIMEOUT.
+        if (threadIdx.x == 0) s_timeout = 0;
+        __syncthreads();
+        if (threadIdx.x < n_wait) {
+            uint64_t t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while ((int32_t)(ld_acquire_sys(wait_flags + threadIdx.x) - wait_step) < 0) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 4000000000ull) { s_timeout = 1; break; }      // 4 s
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+    }
     const uint32_t *g = reinterpret_cast<const uint32_t *>(map_subchains + r * n_jobs * BSX_SUBCHAIN_BYTES);
-    for (uint32_t k = threadIdx.x; k < 32 * n_jobs; k += blockDim.x) src[k] = g[k];
+    if (wait_flags) {   // peer-written data: plain (non-cached-readonly) loads after the acquire
+        const volatile uint32_t *gv = g;
+        for (uint32_t k = threadIdx.x; k < 32 * n_jobs; k += blockDim.x) src[k] = gv[k];
+    } else {
+        for (uint32_t k = threadIdx.x; k < 32 * n_jobs; k += blockDim.x) src[k] = g[k];
+    }
     __syncthreads();
     uint32_t off = 0;
     for (uint32_t len = n_jobs; len > 1; len /= 2) {
@@ -280,6 +334,7 @@ __global__ void reduce_subchains_kernel(uint32_t n_jobs, uint32_t B, const uint8
 #pragma unroll
         for (int k = 0; k < 8; k++) ok = ok && src[6 + k] == sh[k] && src[14 + k] == eh[k];
         if (!ok) f |= BSX_FAIL_RESULT;  // builder.rs:398-406
+        if (wait_flags && s_timeout) f |= BSX_FAIL_EXCHANGE_TIMEOUT;
         uint32_t *dc = reinterpret_cast<uint32_t *>(data_commitments + 32 * r);
 #pragma unroll
         for (int k = 0; k < 8; k++) dc[k] = src[22 + k];
@@ -480,6 +535,7 @@ __global__ void __launch_bounds__(B * G < 32 ? 32 : B * G) subchain_commit_kerne
         for (int k = 0; k < 8; k++) rec[22 + k] = bswap32(src[8 * tid + k]);   // tree g's root sits at src[g]
         rec[30] = 0; rec[31] = 0;
     }
+    subchain_signal(a, tid < G);
 }
 
 template <int B>
@@ -593,7 +649,7 @@ extern "C" int bsx_prove_subchain_batch_p2p_dev(bsx_ctx *ctx, void *stream, uint
     if (n_jobs == 0) return BSX_OK;
     SubchainArgs a{dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, batch_start, batch_end, global_end,
                    global_end_header, 0, nullptr, nullptr, nullptr, digests, nullptr, {nullptr}, n_peers, rank, jobs_per_rank,
-                   total_jobs, ranges_per_owner};
+                   total_jobs, ranges_per_owner, nullptr, {nullptr}, 0u};
     for (uint32_t w = 0; w < n_peers; w++) {
         BSX_REQUIRE(ctx, peer_bases[w] != 0 && (peer_bases[w] & 15) == 0);
         a.peers[w] = reinterpret_cast<uint8_t *>(peer_bases[w]);
@@ -601,17 +657,18 @@ extern "C" int bsx_prove_subchain_batch_p2p_dev(bsx_ctx *ctx, void *stream, uint
     return dispatch_subchain(ctx, (cudaStream_t)stream, B, n_jobs, a);
 }
 
-extern "C" int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs,
-                                        const uint8_t *map_subchains, const uint64_t *start_blocks,
-                                        const uint8_t *start_header, const uint64_t *end_blocks,
-                                        const uint8_t *end_header, uint32_t B, uint8_t *reduce_digests,
-                                        uint8_t *reduce_nodes, uint8_t *data_commitments, uint32_t *fail) {
+int bsx_reduce_subchains_wait_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs, const uint8_t *map_subchains,
+                                  const uint64_t *start_blocks, const uint8_t *start_header, const uint64_t *end_blocks,
+                                  const uint8_t *end_header, uint32_t B, uint8_t *reduce_digests, uint8_t *reduce_nodes,
+                                  uint8_t *data_commitments, uint32_t *fail, const uint32_t *wait_flags, uint32_t n_wait,
+                                  uint32_t wait_step) {
     BSX_REQUIRE(ctx, ctx && map_subchains && start_blocks && start_header && end_blocks && end_header && data_commitments);
     BSX_REQUIRE(ctx, n_jobs >= 1 && n_jobs <= 1024 && (n_jobs & (n_jobs - 1)) == 0);
     BSX_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(map_subchains) | reinterpret_cast<uintptr_t>(reduce_digests) |
                        reinterpret_cast<uintptr_t>(reduce_nodes)) & 15) == 0 &&
                          ((reinterpret_cast<uintptr_t>(start_header) | reinterpret_cast<uintptr_t>(end_header) |
                            reinterpret_cast<uintptr_t>(data_commitments)) & 3) == 0);
+    BSX_REQUIRE(ctx, !wait_flags || (n_wait >= 1 && n_wait <= BSX_MAX_PEERS && fail));
     if (n_ranges == 0) return BSX_OK;
     uint32_t threads = n_jobs / 2 < 32 ? 32 : n_jobs / 2;
     size_t smem = 4 * (32 * (size_t)n_jobs + 16 * (size_t)n_jobs);
@@ -620,9 +677,44 @@ extern "C" int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_r
     if (smem <= 48 * 1024) BSX_PIN_CARVEOUT(reduce_subchains_kernel);
     reduce_subchains_kernel<<<n_ranges, threads, smem, (cudaStream_t)stream>>>(
         n_jobs, B, map_subchains, start_blocks, start_header, end_blocks, end_header, reduce_digests, reduce_nodes,
-        data_commitments, fail);
+        data_commitments, fail, wait_flags, n_wait, wait_step);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
+}
+
+extern "C" int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs,
+                                        const uint8_t *map_subchains, const uint64_t *start_blocks,
+                                        const uint8_t *start_header, const uint64_t *end_blocks,
+                                        const uint8_t *end_header, uint32_t B, uint8_t *reduce_digests,
+                                        uint8_t *reduce_nodes, uint8_t *data_commitments, uint32_t *fail) {
+    return bsx_reduce_subchains_wait_dev(ctx, stream, n_ranges, n_jobs, map_subchains, start_blocks, start_header, end_blocks,
+                                         end_header, B, reduce_digests, reduce_nodes, data_commitments, fail, nullptr, 0, 0);
+}
+
+// map stage of the sharded engine (k_shard.cu): peer stores + completion flags
+int bsx_subchain_map_signal_dev(bsx_ctx *ctx, void *stream, uint32_t B, uint32_t n_jobs, const uint8_t *dh_leaf,
+                                const uint8_t *dh_aunts, const uint8_t *lb_leaf, const uint8_t *lb_aunts,
+                                const uint8_t *start_headers, const uint8_t *end_headers, const uint64_t *batch_start,
+                                const uint64_t *batch_end, const uint64_t *global_end, const uint8_t *global_end_header,
+                                uint8_t *digests, uint8_t *const *peer_bases, uint32_t n_peers, uint32_t rank,
+                                uint32_t jobs_per_rank, uint32_t total_jobs, uint32_t ranges_per_owner, uint32_t *sig_done,
+                                uint32_t *const *sig_flags, uint32_t sig_step) {
+    BSX_REQUIRE(ctx, ctx && dh_leaf && dh_aunts && lb_leaf && lb_aunts && start_headers && end_headers && batch_start &&
+                         batch_end && global_end && global_end_header && digests && peer_bases && sig_done && sig_flags);
+    BSX_REQUIRE(ctx, n_peers >= 1 && n_peers <= BSX_MAX_PEERS && rank < n_peers && jobs_per_rank >= 1 && ranges_per_owner >= 1 &&
+                         total_jobs == jobs_per_rank * n_peers && n_jobs % jobs_per_rank == 0 &&
+                         (n_jobs / jobs_per_rank) == ranges_per_owner * n_peers);
+    BSX_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(digests) & 15) == 0 && (reinterpret_cast<uintptr_t>(start_headers) & 3) == 0);
+    if (n_jobs == 0) return BSX_OK;
+    SubchainArgs a{dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers, batch_start, batch_end, global_end,
+                   global_end_header, 0, nullptr, nullptr, nullptr, digests, nullptr, {nullptr}, n_peers, rank, jobs_per_rank,
+                   total_jobs, ranges_per_owner, sig_done, {nullptr}, sig_step};
+    for (uint32_t w = 0; w < n_peers; w++) {
+        BSX_REQUIRE(ctx, peer_bases[w] && (reinterpret_cast<uintptr_t>(peer_bases[w]) & 15) == 0 && sig_flags[w]);
+        a.peers[w] = peer_bases[w];
+        a.sig_flags[w] = sig_flags[w];
+    }
+    return dispatch_subchain(ctx, (cudaStream_t)stream, B, n_jobs, a);
 }
 
 extern "C" int bsx_prove_data_commitment_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs, uint32_t B,

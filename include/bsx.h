@@ -152,6 +152,7 @@ int bsx_attestation_proofs_dev(bsx_ctx *ctx, void *stream, const uint8_t *digest
 #define BSX_FAIL_REDUCE_LINK 32u      /* :349-355 */
 #define BSX_FAIL_RANGE 64u            /* :291-297 */
 #define BSX_FAIL_RESULT 128u          /* :398-406 */
+#define BSX_FAIL_EXCHANGE_TIMEOUT 2048u /* sharded engine: a peer rank's subchain records did not arrive within 4 s */
 #define BSX_FAIL_INPUT_LEAF 256u      /* input shaping: a proven header field does not have the circuit's fixed size */
 int bsx_prove_subchain_batch(bsx_ctx *ctx, uint32_t B, uint32_t n_jobs, const uint8_t *dh_leaf,
                              const uint8_t *dh_aunts, const uint8_t *lb_leaf, const uint8_t *lb_aunts,
@@ -206,6 +207,52 @@ int bsx_reduce_subchains_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint
                              const uint8_t *map_subchains, const uint64_t *start_blocks, const uint8_t *start_header,
                              const uint64_t *end_blocks, const uint8_t *end_header, uint32_t B, uint8_t *reduce_digests,
                              uint8_t *reduce_nodes, uint8_t *data_commitments, uint32_t *fail);
+
+/* ------------------------------------------------------------------------------------------
+ * Sharded map/reduce across the GPUs of one node
+ * replaces: the sequential loop of LocalProver::batch_prove (PX/backend/prover/local.rs:34-57) / the HTTP fan-out of
+ *           RemoteProver (PX/backend/prover/remote.rs:98-153) under MapReduceGenerator::run_once
+ *           (PX/frontend/mapreduce/generator.rs:86-151; map jobs independent :97-111, reduce layers :113-151).
+ * One bsx_shard per rank (= per GPU, on that rank's ctx).  `n_ranges` ranges are in flight per step over all ranks; rank r
+ * of `world` owns jobs [r*n_jobs/world, (r+1)*n_jobs/world) of EVERY range and reduces ranges [r*n_ranges/world, ...).
+ * The subchain records travel by peer-memory stores from the kernel that computes them, completion by one flag word per
+ * (source rank, step parity) published by that kernel's last CTA and acquired by the reduce kernel: no collective and no
+ * barrier launch on the data path.
+ * Setup: create on every rank; exchange either bsx_shard_ipc_handle -> bsx_shard_open_peer (ranks in different processes)
+ * or bsx_shard_exchange_buffer -> bsx_shard_set_peer (same process, or buffers the caller mapped itself, e.g. symmetric
+ * memory passed as `exchange_buf`, whose size is bsx_shard_exchange_bytes); then every rank calls bsx_shard_step_dev once
+ * per step, each on ONE stream of its own (steps of a rank must be stream-ordered).
+ * fail[r] gains BSX_FAIL_EXCHANGE_TIMEOUT if a rank's records have not arrived after 4 s (never a hang).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct bsx_shard bsx_shard;
+#define BSX_IPC_HANDLE_BYTES 64
+typedef struct {              /* device pointers */
+    /* this rank's job slice of every range in flight: n_ranges * n_jobs/world jobs, range-major, then local job */
+    const uint8_t *dh_leaf, *dh_aunts, *lb_leaf, *lb_aunts; /* per job: B*34, B*128, B*72, B*128 */
+    const uint8_t *start_headers, *end_headers;             /* per job: 32 */
+    const uint64_t *batch_start, *batch_end, *global_end;   /* per job */
+    const uint8_t *global_end_header;                       /* per job: 32 */
+    /* public inputs of the n_ranges/world ranges this rank reduces */
+    const uint64_t *start_blocks, *end_blocks;
+    const uint8_t *start_header, *end_header;               /* 32 each */
+} bsx_shard_in;
+typedef struct {              /* device pointers */
+    uint8_t *map_digests;      /* n_ranges * n_jobs/world * (20B-1) * 32: the digests of this rank's jobs */
+    uint8_t *map_subchains;    /* optional (may be NULL): n_ranges/world * n_jobs * 128, the gathered records of this rank's ranges */
+    uint8_t *reduce_digests;   /* optional: n_ranges/world * (n_jobs-1) * 32 */
+    uint8_t *reduce_nodes;     /* optional: n_ranges/world * (n_jobs-1) * 128 */
+    uint8_t *data_commitments; /* n_ranges/world * 32 */
+    uint32_t *fail;            /* n_ranges/world */
+} bsx_shard_out;
+size_t bsx_shard_exchange_bytes(uint32_t world, uint32_t n_ranges, uint32_t n_jobs);
+int bsx_shard_create(bsx_ctx *ctx, uint32_t rank, uint32_t world, uint32_t n_ranges, uint32_t n_jobs, uint32_t B,
+                     void *exchange_buf /* NULL: allocated here (cudaMalloc, IPC-exportable) */, bsx_shard **out);
+void bsx_shard_destroy(bsx_shard *sh);
+int bsx_shard_exchange_buffer(bsx_shard *sh, void **dev_ptr, size_t *bytes);
+int bsx_shard_ipc_handle(bsx_shard *sh, uint8_t *handle /* BSX_IPC_HANDLE_BYTES */);
+int bsx_shard_open_peer(bsx_shard *sh, uint32_t peer, const uint8_t *handle /* BSX_IPC_HANDLE_BYTES */);
+int bsx_shard_set_peer(bsx_shard *sh, uint32_t peer, void *dev_ptr);
+int bsx_shard_step_dev(bsx_shard *sh, void *stream, const bsx_shard_in *in, const bsx_shard_out *out);
 
 /* ------------------------------------------------------------------------------------------
  * K4+K5  batched Ed25519 witness generation
