@@ -977,7 +977,7 @@ def run_shape(args):
     P = lambda t: ptr(t.data_ptr())
 
     def step():
-        ctx.call_dev("bsx_header_range_inputs_dev", stream, u32(R), u32(J), u32(B), P(d_rec), P(d_sb), P(d_eb),
+        ctx.call_dev("bsx_header_range_inputs_dev", stream, u32(R), u32(J), u32(B), P(d_rec), P(d_sb), P(d_eb), ptr(0),
                      *[P(d_out[k]) for k in shapes])
 
     step()

@@ -54,7 +54,8 @@ pub fn header_fields(h: &Header) -> bsx_header_fields {
 }
 
 /// The arrays of `DataCommitmentProofValueType` for the `n_jobs` map jobs of ONE range, byte for byte what
-/// `get_data_commitment_inputs` returns job by job (slots beyond `end` zero, dummy jobs zero).
+/// `get_data_commitment_inputs` returns job by job: each job is clamped to `latest_safe` (= latest_block - 2), not to the
+/// range's `end`; slots beyond `latest_safe` are zero.
 pub struct RangeMapInputs {
     pub dh_leaf: Vec<u8>,       // n_jobs * B * 34
     pub dh_aunts: Vec<u8>,      // n_jobs * B * 4 * 32
@@ -66,8 +67,8 @@ pub struct RangeMapInputs {
     pub end_header: [u8; 32],
 }
 
-/// `headers`: blocks `start ..= start + n_jobs * B` (missing blocks beyond the chain tip: any value, they are ignored).
-pub fn shape_range(headers: &[Header], start: u64, end: u64, n_jobs: u32, b: u32) -> RangeMapInputs {
+/// `headers`: blocks `start ..= start + n_jobs * B` (blocks beyond `latest_safe`: any value, they are ignored).
+pub fn shape_range(headers: &[Header], start: u64, end: u64, latest_safe: u64, n_jobs: u32, b: u32) -> RangeMapInputs {
     let n = headers.len();
     assert_eq!(n as u32, n_jobs * b + 1);
     let fields: Vec<bsx_header_fields> = headers.iter().map(header_fields).collect();
@@ -89,7 +90,7 @@ pub fn shape_range(headers: &[Header], start: u64, end: u64, n_jobs: u32, b: u32
         check(
             ctx,
             bsx_header_range_inputs(
-                ctx, 1, n_jobs, b, records.as_ptr(), &start, &end, out.dh_leaf.as_mut_ptr(), out.dh_aunts.as_mut_ptr(),
+                ctx, 1, n_jobs, b, records.as_ptr(), &start, &end, &latest_safe, out.dh_leaf.as_mut_ptr(), out.dh_aunts.as_mut_ptr(),
                 out.lb_leaf.as_mut_ptr(), out.lb_aunts.as_mut_ptr(), out.start_headers.as_mut_ptr(),
                 out.end_headers.as_mut_ptr(), out.start_header.as_mut_ptr(), out.end_header.as_mut_ptr(), &mut fail,
             ),

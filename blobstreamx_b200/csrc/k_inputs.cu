@@ -69,31 +69,34 @@ __global__ void __launch_bounds__(128) header_trees_kernel(const uint8_t *__rest
 
 struct RangeInputsArgs {
     const uint8_t *headers;          // n_ranges * (J*B + 1) records: blocks start .. start + J*B
-    const uint64_t *start_blocks, *end_blocks;
+    const uint64_t *start_blocks, *end_blocks, *latest_blocks;   // latest_blocks == nullptr: the range ends at the chain tip
     uint8_t *dh_leaf, *dh_aunts, *lb_leaf, *lb_aunts, *start_headers, *end_headers, *start_header, *end_header;
     uint32_t *fail;
     uint32_t n_ranges, J, B;
 };
 
-// thread (r, o): header at block start_r + o.  With total = min(end - start, J*B) headers in the range:
-//   data_hash proof (leaf 6, 34 B)      -> slot o      for o <  total      (blocks [start, end-1],  input.rs:205-233)
-//   last_block_id proof (leaf 4, 72 B)  -> slot o - 1  for 1 <= o <= total (blocks [start+1, end])
-//   job j = o / B starts at root(o = jB) and ends at root(min((j+1)B, total)); slots beyond total stay zero.
+// thread (r, o): header at block start_r + o.  The hint of job j (DataCommitmentOffchainInputs, BX/circuits/data_commitment.rs:
+// 22-44) is called with (start + jB, start + (j+1)B) and clamps only to the last fetchable block `latest` (latest_block - 2,
+// BX/circuits/input.rs:160-163), not to the range's end: with avail = min(latest - start, J*B)
+//   data_hash proof (leaf 6, 34 B)      -> slot o      for o <  avail       (blocks [bs, req_end),  input.rs:165-181)
+//   last_block_id proof (leaf 4, 72 B)  -> slot o - 1  for 1 <= o <= avail  (blocks (bs, req_end],  :183-197)
+//   job j = o / B starts at root(o = jB) and ends at root(min((j+1)B, avail)) when jB < avail (:247-262); everything past
+//   `avail` stays zero (:221-241).  The range's own start / end header hashes are taken at o = 0 and o = end - start.
 __global__ void __launch_bounds__(128) range_inputs_kernel(RangeInputsArgs a) {
     const uint32_t per = a.J * a.B + 1;
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)a.n_ranges * per) return;
     const uint32_t r = (uint32_t)(t / per), o = (uint32_t)(t % per);
-    const uint64_t sb = a.start_blocks[r], eb = a.end_blocks[r];
-    const uint64_t span = eb > sb ? eb - sb : 0;
-    const uint32_t total = span < (uint64_t)(per - 1) ? (uint32_t)span : per - 1;
-    if (o > total || total == 0) return;
+    const uint64_t sb = a.start_blocks[r], eb = a.end_blocks[r], lt = a.latest_blocks ? a.latest_blocks[r] : eb;
+    const uint64_t span = lt > sb ? lt - sb : 0;
+    const uint32_t avail = span < (uint64_t)(per - 1) ? (uint32_t)span : per - 1;
+    if (o > avail || avail == 0) return;
     const uint8_t *rec = a.headers + (size_t)BSX_HEADER_LEAVES_BYTES * t;
     HeaderLevels L;
     uint32_t root[8], off[15];
     header_tree(rec, L, root, off);
     const size_t slot0 = (size_t)r * (per - 1);
-    if (o < total) {
+    if (o < avail) {
         uint8_t *leaf = a.dh_leaf + (slot0 + o) * 34;
         if (rec[6] != 34) atomicOr(a.fail + r, BSX_FAIL_INPUT_LEAF);
         for (uint32_t k = 0; k < 34; k++) leaf[k] = k < rec[6] ? rec[off[6] + k] : (uint8_t)0;
@@ -105,10 +108,12 @@ __global__ void __launch_bounds__(128) range_inputs_kernel(RangeInputsArgs a) {
         if (rec[4] != 72) atomicOr(a.fail + r, BSX_FAIL_INPUT_LEAF);
         for (uint32_t k = 0; k < 72; k++) leaf[k] = k < rec[4] ? rec[off[4] + k] : (uint8_t)0;
         put_aunts(a.lb_aunts + (slot0 + o - 1) * 128, L, 4);
-        if (o % a.B == 0 || o == total) put_digest(a.end_headers + ((size_t)r * a.J + (o - 1) / a.B) * 32, root);
+        if (o % a.B == 0 || o == avail) put_digest(a.end_headers + ((size_t)r * a.J + (o - 1) / a.B) * 32, root);
     }
-    if (o == 0) put_digest(a.start_header + 32 * (size_t)r, root);
-    if (o == total) put_digest(a.end_header + 32 * (size_t)r, root);
+    if (eb > sb && eb - sb <= (uint64_t)avail) {
+        if (o == 0) put_digest(a.start_header + 32 * (size_t)r, root);
+        if ((uint64_t)o == eb - sb) put_digest(a.end_header + 32 * (size_t)r, root);
+    }
 }
 
 }  // namespace bsx
@@ -127,7 +132,7 @@ extern "C" int bsx_header_trees_dev(bsx_ctx *ctx, void *stream, const uint8_t *h
 
 extern "C" int bsx_header_range_inputs_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs, uint32_t B,
                                            const uint8_t *headers, const uint64_t *start_blocks, const uint64_t *end_blocks,
-                                           uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts,
+                                           const uint64_t *latest_blocks, uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts,
                                            uint8_t *start_headers, uint8_t *end_headers, uint8_t *start_header, uint8_t *end_header,
                                            uint32_t *fail) {
     BSX_REQUIRE(ctx, ctx && headers && start_blocks && end_blocks && dh_leaf && dh_aunts && lb_leaf && lb_aunts && start_headers &&
@@ -139,7 +144,7 @@ extern "C" int bsx_header_range_inputs_dev(bsx_ctx *ctx, void *stream, uint32_t 
     if (n_ranges == 0) return BSX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t slots = (size_t)n_ranges * n_jobs * B, jobs = (size_t)n_ranges * n_jobs;
-    // slots and job headers beyond a range's end are zero (dummy proofs / dummy jobs, input.rs:243-262)
+    // slots and job headers beyond the last fetchable block are zero (input.rs:221-241, 247-262)
     BSX_CUDA(ctx, cudaMemsetAsync(dh_leaf, 0, slots * 34, st));
     BSX_CUDA(ctx, cudaMemsetAsync(dh_aunts, 0, slots * 128, st));
     BSX_CUDA(ctx, cudaMemsetAsync(lb_leaf, 0, slots * 72, st));
@@ -149,7 +154,7 @@ extern "C" int bsx_header_range_inputs_dev(bsx_ctx *ctx, void *stream, uint32_t 
     BSX_CUDA(ctx, cudaMemsetAsync(start_header, 0, (size_t)n_ranges * 32, st));
     BSX_CUDA(ctx, cudaMemsetAsync(end_header, 0, (size_t)n_ranges * 32, st));
     BSX_CUDA(ctx, cudaMemsetAsync(fail, 0, (size_t)n_ranges * 4, st));
-    RangeInputsArgs a{headers, start_blocks, end_blocks, dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers,
+    RangeInputsArgs a{headers, start_blocks, end_blocks, latest_blocks, dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers,
                       start_header, end_header, fail, n_ranges, n_jobs, B};
     const size_t threads = (size_t)n_ranges * ((size_t)n_jobs * B + 1);
     BSX_PIN_CARVEOUT(range_inputs_kernel);
@@ -178,7 +183,8 @@ extern "C" int bsx_header_trees(bsx_ctx *ctx, const uint8_t *headers, uint32_t n
 }
 
 extern "C" int bsx_header_range_inputs(bsx_ctx *ctx, uint32_t n_ranges, uint32_t n_jobs, uint32_t B, const uint8_t *headers,
-                                       const uint64_t *start_blocks, const uint64_t *end_blocks, uint8_t *dh_leaf, uint8_t *dh_aunts,
+                                       const uint64_t *start_blocks, const uint64_t *end_blocks, const uint64_t *latest_blocks,
+                                       uint8_t *dh_leaf, uint8_t *dh_aunts,
                                        uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers, uint8_t *end_headers,
                                        uint8_t *start_header, uint8_t *end_header, uint32_t *fail) {
     BSX_REQUIRE(ctx, ctx && headers && start_blocks && end_blocks && dh_leaf && dh_aunts && lb_leaf && lb_aunts && start_headers &&
@@ -187,11 +193,11 @@ extern "C" int bsx_header_range_inputs(bsx_ctx *ctx, uint32_t n_ranges, uint32_t
     if (n_ranges == 0) return BSX_OK;
     BSX_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t R = n_ranges, slots = R * n_jobs * B, jobs = R * n_jobs, s_in = R * ((size_t)n_jobs * B + 1) * BSX_HEADER_LEAVES_BYTES;
-    int rc = ws_begin(ctx, ws_size(s_in) + 2 * ws_size(8 * R) + ws_size(slots * 34) + 2 * ws_size(slots * 128) + ws_size(slots * 72) +
+    int rc = ws_begin(ctx, ws_size(s_in) + 3 * ws_size(8 * R) + ws_size(slots * 34) + 2 * ws_size(slots * 128) + ws_size(slots * 72) +
                                2 * ws_size(jobs * 32) + 2 * ws_size(32 * R) + ws_size(4 * R));
     if (rc) return rc;
     uint8_t *d_in = ws_take<uint8_t>(ctx, s_in);
-    uint64_t *d_sb = ws_take<uint64_t>(ctx, R), *d_eb = ws_take<uint64_t>(ctx, R);
+    uint64_t *d_sb = ws_take<uint64_t>(ctx, R), *d_eb = ws_take<uint64_t>(ctx, R), *d_lt = ws_take<uint64_t>(ctx, R);
     uint8_t *d_dhl = ws_take<uint8_t>(ctx, slots * 34), *d_dha = ws_take<uint8_t>(ctx, slots * 128);
     uint8_t *d_lbl = ws_take<uint8_t>(ctx, slots * 72), *d_lba = ws_take<uint8_t>(ctx, slots * 128);
     uint8_t *d_sh = ws_take<uint8_t>(ctx, jobs * 32), *d_eh = ws_take<uint8_t>(ctx, jobs * 32);
@@ -201,7 +207,8 @@ extern "C" int bsx_header_range_inputs(bsx_ctx *ctx, uint32_t n_ranges, uint32_t
     BSX_CUDA(ctx, cudaMemcpyAsync(d_in, headers, s_in, cudaMemcpyHostToDevice, st));
     BSX_CUDA(ctx, cudaMemcpyAsync(d_sb, start_blocks, 8 * R, cudaMemcpyHostToDevice, st));
     BSX_CUDA(ctx, cudaMemcpyAsync(d_eb, end_blocks, 8 * R, cudaMemcpyHostToDevice, st));
-    rc = bsx_header_range_inputs_dev(ctx, st, n_ranges, n_jobs, B, d_in, d_sb, d_eb, d_dhl, d_dha, d_lbl, d_lba, d_sh, d_eh, d_rsh, d_reh,
+    if (latest_blocks) BSX_CUDA(ctx, cudaMemcpyAsync(d_lt, latest_blocks, 8 * R, cudaMemcpyHostToDevice, st));
+    rc = bsx_header_range_inputs_dev(ctx, st, n_ranges, n_jobs, B, d_in, d_sb, d_eb, latest_blocks ? d_lt : nullptr, d_dhl, d_dha, d_lbl, d_lba, d_sh, d_eh, d_rsh, d_reh,
                                      d_fail);
     if (rc) return rc;
     BSX_CUDA(ctx, cudaMemcpyAsync(dh_leaf, d_dhl, slots * 34, cudaMemcpyDeviceToHost, st));

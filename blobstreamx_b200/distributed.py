@@ -7,11 +7,15 @@ own BATCH_SIZE headers -- and then log2(jobs) reduce layers (generator.rs:113-15
 337-395).  The reference's only multi-worker story is `PROVER=remote` (HTTP, PX/backend/prover/remote.rs:98-153).
 Here rank r of W owns jobs [r*J/W, (r+1)*J/W) of EVERY range in flight (contiguous job slice = contiguous header
 range) and reduces ranges [r*R/W, (r+1)*R/W).  The exchange between the two is 128 bytes per job:
-  * on GPUs the map kernels store each record straight into the reducing rank's gathered array through NVLink peer
-    memory (torch symmetric memory gives every rank the peers' buffer addresses; `bsx_prove_subchain_batch_p2p_dev`),
-    followed by one device-side barrier -- compute and exchange are ONE kernel, no collective kernel competes with the
-    Ed25519 CTAs for an SM (the NCCL all-gather could only start once an SM had drained: 8 GPUs 3.20 ms per step);
-  * if symmetric memory cannot be set up, and in the CPU tests (gloo), one `all_gather_into_tensor`.
+  * on GPUs the engine is libbsx's `bsx_shard_*` C ABI (csrc/k_shard.cu; this module only sets it up and calls
+    `bsx_shard_step_dev`): the kernel that computes a record stores it straight into the reducing rank's gathered array
+    through NVLink peer memory, its last CTA publishes a per-(rank, step) flag on every peer and the reduce kernel
+    acquires the flags -- compute, exchange and synchronisation are the map and reduce kernels themselves; no collective
+    and no barrier kernel competes with the Ed25519 CTAs for an SM (the NCCL all-gather could only start once an SM had
+    drained: 8 GPUs 3.20 ms per step; the separate barrier kernel of round 1 made the step time unstable by +-30 %).
+    The peers' exchange buffers are mapped with CUDA IPC handles (exchanged once over the process group); if that is
+    refused, with torch symmetric memory;
+  * if neither works, and in the CPU tests (gloo), one `all_gather_into_tensor`.
 No other collective is on the data path.
 
 The compute backend is injected: `CudaBackend` (below) drives libbsx through device pointers on torch's current
@@ -77,6 +81,9 @@ class CudaBackend:
     def empty(self, nbytes: int) -> torch.Tensor:
         return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
 
+    def shard(self, rank, world, n_ranges, n_jobs, batch, exchange_buf=0):
+        return self.lib.Shard(self.ctx, rank, world, n_ranges, n_jobs, batch, exchange_buf)
+
     def map(self, B, n_jobs, t, digests, subchains):
         P = lambda x: self.lib.ptr(x.data_ptr())
         self.ctx.call_dev("bsx_prove_subchain_batch_dev", torch.cuda.current_stream().cuda_stream, self.lib.u32(B), self.lib.u32(n_jobs),
@@ -116,40 +123,71 @@ class ShardedHeaderRange:
         self.map_digests = e(R * per * (20 * B - 1) * 32)
         self.local_sub = e(R * per * SUBCHAIN_BYTES)
         Ro = R // world
-        self.p2p = None          # (handles, buffers, peer pointer lists) of the two alternating gathered arrays
+        self.shard = None        # bsx_shard (CUDA backend, world > 1): peer stores + in-kernel flags
+        self._symm = None
         self.exchange = "none" if world == 1 else "all_gather"
-        if world > 1 and hasattr(backend, "map_p2p") and os.environ.get("BSX_EXCHANGE", "p2p") == "p2p":
-            self.p2p = self._setup_peer_memory(Ro * n_jobs * SUBCHAIN_BYTES)
-            if self.p2p:
-                self.exchange = "peer stores"
-        self.gathered = e(world * R * per * SUBCHAIN_BYTES) if world > 1 and not self.p2p else None
-        self.all_sub = (e(R * n_jobs * SUBCHAIN_BYTES) if not self.p2p else None) if world > 1 else self.local_sub
-        self._flip = 0
+        if world > 1 and hasattr(backend, "shard") and os.environ.get("BSX_EXCHANGE", "p2p") == "p2p":
+            self.shard = self._setup_shard()
+            if self.shard:
+                self.map_subchains = e(Ro * n_jobs * SUBCHAIN_BYTES)
+        self.gathered = e(world * R * per * SUBCHAIN_BYTES) if world > 1 and not self.shard else None
+        self.all_sub = (e(R * n_jobs * SUBCHAIN_BYTES) if not self.shard else None) if world > 1 else self.local_sub
         self.reduce_digests = e(Ro * max(n_jobs - 1, 1) * 32)
         self.reduce_nodes = e(Ro * max(n_jobs - 1, 1) * SUBCHAIN_BYTES)
         self.data_commitments = e(Ro * 32)
         self.fail = e(Ro * 4)
         self.t: Optional[dict] = None
+        self._sio = None
 
-    def _setup_peer_memory(self, nbytes: int):
-        """Two [R/W, J, 128] arrays per rank in symmetric memory (alternating per step, so one barrier per step is enough:
-        when the barrier of step k+1 completes every rank has finished the reduce of step k, whose array step k+2 reuses)."""
+    def _all_ok(self, ok: bool) -> bool:
+        """True only if every rank succeeded (all ranks must take the same exchange path)."""
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(ok), group=self.group)
+        return all(flags)
+
+    def _setup_shard(self):
+        """bsx_shard on every rank + the peers' exchange buffers: CUDA IPC handles first, torch symmetric memory second."""
+        import warnings
+        R, J, B, W = self.R, self.J, self.B, self.world
+        mode = os.environ.get("BSX_SHARD_MAP", "ipc")        # "ipc" | "symm": how the peers' buffers are mapped
+        if mode == "ipc":
+            sh, err = None, None
+            try:
+                sh = self.be.shard(self.rank, W, R, J, B)
+                handles = [None] * W
+                dist.all_gather_object(handles, sh.ipc_handle(), group=self.group)
+                for w in range(W):
+                    if w != self.rank:
+                        sh.open_peer(w, handles[w])
+            except Exception as exc:
+                err = exc
+            if self._all_ok(err is None):
+                self.exchange = "peer stores + in-kernel flags (CUDA IPC)"
+                dist.barrier(group=self.group)
+                return sh
+            if sh:
+                sh.close()
+            warnings.warn(f"CUDA IPC mapping of the exchange buffers failed on some rank ({err}); trying symmetric memory")
+        sh, err = None, None
         try:
             import torch.distributed._symmetric_memory as symm
-            group = self.group or dist.group.WORLD
-            out = []
-            for _ in range(2):
-                buf = symm.empty(nbytes, dtype=torch.uint8, device=self.be.device)
-                buf.zero_()
-                hdl = symm.rendezvous(buf, group)
-                out.append((hdl, buf, [int(p) for p in hdl.buffer_ptrs]))
+            nbytes = self.be.lib.Shard.exchange_bytes(W, R, J)
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=self.be.device)
+            hdl = symm.rendezvous(buf, self.group or dist.group.WORLD)
+            sh = self.be.shard(self.rank, W, R, J, B, exchange_buf=buf.data_ptr())
+            for w in range(W):
+                if w != self.rank:
+                    sh.set_peer(w, int(hdl.buffer_ptrs[w]))
+            self._symm = (buf, hdl)
+        except Exception as exc:
+            err = exc
+        if self._all_ok(err is None):
+            self.exchange = "peer stores + in-kernel flags (symmetric memory)"
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
-            return out
-        except Exception as exc:   # no peer access / no fabric handles in this environment: NCCL all-gather instead
-            import warnings
-            warnings.warn(f"symmetric memory unavailable ({type(exc).__name__}: {exc}); using all_gather_into_tensor")
-            return None
+            return sh
+        warnings.warn(f"no peer mapping of the exchange buffers ({type(err).__name__}: {err}); using all_gather_into_tensor")
+        return None
 
     def load(self, host: Dict[str, np.ndarray]):
         """host arrays of ALL ranges -> device-resident shard + this rank's public inputs for the reduce."""
@@ -164,13 +202,18 @@ class ShardedHeaderRange:
 
     def step(self):
         R, J, per, W = self.R, self.J, self.per, self.world
-        if self.p2p:
-            hdl, buf, ptrs = self.p2p[self._flip]
-            self._flip ^= 1
-            self.be.map_p2p(self.B, R * per, self.t, self.map_digests, ptrs, self.rank, per, J, R // W)
-            hdl.barrier(channel=0)          # device-side, on the current stream: every rank's records have landed
-            self._last = buf
-            self.be.reduce(R // W, J, self.B, buf, self.t, self.reduce_digests, self.reduce_nodes, self.data_commitments, self.fail)
+        if self.shard:
+            if self._sio is None:
+                lib_ = self.be.lib
+                t = self.t
+                sin = lib_.fill_struct(lib_.ShardIn(), **{k: t[k].data_ptr() for k in (
+                    "dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers", "batch_start", "batch_end",
+                    "global_end", "global_end_header", "start_blocks", "end_blocks", "start_header", "end_header")})
+                sout = lib_.fill_struct(lib_.ShardOut(), map_digests=self.map_digests.data_ptr(), map_subchains=self.map_subchains.data_ptr(),
+                                        reduce_digests=self.reduce_digests.data_ptr(), reduce_nodes=self.reduce_nodes.data_ptr(),
+                                        data_commitments=self.data_commitments.data_ptr(), fail=self.fail.data_ptr())
+                self._sio = (sin, sout)
+            self.shard.step_dev(torch.cuda.current_stream().cuda_stream, *self._sio)
             return
         self.be.map(self.B, R * per, self.t, self.map_digests, self.local_sub)
         if W > 1:
@@ -183,14 +226,14 @@ class ShardedHeaderRange:
         self.be.reduce(R // W, J, self.B, sub, self.t, self.reduce_digests, self.reduce_nodes, self.data_commitments, self.fail)
 
     def exchange_text(self) -> str:
-        return {"peer stores": "peer-memory stores from the map kernel + one device barrier",
-                "all_gather": "one all_gather_into_tensor", "none": "nothing (one rank)"}.get(self.exchange, self.exchange)
+        return {"all_gather": "one all_gather_into_tensor", "none": "nothing (one rank)"}.get(
+            self.exchange, f"{self.exchange}: bsx_shard_step_dev, no collective and no barrier launch")
 
     def results(self):
         Ro = self.R // self.world
         return dict(data_commitments=self.data_commitments.cpu().numpy().reshape(Ro, 32),
                     fail=self.fail.cpu().numpy().view(np.uint32).reshape(Ro),
                     reduce_nodes=self.reduce_nodes.cpu().numpy().reshape(Ro, max(self.J - 1, 1), SUBCHAIN_BYTES),
-                    map_subchains=(self._last.cpu().numpy().reshape(Ro, self.J, SUBCHAIN_BYTES) if self.p2p else
+                    map_subchains=(self.map_subchains.cpu().numpy().reshape(Ro, self.J, SUBCHAIN_BYTES) if self.shard else
                                    self.all_sub.cpu().numpy().reshape(self.R, self.J, SUBCHAIN_BYTES)[self.own]),
                     local_map_digests=self.map_digests.cpu().numpy().reshape(self.R, self.per, 20 * self.B - 1, 32))

@@ -319,19 +319,27 @@ class HeaderRangeMapInputs:
 
 
 def get_header_range_map_inputs(trees: Dict[int, HeaderTree], start: int, end: int, n_jobs: int,
-                                batch_size: int) -> HeaderRangeMapInputs:
+                                batch_size: int, latest_safe: Optional[int] = None) -> HeaderRangeMapInputs:
     """What the 32 `DataCommitmentOffchainInputs` hints return for one range (BX/circuits/builder.rs:316-333):
-    job j covers [start+jB, start+(j+1)B) and fetches with end clamped to the chain tip (= `end`)."""
+    the hint of job j is called with (start+jB, start+(j+1)B) -- not with the range's end -- and clamps only to the last
+    block it can fetch, latest_block - 2 (BX/circuits/input.rs:160-163) = `latest_safe`; default: the last block of the
+    contiguous run start, start+1, ... present in `trees` (for a chain generated up to `end` that is `end`: the range ends
+    at the chain tip)."""
     J, B = n_jobs, batch_size
+    if latest_safe is None:
+        latest_safe = start
+        while latest_safe + 1 in trees:
+            latest_safe += 1
+    latest_safe = min(latest_safe, start + J * B)
     m = HeaderRangeMapInputs(J, B, start, end, np.frombuffer(trees[start].root, np.uint8).copy(),
                              np.frombuffer(trees[end].root, np.uint8).copy(), np.zeros((J * B, 34), np.uint8),
                              np.zeros((J * B, 128), np.uint8), np.zeros((J * B, 72), np.uint8),
                              np.zeros((J * B, 128), np.uint8), np.zeros((J, 32), np.uint8), np.zeros((J, 32), np.uint8))
     for j in range(J):
         bs, be = start + j * B, start + (j + 1) * B
-        if bs >= end:
-            continue  # dummy job: zero proofs, zero headers
-        d = get_data_commitment_inputs(trees, bs, be, B, latest_safe=end)
+        if bs >= latest_safe:
+            continue  # nothing to fetch (start >= request_end): zero proofs, zero headers
+        d = get_data_commitment_inputs(trees, bs, be, B, latest_safe=latest_safe)
         sl = slice(j * B, (j + 1) * B)
         m.dh_leaf[sl], m.dh_aunts[sl] = d.dh_leaf, d.dh_aunts.reshape(B, 128)
         m.lb_leaf[sl], m.lb_aunts[sl] = d.lb_leaf, d.lb_aunts.reshape(B, 128)

@@ -258,11 +258,12 @@ class Context:
         self._call("bsx_header_trees", _ptr(rec), C.c_uint32(n), _ptr(roots), _ptr(lv))
         return (roots, lv) if levels else roots
 
-    def header_range_inputs(self, records, start_blocks, end_blocks, n_jobs: int, batch_size: int) -> dict:
+    def header_range_inputs(self, records, start_blocks, end_blocks, n_jobs: int, batch_size: int, latest_blocks=None) -> dict:
         """Map-circuit inputs of n ranges from their header records [n, n_jobs*B+1, 512] -> the input arrays of
         header_range / prove_data_commitment (dh_leaf, dh_aunts, lb_leaf, lb_aunts, start_headers, end_headers,
-        start_header, end_header) + fail[n]."""
+        start_header, end_header) + fail[n].  latest_blocks: last fetchable block per range (None: the range's end)."""
         sb, eb = _in(start_blocks, np.uint64).reshape(-1), _in(end_blocks, np.uint64).reshape(-1)
+        lt = None if latest_blocks is None else _in(latest_blocks, np.uint64).reshape(-1)
         n, J, B = len(sb), n_jobs, batch_size
         rec = _in(records).reshape(n, J * B + 1, 512)
         out = dict(dh_leaf=np.zeros((n, J * B, 34), np.uint8), dh_aunts=np.zeros((n, J * B, 128), np.uint8),
@@ -270,7 +271,7 @@ class Context:
                    start_headers=np.zeros((n, J, 32), np.uint8), end_headers=np.zeros((n, J, 32), np.uint8),
                    start_header=np.zeros((n, 32), np.uint8), end_header=np.zeros((n, 32), np.uint8), fail=np.zeros(n, np.uint32))
         self._call("bsx_header_range_inputs", C.c_uint32(n), C.c_uint32(J), C.c_uint32(B), _ptr(rec), _ptr(sb), _ptr(eb),
-                   *[_ptr(out[k]) for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers",
+                   _ptr(lt) if lt is not None else C.c_void_p(0), *[_ptr(out[k]) for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers",
                                             "start_header", "end_header", "fail")])
         return out
 
@@ -417,6 +418,76 @@ class RangeBatch(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers",
                                           "start_blocks", "end_blocks", "start_header", "end_header", "map_digests",
                                           "map_subchains", "reduce_digests", "reduce_nodes", "data_commitments", "fail")]
+
+
+class ShardIn(C.Structure):
+    """bsx_shard_in"""
+    _fields_ = [(k, C.c_void_p) for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers", "end_headers",
+                                          "batch_start", "batch_end", "global_end", "global_end_header", "start_blocks",
+                                          "end_blocks", "start_header", "end_header")]
+
+
+class ShardOut(C.Structure):
+    """bsx_shard_out"""
+    _fields_ = [(k, C.c_void_p) for k in ("map_digests", "map_subchains", "reduce_digests", "reduce_nodes", "data_commitments", "fail")]
+
+
+IPC_HANDLE_BYTES = 64
+
+
+class Shard:
+    """bsx_shard: one rank of the sharded header_range map/reduce (include/bsx.h).  Setup: exchange `ipc_handle()` between
+    processes and `open_peer`, or `exchange_buffer()` pointers inside one process and `set_peer`; then `step_dev` per step."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, n_ranges: int, n_jobs: int, batch: int, exchange_buf: int = 0):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        lib_ = ctx._lib
+        lib_.bsx_shard_exchange_bytes.restype = C.c_size_t
+        h = C.c_void_p()
+        ctx._call("bsx_shard_create", C.c_uint32(rank), C.c_uint32(world), C.c_uint32(n_ranges), C.c_uint32(n_jobs), C.c_uint32(batch),
+                  C.c_void_p(int(exchange_buf)), C.byref(h))
+        self._h = h
+
+    @staticmethod
+    def exchange_bytes(world: int, n_ranges: int, n_jobs: int) -> int:
+        lib_ = load()
+        lib_.bsx_shard_exchange_bytes.restype = C.c_size_t
+        return int(lib_.bsx_shard_exchange_bytes(C.c_uint32(world), C.c_uint32(n_ranges), C.c_uint32(n_jobs)))
+
+    def _call(self, name, *args):
+        rc = getattr(self.ctx._lib, name)(self._h, *args)
+        if rc != 0:
+            raise BsxError(f"{name} failed ({rc}): {self.ctx._lib.bsx_last_error(self.ctx._h).decode()}")
+
+    def exchange_buffer(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._call("bsx_shard_exchange_buffer", C.byref(p), C.byref(n))
+        return int(p.value), int(n.value)
+
+    def ipc_handle(self) -> bytes:
+        b = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        self._call("bsx_shard_ipc_handle", b)
+        return bytes(b)
+
+    def open_peer(self, peer: int, handle: bytes):
+        self._call("bsx_shard_open_peer", C.c_uint32(peer), (C.c_uint8 * IPC_HANDLE_BYTES).from_buffer_copy(handle))
+
+    def set_peer(self, peer: int, dev_ptr: int):
+        self._call("bsx_shard_set_peer", C.c_uint32(peer), C.c_void_p(int(dev_ptr)))
+
+    def step_dev(self, stream: int, sin: "ShardIn", sout: "ShardOut"):
+        self._call("bsx_shard_step_dev", C.c_void_p(int(stream)), C.byref(sin), C.byref(sout))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.bsx_shard_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _addr(a) -> int:

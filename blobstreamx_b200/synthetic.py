@@ -124,17 +124,19 @@ def make_commit(chain: Chain, height: int, round_: int = 0, absent: Tuple[int, .
 
 
 def header_range_inputs(n_jobs: int, batch_size: int, n_blocks: Optional[int] = None, start: int = 1_000_000,
-                        seed: int = SEED, valset: Optional[ValidatorSet] = None, with_skip: bool = True):
+                        seed: int = SEED, valset: Optional[ValidatorSet] = None, with_skip: bool = True, extra_blocks: int = 0):
     """One header_range instance: trusted block = start, target = start + n_blocks
-    (default: the full range n_jobs*batch_size).  Returns (map_inputs, skip_inputs or None, chain)."""
+    (default: the full range n_jobs*batch_size).  `extra_blocks`: the chain continues that many blocks past the target
+    (the map jobs past the range's end then carry real proofs, as the reference's hints fetch them).
+    Returns (map_inputs, skip_inputs or None, chain)."""
     n_blocks = n_jobs * batch_size if n_blocks is None else n_blocks
-    chain = make_chain(n_blocks + 1, start, seed, valset)
+    chain = make_chain(n_blocks + 1 + extra_blocks, start, seed, valset)
     m = I.get_header_range_map_inputs(chain.trees, start, start + n_blocks, n_jobs, batch_size)
     skip = None
     if with_skip:
         target = start + n_blocks
         commit = make_commit(chain, target, seed=seed)
-        skip = I.get_skip_inputs(chain.headers[0], chain.valset.validators, chain.headers[-1], commit,
+        skip = I.get_skip_inputs(chain.headers[0], chain.valset.validators, chain.headers[n_blocks], commit,
                                  chain.valset.validators, expected_chain_id=chain.headers[0]["chain_id"].encode())
     return m, skip, chain
 

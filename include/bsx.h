@@ -455,20 +455,24 @@ int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, uin
  *   bytes [16, 16+sum) = the fields back to back; sum <= 496.
  * bsx_header_trees: roots[n*32] = header hashes; levels (optional) n*27*32 = l0[14] l1[7] l2[4] l3[2].
  * bsx_header_range_inputs: headers = n_ranges * (n_jobs*B + 1) records, record o of range r = block
- *   start_blocks[r] + o (records beyond end_blocks[r] are ignored); outputs are exactly the input arrays of
- *   bsx_range_batch (slots beyond the range end zero); fail[r] = BSX_FAIL_INPUT_LEAF if a data_hash /
- *   last_block_id field is not 34 / 72 bytes (the host shaper returns an error there).
+ *   start_blocks[r] + o.  latest_blocks[r] = the last block whose header can be fetched (latest_block - 2 in the
+ *   reference, input.rs:160-163); NULL = end_blocks (the range ends at the chain tip).  As in the reference, the hint of
+ *   job j is asked for (start + jB, start + (j+1)B) and clamps ONLY to latest_blocks[r] -- a job past the range's end still
+ *   gets real proofs and headers when the chain has those blocks (the circuit disables them); records beyond
+ *   latest_blocks[r] are ignored and their slots are zero.  Outputs are exactly the input arrays of bsx_range_batch;
+ *   fail[r] = BSX_FAIL_INPUT_LEAF if a data_hash / last_block_id field is not 34 / 72 bytes (the host shaper returns an
+ *   error there).
  * ------------------------------------------------------------------------------------------ */
 #define BSX_HEADER_LEAVES_BYTES 512
 int bsx_header_trees(bsx_ctx *ctx, const uint8_t *headers, uint32_t n, uint8_t *roots, uint8_t *levels);
 int bsx_header_trees_dev(bsx_ctx *ctx, void *stream, const uint8_t *headers, uint32_t n, uint8_t *roots, uint8_t *levels);
 int bsx_header_range_inputs(bsx_ctx *ctx, uint32_t n_ranges, uint32_t n_jobs, uint32_t B, const uint8_t *headers,
-                            const uint64_t *start_blocks, const uint64_t *end_blocks, uint8_t *dh_leaf, uint8_t *dh_aunts,
-                            uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers, uint8_t *end_headers,
-                            uint8_t *start_header, uint8_t *end_header, uint32_t *fail);
+                            const uint64_t *start_blocks, const uint64_t *end_blocks, const uint64_t *latest_blocks,
+                            uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers,
+                            uint8_t *end_headers, uint8_t *start_header, uint8_t *end_header, uint32_t *fail);
 int bsx_header_range_inputs_dev(bsx_ctx *ctx, void *stream, uint32_t n_ranges, uint32_t n_jobs, uint32_t B,
                                 const uint8_t *headers, const uint64_t *start_blocks, const uint64_t *end_blocks,
-                                uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts,
+                                const uint64_t *latest_blocks, uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts,
                                 uint8_t *start_headers, uint8_t *end_headers, uint8_t *start_header, uint8_t *end_header,
                                 uint32_t *fail);
 

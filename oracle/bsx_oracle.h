@@ -47,7 +47,7 @@ void orc_tm_root_from_slices(const uint8_t *items, const uint32_t *offsets, uint
 uint32_t orc_tm_aunts_from_slices(const uint8_t *items, const uint32_t *offsets, uint32_t n, uint32_t index, uint8_t *aunts,
                                   uint8_t root[32]);
 /* inputs of the map circuits of one range from its encoded headers (BX/circuits/input.rs:149-271, builder.rs:316-333) */
-int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers, uint64_t start, uint64_t end,
+int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers, uint64_t start, uint64_t end, uint64_t latest,
                             uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers,
                             uint8_t *end_headers, uint8_t start_header[32], uint8_t end_header[32]);
 /* off-chain input shaping: the 14 protobuf field encoders of a header (TX/input/tendermint_utils.rs:374-393),

@@ -106,8 +106,10 @@ def tm_aunts_from_slices(items, index: int):
     return aunts[:d].copy(), root.tobytes()
 
 
-def header_range_inputs(n_jobs: int, B: int, headers, start: int, end: int):
-    """Map-circuit inputs of one range from its header records (n_jobs*B + 1 records of 512 bytes)."""
+def header_range_inputs(n_jobs: int, B: int, headers, start: int, end: int, latest: int = None):
+    """Map-circuit inputs of one range from its header records (n_jobs*B + 1 records of 512 bytes).  `latest`: the last
+    block whose header can be fetched (latest_block - 2 in the reference); default = `end` (the range ends at the chain tip)."""
+    latest = end if latest is None else latest
     h = _u8(headers)
     assert h.size == (n_jobs * B + 1) * 512
     slots = n_jobs * B
@@ -115,7 +117,7 @@ def header_range_inputs(n_jobs: int, B: int, headers, start: int, end: int):
                lb_leaf=np.zeros((slots, 72), np.uint8), lb_aunts=np.zeros((slots, 128), np.uint8),
                start_headers=np.zeros((n_jobs, 32), np.uint8), end_headers=np.zeros((n_jobs, 32), np.uint8),
                start_header=np.zeros(32, np.uint8), end_header=np.zeros(32, np.uint8))
-    out["bad"] = lib().orc_header_range_inputs(C.c_uint32(n_jobs), C.c_uint32(B), _p(h), C.c_uint64(start), C.c_uint64(end),
+    out["bad"] = lib().orc_header_range_inputs(C.c_uint32(n_jobs), C.c_uint32(B), _p(h), C.c_uint64(start), C.c_uint64(end), C.c_uint64(latest),
                                                *[_p(out[k]) for k in ("dh_leaf", "dh_aunts", "lb_leaf", "lb_aunts", "start_headers",
                                                                       "end_headers", "start_header", "end_header")])
     return out

@@ -92,10 +92,13 @@ uint32_t orc_tm_aunts_from_slices(const uint8_t *items, const uint32_t *offsets,
 
 /* BX/circuits/input.rs:149-271 + BX/circuits/builder.rs:316-333: the inputs of the n_jobs map circuits of one range from
  * the encoded headers of blocks start .. start + n_jobs*B (records as include/bsx.h BSX_HEADER_LEAVES_BYTES: 14 lengths,
- * then at byte 16 the fields).  Job j covers [start + jB, start + (j+1)B) clamped to `end`; data_hash proofs (leaf 6)
- * for blocks [bs, req_end), last_block_id proofs (leaf 4) for (bs, req_end]; unused slots and dummy jobs are zero.
+ * then at byte 16 the fields).  The hint of job j is called with (bs, be) = (start + jB, start + (j+1)B) -- NOT with the
+ * range's end -- and clamps only to the last block it can fetch, `latest` (= latest_block - 2, input.rs:160-163):
+ * req_end = min(be, latest); data_hash proofs (leaf 6) for blocks [bs, req_end), last_block_id proofs (leaf 4) for
+ * (bs, req_end]; slots past req_end are zero, and so is a job with bs >= latest (:243-262).  So a job beyond the range's
+ * end still carries real proofs whenever the chain has those blocks (its slots are disabled inside the circuit).
  * Returns 0, or 1 if a proven field does not have the circuit's fixed size (the reference errors out). */
-int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers, uint64_t start, uint64_t end,
+int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers, uint64_t start, uint64_t end, uint64_t latest,
                             uint8_t *dh_leaf, uint8_t *dh_aunts, uint8_t *lb_leaf, uint8_t *lb_aunts, uint8_t *start_headers,
                             uint8_t *end_headers, uint8_t start_header[32], uint8_t end_header[32]) {
     const size_t slots = (size_t)n_jobs * B;
@@ -104,11 +107,11 @@ int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers,
     memset(lb_leaf, 0, slots * 72); memset(lb_aunts, 0, slots * 128);
     memset(start_headers, 0, (size_t)n_jobs * 32); memset(end_headers, 0, (size_t)n_jobs * 32);
     memset(start_header, 0, 32); memset(end_header, 0, 32);
-    if (end <= start) return 0;
+    if (latest > start + slots) latest = start + slots; /* records exist for blocks start .. start + n_jobs*B only */
     for (uint32_t j = 0; j < n_jobs; j++) {
         const uint64_t bs = start + (uint64_t)j * B, be = bs + B;
-        if (bs >= end) continue; /* dummy job */
-        const uint64_t req_end = be < end ? be : end;
+        if (bs >= latest) continue; /* nothing to fetch: start >= request_end, all zero */
+        const uint64_t req_end = be < latest ? be : latest;
         uint32_t k_dh = 0, k_lb = 0;
         for (uint64_t i = bs; i <= req_end; i++) {
             const uint8_t *rec = headers + (size_t)(i - start) * 512;
@@ -138,9 +141,17 @@ int orc_header_range_inputs(uint32_t n_jobs, uint32_t B, const uint8_t *headers,
                 orc_tm_root_from_slices(rec + 16, offs, 14, root);
                 if (i == bs) memcpy(start_headers + 32 * (size_t)j, root, 32);
                 if (i == req_end) memcpy(end_headers + 32 * (size_t)j, root, 32);
-                if (i == start) memcpy(start_header, root, 32);
-                if (i == end) memcpy(end_header, root, 32);
             }
+        }
+    }
+    /* the range's own public inputs: header hashes at `start` and `end` (evm inputs of the circuit, not part of the hint) */
+    if (end > start && end <= latest) {
+        for (int which = 0; which < 2; which++) {
+            const uint8_t *rec = headers + (size_t)((which ? end : start) - start) * 512;
+            uint32_t offs[15];
+            offs[0] = 0;
+            for (int f = 0; f < 14; f++) offs[f + 1] = offs[f] + rec[f];
+            orc_tm_root_from_slices(rec + 16, offs, 14, which ? end_header : start_header);
         }
     }
     return bad;

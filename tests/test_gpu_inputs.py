@@ -93,3 +93,28 @@ def test_range_inputs_full_size_property(ctx):
     a = ctx.prove_data_commitment(1, J, B, *[g[k][0] for k in FIELDS[:6]], np.array([m.start_block], np.uint64), g["start_header"][0],
                                   np.array([m.end_block], np.uint64), g["end_header"][0])
     assert a["fail"][0] == 0
+
+
+@pytest.mark.parametrize("extra", [0, 5, 64])
+def test_range_inputs_latest_block_beyond_the_range_end(ctx, orc, extra):
+    """latest_blocks: jobs are clamped to the last fetchable block, not to the range's end (BX/circuits/input.rs:160-163) --
+    device == oracle == host shaper for a chain that goes on past the target, several fills in one call."""
+    from blobstreamx_b200 import inputs as I
+    from blobstreamx_b200 import synthetic as S
+    J, B = 4, 8
+    fills = (19, 1, 8, 25, 32, 3)
+    sets = [S.header_range_inputs(J, B, nb, start=8_000_000 + 100 * r, seed=S.SEED + 5 * r, with_skip=False, extra_blocks=extra)
+            for r, nb in enumerate(fills)]
+    recs = np.stack([I.pack_range_headers(c.trees, m.start_block, J, B) for m, _, c in sets])
+    sb = np.array([m.start_block for m, _, _ in sets], np.uint64)
+    eb = np.array([m.end_block for m, _, _ in sets], np.uint64)
+    lt = np.array([m.start_block + nb + extra for (m, _, _), nb in zip(sets, fills)], np.uint64)
+    g = ctx.header_range_inputs(recs, sb, eb, J, B, latest_blocks=lt)
+    assert not g["fail"].any()
+    for r, (m, _, _) in enumerate(sets):
+        o = orc.header_range_inputs(J, B, recs[r], m.start_block, m.end_block, int(lt[r]))
+        for k in FIELDS:
+            assert (g[k][r].reshape(-1) == o[k].reshape(-1)).all(), (r, k)
+            assert (g[k][r].reshape(-1) == getattr(m, k).reshape(-1)).all(), (r, k)
+    a = ctx.prove_data_commitment(len(fills), J, B, *[g[k] for k in FIELDS[:6]], sb, g["start_header"], eb, g["end_header"])
+    assert not a["fail"].any()

@@ -35,8 +35,8 @@ def test_range_inputs_fixture(golden):
     """10000 -> 10004 in the shapes of the reference's small test circuits (BX/circuits/header_range.rs:193-214)."""
     trees = {int(k): I.HeaderTree.build(I.header_leaves(v)) for k, v in golden["headers"].items()}
     for (a, b, J, B) in ((10000, 10004, 2, 4), (10000, 10004, 4, 2), (10002, 10004, 2, 2), (10000, 10001, 2, 4)):
-        m = I.get_header_range_map_inputs(trees, a, b, J, B)
-        o = orc.header_range_inputs(J, B, I.pack_range_headers(trees, a, J, B), a, b)
+        m = I.get_header_range_map_inputs(trees, a, b, J, B)          # the fixture chain goes on to 10004: latest = 10004
+        o = orc.header_range_inputs(J, B, I.pack_range_headers(trees, a, J, B), a, b, min(10004, a + J * B))
         assert o["bad"] == 0
         _same(o, m)
         w = orc.prove_data_commitment(J, B, *[o[k] for k in FIELDS[:6]], a, o["start_header"], b, o["end_header"])
@@ -63,3 +63,26 @@ def test_range_inputs_wrong_leaf_size():
     leaves[6] = leaves[6][:-1]                       # a 33-byte data_hash field
     rec[2] = I.pack_header_record(leaves)
     assert orc.header_range_inputs(2, 4, rec, m.start_block, m.end_block)["bad"] == 1
+
+
+@pytest.mark.parametrize("J,B,nb,extra", [(4, 8, 19, 13), (4, 8, 19, 40), (2, 4, 1, 7), (8, 4, 12, 3), (4, 4, 5, 0), (4, 4, 16, 9)])
+def test_range_inputs_chain_longer_than_the_range(J, B, nb, extra):
+    """The hint of a map job is clamped to the last fetchable block (latest_block - 2, BX/circuits/input.rs:160-163), NOT to
+    the range's end: when the chain goes on past the target, the job holding the end and the jobs after it carry real
+    proofs and headers.  Oracle == host shaper; the circuit's outputs (subchain records, commitment) are what the
+    chain-tip case gives, only the witness of the disabled slots differs."""
+    m, _, chain = S.header_range_inputs(J, B, nb, with_skip=False, extra_blocks=extra)
+    latest = min(m.start_block + nb + extra, m.start_block + J * B)
+    trees = {k: v for k, v in chain.trees.items() if k <= latest}
+    rec = I.pack_range_headers(trees, m.start_block, J, B)
+    o = orc.header_range_inputs(J, B, rec, m.start_block, m.end_block, latest)
+    assert o["bad"] == 0
+    _same(o, m)
+    tip = orc.header_range_inputs(J, B, rec, m.start_block, m.end_block)          # as if the chain ended at the target
+    w = orc.prove_data_commitment(J, B, *[o[k] for k in FIELDS[:6]], m.start_block, o["start_header"], m.end_block, o["end_header"])
+    wt = orc.prove_data_commitment(J, B, *[tip[k] for k in FIELDS[:6]], m.start_block, tip["start_header"], m.end_block, tip["end_header"])
+    assert w["fail"] == 0 == wt["fail"] and w["data_commitment"] == wt["data_commitment"]
+    assert (w["reduce_nodes"] == wt["reduce_nodes"]).all()
+    if extra and nb < J * B:
+        assert not (o["lb_leaf"] == tip["lb_leaf"]).all()      # real proofs where the chain-tip case has zeros
+        assert int(o["dh_leaf"].reshape(J * B, 34).any(axis=1).sum()) == latest - m.start_block   # data_hash proofs of [start, latest)
