@@ -1248,14 +1248,296 @@ def run_tree(args):
                       "cpu_baseline": cpu}))
 
 
+def run_sweeps(args):
+    """BASELINE configs 4 and 5 in one JSON line: the data_commitment Merkle sweep (T independent 2048-leaf trees,
+    T in {1, 16, 256, 4096, 65 536}: SHA-256 GB/s of algorithmic bytes) and the Ed25519 witness batch sweep (n in
+    {100, 300, 1000, 3000, 10 000} signatures with 1 % inactive (DUMMY) lanes and one corrupted signature that must not
+    verify), each point checked against the oracle and reported beside the single-thread CPU port."""
+    import torch
+    from blobstreamx_b200 import lib, synthetic as S
+    from blobstreamx_b200.lib import ptr, u32
+    from oracle import cbind as orc
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = lib.Context(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    P = lambda t: ptr(t.data_ptr())
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def timed(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record()
+        for _ in range(reps):
+            fn()
+        e[1].record()
+        torch.cuda.synchronize()
+        return e[0].elapsed_time(e[1]) / reps
+
+    N = 2048
+    trees = []
+    cpu_tree = None
+    with ClockSampler(0) as clk:
+        for T in (1, 16, 256, 4096, 65536):
+            g = torch.Generator(device=dev)
+            g.manual_seed(7)
+            dh = torch.randint(0, 256, (T * N * 32,), generator=g, device=dev, dtype=torch.uint8)
+            starts = torch.arange(T, device=dev, dtype=torch.int64) * N + 1_000_000
+            ends = starts + N
+            dig = torch.zeros(T * (2 * N - 1) * 32, dtype=torch.uint8, device=dev)
+            roots = torch.zeros(T * 32, dtype=torch.uint8, device=dev)
+            fail = torch.zeros(T, dtype=torch.int32, device=dev)
+            step = lambda: ctx.call_dev("bsx_data_commitment_batch_dev", stream, P(dh), u32(N), u32(T), P(starts), P(ends), P(dig), P(roots), P(fail))
+            step()
+            torch.cuda.synchronize()
+            assert int(fail.abs().sum().item()) == 0
+            for t in sorted({0, T - 1}):
+                wd, wr, _ = orc.get_data_commitment(dh[t * N * 32:(t + 1) * N * 32].cpu().numpy().reshape(N, 32), int(starts[t]), int(ends[t]))
+                assert (dig[t * (2 * N - 1) * 32:(t + 1) * (2 * N - 1) * 32].cpu().numpy().reshape(-1, 32) == wd).all()
+                assert roots[t * 32:(t + 1) * 32].cpu().numpy().tobytes() == wr
+            if cpu_tree is None:
+                a = dh[: N * 32].cpu().numpy().reshape(N, 32)
+                t0 = time.perf_counter()
+                for _ in range(8):
+                    orc.get_data_commitment(a, 1_000_000, 1_000_000 + N)
+                cpu_tree = 8 * N / (time.perf_counter() - t0)
+            reps = 3 if T >= 65536 else args.steps
+            ms = timed(step, reps, 3)
+            alg = T * (64 * (4 * N - 2) + 32 * (2 * N - 1))
+            trees.append({"trees": T, "input_MB": T * N * 32 / 1e6, "output_MB": dig.numel() / 1e6, "ms": ms, "data_roots_per_s": T * N / (ms * 1e-3),
+                          "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak,
+                          "sha256_compressions_per_s": T * (4 * N - 2) / (ms * 1e-3),
+                          "l2": "fits L2 (compute-bound, no flush)" if (dh.numel() + dig.numel()) < 126e6 else "> 126 MB L2"})
+            del dh, dig, roots, fail
+        eds = []
+        base = S.ed25519_batch_inputs(2000)
+        cpu_ed = None
+        for n in (100, 300, 1000, 3000, 10000):
+            rep = -(-n // len(base[0]))
+            pks, sigs, msgs, lens, active = (np.ascontiguousarray(np.concatenate([a] * rep)[:n]) for a in base)
+            bad = n // 2
+            sigs[bad, 7] ^= 0x20                                   # the must-fail lane (eddsa.rs:344-386)
+            active[bad] = 1
+            d = [torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev) for a in (pks, sigs, msgs, lens, active)]
+            out = torch.zeros(n * 576, dtype=torch.uint8, device=dev)
+            step = lambda: ctx.call_dev("bsx_ed25519_batch_dev", stream, u32(n), P(d[0]), P(d[1]), P(d[2]), u32(124), P(d[3]), P(d[4]), P(out))
+            step()
+            torch.cuda.synchronize()
+            rec = out.cpu().numpy().reshape(n, 576)
+            k = min(n, 400)
+            sel = np.unique(np.concatenate([np.arange(k), [bad]]))
+            want = orc.ed25519_batch(pks[sel], sigs[sel], msgs[sel], lens[sel], active[sel], threads=8)
+            assert (rec[sel] == want).all(), "Ed25519 records differ from the oracle"
+            assert rec[bad, 520] & 8 == 0 and (np.delete(rec[:, 520], bad) == 0xF).all()
+            if cpu_ed is None:
+                t0 = time.perf_counter()
+                orc.ed25519_batch(pks[:100], sigs[:100], msgs[:100], lens[:100], active[:100], threads=1)
+                cpu_ed = 100 / (time.perf_counter() - t0)
+            ms = timed(step, args.steps, 3)
+            eds.append({"signatures": n, "inactive_lanes": int((active == 0).sum()), "must_fail_lane": int(bad), "ms": ms,
+                        "sigs_per_s": n / (ms * 1e-3), "path": "three-stage quad-lane kernels" if n <= 16384 else "thread per signature",
+                        "vs_cpu_port_1_thread": n / (ms * 1e-3) / cpu_ed})
+    print(json.dumps({"metric": "sweeps: data_commitment Merkle (config 4) and Ed25519 witness batch (config 5)", "n_gpus": 1, "steps": args.steps,
+                      "data": "synthetic", "clocks": clk.summary(), "hbm_peak_GBps": peak,
+                      "data_commitment_tree_sweep": {"workload": "get_data_commitment<2048>: 4095 digests / 8190 SHA-256 compressions per tree",
+                                                     "unit": "GB/s = (64 B per compression + 32 B per digest) / time", "points": trees,
+                                                     "cpu_baseline": {"value": cpu_tree, "unit": "data roots/s", "cores": 1, "kind": "port", "sample": "8 trees"},
+                                                     "note": "SHA-256 is int32-ALU-bound (~20 ops/byte): ~18 % of HBM peak is the pipe's ceiling"},
+                      "ed25519_sweep": {"workload": "CanonicalVote sign-bytes (108-109 B padded to 124), 1 % DUMMY lanes, one corrupted signature",
+                                        "points": eds, "cpu_baseline": {"value": cpu_ed, "unit": "sigs/s", "cores": 1, "kind": "port", "sample": "100 signatures"}}}))
+
+
+def run_plonk(args):
+    """Prover inner loops on a device-resident trace: W wire polynomials of n = 2^--log-rows rows ->
+    coefficients (inverse transform) -> coset extension at rate 8 -> Poseidon Merkle cap over the extension + quotient-style
+    U32Arithmetic constraint evaluation.  Each stage against the HBM roofline (algorithmic bytes = every input read once,
+    every output written once), the chain checked on a small instance against the CPU restatement before timing."""
+    import torch
+    from blobstreamx_b200 import lib
+    from blobstreamx_b200.plonk import Prover, bitrev_indices
+    from oracle import cbind as orc
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = lib.Context(0)
+    pv = Prover(ctx, dev)
+    gate, p0, p1, _ = GATE_CONFIGS["arithmetic"]
+    W, ncn = ctx.gate_num_wires(gate, p0, p1), ctx.gate_num_constraints(gate, p0, p1)
+    log_n, r, cap_h = args.log_rows, 3, 4
+    n, N = 1 << log_n, 1 << (log_n + 3)
+    P_ = 2**64 - 2**32 + 1
+    if not args.no_check:      # small instance, bit-exact against the oracle
+        rng = np.random.default_rng(1)
+        w = rng.integers(0, P_, (W, 1 << 8), dtype=np.uint64)
+        td = torch.from_numpy(w.view(np.int64)).to(dev)
+        co = pv.ntt(td, inverse=True, natural_out=True)
+        ext = pv.lde(co, r)
+        perm = bitrev_indices(8 + r)
+        want_ext = orc.gl_lde(orc.gl_ntt(w, inverse=True), r)[:, perm]
+        assert (ext.cpu().numpy().view(np.uint64) == want_ext).all(), "extension differs from the oracle"
+        _, cap = pv.merkle_caps(ext, cap_h)
+        assert (cap.cpu().numpy().view(np.uint64) == orc.gl_merkle(np.ascontiguousarray(want_ext.T), cap_h)[-16:]).all(), "Merkle cap differs"
+        ap, zh = pv.quotient_tables([11, 13], ncn, 8, r)
+        q = pv.gate_quotient(gate, p0, p1, ext, ap, 2, zh, 8)
+        wq = orc.gl_quotient_combine(orc.gate_eval(gate, p0, p1, want_ext, threads=4), [11, 13], np.repeat(zh.cpu().numpy().view(np.uint64), 1 << 8))
+        assert (q.cpu().numpy().view(np.uint64) == wq).all(), "quotient differs from the oracle"
+    g = torch.Generator(device=dev)
+    g.manual_seed(2)
+    trace = torch.randint(0, 2**62, (W, n), generator=g, device=dev, dtype=torch.int64)
+    coeffs = torch.empty_like(trace)
+    scratch = torch.empty_like(trace)
+    ext = torch.empty((W, N), dtype=torch.int64, device=dev)
+    words = int(ctx._lib.bsx_gl_merkle_digest_words(lib.u32(N), lib.u32(cap_h)))
+    dig = torch.empty(words, dtype=torch.int64, device=dev)
+    qout = torch.empty((2, N), dtype=torch.int64, device=dev)
+    ap, zh = pv.quotient_tables([0x123456789, 0xABCDEF0123], ncn, log_n, r)
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    P = lambda t: lib.ptr(t.data_ptr())
+    import ctypes as C
+    stages = {
+        "intt (values -> coefficients, natural order)": (lambda: ctx.call_dev("bsx_gl_ntt_dev", st(), P(trace), P(coeffs), lib.u32(log_n), lib.u32(W),
+                                                                             C.c_size_t(n), C.c_size_t(n), C.c_int(1), C.c_int(1), P(scratch)), 16 * n * W),
+        "coset lde (rate 8, bit-reversed)": (lambda: pv.lde(coeffs, r, out=ext), 8 * n * W + 8 * N * W),
+        "poseidon merkle cap (leaves of %d elements + layers)" % W: (lambda: pv.merkle_caps(ext, cap_h, out=dig), 8 * N * W + 8 * words),
+        "quotient (U32Arithmetic constraints, 2 alphas, / Z_H)": (lambda: pv.gate_quotient(gate, p0, p1, ext, ap, 2, zh, log_n, out=qout), 8 * N * W + 16 * N),
+    }
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    res, total_ms = {}, 0.0
+    with ClockSampler(0) as clk:
+        for name, (fn, alg) in stages.items():
+            reps = max(3, args.steps // 5) if "merkle" in name else args.steps
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e[0].record()
+            for _ in range(reps):
+                fn()
+            e[1].record()
+            torch.cuda.synchronize()
+            ms = e[0].elapsed_time(e[1]) / reps
+            total_ms += ms
+            res[name] = {"ms": ms, "algorithmic_bytes": alg, "GBps": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak}
+    perms = N * ((W + 7) // 8) + N - (1 << cap_h)
+    res[[k for k in res if "merkle" in k][0]]["poseidon_permutations_per_s"] = perms / (res[[k for k in res if "merkle" in k][0]]["ms"] * 1e-3)
+    cpu = None
+    if not args.no_cpu:
+        k = 1 << 12
+        x = np.random.default_rng(3).integers(0, P_, (8, k), dtype=np.uint64)
+        t0 = time.perf_counter()
+        orc.gl_lde(orc.gl_ntt(x, inverse=True), r)
+        cpu = {"value": 8 * k / (time.perf_counter() - t0), "unit": "trace elements/s (intt + lde only)", "cores": 1, "kind": "port", "sample": "8 polynomials x 4096 rows"}
+    print(json.dumps({"metric": "trace elements/sec, trace -> coefficients -> rate-8 extension -> Merkle cap + quotient", "value": n * W / (total_ms * 1e-3),
+                      "unit": "elements/s", "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": total_ms, "higher_is_better": True,
+                      "dtype": "u64 mod 2^64-2^32+1", "data": "synthetic",
+                      "config": {"workload": f"{W} wire polynomials x 2^{log_n} rows (U32ArithmeticGate trace), rate_bits 3, cap_height 4 (standard_recursion_config)",
+                                 "l2": f"extension = {8 * N * W / 1e9:.2f} GB > 126 MB L2", "parity": "unpinned vs plonky2 (un-vendored): algebraic pins, tests/test_oracle_plonk.py"},
+                      "gpu_launches": None, "clocks": clk.summary(), "stages": res,
+                      "roofline": {"kernel": "ntt_dif_strided_kernel + ntt_dif_contig_kernel (coset lde)", "bound": "hbm",
+                                   "achieved": res["coset lde (rate 8, bit-reversed)"]["GBps"], "peak": peak, "unit": "GB/s",
+                                   "frac": res["coset lde (rate 8, bit-reversed)"]["frac_of_hbm_peak"], "traffic": None,
+                                   "algorithmic_bytes_per_launch": res["coset lde (rate 8, bit-reversed)"]["algorithmic_bytes"],
+                                   "note": "two passes over HBM per 2^20-point transform: the floor of this plan is 0.5 x peak"},
+                      "cpu_baseline": cpu}))
+
+
+def run_trace(args):
+    """SHA-256 execution trace of one header_range_1024 map circuit's accelerator: 1246 chunks -> 2^17 rows
+    x 176 columns, written column-major from HashInputData on the device; a pure HBM write stream."""
+    import torch
+    from blobstreamx_b200 import lib
+    from blobstreamx_b200.plonk import Prover, SHA256_TRACE_COLS
+    from oracle import cbind as orc
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    ctx = lib.Context(0)
+    pv = Prover(ctx, dev)
+    B = BATCH
+    rng = np.random.default_rng(4)
+    # the request schedule of prove_subchain<32> (SURVEY A.7): per header a 34-byte and a 72-byte leaf (35 / 73 bytes hashed)
+    # and 8 + 8 inner nodes (65 bytes), then B tuple leaves (65) and B - 1 inner nodes (65): 639 requests, 1246 chunks
+    sizes = ([35] + [65] * 8 + [73] + [65] * 8) * B + [65] * B + [65] * (B - 1)
+    bufs = rng.integers(0, 256, sum(sizes), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    hid = ctx.hash_input_data(bufs, offs, np.array(sizes, np.uint32), np.zeros(len(sizes), np.uint8))
+    n = len(hid["padded_chunks"])
+    assert n == 39 * B - 2
+    jobs = args.trace_jobs
+    log_rows = int(np.ceil(np.log2(64 * n)))
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pc, eb, db = to(hid["padded_chunks"].view(np.int32)), to(hid["end_bits"]), to(hid["digest_bits"])
+    outs = [torch.empty((SHA256_TRACE_COLS, 1 << log_rows), dtype=torch.int64, device=dev) for _ in range(jobs)]
+
+    def step():
+        for o in outs:
+            pv.sha256_trace(pc, eb, db, log_rows, out=o)
+
+    step()
+    torch.cuda.synchronize()
+    if not args.no_check:
+        want = orc.sha256_trace(hid["padded_chunks"], hid["end_bits"], hid["digest_bits"], log_rows)
+        assert (outs[-1].cpu().numpy().view(np.uint64) == want).all(), "trace differs from the oracle"
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    with ClockSampler(0) as clk:
+        e[0].record()
+        for _ in range(args.steps):
+            step()
+        e[1].record()
+        torch.cuda.synchronize()
+    ms = e[0].elapsed_time(e[1]) / args.steps
+    alg = jobs * (8 * SHA256_TRACE_COLS * (1 << log_rows) + 64 * n)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    cpu = None
+    if not args.no_cpu:
+        t0 = time.perf_counter()
+        orc.sha256_trace(hid["padded_chunks"], hid["end_bits"], hid["digest_bits"], log_rows)
+        cpu = {"value": 64 * n / (time.perf_counter() - t0), "unit": "trace rows/s", "cores": 1, "kind": "port", "sample": "one map circuit (1246 chunks)"}
+    print(json.dumps({"metric": "trace rows/sec, SHA-256 execution trace of the header_range_1024 map circuits", "value": jobs * 64 * n / (ms * 1e-3),
+                      "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "dtype": "u32 -> u64 elements",
+                      "data": "synthetic",
+                      "config": {"workload": f"{jobs} map circuits x {n} chunks -> 2^{log_rows} rows x {SHA256_TRACE_COLS} columns each (column-major)",
+                                 "l2": f"{alg / 1e6:.0f} MB per step > 126 MB L2", "parity": "layout our own (starkyx un-vendored): unpinned vs the reference, "
+                                 "pinned by recomputing every digest from the columns (tests/test_oracle_trace.py)",
+                                 "reference_size": "418 free + 912 extended columns = 1.4 GB per map circuit at 2^17 rows"},
+                      "gpu_launches": jobs * args.steps, "clocks": clk.summary(),
+                      "roofline": {"kernel": "sha256_trace_kernel", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg // jobs,
+                                   "note": "almost write-only; peak = measured copy bandwidth (read + write)"},
+                      "cpu_baseline": cpu}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon", "shape", "encode", "pack"])
+    ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon", "shape", "encode", "pack", "sweeps", "plonk", "trace"])
     ap.add_argument("--trees", type=int, default=4096)
     ap.add_argument("--hashes", type=int, default=1 << 20)
     ap.add_argument("--pack-bytes", type=int, default=1 << 25)
     ap.add_argument("--hash-len", type=int, default=8)
     ap.add_argument("--rows", type=int, default=1 << 20)
+    ap.add_argument("--trace-jobs", type=int, default=32, help="--mode trace: map circuits per step")
+    ap.add_argument("--log-rows", type=int, default=18, help="--mode plonk: trace rows = 2^log_rows")
     ap.add_argument("--gate", default="arithmetic", choices=["arithmetic", "add_many", "subtraction", "comparison", "range_check"])
     ap.add_argument("--sigs", type=int, default=100000)
     ap.add_argument("--gpus", type=int, default=1)
@@ -1290,6 +1572,12 @@ def main():
         run_encode(args)
     elif args.mode == "pack":
         run_pack(args)
+    elif args.mode == "sweeps":
+        run_sweeps(args)
+    elif args.mode == "plonk":
+        run_plonk(args)
+    elif args.mode == "trace":
+        run_trace(args)
     else:
         run_gpu(args)
 

@@ -117,6 +117,7 @@ extern "C" void bsx_destroy(bsx_ctx *ctx) {
     if (ctx->ev_table) cudaEventDestroy(ctx->ev_table);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->ed_table) cudaFree(ctx->ed_table);
+    bsx_plonk_cache_free(ctx);
     delete ctx;
 }
 

@@ -42,6 +42,7 @@ struct bsx_ctx {
     void *ed_table;            // s*G window table (k_ed25519.cu), built on first use
     cudaEvent_t ev_table;      // recorded after the table build: every consumer stream waits on it (the build runs once,
     int ed_table_pending;      // on whichever stream made the first Ed25519 call); pending until the event has been seen complete
+    struct bsx_plonk_cache *plonk;   // twiddle tables of the transforms (k_plonk.cu), built on first use
     int tun[BSX_TUN_COUNT];    // measurement knobs (bsx_set_tunable; defaults from the BSX_* environment at bsx_init)
     cudaStream_t stream2;      // second stream + events: bsx_header_range runs its two halves concurrently
     cudaEvent_t ev_fork, ev_join;     // bsx_header_range (host path: two copy+compute pipelines)
@@ -63,6 +64,8 @@ static inline bool bsx_ed_fills_waves(const bsx_ctx *ctx, uint64_t n) {
     const uint64_t wave = (uint64_t)ctx->sm_count * 4, ctas = (n + 63) / 64, tail = ctas % wave;
     return ctas * 10 >= wave * 9 && (tail == 0 || tail * 10 >= wave * 9);   // last wave at least 90 % full (378 ranges: 591 of 592 CTAs)
 }
+
+void bsx_plonk_cache_free(bsx_ctx *ctx);   // k_plonk.cu
 
 // stages of verify_* (k_verify.cu), reused by bsx_header_range_dev
 int bsx_verify_launch_ed(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, const uint8_t *validators, uint8_t *ed_out, int ed_corun = 0);

@@ -12,7 +12,7 @@
 // ~400 field multiplications per row puts the arithmetic gate near the HBM/ALU balance point.
 #include "common.cuh"
 #include "goldilocks.cuh"
-#include "poseidon_constants.cuh"
+#include "poseidon.cuh"
 
 namespace bsx {
 
@@ -103,7 +103,37 @@ struct RowIO {
     __device__ __forceinline__ uint64_t raw(uint32_t col) const { return __ldcs(wires + (size_t)col * rows + r); }
     __device__ __forceinline__ uint64_t w(uint32_t col) const { return glf::canon(raw(col)); }
     __device__ __forceinline__ void put(uint64_t v) { __stcs(out + (size_t)(c++) * rows + r, v); }
-    __device__ __forceinline__ void put_at(uint32_t col, uint64_t v) const { __stcs(out + (size_t)col * rows + r, v); }
+    __device__ __forceinline__ void put_at(uint32_t col, uint64_t v) { __stcs(out + (size_t)col * rows + r, v); }
+    // constraints col_top, col_top - 1, ...: the column pointer steps by one row stride (no per-access 64-bit multiply)
+    struct Cursor {
+        uint64_t *cp; size_t rows;
+        __device__ __forceinline__ void put_down(int t, uint64_t v) const { __stcs(cp - (size_t)t * rows, v); }
+    };
+    __device__ __forceinline__ Cursor cursor(uint32_t col_top) { return Cursor{out + (size_t)col_top * rows + r, rows}; }
+};
+
+// The quotient form of the same evaluation (plonky2's compute_quotient_polys reduces the constraint terms of a point with
+// powers of alpha before they ever reach memory): every constraint is folded into NA running sums  acc_a += alpha_a^c C_c
+// instead of being stored, so a point costs its wire reads and NA words written.
+template <int NA>
+struct RowReduce {
+    const uint64_t *__restrict__ wires;
+    const uint64_t *apow;            // shared memory: apow[a * ncn + c] = alpha_a^c
+    size_t rows, r;
+    uint32_t c, ncn;
+    uint64_t acc[NA];
+    __device__ __forceinline__ uint64_t raw(uint32_t col) const { return __ldcs(wires + (size_t)col * rows + r); }
+    __device__ __forceinline__ uint64_t w(uint32_t col) const { return glf::canon(raw(col)); }
+    __device__ __forceinline__ void put_at(uint32_t col, uint64_t v) {
+#pragma unroll
+        for (int a = 0; a < NA; a++) acc[a] = glf::add(acc[a], glf::mul(v, apow[a * ncn + col]));
+    }
+    __device__ __forceinline__ void put(uint64_t v) { put_at(c++, v); }
+    struct Cursor {
+        RowReduce *io; uint32_t top;
+        __device__ __forceinline__ void put_down(int t, uint64_t v) const { io->put_at(top - (uint32_t)t, v); }
+    };
+    __device__ __forceinline__ Cursor cursor(uint32_t col_top) { return Cursor{this, col_top}; }
 };
 
 // N 2-bit limbs (wires w0 .. w0+N-1, least significant first): their range-check products go to constraints
@@ -112,18 +142,18 @@ struct RowIO {
 // over groups of <= 8 limbs WITHOUT unrolling, so the hot code is one copy of this body (~600 instructions): fully
 // unrolled the arithmetic gate was 58 KB of SASS and a quarter of its issue stalls were instruction-cache misses
 // (profiles/r01i_gl_gate_eval_ncu_full.csv).
-template <int N>
-__device__ __forceinline__ glf::Radix4Sum limb_group(const RowIO &io, uint32_t w0, uint32_t c_top) {
+template <int N, class IO>
+__device__ __forceinline__ glf::Radix4Sum limb_group(IO &io, uint32_t w0, uint32_t c_top) {
     // column pointers advance by one row stride per limb (no per-access 64-bit multiply)
     const uint64_t *wp = io.wires + (size_t)w0 * io.rows + io.r;
-    uint64_t *cp = io.out + (size_t)(c_top + N - 1) * io.rows + io.r;
+    const auto cur = io.cursor(c_top + N - 1);
     uint64_t limb[N];
 #pragma unroll
     for (int t = 0; t < N; t++) limb[t] = __ldcs(wp + (size_t)t * io.rows);   // raw: limb_product4 and the sum take any representative
     glf::Radix4Sum s;
 #pragma unroll
     for (int t = 0; t < N; t++) {
-        __stcs(cp - (size_t)t * io.rows, glf::limb_product4(limb[t]));
+        cur.put_down(t, glf::limb_product4(limb[t]));
         s.add(limb[t], t);
     }
     return s;
@@ -131,7 +161,8 @@ __device__ __forceinline__ glf::Radix4Sum limb_group(const RowIO &io, uint32_t w
 
 // arithmetic_u32.rs:280-349: per op  [hi_not_max * out_lo, out_hi 2^32 + out_lo - (m0 m1 + addend),
 //   32 limb products (limb 31 first), low16 - out_lo, high16 - out_hi]
-__device__ __forceinline__ void eval_arithmetic(RowIO &io, uint32_t num_ops) {
+template <class IO>
+__device__ __forceinline__ void eval_arithmetic(IO &io, uint32_t num_ops) {
 #pragma unroll 1
     for (uint32_t i = 0; i < num_ops; i++) {
         const uint32_t cb = 36 * i, wl = 6 * num_ops + 32 * i;
@@ -156,7 +187,8 @@ __device__ __forceinline__ void eval_arithmetic(RowIO &io, uint32_t num_ops) {
 
 // add_many_u32.rs:107-146: per op  [out_carry 2^32 + out_res - sum(addends, carry_in),
 //   19 limb products (limb 18 first: 3 carry limbs, then 16 result limbs), res16 - out_res, carry3 - out_carry]
-__device__ __forceinline__ void eval_add_many(RowIO &io, uint32_t na, uint32_t num_ops) {
+template <class IO>
+__device__ __forceinline__ void eval_add_many(IO &io, uint32_t na, uint32_t num_ops) {
 #pragma unroll 1
     for (uint32_t i = 0; i < num_ops; i++) {
         const uint32_t b = (na + 3) * i, cb = 22 * i, wl = (na + 3) * num_ops + 19 * i;
@@ -182,7 +214,8 @@ __device__ __forceinline__ void eval_add_many(RowIO &io, uint32_t na, uint32_t n
 
 // subtraction_u32.rs:101-135: per op  [out_res - (x - y - borrow_in + 2^32 out_borrow), 16 limb products (limb 15
 //   first), limbs16 - out_res, out_borrow (1 - out_borrow)]
-__device__ __forceinline__ void eval_subtraction(RowIO &io, uint32_t num_ops) {
+template <class IO>
+__device__ __forceinline__ void eval_subtraction(IO &io, uint32_t num_ops) {
 #pragma unroll 1
     for (uint32_t i = 0; i < num_ops; i++) {
         const uint32_t cb = 19 * i, wl = 5 * num_ops + 16 * i;
@@ -213,7 +246,8 @@ __device__ __forceinline__ uint64_t chunk_product(uint64_t l, uint32_t base) {
 }
 
 // comparison.rs:118-195
-__device__ __forceinline__ void eval_comparison(RowIO &io, uint32_t num_bits, uint32_t nc) {
+template <class IO>
+__device__ __forceinline__ void eval_comparison(IO &io, uint32_t num_bits, uint32_t nc) {
     const uint32_t cb = (num_bits + nc - 1) / nc;
     const uint64_t chunk_size = 1ULL << cb;
     // first / second input recombined from their chunks: sum chunk_i 2^(cb i) as Horner steps (chunks are canonical,
@@ -254,7 +288,8 @@ __device__ __forceinline__ void eval_comparison(RowIO &io, uint32_t num_bits, ui
 }
 
 // range_check_u32.rs:69-91: per value  [aux16 - value, then the 16 limb products in INCREASING limb order]
-__device__ __forceinline__ void eval_range_check(RowIO &io, uint32_t nl) {
+template <class IO>
+__device__ __forceinline__ void eval_range_check(IO &io, uint32_t nl) {
 #pragma unroll 1
     for (uint32_t i = 0; i < nl; i++) {
         const uint32_t cb = 17 * i;
@@ -288,6 +323,33 @@ __global__ void __launch_bounds__(128) gl_gate_eval_kernel(uint32_t p0, uint32_t
     else if (GATE == BSX_GATE_U32_SUBTRACTION) eval_subtraction(io, p0);
     else if (GATE == BSX_GATE_U32_COMPARISON) eval_comparison(io, p0, p1);
     else eval_range_check(io, p0);
+}
+
+// Quotient-style evaluation over a low-degree extension (plonky2 compute_quotient_polys, un-vendored; call site
+// PX/backend/circuit/build.rs:69-75): for every point x of the coset LDE, out[a][x] = zh_inv(x) * sum_c alpha_a^c C_c(x).
+// `wires` are the LDE values poly-major (wire w of point r at wires[w * rows + r], the layout bsx_gl_lde_dev writes),
+// zh_inv has one entry per block of 2^log_block points (Z_H = x^n - 1 takes 2^rate_bits values on the coset).
+template <int GATE, int NA>
+__global__ void __launch_bounds__(128) gl_gate_quotient_kernel(uint32_t p0, uint32_t p1, const uint64_t *__restrict__ wires, uint32_t rows,
+                                                               const uint64_t *__restrict__ alpha_pows, uint32_t ncn,
+                                                               const uint64_t *__restrict__ zh_inv, uint32_t log_block,
+                                                               uint64_t *__restrict__ out) {
+    extern __shared__ uint64_t s_apow[];
+    for (uint32_t k = threadIdx.x; k < NA * ncn; k += blockDim.x) s_apow[k] = alpha_pows[k];
+    __syncthreads();
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    RowReduce<NA> io{wires, s_apow, rows, r, 0, ncn, {}};
+#pragma unroll
+    for (int a = 0; a < NA; a++) io.acc[a] = 0;
+    if (GATE == BSX_GATE_U32_ARITHMETIC) eval_arithmetic(io, p0);
+    else if (GATE == BSX_GATE_U32_ADD_MANY) eval_add_many(io, p0, p1);
+    else if (GATE == BSX_GATE_U32_SUBTRACTION) eval_subtraction(io, p0);
+    else if (GATE == BSX_GATE_U32_COMPARISON) eval_comparison(io, p0, p1);
+    else eval_range_check(io, p0);
+    const uint64_t zi = zh_inv[r >> log_block];
+#pragma unroll
+    for (int a = 0; a < NA; a++) __stcs(out + (size_t)a * rows + r, glf::mul(io.acc[a], zi));
 }
 
 // ---- witness generators (SimpleGenerator::run_once): fill the dependent wires of each row in place ----
@@ -356,81 +418,6 @@ __global__ void __launch_bounds__(128) gl_gate_witness_kernel(uint32_t gate, uin
         for (uint32_t i = 0; i <= cb; i++) { w.set(4 + 5 * nc + i, t & 1); t >>= 1; }
     } else {
         for (uint32_t i = 0; i < p0; i++) w.split((uint32_t)w.get(i), 16, 2, p0 + 16 * i);
-    }
-}
-
-// ---- Poseidon (width 12, x^7, 4 + 22 + 4 rounds) ----
-// The state is kept as arbitrary 64-bit representatives (weak reductions, glf::): every step below is correct for
-// any representative, and only the four squeezed words are made canonical at the end.
-__device__ __forceinline__ uint64_t gl_mul_weak(uint64_t a, uint64_t b) {
-    uint64_t hi, lo;
-    glf::mul128(a, b, 0, hi, lo);
-    return glf::reduce128_weak(hi, lo);
-}
-__device__ __forceinline__ uint64_t gl_pow7(uint64_t x) {
-    const uint64_t x2 = gl_mul_weak(x, x), x4 = gl_mul_weak(x2, x2);
-    return gl_mul_weak(gl_mul_weak(x4, x2), x);
-}
-// s + c for any 64-bit s and canonical c: wrapped + eps on carry (cannot carry twice because c < p)
-__device__ __forceinline__ uint64_t gl_add_const_weak(uint64_t s, uint64_t c) {
-    uint64_t r;
-    asm("{\n\t"
-        ".reg .u32 cy;\n\t"
-        "add.cc.u64 %0, %1, %2;\n\t"
-        "addc.u32 cy, 0, 0;\n\t"
-        "mad.wide.u32 %0, cy, 0xFFFFFFFF, %0;\n\t"
-        "}"
-        : "=&l"(r)
-        : "l"(s), "l"(c));
-    return r;
-}
-
-// MDS = circulant(CIRC) + diag(8, 0, ...).  The constants are below 2^6 and sum to 284 < 2^8.2, so with the state cut
-// into limbs of 22 / 21 / 21 bits every column sum stays below 2^31.2: plain 32-bit IMADs (2 issue cycles on the FMA
-// pipe) instead of IMAD.WIDE (4 cycles), 3 x 144 of them per round instead of 2 x 144 wide ones; the three sums of an
-// output are folded into one 128-bit value (a0 + a1 2^22 + a2 2^43) and reduced once, weakly.  Measured against the
-// form with two IMAD.WIDE sums of 32-bit halves: 490 -> 623 M permutations/s (profiles/r01o_poseidon_*.json).
-__device__ __forceinline__ void poseidon_mds(uint64_t s[12]) {
-    constexpr uint32_t CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    uint32_t l0[12], l1[12], l2[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        l0[i] = (uint32_t)s[i] & 0x3fffffu;
-        l1[i] = (uint32_t)(s[i] >> 22) & 0x1fffffu;
-        l2[i] = (uint32_t)(s[i] >> 43);
-    }
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-        uint32_t a0 = 0, a1 = 0, a2 = 0;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            a0 += l0[(i + k) % 12] * CIRC[i];
-            a1 += l1[(i + k) % 12] * CIRC[i];
-            a2 += l2[(i + k) % 12] * CIRC[i];
-        }
-        if (k == 0) { a0 += l0[0] * 8; a1 += l1[0] * 8; a2 += l2[0] * 8; }  // MDS_MATRIX_DIAG = [8, 0, ...]
-        // value = a0 + a1 2^22 + a2 2^43  (< 2^75)
-        uint64_t lo = (uint64_t)a0 + ((uint64_t)a1 << 22), hi = (uint64_t)a2 >> 21;
-        asm("add.cc.u64 %0, %0, %2;\n\t"
-            "addc.u64 %1, %1, 0;"
-            : "+l"(lo), "+l"(hi)
-            : "l"((uint64_t)a2 << 43));
-        s[k] = glf::reduce128_weak(hi, lo);
-    }
-}
-
-__device__ __forceinline__ void poseidon_permute(uint64_t s[12]) {
-#pragma unroll 1
-    for (int r = 0; r < 30; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = gl_add_const_weak(s[i], BSX_POSEIDON_RC[12 * r + i]);
-        if (r < 4 || r >= 26) {
-#pragma unroll
-            for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
-        } else {
-            s[0] = gl_pow7(s[0]);
-        }
-        poseidon_mds(s);
     }
 }
 
@@ -503,6 +490,36 @@ extern "C" int bsx_gl_gate_eval_dev(bsx_ctx *ctx, void *stream, uint32_t gate, u
     }
     BSX_LAUNCHED(ctx);
     return BSX_OK;
+}
+
+template <int NA>
+static int launch_quotient(bsx_ctx *ctx, cudaStream_t st, uint32_t gate, uint32_t p0, uint32_t p1, const uint64_t *wires, uint32_t rows,
+                           const uint64_t *alpha_pows, uint32_t ncn, const uint64_t *zh_inv, uint32_t log_block, uint64_t *out) {
+    const unsigned grid = (rows + 127) / 128;
+    const size_t smem = sizeof(uint64_t) * NA * ncn;
+    switch (gate) {
+        case BSX_GATE_U32_ARITHMETIC: gl_gate_quotient_kernel<BSX_GATE_U32_ARITHMETIC, NA><<<grid, 128, smem, st>>>(p0, p1, wires, rows, alpha_pows, ncn, zh_inv, log_block, out); break;
+        case BSX_GATE_U32_ADD_MANY: gl_gate_quotient_kernel<BSX_GATE_U32_ADD_MANY, NA><<<grid, 128, smem, st>>>(p0, p1, wires, rows, alpha_pows, ncn, zh_inv, log_block, out); break;
+        case BSX_GATE_U32_SUBTRACTION: gl_gate_quotient_kernel<BSX_GATE_U32_SUBTRACTION, NA><<<grid, 128, smem, st>>>(p0, p1, wires, rows, alpha_pows, ncn, zh_inv, log_block, out); break;
+        case BSX_GATE_U32_COMPARISON: gl_gate_quotient_kernel<BSX_GATE_U32_COMPARISON, NA><<<grid, 128, smem, st>>>(p0, p1, wires, rows, alpha_pows, ncn, zh_inv, log_block, out); break;
+        default: gl_gate_quotient_kernel<BSX_GATE_U32_RANGE_CHECK, NA><<<grid, 128, smem, st>>>(p0, p1, wires, rows, alpha_pows, ncn, zh_inv, log_block, out); break;
+    }
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+// Quotient-style constraint evaluation over an LDE (see gl_gate_quotient_kernel).  alpha_pows: device, n_alphas x
+// num_constraints (alpha_a^c); zh_inv: device, rows >> log_block entries; out: n_alphas x rows.
+extern "C" int bsx_gl_gate_quotient_dev(bsx_ctx *ctx, void *stream, uint32_t gate, uint32_t p0, uint32_t p1, const uint64_t *wires,
+                                        uint32_t rows, const uint64_t *alpha_pows, uint32_t n_alphas, const uint64_t *zh_inv,
+                                        uint32_t log_block, uint64_t *out) {
+    BSX_REQUIRE(ctx, ctx && wires && alpha_pows && zh_inv && out && gate <= BSX_GATE_U32_RANGE_CHECK && (n_alphas == 1 || n_alphas == 2));
+    BSX_REQUIRE(ctx, log_block <= 31);
+    if (rows == 0) return BSX_OK;
+    const uint32_t ncn = bsx_gate_num_constraints(gate, p0, p1);
+    BSX_REQUIRE(ctx, ncn >= 1 && sizeof(uint64_t) * 2 * ncn <= 48 * 1024);
+    return n_alphas == 1 ? launch_quotient<1>(ctx, (cudaStream_t)stream, gate, p0, p1, wires, rows, alpha_pows, ncn, zh_inv, log_block, out)
+                         : launch_quotient<2>(ctx, (cudaStream_t)stream, gate, p0, p1, wires, rows, alpha_pows, ncn, zh_inv, log_block, out);
 }
 
 extern "C" int bsx_gl_gate_witness_dev(bsx_ctx *ctx, void *stream, uint32_t gate, uint32_t p0, uint32_t p1, uint64_t *wires,

@@ -107,12 +107,14 @@ __device__ __forceinline__ bool root_is(const uint32_t root[8], const uint8_t *e
 __device__ __forceinline__ void validator_set_cta(uint32_t N, uint32_t P, const uint8_t *pk, uint32_t pk_stride,
                                                   const uint8_t *power, uint32_t power_stride, const uint8_t *blen,
                                                   uint32_t blen_stride, uint64_t nb_enabled, uint32_t *sA, uint32_t *sB,
-                                                  uint8_t *out, uint32_t root[8]) {
+                                                  uint8_t *out, uint32_t root[8], uint32_t *s_fail, uint32_t msb_bit) {
     for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
         uint32_t d[8];
         if (i < N) {
-            validator_leaf_hash(pk + (size_t)pk_stride * i, ld_u64(power + (size_t)power_stride * i),
-                                ld_u32(blen + (size_t)blen_stride * i), d);
+            const uint64_t pw = ld_u64(power + (size_t)power_stride * i);
+            // marshal_int64_varint asserts that bit 63 of the voting power is zero (TX/builder/shared.rs:77-80)
+            if (pw >> 63) atomicOr(s_fail, msb_bit);
+            validator_leaf_hash(pk + (size_t)pk_stride * i, pw, ld_u32(blen + (size_t)blen_stride * i), d);
             store_digest_be(out + 32 * (size_t)i, d);
         } else {
 #pragma unroll
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(256) verify_kernel(VerifyArgs a) {
         out += 9 * 32;
         validator_set_cta(N, P, a.trusted_pubkeys + inst * N * 32, 32, reinterpret_cast<const uint8_t *>(a.trusted_powers + inst * N), 8,
                           reinterpret_cast<const uint8_t *>(a.trusted_byte_lengths + inst * N), 4, S->trusted_nb_enabled, sA, sB,
-                          out, root);
+                          out, root, &s_fail, BSX_VFAIL_TRUSTED_VALHASH);
         out += 32 * (size_t)(N + P - 1);
         if (tid == 0 && !root_is(root, S->trusted_validators_hash_proof + 2)) atomicOr(&s_fail, BSX_VFAIL_TRUSTED_VALHASH);
         // present_on_trusted_header => signed, and the pubkey really is in the trusted set (O(N^2), :381-415)
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(256) verify_kernel(VerifyArgs a) {
     //     high-priority stream; ed25519_flags_kernel folds their flags into fail[] after both have finished.
     // (2) validators hash (:253-267)
     validator_set_cta(N, P, vals, BSX_VAL_IN_BYTES, vals + 224, BSX_VAL_IN_BYTES, vals + 232, BSX_VAL_IN_BYTES, H->nb_enabled, sA,
-                      sB, out, root);
+                      sB, out, root, &s_fail, BSX_VFAIL_VALHASH);
     out += 32 * (size_t)(N + P - 1);
     if (tid == 0 && !root_is(root, H->validators_hash_proof + 2)) atomicOr(&s_fail, BSX_VFAIL_VALHASH);
     // (3) validators-hash proof, (6) chain id, (7) height: three independent chains, one thread each
@@ -229,6 +231,10 @@ __global__ void __launch_bounds__(256) verify_kernel(VerifyArgs a) {
         if (f) atomicOr(&s_fail, f);
     }
     out += 27 * 32;
+    // marshal_int64_varint(height) asserts bit 63 == 0 (shared.rs:77-80, called from verify_block_height :178);
+    // verify_non_negative_round asserts the round's sign bit == 0 (validator.rs:73-78, once per validator)
+    if (tid == 0 && ((H->height >> 63) || (H->round >> 63)))
+        atomicOr(&s_fail, ((H->height >> 63) ? BSX_VFAIL_HEIGHT : 0u) | ((H->round >> 63) ? BSX_VFAIL_MESSAGE : 0u));
     // (4) 2/3 threshold over `signed` (:279-288)
     if (tid == 32 && !voting_threshold(N, vals, H->nb_enabled, 2, 3, 236)) atomicOr(&s_fail, BSX_VFAIL_THRESHOLD);
     // (5) per-validator message checks (validator.rs:80-183, verify.rs:290-312)

@@ -442,6 +442,35 @@ int bsx_header_range_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t N, uin
                          const bsx_skip_batch *skip, const bsx_range_batch *range);
 
 /* ------------------------------------------------------------------------------------------
+ * Prover inner loops over Goldilocks: transforms, coset LDE, Poseidon Merkle caps, quotient, FRI fold
+ * replaces (restated, PARITY UNPINNED -- plonky2 0.2.1 is un-vendored): the inner loops of
+ *   prove_with_partition_witness (call site PX/backend/circuit/build.rs:69-75; config standard_recursion_config,
+ *   PX/frontend/builder/mod.rs:69: rate_bits 3, cap_height 4, 135 wires): PolynomialBatch::from_values (ifft + lde +
+ *   coset fft + MerkleTree::new over the transposed, index-bit-reversed values), compute_quotient_polys (gate constraints
+ *   reduced with powers of alpha, divided by Z_H on the coset), fri_committed_trees (reduce_with_powers fold).
+ * Layouts: polynomials are poly-major (element i of polynomial p at base[p * stride + i]); transforms take natural order
+ * and produce BIT-REVERSED order (position i holds the value at w^bitrev(i)) -- the order the Merkle leaves are hashed in,
+ * so leaf i = position i.  An extension of rate 2^r: position i of the 2^(log_n+r) outputs holds the value at
+ * shift * w_N^bitrev(i).  Digests are 4 canonical words.  All pointers are device pointers.
+ * ------------------------------------------------------------------------------------------ */
+uint64_t bsx_gl_root_of_unity(uint32_t log_n);   /* primitive 2^log_n-th root: POWER_OF_TWO_GENERATOR^(2^(32-log_n)) */
+uint64_t bsx_gl_coset_shift(void);               /* MULTIPLICATIVE_GROUP_GENERATOR */
+int bsx_gl_ntt_dev(bsx_ctx *ctx, void *stream, const uint64_t *in, uint64_t *out, uint32_t log_n, uint32_t n_polys,
+                   size_t in_stride, size_t out_stride, int inverse, int natural_out, uint64_t *scratch);
+int bsx_gl_lde_dev(bsx_ctx *ctx, void *stream, const uint64_t *coeffs, uint64_t *out, uint32_t log_n, uint32_t rate_bits,
+                   uint32_t n_polys, size_t in_stride, size_t out_stride, uint64_t shift);
+size_t bsx_gl_merkle_digest_words(uint32_t n_leaves, uint32_t cap_height);
+int bsx_gl_merkle_caps_dev(bsx_ctx *ctx, void *stream, const uint64_t *data, size_t poly_stride, uint32_t width,
+                           uint32_t n_leaves, uint32_t cap_height, uint64_t *digests);
+int bsx_gl_quotient_tables_dev(bsx_ctx *ctx, void *stream, const uint64_t *alphas, uint32_t n_alphas, uint32_t n_constraints,
+                               uint32_t log_n, uint32_t rate_bits, uint64_t shift, uint64_t *alpha_pows, uint64_t *zh_inv);
+int bsx_gl_gate_quotient_dev(bsx_ctx *ctx, void *stream, uint32_t gate, uint32_t p0, uint32_t p1, const uint64_t *wires,
+                             uint32_t rows, const uint64_t *alpha_pows, uint32_t n_alphas, const uint64_t *zh_inv,
+                             uint32_t log_block, uint64_t *out);
+int bsx_gl_fri_fold_dev(bsx_ctx *ctx, void *stream, const uint64_t *in, uint32_t n_in, uint32_t arity_bits, uint64_t beta0,
+                        uint64_t beta1, uint64_t *out);
+
+/* ------------------------------------------------------------------------------------------
  * Input shaping on the device
  * The 14-leaf Tendermint tree of every header of a range and the inclusion proofs the map circuits consume.
  * Replaces the per-header host work of generate_proofs_from_header / compute_hash_from_aunts
@@ -566,6 +595,21 @@ int bsx_present_on_trusted_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t 
  * Field-element encodings: ByteVariable = 8 big-endian bit elements (PX/frontend/vars/byte.rs:49-66);
  *   SHA-256 digest = 8 big-endian u32 words, one element each (PX/frontend/hash/sha/sha256/curta.rs:81-92).
  * ------------------------------------------------------------------------------------------ */
+/* SHA-256 execution trace: the per-round table a STARK over the SHA-256 accelerator commits to, one
+ * polynomial per column (column c, row r at trace[c * 2^log_rows + r]), 64 rows per padded chunk, from the
+ * padded_chunks / end_bits / digest_bits of bsx_hash_input_data (sha512 = 0).
+ * replaces: the row-by-row fill of HashStark::prove (PX/frontend/hash/curta/stark.rs:107-133, TraceWriter::
+ *   write_row_instructions).  The reference's column assignment is starkyx's (un-vendored): this layout is our own and
+ *   PARITY IS UNPINNED; tests pin it by recomputing every digest from the trace columns.
+ * Columns (32-bit words as 4 little-endian byte limbs, one field element per byte; t = row within the chunk):
+ *   0 w_t | 4..35 a b c d e f g h entering round t | 36 rotr6(e) 40 rotr11(e) 44 rotr25(e) 48 Sigma1 | 52 e&f 56 ~e&g 60 ch
+ *   64 rotr2(a) 68 rotr13(a) 72 rotr22(a) 76 Sigma0 | 80 a&b 84 a&c 88 b&c 92 maj | 96 temp1 (100 carry) | 101 temp2 (105 carry)
+ *   106 a' (110 carry) | 111 e' (115 carry) | schedule step for w_{t+16}, t < 48: 116 w_{t+1} 120 rotr7 124 rotr18 128 shr3
+ *   132 sigma0 | 136 w_{t+14} 140 rotr17 144 rotr19 148 shr10 152 sigma1 | 156 w_{t+9} 160 w_{t+16} (164 carry)
+ *   165 first row of chunk 166 last row 167 end_bit 168 digest_bit | 169..174 bits of t | 175 K_t */
+#define BSX_SHA256_TRACE_COLS 176
+int bsx_sha256_trace_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chunks, const uint8_t *end_bits,
+                         const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace);
 uint32_t bsx_hash_input_chunks(int sha512, uint32_t buf_len, int variable);
 int bsx_hash_input_data(bsx_ctx *ctx, int sha512, uint32_t n_req, const uint8_t *bufs, const uint32_t *buf_offsets,
                         const uint32_t *lens, const uint8_t *kinds, void *padded_chunks, uint8_t *end_bits,

@@ -242,6 +242,19 @@ void orc_poseidon_hash_no_pad(const uint64_t *in, uint32_t n, uint64_t out[4]);
 void orc_poseidon_batch(const uint64_t *in, const uint32_t *offsets, uint32_t n, uint64_t *out, int threads);
 const uint64_t *orc_poseidon_round_constants(void); /* 360 */
 
+/* ---- prover inner loops over Goldilocks (oracle/plonk.c; plonky2 0.2.1 un-vendored: PARITY UNPINNED) ---- */
+uint64_t orc_gl_root_of_unity(uint32_t log_n);
+uint64_t orc_gl_coset_shift(void);
+void orc_gl_ntt(uint64_t *x, uint32_t log_n, int inverse);
+void orc_gl_lde(const uint64_t *coeffs, uint32_t log_n, uint32_t rate_bits, uint64_t shift, uint64_t *out);
+void orc_gl_merkle(const uint64_t *leaves, uint32_t width, uint32_t n_leaves, uint32_t cap_height, uint64_t *digests);
+void orc_gl_quotient_combine(const uint64_t *constraints, uint32_t n_constraints, uint32_t rows, const uint64_t *alphas,
+                             uint32_t n_alphas, const uint64_t *zh_inv, uint64_t *out);
+/* SHA-256 execution trace (oracle/trace.c): columns documented in include/bsx.h (BSX_SHA256_TRACE_COLS = 176) */
+void orc_sha256_trace(const uint32_t *chunks, const uint8_t *end_bits, const uint8_t *digest_bits, uint32_t n_chunks,
+                      uint32_t log_rows, uint64_t *trace);
+void orc_gl_fri_fold(const uint64_t *in, uint32_t n_in, uint32_t arity_bits, uint64_t beta0, uint64_t beta1, uint64_t *out);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

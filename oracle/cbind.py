@@ -484,3 +484,85 @@ def poseidon_round_constants() -> np.ndarray:
 
 def max_threads() -> int:
     return lib().orc_max_threads()
+
+
+# ---- prover inner loops over Goldilocks (oracle/plonk.c) ----
+GL_P = 2**64 - 2**32 + 1
+
+
+def gl_root_of_unity(log_n: int) -> int:
+    lib().orc_gl_root_of_unity.restype = C.c_uint64
+    return int(lib().orc_gl_root_of_unity(C.c_uint32(log_n)))
+
+
+def gl_coset_shift() -> int:
+    lib().orc_gl_coset_shift.restype = C.c_uint64
+    return int(lib().orc_gl_coset_shift())
+
+
+def gl_ntt(x, inverse: bool = False) -> np.ndarray:
+    """natural order in and out; x: [..., n] (each row transformed)"""
+    a = np.ascontiguousarray(x, np.uint64).copy()
+    n = a.shape[-1]
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    flat = a.reshape(-1, n)
+    for row in flat:
+        lib().orc_gl_ntt(_p(row), C.c_uint32(log_n), C.c_int(1 if inverse else 0))
+    return a
+
+
+def gl_lde(coeffs, rate_bits: int, shift: int = 0) -> np.ndarray:
+    """[..., n] coefficients -> [..., n * 2^rate_bits] evaluations on shift * H_N, natural order"""
+    a = np.ascontiguousarray(coeffs, np.uint64)
+    n = a.shape[-1]
+    log_n = n.bit_length() - 1
+    flat = a.reshape(-1, n)
+    out = np.zeros((flat.shape[0], n << rate_bits), np.uint64)
+    for i, row in enumerate(flat):
+        lib().orc_gl_lde(_p(np.ascontiguousarray(row)), C.c_uint32(log_n), C.c_uint32(rate_bits), C.c_uint64(shift), _p(out[i]))
+    return out.reshape(a.shape[:-1] + (n << rate_bits,))
+
+
+def gl_merkle(leaves, cap_height: int) -> np.ndarray:
+    """leaves [n_leaves, width] -> digests [sum of layer sizes, 4] (layer 0 first, the cap last)"""
+    a = np.ascontiguousarray(leaves, np.uint64)
+    n, w = a.shape
+    total, l = 0, n
+    while l >= (1 << cap_height):
+        total += l
+        if l == 1:
+            break
+        l >>= 1
+    out = np.zeros((total, 4), np.uint64)
+    lib().orc_gl_merkle(_p(a), C.c_uint32(w), C.c_uint32(n), C.c_uint32(cap_height), _p(out))
+    return out
+
+
+def gl_quotient_combine(constraints, alphas, zh_inv) -> np.ndarray:
+    c = np.ascontiguousarray(constraints, np.uint64)
+    al = np.ascontiguousarray(alphas, np.uint64)
+    z = np.ascontiguousarray(zh_inv, np.uint64)
+    out = np.zeros((len(al), c.shape[1]), np.uint64)
+    lib().orc_gl_quotient_combine(_p(c), C.c_uint32(c.shape[0]), C.c_uint32(c.shape[1]), _p(al), C.c_uint32(len(al)), _p(z), _p(out))
+    return out
+
+
+def gl_fri_fold(pairs, arity_bits: int, beta) -> np.ndarray:
+    a = np.ascontiguousarray(pairs, np.uint64)
+    n = a.shape[0]
+    out = np.zeros((n >> arity_bits, 2), np.uint64)
+    lib().orc_gl_fri_fold(_p(a), C.c_uint32(n), C.c_uint32(arity_bits), C.c_uint64(int(beta[0])), C.c_uint64(int(beta[1])), _p(out))
+    return out
+
+
+SHA256_TRACE_COLS = 176
+
+
+def sha256_trace(chunks, end_bits, digest_bits, log_rows: int) -> np.ndarray:
+    """padded chunks [n, 16] u32 (big-endian words) -> trace [176, 2^log_rows] u64"""
+    c = np.ascontiguousarray(chunks, np.uint32).reshape(-1, 16)
+    eb, db = np.ascontiguousarray(end_bits, np.uint8), np.ascontiguousarray(digest_bits, np.uint8)
+    out = np.zeros((SHA256_TRACE_COLS, 1 << log_rows), np.uint64)
+    lib().orc_sha256_trace(_p(c), _p(eb), _p(db), C.c_uint32(len(c)), C.c_uint32(log_rows), _p(out))
+    return out

@@ -80,6 +80,12 @@ uint32_t orc_verify_header(const orc_verify_header_in *in, uint8_t *sha256_diges
     uint8_t vh[32];
     d += 32 * (size_t)compute_validators_hash_fields(n, pks, powers, blens, in->nb_enabled, d, vh);
     if (memcmp(in->validators_hash_proof + 2, vh, 32) != 0) fail |= ORC_VFAIL_VALHASH;
+    /* marshal_int64_varint asserts bit 63 of its argument is zero (TX/builder/shared.rs:77-80): voting powers here, the
+     * height in verify_block_height (:178); verify_non_negative_round asserts the round's sign bit (validator.rs:73-78) */
+    for (uint32_t i = 0; i < n; i++)
+        if (powers[i] >> 63) fail |= ORC_VFAIL_VALHASH;
+    if (in->height >> 63) fail |= ORC_VFAIL_HEIGHT;
+    if (in->round >> 63) fail |= ORC_VFAIL_MESSAGE;
     /* (3) validators-hash inclusion proof, :269-277 ; VALIDATORS_HASH_INDEX = 7 */
     uint8_t root[32];
     orc_tm_merkle_proof(in->validators_hash_proof, 34, in->validators_hash_proof + 34, 4, 7, 0, d, root);
@@ -144,6 +150,8 @@ uint32_t orc_verify_skip(const orc_verify_skip_in *in, uint8_t *sha256_digests, 
     d += 32 * (size_t)compute_validators_hash_fields(n, in->trusted_pubkeys, in->trusted_powers,
                                                      in->trusted_byte_lengths, in->trusted_nb_enabled, d, vh);
     if (memcmp(vh, in->trusted_validators_hash_proof + 2, 32) != 0) fail |= ORC_VFAIL_TRUSTED_VALHASH;
+    for (uint32_t i = 0; i < n; i++)
+        if (in->trusted_powers[i] >> 63) fail |= ORC_VFAIL_TRUSTED_VALHASH; /* marshal_int64_varint, shared.rs:77-80 */
     /* present_on_trusted_header => signed ; and really present (O(N^2) pubkey match) */
     uint8_t *present = (uint8_t *)malloc(n);
     for (uint32_t i = 0; i < n; i++) {

@@ -1,0 +1,185 @@
+"""GPU parity for the prover inner loops (k_plonk.cu, gl_gate_quotient_kernel) against the CPU restatement
+(oracle/plonk.c, natural index order): transforms of every pass plan (1, 2 and 3 passes over HBM), coset extension,
+Poseidon Merkle caps, quotient over the extension, FRI fold -- and the chain trace -> coefficients -> extension ->
+{Merkle cap, quotient} run end to end on the device with a VALID trace, whose quotient must be a polynomial of degree < 3n."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+P = 2**64 - 2**32 + 1
+
+
+@pytest.fixture(scope="module")
+def pv():
+    import torch
+    from blobstreamx_b200 import lib
+    from blobstreamx_b200.plonk import Prover
+    ctx = lib.Context(0)
+    yield Prover(ctx, torch.device("cuda", 0))
+    ctx.close()
+
+
+def _dev(pv, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(pv.dev)
+
+
+def _host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("log_n,n_polys", [(1, 3), (5, 2), (10, 3), (11, 5), (12, 2), (16, 3), (20, 2), (21, 1)])
+def test_ntt_forward_inverse(pv, log_n, n_polys):
+    from blobstreamx_b200.plonk import bitrev_indices
+    from oracle import cbind as orc
+    rng = np.random.default_rng(log_n)
+    x = rng.integers(0, 2**64, (n_polys, 1 << log_n), dtype=np.uint64)          # any 64-bit representative
+    xc = (x.astype(object) % P).astype(np.uint64)
+    got = _host(pv.ntt(_dev(pv, x)))
+    assert (got < P).all()
+    perm = bitrev_indices(log_n)
+    if log_n <= 16:
+        want = orc.gl_ntt(xc)
+        assert (got == want[:, perm]).all()
+        assert (_host(pv.ntt(_dev(pv, x), natural_out=True)) == want).all()
+    # inverse of the forward transform (fed back in natural order) is the identity, at every size
+    nat = np.empty_like(got)
+    nat[:, perm] = got
+    back = _host(pv.ntt(_dev(pv, nat), inverse=True, natural_out=True))
+    assert (back == xc).all()
+
+
+@pytest.mark.parametrize("log_n,rate_bits,n_polys", [(3, 3, 2), (10, 3, 3), (12, 1, 2), (13, 3, 4), (16, 3, 2)])
+def test_lde_matches_oracle(pv, log_n, rate_bits, n_polys):
+    from blobstreamx_b200.plonk import bitrev_indices
+    from oracle import cbind as orc
+    rng = np.random.default_rng(100 + log_n)
+    c = rng.integers(0, P, (n_polys, 1 << log_n), dtype=np.uint64)
+    got = _host(pv.lde(_dev(pv, c), rate_bits))
+    want = orc.gl_lde(c, rate_bits)
+    assert (got == want[:, bitrev_indices(log_n + rate_bits)]).all()
+    # an explicit shift: the extension on another coset
+    got2 = _host(pv.lde(_dev(pv, c[:1]), rate_bits, shift=7))
+    assert (got2 == orc.gl_lde(c[:1], rate_bits, shift=7)[:, bitrev_indices(log_n + rate_bits)]).all()
+
+
+def test_lde_large_is_evaluation_at_sampled_points(pv):
+    """2^20 coefficients, rate 8 (the standard_recursion_config shape): sampled positions against Horner evaluation."""
+    from blobstreamx_b200.plonk import bitrev_indices
+    rng = np.random.default_rng(5)
+    log_n, r = 20, 3
+    c = rng.integers(0, P, (1, 1 << log_n), dtype=np.uint64)
+    got = _host(pv.lde(_dev(pv, c), r))[0]
+    g, wN = pv.coset_shift(), pv.root_of_unity(log_n + r)
+    coeffs = [int(v) for v in c[0][::-1]]
+    perm = bitrev_indices(log_n + r)
+    for pos in (0, 1, 12345, (1 << 20) + 7, (1 << 23) - 1):
+        x = g * pow(wN, int(perm[pos]), P) % P
+        acc = 0
+        for cj in coeffs:
+            acc = (acc * x + cj) % P
+        assert int(got[pos]) == acc, pos
+
+
+@pytest.mark.parametrize("width,n_leaves,cap", [(3, 8, 1), (4, 16, 0), (11, 64, 2), (135, 256, 4), (135, 32, 5), (9, 1, 0)])
+def test_merkle_caps(pv, width, n_leaves, cap):
+    from oracle import cbind as orc
+    rng = np.random.default_rng(width)
+    data = rng.integers(0, 2**64, (width, n_leaves), dtype=np.uint64)
+    d, capd = pv.merkle_caps(_dev(pv, data), cap)
+    want = orc.gl_merkle(np.ascontiguousarray((data.astype(object) % P).astype(np.uint64).T), cap)
+    assert (_host(d) == want).all()
+    assert (_host(capd) == want[-(1 << cap):]).all()
+
+
+@pytest.mark.parametrize("gate,p0,p1", [(0, 3, 0), (1, 2, 5), (2, 6, 0), (3, 32, 16), (4, 7, 0)])
+def test_gate_quotient_matches_oracle(pv, gate, p0, p1):
+    from oracle import cbind as orc
+    rng = np.random.default_rng(gate)
+    log_n, r = 6, 3
+    rows = 1 << (log_n + r)
+    nw, ncn = orc.gate_num_wires(gate, p0, p1), orc.gate_num_constraints(gate, p0, p1)
+    w = rng.integers(0, P, (nw, rows), dtype=np.uint64)
+    alphas = [int(v) for v in rng.integers(0, P, 2, dtype=np.uint64)]
+    for na in (1, 2):
+        ap, zh = pv.quotient_tables(alphas[:na], ncn, log_n, r)
+        zhh = _host(zh)
+        got = _host(pv.gate_quotient(gate, p0, p1, _dev(pv, w), ap, na, zh, log_n))
+        want = orc.gl_quotient_combine(orc.gate_eval(gate, p0, p1, w), alphas[:na], np.repeat(zhh, 1 << log_n))
+        assert (got == want).all()
+    # the table: 1 / (x^n - 1) on block rev(q) of the coset
+    g, wN = pv.coset_shift(), pv.root_of_unity(log_n + r)
+    for q in range(1 << r):
+        rq = int(f"{q:0{r}b}"[::-1], 2)
+        xn = pow(g * pow(wN, q, P) % P, 1 << log_n, P)
+        assert int(zhh[rq]) * ((xn - 1) % P) % P == 1
+
+
+@pytest.mark.parametrize("arity_bits", [1, 3, 4])
+def test_fri_fold(pv, arity_bits):
+    from oracle import cbind as orc
+    rng = np.random.default_rng(arity_bits)
+    f = rng.integers(0, 2**64, (1 << 12, 2), dtype=np.uint64)
+    beta = [int(v) for v in rng.integers(0, P, 2, dtype=np.uint64)]
+    got = _host(pv.fri_fold(_dev(pv, f), arity_bits, beta))
+    assert (got == orc.gl_fri_fold(f, arity_bits, beta)).all()
+
+
+def test_trace_to_quotient_chain_on_device(pv):
+    """A VALID U32Arithmetic trace (n = 2^10 rows, 114 wires) stays on the device: iNTT -> coset LDE (rate 8) -> Merkle cap
+    of the extension + quotient.  Every constraint vanishes on the subgroup, so the alpha-combination is divisible by Z_H:
+    the quotient (degree-4 constraints) must interpolate to a polynomial of degree < 3n -- its upper coefficients are zero.
+    A corrupted trace must not pass that test."""
+    import torch
+    from blobstreamx_b200.plonk import bitrev_indices
+    from oracle import cbind as orc
+    rng = np.random.default_rng(21)
+    log_n, r, gate, p0 = 10, 3, 0, 3
+    n, N = 1 << log_n, 1 << (log_n + r)
+    nw, ncn = orc.gate_num_wires(gate, p0, 0), orc.gate_num_constraints(gate, p0, 0)
+    w = np.zeros((nw, n), np.uint64)
+    for i in range(p0):
+        w[6 * i:6 * i + 3] = rng.integers(0, 2**32, (3, n), dtype=np.uint64)
+    w = orc.gate_witness(gate, p0, 0, w)
+    assert not orc.gate_eval(gate, p0, 0, w).any()
+    ap, zh = pv.quotient_tables([0x1234567, 0xABCDEF01], ncn, log_n, r)
+    perm = bitrev_indices(log_n + r)
+    g = pv.coset_shift()
+
+    def chain(trace):
+        coeffs = pv.ntt(_dev(pv, trace), inverse=True, natural_out=True)
+        ext = pv.lde(coeffs, r)
+        _, cap = pv.merkle_caps(ext, 4)
+        q = pv.gate_quotient(gate, p0, 0, ext, ap, 2, zh, log_n)
+        # back to coefficients: the buffer is bit-reversed, so un-permute, inverse transform, undo the coset shift
+        qn = torch.empty_like(q)
+        qn[:, torch.from_numpy(perm).to(pv.dev)] = q
+        qc = _host(pv.ntt(qn, inverse=True, natural_out=True))
+        return _host(ext), _host(cap), qc
+
+    ext, cap, qc = chain(w)
+    assert (ext == orc.gl_lde(orc.gl_ntt(w, inverse=True), r)[:, perm]).all()
+    assert (cap == orc.gl_merkle(np.ascontiguousarray(ext.T), 4)[-16:]).all()
+    assert not qc[:, 3 * n:].any() and qc[:, :3 * n].any()          # degree < 3n (coset scaling g^-j does not move zeros)
+    bad = w.copy()
+    bad[3, 17] ^= 1
+    _, cap2, qc2 = chain(bad)
+    assert qc2[:, 3 * n:].any() and (cap2 != cap).any()
+
+
+@pytest.mark.parametrize("n_req", [1, 7, 400])
+def test_sha256_trace_matches_oracle(pv, n_req):
+    """SHA-256 execution trace on the device == the CPU restatement, whose columns tests/test_oracle_trace.py
+    pins by recomputing every digest: fixed, variable and multi-chunk requests, padding rows zero."""
+    import torch
+    from oracle import cbind as orc
+    from tests.test_oracle_trace import _requests
+    rng = np.random.default_rng(n_req)
+    bufs, offs, lens, kinds, _ = _requests(rng, n_req)
+    hid = pv.ctx.hash_input_data(np.frombuffer(bufs, np.uint8), offs, lens, kinds)
+    n = len(hid["padded_chunks"])
+    log_rows = max(7, int(np.ceil(np.log2(64 * n))) + (1 if n_req == 7 else 0))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(pv.dev)
+    got = pv.sha256_trace(dev(hid["padded_chunks"].view(np.int32)), dev(hid["end_bits"]), dev(hid["digest_bits"]), log_rows)
+    want = orc.sha256_trace(hid["padded_chunks"], hid["end_bits"], hid["digest_bits"], log_rows)
+    assert (_host(got) == want).all()

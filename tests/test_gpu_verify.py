@@ -159,3 +159,26 @@ def test_header_range_chunked_pipeline(ctx, orc):
     for r in (0, 5, 12):
         ws = orc.verify_skip(skips[r], threads=8)
         assert (got["skip"]["sha256_digests"][r] == ws["sha256_digests"]).all() and (got["skip"]["ed"][r] == ws["ed"]).all()
+
+
+def test_sign_bit_assertions(ctx, orc):
+    """marshal_int64_varint asserts bit 63 of its argument is zero (TX/builder/shared.rs:77-80: voting powers, the height)
+    and verify_non_negative_round asserts the round's sign bit (TX/builder/validator.rs:73-78): a power, height or round
+    >= 2^63 must be flagged (circuit witness generation would abort), the same in the kernel and in the oracle."""
+    from blobstreamx_b200 import synthetic as S
+    vs = S.ValidatorSet.make()
+    _, skip, _ = S.header_range_inputs(2, 4, valset=vs)
+    cases, bits = [], []
+    for what in range(4):
+        kk = copy.deepcopy(skip)
+        t = kk["target"]
+        if what == 0: t["validators"][11, 231] |= 0x80; bits.append(2)            # target voting power, bit 63
+        if what == 1: kk["trusted_powers"][4] |= np.uint64(1 << 63); bits.append(256)
+        if what == 2: t["height"] = int(t["height"]) | (1 << 63); bits.append(64)
+        if what == 3: t["round"] = 1 << 63; bits.append(16)
+        cases.append(kk)
+    got = ctx.verify_skip(cases)
+    for i, kk in enumerate(cases):
+        want = orc.verify_skip(kk, threads=8)
+        _same(got, want, i)
+        assert want["fail"] & bits[i], (i, want["fail"])
