@@ -80,10 +80,10 @@ __global__ void __launch_bounds__(256) ntt_dif_strided_kernel(NttArgs a) {
     }
     __syncthreads();
     for (int b = (int)a.hi - 1; b >= (int)a.lo; b--) {
-        const uint32_t half = 1u << (b - a.lo), sh = a.L - 1 - b;
+        const uint32_t hb = b - a.lo, half = 1u << hb, sh = a.L - 1 - b;
         for (uint32_t k = threadIdx.x; k < (rows / 2) * C; k += blockDim.x) {
             const uint32_t c = k % C, pr = k / C;
-            const uint32_t t0 = ((pr / half) * 2 * half) + (pr % half), t1 = t0 + half;
+            const uint32_t t0 = ((pr >> hb) << (hb + 1)) | (pr & (half - 1)), t1 = t0 + half;
             const uint64_t x = sm[t0 * C + c], y = sm[t1 * C + c];
             const uint32_t imod = ((t0 & (half - 1)) << a.lo) | (u_lo * C + c);      // i mod 2^b
             sm[t0 * C + c] = add(x, y);
@@ -315,17 +315,27 @@ extern "C" int bsx_gl_ntt_dev(bsx_ctx *ctx, void *stream, const uint64_t *in, ui
     const uint64_t *tw = nullptr;
     int rc = get_twiddles(ctx, st, log_n, inverse, &tw);
     if (rc) return rc;
-    NttArgs a{};
-    a.src = in; a.dst = natural_out ? scratch : out;
-    a.src_poly_stride = in_stride; a.dst_poly_stride = natural_out ? ((size_t)1 << log_n) : out_stride;
-    a.tw = tw; a.L = log_n;
-    a.final_scale = inverse ? h_inv((uint64_t)1 << log_n) : 0;
-    rc = run_dif(ctx, st, a, n_polys, 1);
-    if (rc) return rc;
-    if (natural_out) {
-        const uint32_t gx = log_n >= 10 ? 1u << (log_n - 10) : 1;
-        gl_bitrev_kernel<<<dim3(gx, n_polys), 256, 0, st>>>(scratch, out, log_n, (size_t)1 << log_n, out_stride);
-        BSX_LAUNCHED(ctx);
+    // Polynomials are processed in groups whose working set (~48 MB) fits the 126 MB L2: the passes of one group run back
+    // to back, so what a pass writes is still in L2 when the next pass (and the index permutation) reads it -- HBM then sees
+    // each element about once in and once out instead of once per pass.
+    const size_t n = (size_t)1 << log_n;
+    uint32_t group = (uint32_t)(((size_t)48 << 20) / (n * sizeof(uint64_t)));
+    if (group < 1) group = 1;
+    for (uint32_t p0 = 0; p0 < n_polys; p0 += group) {
+        const uint32_t g = n_polys - p0 < group ? n_polys - p0 : group;
+        NttArgs a{};
+        a.src = in + (size_t)p0 * in_stride;
+        a.dst = natural_out ? scratch + (size_t)p0 * n : out + (size_t)p0 * out_stride;
+        a.src_poly_stride = in_stride; a.dst_poly_stride = natural_out ? n : out_stride;
+        a.tw = tw; a.L = log_n;
+        a.final_scale = inverse ? h_inv((uint64_t)1 << log_n) : 0;
+        rc = run_dif(ctx, st, a, g, 1);
+        if (rc) return rc;
+        if (natural_out) {
+            const uint32_t gx = log_n >= 10 ? 1u << (log_n - 10) : 1;
+            gl_bitrev_kernel<<<dim3(gx, g), 256, 0, st>>>(scratch + (size_t)p0 * n, out + (size_t)p0 * out_stride, log_n, n, out_stride);
+            BSX_LAUNCHED(ctx);
+        }
     }
     return BSX_OK;
 }
@@ -355,11 +365,17 @@ extern "C" int bsx_gl_lde_dev(bsx_ctx *ctx, void *stream, const uint64_t *coeffs
         gl_powers_kernel<<<4, 256, 0, st>>>(sq, 1, 1024, t_lo + (size_t)q * 1024);
         ctx->launches += 2;
     }
-    NttArgs a{};
-    a.src = coeffs; a.dst = out; a.src_poly_stride = in_stride; a.dst_poly_stride = out_stride;
-    a.src_block_stride = 0; a.dst_block_stride = n; a.block_perm_bits = rate_bits;
-    a.tw = tw; a.L = log_n; a.scale_hi = t_hi; a.scale_lo = t_lo; a.scale_hi_stride = n_hi;
-    rc = run_dif(ctx, st, a, n_polys, Q);
+    // groups of polynomials whose extension (~48 MB) fits L2, both passes of a group back to back (see bsx_gl_ntt_dev)
+    uint32_t group = (uint32_t)(((size_t)48 << 20) / (N * sizeof(uint64_t)));
+    if (group < 1) group = 1;
+    for (uint32_t p0 = 0; p0 < n_polys && rc == BSX_OK; p0 += group) {
+        NttArgs a{};
+        a.src = coeffs + (size_t)p0 * in_stride; a.dst = out + (size_t)p0 * out_stride;
+        a.src_poly_stride = in_stride; a.dst_poly_stride = out_stride;
+        a.src_block_stride = 0; a.dst_block_stride = n; a.block_perm_bits = rate_bits;
+        a.tw = tw; a.L = log_n; a.scale_hi = t_hi; a.scale_lo = t_lo; a.scale_hi_stride = n_hi;
+        rc = run_dif(ctx, st, a, n_polys - p0 < group ? n_polys - p0 : group, Q);
+    }
     const cudaError_t ef = cudaFreeAsync(tabs, st);
     if (rc) return rc;
     if (ef != cudaSuccess) return bsx::fail(ctx, BSX_ERR_CUDA, "cudaFreeAsync: %s%s", cudaGetErrorString(ef));

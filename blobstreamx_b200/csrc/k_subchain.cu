@@ -383,11 +383,10 @@ __global__ void __launch_bounds__(128, MIN_CTAS) subchain_proofs_kernel(Subchain
 template <int B, int G>
 __global__ void __launch_bounds__(B * G < 32 ? 32 : B * G) subchain_commit_kernel(SubchainArgs a, uint32_t n_jobs) {
     constexpr int T = B * G;
-    __shared__ __align__(16) uint32_t s_dh_root[8 * T];
-    __shared__ __align__(16) uint32_t s_lb_root[8 * T];
-    __shared__ __align__(16) uint32_t s_A[8 * T];
-    __shared__ __align__(16) uint32_t s_Bf[4 * T + 8];
-    __shared__ uint32_t s_fail[G];
+    // 112 bytes of shared memory per thread (dynamic: the wide variants exceed the 48 KB static limit)
+    extern __shared__ __align__(16) uint32_t s_commit[];
+    uint32_t *s_dh_root = s_commit, *s_lb_root = s_dh_root + 8 * T, *s_A = s_lb_root + 8 * T, *s_Bf = s_A + 8 * T;
+    uint32_t *s_fail = s_Bf + 4 * T + 8;
     const uint32_t tid = threadIdx.x, g = tid / B, i = tid % B;
     const size_t job = (size_t)blockIdx.x * G + g;
     const bool live = tid < T && job < n_jobs;
@@ -538,6 +537,22 @@ __global__ void __launch_bounds__(B * G < 32 ? 32 : B * G) subchain_commit_kerne
     subchain_signal(a, tid < G);
 }
 
+template <int B, int G>
+static int launch_commit(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const SubchainArgs &a) {
+    constexpr int T = B * G < 32 ? 32 : B * G;
+    constexpr size_t smem = sizeof(uint32_t) * (28 * (B * G) + 8 + G);
+    auto k = subchain_commit_kernel<B, G>;
+    if (smem > 48 * 1024) {
+        static const cudaError_t once = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (once != cudaSuccess) return bsx::fail(ctx, BSX_ERR_CUDA, "cudaFuncSetAttribute(commit kernel): %s%s", cudaGetErrorString(once));
+    } else {
+        BSX_PIN_CARVEOUT(k);
+    }
+    k<<<(n_jobs + G - 1) / G, T, smem, st>>>(a, n_jobs);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
 template <int B>
 static int launch_subchain_split(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs, const SubchainArgs &a) {
     const size_t total = (size_t)n_jobs * 2 * B;
@@ -546,12 +561,16 @@ static int launch_subchain_split(bsx_ctx *ctx, cudaStream_t st, uint32_t n_jobs,
     if (occ >= 8) subchain_proofs_kernel<8><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, B, n_jobs);   // 64 registers
     else subchain_proofs_kernel<6><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, B, n_jobs);             // 80 registers
     BSX_LAUNCHED(ctx);
-    constexpr int G = B >= 128 ? 1 : 128 / B;
-    constexpr int T = B * G < 32 ? 32 : B * G;
-    BSX_PIN_CARVEOUT((subchain_commit_kernel<B, G>));
-    subchain_commit_kernel<B, G><<<(n_jobs + G - 1) / G, T, 0, st>>>(a, n_jobs);
-    BSX_LAUNCHED(ctx);
-    return BSX_OK;
+    // COMMIT_THREADS (tunable): threads per CTA of the commit kernel = jobs per CTA x B.  The tree levels run at T/2, T/4, ...
+    // active threads, so a wider CTA keeps more of them whole warps (B = 32: 128 threads -> levels of 64 .. 4 threads,
+    // three of five below a warp; 1024 threads -> 512 .. 32, all whole warps) at the price of fewer, fatter barriers.
+    const int want = ctx->tun[BSX_TUN_COMMIT_THREADS];
+    if ((B == 32 || B == 64) && want >= 256) {
+        if (want >= 1024) return launch_commit<B, 1024 / B>(ctx, st, n_jobs, a);
+        if (want >= 512) return launch_commit<B, 512 / B>(ctx, st, n_jobs, a);
+        return launch_commit<B, 256 / B>(ctx, st, n_jobs, a);
+    }
+    return launch_commit<B, (B >= 128 ? 1 : 128 / B)>(ctx, st, n_jobs, a);
 }
 
 template <int B>

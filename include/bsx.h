@@ -53,7 +53,8 @@ uint64_t bsx_launch_count(const bsx_ctx *ctx);
 int bsx_sync(bsx_ctx *ctx);
 /* Measurement knobs of one ctx (kernel-build and stream-arrangement choices; defaults = the measured best; the
  * environment variable BSX_<name> sets the default a new ctx starts with).  Names: ED_MODE, ED_QUAD_MAX, ED_INLINE,
- * ED_OCC, ED_REGS, ED_FP64, HR_HASH_STREAM, HR_TRACE, PIPE_CHUNK, PIPE_ED, PIPE_TRACE, PROOFS_OCC, SUBCHAIN_FUSED
+ * ED_OCC, ED_REGS, ED_FP64, HR_HASH_STREAM, HR_TRACE, PIPE_CHUNK, PIPE_ED, PIPE_TRACE, PROOFS_OCC, SUBCHAIN_FUSED,
+ * COMMIT_THREADS
  * (DESIGN.md section 4).  No reference counterpart: results are identical under every setting. */
 int bsx_set_tunable(bsx_ctx *ctx, const char *name, int value);
 int bsx_get_tunable(const bsx_ctx *ctx, const char *name, int *value);
