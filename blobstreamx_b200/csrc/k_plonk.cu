@@ -432,10 +432,10 @@ extern "C" int bsx_gl_quotient_tables_dev(bsx_ctx *ctx, void *stream, const uint
     const uint64_t wN = h_root(log_n + rate_bits);
     for (uint32_t q = 0; q < Q; q++) {
         const uint64_t x_n = h_pow(h_mul(shift, h_pow(wN, q)), (uint64_t)1 << log_n);
-        BSX_REQUIRE(ctx, x_n != 1);     // the coset must not meet the subgroup
+        BSX_REQUIRE(ctx, x_n > 1);      // the coset must not meet the subgroup
         uint32_t r = 0;
         for (uint32_t b = 0; b < rate_bits; b++) r |= ((q >> b) & 1) << (rate_bits - 1 - b);
-        z.v[r] = h_inv((x_n + GLP - 1) % GLP);
+        z.v[r] = h_inv(x_n - 1);     // x_n is canonical and != 0, 1
     }
     gl_store_small_kernel<<<1, 64, 0, st>>>(z, Q, zh_inv);
     BSX_LAUNCHED(ctx);

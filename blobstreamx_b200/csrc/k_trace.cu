@@ -15,6 +15,7 @@
 // then lane l expands rows l and l + 32, so that for every column a warp stores 32 consecutive rows (256 bytes).
 #include "common.cuh"
 #include "sha256.cuh"
+#include "sha512.cuh"
 
 namespace bsx {
 
@@ -136,6 +137,111 @@ __global__ void __launch_bounds__(128) sha256_trace_kernel(const uint32_t *__res
     }
 }
 
+// ---- SHA-512 (the EdDSA accelerator: SHA512(R ‖ A ‖ M), PX/frontend/hash/sha/sha512/curta.rs): 80 rows per 128-byte chunk,
+// 64-bit words as 8 little-endian byte limbs; same construction as above ----
+struct TraceRow64 {
+    uint64_t *base;
+    size_t stride;
+    __device__ __forceinline__ void byte8(int col, uint64_t v) const {
+#pragma unroll
+        for (int k = 0; k < 8; k++) __stcs(base + (size_t)(col + k) * stride, (v >> (8 * k)) & 0xff);
+    }
+    __device__ __forceinline__ void put(int col, uint64_t v) const { __stcs(base + (size_t)col * stride, v); }
+};
+
+__device__ __forceinline__ void tr512_round(uint64_t s[8], uint64_t w, uint64_t k) {
+    const uint64_t S1 = rotr64(s[4], 14) ^ rotr64(s[4], 18) ^ rotr64(s[4], 41), ch = (s[4] & s[5]) ^ (~s[4] & s[6]);
+    const uint64_t t1 = s[7] + S1 + ch + k + w;
+    const uint64_t S0 = rotr64(s[0], 28) ^ rotr64(s[0], 34) ^ rotr64(s[0], 39), mj = (s[0] & s[1]) ^ (s[0] & s[2]) ^ (s[1] & s[2]);
+    const uint64_t t2 = S0 + mj;
+    s[7] = s[6]; s[6] = s[5]; s[5] = s[4]; s[4] = s[3] + t1; s[3] = s[2]; s[2] = s[1]; s[1] = s[0]; s[0] = t1 + t2;
+}
+
+__device__ __forceinline__ void tr512_expand_row(const TraceRow64 &o, int t, const uint64_t *W, const uint64_t *st, bool end_bit, bool digest_bit) {
+    typedef unsigned __int128 u128;
+    const uint64_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7], w = W[t];
+    o.byte8(0, w);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o.byte8(8 + 8 * k, st[k]);
+    const uint64_t r14 = rotr64(e, 14), r18 = rotr64(e, 18), r41 = rotr64(e, 41), S1 = r14 ^ r18 ^ r41;
+    o.byte8(72, r14); o.byte8(80, r18); o.byte8(88, r41); o.byte8(96, S1);
+    const uint64_t ef = e & f, neg = ~e & g, ch = ef ^ neg;
+    o.byte8(104, ef); o.byte8(112, neg); o.byte8(120, ch);
+    const uint64_t r28 = rotr64(a, 28), r34 = rotr64(a, 34), r39 = rotr64(a, 39), S0 = r28 ^ r34 ^ r39;
+    o.byte8(128, r28); o.byte8(136, r34); o.byte8(144, r39); o.byte8(152, S0);
+    const uint64_t ab = a & b, ac = a & c, bc = b & c, mj = ab ^ ac ^ bc;
+    o.byte8(160, ab); o.byte8(168, ac); o.byte8(176, bc); o.byte8(184, mj);
+    const u128 t1w = (u128)h + S1 + ch + K512[t] + w;
+    const uint64_t t1 = (uint64_t)t1w;
+    o.byte8(192, t1); o.put(200, (uint64_t)(t1w >> 64));
+    const u128 t2w = (u128)S0 + mj;
+    const uint64_t t2 = (uint64_t)t2w;
+    o.byte8(201, t2); o.put(209, (uint64_t)(t2w >> 64));
+    const u128 aw = (u128)t1 + t2, ew = (u128)d + t1;
+    o.byte8(210, (uint64_t)aw); o.put(218, (uint64_t)(aw >> 64));
+    o.byte8(219, (uint64_t)ew); o.put(227, (uint64_t)(ew >> 64));
+    if (t < 64) {
+        const uint64_t w1 = W[t + 1], w14 = W[t + 14], w9 = W[t + 9];
+        const uint64_t q1 = rotr64(w1, 1), q8 = rotr64(w1, 8), q7 = w1 >> 7, s0 = q1 ^ q8 ^ q7;
+        const uint64_t q19 = rotr64(w14, 19), q61 = rotr64(w14, 61), q6 = w14 >> 6, s1 = q19 ^ q61 ^ q6;
+        o.byte8(228, w1); o.byte8(236, q1); o.byte8(244, q8); o.byte8(252, q7); o.byte8(260, s0);
+        o.byte8(268, w14); o.byte8(276, q19); o.byte8(284, q61); o.byte8(292, q6); o.byte8(300, s1);
+        const u128 ww = (u128)s1 + w9 + s0 + w;
+        o.byte8(308, w9); o.byte8(316, (uint64_t)ww); o.put(324, (uint64_t)(ww >> 64));
+    } else {
+#pragma unroll 1
+        for (int col = 228; col <= 324; col++) o.put(col, 0);
+    }
+    o.put(325, t == 0); o.put(326, t == 79); o.put(327, end_bit && t == 79); o.put(328, digest_bit && t == 79);
+#pragma unroll
+    for (int k = 0; k < 7; k++) o.put(329 + k, (t >> k) & 1);
+    o.put(336, (uint32_t)K512[t]); o.put(337, K512[t] >> 32);
+}
+
+__global__ void __launch_bounds__(64) sha512_trace_kernel(const uint64_t *__restrict__ chunks, const uint8_t *__restrict__ end_bits,
+                                                          const uint8_t *__restrict__ digest_bits, uint32_t n_chunks, size_t n_rows,
+                                                          uint64_t *__restrict__ trace) {
+    __shared__ uint64_t sW[2][80], sS[2][80][8];
+    const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t blk = blockIdx.x * 2 + wid;
+    if (blk >= n_chunks) return;
+    if (lane == 0) {
+        uint32_t s0 = blk;
+        while (s0 > 0 && !end_bits[s0 - 1]) s0--;
+        uint64_t hst[8];
+        sha512_init(hst);
+        for (uint32_t q = s0; q < blk; q++) {
+            uint64_t w[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) w[k] = chunks[(size_t)q * 16 + k];
+            sha512_compress(hst, w);
+        }
+        uint64_t *W = sW[wid];
+        for (int k = 0; k < 16; k++) W[k] = chunks[(size_t)blk * 16 + k];
+        for (int t = 16; t < 80; t++) {
+            const uint64_t w1 = W[t - 15], w14 = W[t - 2];
+            W[t] = (rotr64(w14, 19) ^ rotr64(w14, 61) ^ (w14 >> 6)) + W[t - 7] + (rotr64(w1, 1) ^ rotr64(w1, 8) ^ (w1 >> 7)) + W[t - 16];
+        }
+        uint64_t s[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = hst[k];
+        for (int t = 0; t < 80; t++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) sS[wid][t][k] = s[k];
+            tr512_round(s, W[t], K512[t]);
+        }
+    }
+    __syncwarp();
+    const bool eb = end_bits[blk] != 0, db = digest_bits[blk] != 0;
+#pragma unroll 1
+    for (int part = 0; part < 3; part++) {
+        const int t = (int)lane + 32 * part;
+        if (t >= 80) break;
+        TraceRow64 o{trace + (size_t)blk * 80 + t, n_rows};
+        tr512_expand_row(o, t, sW[wid], sS[wid][t], eb, db);
+    }
+}
+
 }  // namespace bsx
 
 using namespace bsx;
@@ -153,6 +259,23 @@ extern "C" int bsx_sha256_trace_dev(bsx_ctx *ctx, void *stream, const uint32_t *
         BSX_CUDA(ctx, cudaMemset2DAsync(trace + used, n_rows * sizeof(uint64_t), 0, (n_rows - used) * sizeof(uint64_t), TR_COLS, st));
     if (n_chunks == 0) return BSX_OK;
     sha256_trace_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(padded_chunks, end_bits, digest_bits, n_chunks, n_rows, trace);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+// SHA-512 trace: BSX_SHA512_TRACE_COLS columns of 2^log_rows rows, 80 rows per 128-byte chunk (padded_chunks = u64 words,
+// bsx_hash_input_data with sha512 = 1)
+extern "C" int bsx_sha512_trace_dev(bsx_ctx *ctx, void *stream, const uint64_t *padded_chunks, const uint8_t *end_bits,
+                                    const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace) {
+    BSX_REQUIRE(ctx, ctx && padded_chunks && end_bits && digest_bits && trace && log_rows <= 30);
+    const size_t n_rows = (size_t)1 << log_rows;
+    BSX_REQUIRE(ctx, (size_t)n_chunks * 80 <= n_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t used = (size_t)n_chunks * 80;
+    if (used < n_rows)
+        BSX_CUDA(ctx, cudaMemset2DAsync(trace + used, n_rows * sizeof(uint64_t), 0, (n_rows - used) * sizeof(uint64_t), BSX_SHA512_TRACE_COLS, st));
+    if (n_chunks == 0) return BSX_OK;
+    sha512_trace_kernel<<<(n_chunks + 1) / 2, 64, 0, st>>>(padded_chunks, end_bits, digest_bits, n_chunks, n_rows, trace);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }

@@ -609,6 +609,15 @@ int bsx_present_on_trusted_dev(bsx_ctx *ctx, void *stream, uint32_t n, uint32_t 
  *   132 sigma0 | 136 w_{t+14} 140 rotr17 144 rotr19 148 shr10 152 sigma1 | 156 w_{t+9} 160 w_{t+16} (164 carry)
  *   165 first row of chunk 166 last row 167 end_bit 168 digest_bit | 169..174 bits of t | 175 K_t */
 #define BSX_SHA256_TRACE_COLS 176
+/* SHA-512 (the EdDSA accelerator): the same construction with 64-bit words as 8 byte limbs and 80 rows per 128-byte chunk.
+ *   0 w_t | 8..71 a..h | 72 rotr14(e) 80 rotr18(e) 88 rotr41(e) 96 Sigma1 | 104 e&f 112 ~e&g 120 ch | 128 rotr28(a) 136 rotr34(a)
+ *   144 rotr39(a) 152 Sigma0 | 160 a&b 168 a&c 176 b&c 184 maj | 192 temp1 (200 carry) | 201 temp2 (209) | 210 a' (218) | 219 e' (227)
+ *   schedule step for w_{t+16}, t < 64: 228 w_{t+1} 236 rotr1 244 rotr8 252 shr7 260 sigma0 | 268 w_{t+14} 276 rotr19 284 rotr61
+ *   292 shr6 300 sigma1 | 308 w_{t+9} 316 w_{t+16} (324 carry) | 325 first row 326 last row 327 end_bit 328 digest_bit
+ *   329..335 bits of t | 336, 337 K_t as two 32-bit limbs */
+#define BSX_SHA512_TRACE_COLS 338
+int bsx_sha512_trace_dev(bsx_ctx *ctx, void *stream, const uint64_t *padded_chunks, const uint8_t *end_bits,
+                         const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace);
 int bsx_sha256_trace_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chunks, const uint8_t *end_bits,
                          const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace);
 uint32_t bsx_hash_input_chunks(int sha512, uint32_t buf_len, int variable);

@@ -253,6 +253,8 @@ void orc_gl_quotient_combine(const uint64_t *constraints, uint32_t n_constraints
 /* SHA-256 execution trace (oracle/trace.c): columns documented in include/bsx.h (BSX_SHA256_TRACE_COLS = 176) */
 void orc_sha256_trace(const uint32_t *chunks, const uint8_t *end_bits, const uint8_t *digest_bits, uint32_t n_chunks,
                       uint32_t log_rows, uint64_t *trace);
+void orc_sha512_trace(const uint64_t *chunks, const uint8_t *end_bits, const uint8_t *digest_bits, uint32_t n_chunks,
+                      uint32_t log_rows, uint64_t *trace);
 void orc_gl_fri_fold(const uint64_t *in, uint32_t n_in, uint32_t arity_bits, uint64_t beta0, uint64_t beta1, uint64_t *out);
 
 int orc_max_threads(void);

@@ -566,3 +566,15 @@ def sha256_trace(chunks, end_bits, digest_bits, log_rows: int) -> np.ndarray:
     out = np.zeros((SHA256_TRACE_COLS, 1 << log_rows), np.uint64)
     lib().orc_sha256_trace(_p(c), _p(eb), _p(db), C.c_uint32(len(c)), C.c_uint32(log_rows), _p(out))
     return out
+
+
+SHA512_TRACE_COLS = 338
+
+
+def sha512_trace(chunks, end_bits, digest_bits, log_rows: int) -> np.ndarray:
+    """padded chunks [n, 16] u64 (big-endian words) -> trace [338, 2^log_rows] u64"""
+    c = np.ascontiguousarray(chunks, np.uint64).reshape(-1, 16)
+    eb, db = np.ascontiguousarray(end_bits, np.uint8), np.ascontiguousarray(digest_bits, np.uint8)
+    out = np.zeros((SHA512_TRACE_COLS, 1 << log_rows), np.uint64)
+    lib().orc_sha512_trace(_p(c), _p(eb), _p(db), C.c_uint32(len(c)), C.c_uint32(log_rows), _p(out))
+    return out

@@ -4,6 +4,7 @@ OUT=gpurun_out/r02f
 mkdir -p $OUT
 export PATH=/usr/local/cuda/bin:$PATH
 ARGS="--steps 2 --warmup 3 --no-cpu --no-check --e2e-threads 1 --no-2048"
+echo "== pytest plonk"; timeout 600 python -m pytest tests/test_gpu_plonk.py -m gpu -q 2>&1 | tail -4 | tee $OUT/pytest_plonk.log
 echo "== launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py $ARGS > $OUT/ncu_bench.log 2>&1
 grep -c "gpu__time_duration" $OUT/launches.csv

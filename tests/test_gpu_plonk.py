@@ -183,3 +183,21 @@ def test_sha256_trace_matches_oracle(pv, n_req):
     got = pv.sha256_trace(dev(hid["padded_chunks"].view(np.int32)), dev(hid["end_bits"]), dev(hid["digest_bits"]), log_rows)
     want = orc.sha256_trace(hid["padded_chunks"], hid["end_bits"], hid["digest_bits"], log_rows)
     assert (_host(got) == want).all()
+
+
+def test_sha512_trace_matches_oracle(pv):
+    """SHA-512 execution trace (the EdDSA accelerator of verify_skip: 100 requests of R ‖ A ‖ M) == the CPU restatement."""
+    import torch
+    from oracle import cbind as orc
+    rng = np.random.default_rng(51)
+    n_req = 100
+    lens = (64 + rng.integers(100, 125, n_req)).astype(np.uint32)
+    bufs = rng.integers(0, 256, 188 * n_req, dtype=np.uint8)
+    offs = (np.arange(n_req + 1) * 188).astype(np.uint32)
+    hid = pv.ctx.hash_input_data(bufs, offs, lens, np.ones(n_req, np.uint8), sha512=True)
+    n = len(hid["padded_chunks"])
+    assert n == 200
+    log_rows = int(np.ceil(np.log2(80 * n)))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(pv.dev)
+    got = pv.sha512_trace(dev(hid["padded_chunks"].view(np.int64)), dev(hid["end_bits"]), dev(hid["digest_bits"]), log_rows)
+    assert (_host(got) == orc.sha512_trace(hid["padded_chunks"], hid["end_bits"], hid["digest_bits"], log_rows)).all()
