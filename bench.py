@@ -122,18 +122,45 @@ def algorithmic_bytes_map(R, J=N_JOBS, B=BATCH):
 # clocks (nvml, sampled DURING the timed region)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int):
+    """SM clock and throttle reasons sampled DURING the timed region, by a separate `nvidia-smi` process (started early: it
+    needs ~1 s to come up; its samples are cut to the timed window by time stamps).  In-process NVML polling was the source
+    of the step-time outliers of the multi-GPU runs: the 1024 leg (sampled from a thread of every rank) showed single steps
+    of 4.6 ms (N = 8) and 16-30 ms (N = 4) in 50, the 2048 leg of the same runs (not sampled) none
+    (profiles/r02d_8gpu_bench_n8.json, r02d_4gpu_bench_n4.json) -- so only one rank samples, and from outside the process.
+    Falls back to an NVML thread when nvidia-smi is missing."""
+    FIELDS = "timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_power_brake_slowdown," \
+             "clocks_event_reasons.applications_clocks_setting"
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap", "hw_power_brake", "applications_clocks_setting")
+
+    def __init__(self, index: int, enabled: bool = True):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.t0 = self.t1 = None
+        self._proc, self._nv, self._t = None, None, None
         self._stop = threading.Event()
-        self._t = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self._nv = pynvml
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self._nv = None
+        if not enabled:
+            return
+        import shutil
+        import subprocess
+        smi = shutil.which("nvidia-smi")
+        if smi:
+            try:
+                self._proc = subprocess.Popen([smi, "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+                self._lines = []
+                self._reader = threading.Thread(target=lambda: [self._lines.append(l) for l in self._proc.stdout], daemon=True)
+                self._reader.start()
+            except Exception:
+                self._proc = None
+        if not self._proc:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self._nv = pynvml
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            except Exception:
+                self._nv = None
 
     def _run(self):
         nv = self._nv
@@ -148,22 +175,61 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.05)
+
+    def wait_ready(self, timeout: float = 4.0):
+        """nvidia-smi needs a moment to come up: block (outside any timed region) until its first sample has arrived"""
+        t = time.time()
+        while self._proc and not self._lines and time.time() - t < timeout and self._proc.poll() is None:
+            time.sleep(0.02)
 
     def __enter__(self):
-        if self._nv:
+        self.wait_ready()
+        self.t0 = time.time()
+        if self._nv and not self._proc:
             self._t = threading.Thread(target=self._run, daemon=True)
             self._t.start()
         return self
 
     def __exit__(self, *a):
+        self.t1 = time.time()
         self._stop.set()
         if self._t:
             self._t.join()
+        if self._proc:
+            time.sleep(0.06)                      # let the sample that covers the end of the window arrive
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+            self._reader.join(timeout=2)
+            self._parse("".join(self._lines))
+
+    def _parse(self, out: str):
+        import datetime
+        rows = []
+        for line in out.splitlines():
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 3 + len(self.NAMES):
+                continue
+            try:
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, int(float(p[1])), int(float(p[2])), p[3:3 + len(self.NAMES)]))
+            except Exception:
+                continue
+        inside = [r for r in rows if self.t0 - 0.03 <= r[0] <= self.t1 + 0.03] or rows[-3:]
+        for ts, mhz, mx, flags in inside:
+            self.samples.append(mhz)
+            self.max_mhz = mx
+            for nm, f in zip(self.NAMES, flags):
+                if f.lower().startswith("active"):
+                    self.reasons.add(nm)
 
     def summary(self):
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "how": "nvidia-smi -lms 20 in its own process, cut to the timed window" if self._proc else "NVML thread"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -205,7 +271,7 @@ def run_reference(args):
         "config": {"workload": f"header_range_1024 witness-gen (verify_skip with 100 signatures + 32 map jobs x 32 headers + reduce), "
                                f"{sample} ranges/step on the host CPU",
                    "same_workload_as_b200_arm": "per range yes (same generator, same circuits, every witness value); per step no: the CPU arm "
-                                                "proves a bounded sample of ranges per step (--cpu-ranges), the GPU arm 378 per GPU -- both "
+                                                "proves a bounded sample of ranges per step (--cpu-ranges), the GPU arm one Ed25519 wave (757) per GPU -- both "
                                                 "are normalised to headers/s"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} ranges x 1024 headers per step, OpenMP over signatures and map jobs"},
@@ -300,10 +366,12 @@ def run_gpu(args):
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     if args.ranges <= 0:
-        # wave-aligned batch: the Ed25519 kernel keeps 4 CTAs x 64 signatures resident per SM; a step whose signatures
-        # fill exactly one such wave avoids a half-empty second wave (256 ranges = 0.68 wave ran 15 % slower per header)
+        # wave-aligned batch: the Ed25519 kernel keeps 8 CTAs x 64 signatures resident per SM in its 128-register build
+        # (4 in the 240-register one); a step whose signatures fill exactly one such wave avoids a half-empty second wave
+        # (r01: 256 ranges = 0.68 wave of 4 CTAs ran 15 % slower per header; r02g: 757 ranges = one wave of 8 CTAs per SM
+        # 156.1 M headers/s against 146.0 M at 378 ranges = one wave of 4)
         sms = torch.cuda.get_device_properties(local).multi_processor_count
-        args.ranges = max(8, sms * 4 * 64 // N_VAL)
+        args.ranges = max(8, sms * 8 * 64 // N_VAL)
     if args.e2e_ranges <= 0:
         args.e2e_ranges = args.ranges
     R = args.ranges                      # ranges this rank reduces / verifies per step
@@ -450,12 +518,14 @@ def run_gpu(args):
         def time_steps(self, clocks: bool):
             """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the launching stream (one
             after every step for the distribution), max over ranks."""
+            clk = ClockSampler(local, enabled=rank == 0) if clocks else None     # its process starts now, samples are cut later
+            if clk:
+                clk.wait_ready()
             for _ in range(args.warmup):
                 self.step()
             barrier()
             l0 = ctx.launch_count
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-            clk = ClockSampler(local) if clocks else None
             if clk:
                 clk.__enter__()
             ev[0].record()
@@ -723,7 +793,10 @@ def run_gpu(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ranges_per_step": Re, "host_cpus": numa, "host_threads": n_thr, "single_call": e2e_single,
                     "ranges_checked_against_oracle": e2e_checked,
-                    "bound": "PCIe download of the witness (0.74 MB per range)",
+                    "bound": "PCIe download of the witness (0.74 MB per range; one GPU alone: 56 GB/s D2H, 93 GB/s duplex)" if world == 1 else
+                             "host aggregate: every rank downloads 0.74 MB per range over its own x16 link into the same host memory; 8 "
+                             "concurrent ranks reach 121-125 GB/s D2H / 155 GB/s duplex in total against 56 / 93 GB/s for one rank alone "
+                             "(scripts/ubench/pcie.py --ranks 8, profiles/r02d_pcie_8.json; NUMA binding makes no difference on this box)",
                     "note": "one ctx + pinned buffers per host thread, calls dealt round-robin; every call copies its inputs up and its witness down"},
             "header_range_2048": hr2048,
             "constraints": constraints,
@@ -1552,7 +1625,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ranges", type=int, default=0,
                     help="independent header ranges per step per GPU; 0 = one full wave of the Ed25519 kernel "
-                         "(4 CTAs of 64 signatures per SM: 378 ranges of 100 validators on 148 SMs)")
+                         "(8 CTAs of 64 signatures per SM: 757 ranges of 100 validators on 148 SMs)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic chains (tiled to --ranges)")
     ap.add_argument("--e2e-ranges", type=int, default=0, help="ranges per end-to-end call; 0 = the same as --ranges")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one ctx each) issuing the end-to-end calls")

@@ -57,14 +57,27 @@ struct bsx_ctx {
     uint32_t n_ev_chunk;
 };
 
-// Does a batch of n signatures fill whole waves of the thread-per-signature Ed25519 kernel (4 CTAs of 64 per SM)?  Then
-// every SM's register file is full for the kernel's whole run, and the step is arranged to leave room for the SHA-256
-// kernels beside it (192-register build, skip hashes on their own stream: +1..2.6 % at 378 / 756 / 1134 ranges per step).
-// With a partly filled last wave the SMs have room anyway and the same arrangement costs 2..4 % (256 / 512 ranges).
-static inline bool bsx_ed_fills_waves(const bsx_ctx *ctx, uint64_t n) {
-    const uint64_t wave = (uint64_t)ctx->sm_count * 4, ctas = (n + 63) / 64, tail = ctas % wave;
-    return ctas * 10 >= wave * 9 && (tail == 0 || tail * 10 >= wave * 9);   // last wave at least 90 % full (378 ranges: 591 of 592 CTAs)
+// Does a batch of n signatures fill whole waves of the thread-per-signature Ed25519 kernel at `occ` CTAs of 64 per SM?  Then
+// every SM's register file is full for the kernel's whole run (last wave at least 90 % full; 378 ranges: 591 of 592 CTAs).
+static inline bool bsx_ed_fills_waves_at(const bsx_ctx *ctx, uint64_t n, int occ) {
+    const uint64_t wave = (uint64_t)ctx->sm_count * occ, ctas = (n + 63) / 64, tail = ctas % wave;
+    return ctas * 10 >= wave * 9 && (tail == 0 || tail * 10 >= wave * 9);
 }
+// The register budget (CTAs per SM: 8 -> 128 registers, 6 -> 168, 4 -> 216 / 240) whose waves the batch fills, largest first;
+// 0 if none.  r02g (profiles/r02g_ed_occ_wave_sizes.txt, FP64 limbs): a build with more resident warps only pays when the
+// batch fills ITS wave -- 757 ranges per step: 128-register build 156.1 M headers/s against 151.1 M with the 240-register
+// one; 568 ranges: 168 registers 151.8 M against 150.0 M; at 378 ranges (one wave of 4 CTAs per SM) the wider builds
+// would run two thirds or half empty.
+static inline int bsx_ed_wave_occ(const bsx_ctx *ctx, uint64_t n) {
+    if (bsx_ed_fills_waves_at(ctx, n, 8)) return 8;
+    if (bsx_ed_fills_waves_at(ctx, n, 6)) return 6;
+    if (bsx_ed_fills_waves_at(ctx, n, 4)) return 4;
+    return 0;
+}
+// The step is arranged to leave room for the SHA-256 kernels beside a full Ed25519 wave (skip hashes on their own stream:
+// +1..2.6 % at 378 / 756 / 1134 ranges per step); with a partly filled last wave the SMs have room anyway and the same
+// arrangement costs 2..4 % (256 / 512 ranges).
+static inline bool bsx_ed_fills_waves(const bsx_ctx *ctx, uint64_t n) { return bsx_ed_wave_occ(ctx, n) != 0; }
 
 void bsx_plonk_cache_free(bsx_ctx *ctx);   // k_plonk.cu
 

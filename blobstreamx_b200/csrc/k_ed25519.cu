@@ -408,7 +408,12 @@ static int launch_quad(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
 static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in, const ed::ge_niels_slot *tab, uint8_t *out, bool alone,
                        bool corun) {
     const int env_occ = ctx->tun[BSX_TUN_ED_OCC];
-    const int occ = env_occ ? env_occ : corun ? 8 : 4;
+    const int fp64_t = ctx->tun[BSX_TUN_ED_FP64];
+    const bool fp64 = fp64_t < 0 ? BSX_ED_FP64_DEFAULT : fp64_t != 0;
+    // FP64 limbs: the register budget follows the batch size (the widest build whose wave the batch fills, common.cuh);
+    // ED_OCC = 4 / 6 / 8 forces one
+    const int wave_occ = fp64 ? bsx_ed_wave_occ(ctx, n) : 0;
+    const int occ = env_occ ? env_occ : corun ? 8 : (wave_occ > 4 ? wave_occ : 4);
     const int inl = ctx->tun[BSX_TUN_ED_INLINE];   // -1: by call site
     const bool use_inl = inl < 0 ? alone : inl != 0;
     // (Splitting this path into prep / main / finish kernels with a 4-way batched inversion was measured slower:
@@ -417,9 +422,7 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     // each sub-partition keeps room for two 64-register hash warps instead of one (header_range step 2.81 -> 2.77 ms).
     // BSX_ED_REGS: 0 = never, non-zero = always (A/B).
     const int env_cap = ctx->tun[BSX_TUN_ED_REGS];
-    const int fp64_t = ctx->tun[BSX_TUN_ED_FP64];
-    const bool fp64 = fp64_t < 0 ? BSX_ED_FP64_DEFAULT : fp64_t != 0;
-    const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves(ctx, n) && !fp64 ? 192 : 0);
+    const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves_at(ctx, n, 4) && !fp64 ? 192 : 0);
     const unsigned grid = (n + 63) / 64;
 #define BSX_ED_LAUNCH(K)                                  \
     do {                                                  \
