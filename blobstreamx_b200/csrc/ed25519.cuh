@@ -836,29 +836,50 @@ BSX_HD ged_p3 ged_scalarmult(const uint8_t s[32], const ged_p3 &P) {
     return acc;
 }
 
-// one signature on the FP64 pipe: same record as ed::ed25519_witness_core
+// one signature on the FP64 pipe: same record as ed::ed25519_witness_core.
+// r02j: R is not decompressed (a square-root chain of ~265 field operations) when the signature verifies.  R' = sG - hA is
+// formed from the two scalar multiplications and shares their inversion; if its canonical encoding IS the signature's R
+// (y bytes equal, sign bit = parity of x'), then decompress(R) = R' with root = the even one of x', p - x', and
+// R + hA = sG as points, so every byte of the record follows without the chain.  Anything else -- a signature that does not
+// verify, a non-canonical y, an R off the curve -- takes the general path below (decompression, addition, a second
+// inversion), which is the r02b code.  Same bytes either way (tests/test_ed25519_host_check.py, the GPU stress inputs).
 template <bool INL = false>
 BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], const uint8_t digest[64],
                                  const ed::ge_niels_slot *base_table, uint8_t *out) {
     for (int i = 0; i < 64; i++) out[i] = digest[i];
     ed::sc_divrem_l(digest, out + 64, out + 96);
     uint32_t flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
-    fed ax, ay, rx, ry;
+    fed ax, ay;
     if (ged_decompress(pk, ax, ay, out + 200, out + 232, out + 264)) flags |= 2u;
-    if (ged_decompress(sig, rx, ry, out + 360, out + 392, out + 424)) flags |= 4u;
     const ged_p3 sg = ged_scalarmult_base<INL>(sig + 32, base_table);
     const ged_p3 ha = ged_scalarmult<INL>(out + 64, ged_from_affine(ax, ay));
-    const ged_p3 sum = ged_p1p1_to_p3(ged_add_cached(ha, ged_to_cached(ged_from_affine(rx, ry))), false);
-    // one inversion for the three Z's
+    // R' = sG - hA, and one inversion for the three Z's
+    const ged_p3 rp = ged_p1p1_to_p3(ged_add_cached(sg, ged_cached_cneg(ged_to_cached(ha), true)), false);
     const fed z12 = fed_mul(sg.Z, ha.Z);
-    const fed inv = fed_invert(fed_mul(z12, sum.Z));
-    const fed isum = fed_mul(inv, z12);
-    const fed i12 = fed_mul(inv, sum.Z);
+    const fed inv = fed_invert(fed_mul(z12, rp.Z));
+    const fed irp = fed_mul(inv, z12);
+    const fed i12 = fed_mul(inv, rp.Z);
     const fed isg = fed_mul(i12, ha.Z), iha = fed_mul(i12, sg.Z);
     ed::fe_tobytes(out + 136, fe_from_fed(fed_mul(sg.X, isg))); ed::fe_tobytes(out + 168, fe_from_fed(fed_mul(sg.Y, isg)));
     ed::fe_tobytes(out + 296, fe_from_fed(fed_mul(ha.X, iha))); ed::fe_tobytes(out + 328, fe_from_fed(fed_mul(ha.Y, iha)));
-    ed::fe_tobytes(out + 456, fe_from_fed(fed_mul(sum.X, isum))); ed::fe_tobytes(out + 488, fe_from_fed(fed_mul(sum.Y, isum)));
-    if (ed::bytes_eq32(out + 136, out + 456) && ed::bytes_eq32(out + 168, out + 488)) flags |= 8u;
+    const fed rpx = fed_mul(rp.X, irp);
+    ed::fe_tobytes(out + 360, fe_from_fed(rpx)); ed::fe_tobytes(out + 392, fe_from_fed(fed_mul(rp.Y, irp)));
+    const bool sign = (sig[31] >> 7) != 0;
+    bool same = ((out[360] & 1) != 0) == sign && out[392 + 31] == (sig[31] & 0x7f);
+    for (int i = 0; i < 31; i++) same = same && out[392 + i] == sig[i];
+    if (same) {
+        flags |= 4u | 8u;
+        if (sign) ed::fe_tobytes(out + 424, fe_from_fed(fed_neg(rpx)));           // x' odd: the even root is p - x'
+        else for (int i = 0; i < 32; i++) out[424 + i] = out[360 + i];
+        for (int i = 0; i < 64; i++) out[456 + i] = out[136 + i];                   // R + hA = sG
+    } else {
+        fed rx, ry;
+        if (ged_decompress(sig, rx, ry, out + 360, out + 392, out + 424)) flags |= 4u;
+        const ged_p3 sum = ged_p1p1_to_p3(ged_add_cached(ha, ged_to_cached(ged_from_affine(rx, ry))), false);
+        const fed isum = fed_invert(sum.Z);
+        ed::fe_tobytes(out + 456, fe_from_fed(fed_mul(sum.X, isum))); ed::fe_tobytes(out + 488, fe_from_fed(fed_mul(sum.Y, isum)));
+        if (ed::bytes_eq32(out + 136, out + 456) && ed::bytes_eq32(out + 168, out + 488)) flags |= 8u;
+    }
     out[520] = (uint8_t)flags; out[521] = 0; out[522] = 0; out[523] = 0;
     for (int i = 524; i < 576; i++) out[i] = 0;
 }

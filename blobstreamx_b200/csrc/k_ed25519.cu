@@ -424,10 +424,14 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     const int env_cap = ctx->tun[BSX_TUN_ED_REGS];
     const int cap = env_cap >= 0 ? env_cap : (bsx_ed_fills_waves_at(ctx, n, 4) && !fp64 ? 192 : 0);
     const unsigned grid = (n + 63) / 64;
+    // ED_RESIDENT = k: unused dynamic shared memory as ballast so that at most k CTAs of this kernel are resident per SM
+    // (80 KB of the pinned 114 KB carveout shared between them), which leaves registers and issue slots to the hash kernels
+    const int resident = ctx->tun[BSX_TUN_ED_RESIDENT];
+    const size_t ballast = resident > 1 ? (size_t)((80 * 1024 / resident) & ~1023) : 0;
 #define BSX_ED_LAUNCH(K)                                  \
     do {                                                  \
         BSX_PIN_CARVEOUT((K));                            \
-        K<<<grid, 64, 0, st>>>(n, in, tab, out);          \
+        K<<<grid, 64, ballast, st>>>(n, in, tab, out);    \
     } while (0)
     if (cap && (!alone || env_cap > 0) && !env_occ && !corun && inl <= 0) {
         // (caps of 176 and 160 registers spill and were slower: profiles/r01p_step_ab.txt)

@@ -9,6 +9,10 @@
 // launched on the same stream just before; this kernel only reads their flag words.
 // Digest order = Curta request order.
 #include "common.cuh"
+// the verify_* schedules run beside the Ed25519 kernel, which keeps the FMA pipe busy: all additions stay on the ALU pipe (r02j)
+#ifndef BSX_SHA_FMA_ADDS
+#define BSX_SHA_FMA_ADDS 0
+#endif
 #include "sha256.cuh"
 #include "tm_tree.cuh"
 

@@ -75,11 +75,33 @@ __device__ __constant__ uint32_t BSX_SHA256_K[64] = {
     0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070,
     0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3,
     0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+// Pipe steering (r02i).  The ALU pipe (SHF / LOP3 / IADD3: one warp instruction per 2 cycles per sub-partition) is what
+// binds every SHA-256 kernel here (ncu: 92 % busy, `math_pipe_throttle` the top stall) while the FMA pipe idles at 7 %.
+// An addition written as  a * ONE + b  with ONE read from constant memory cannot be folded back into IADD3 by ptxas
+// and issues as IMAD on the FMA pipe.  BSX_SHA_FMA_ADDS is a mask of the addition groups moved there:
+//   1: the T1 chain   2: e = d + T1   4: T2 and a = T1 + T2   8: the message schedule
+// Measured on B200 (profiles/r02j_ab_sha.txt): 2048-leaf trees 2.60 -> 2.10 ms per 4096 with mask 5 (2.48 with 13), map stage
+// 2.02 -> 1.87 ms with 13 (1.92 with 5), input shaping 0.955 -> 0.936; each translation unit picks its mask before the include.
+#ifndef BSX_SHA_FMA_ADDS
+#define BSX_SHA_FMA_ADDS 5
+#endif
+__device__ __constant__ uint32_t BSX_SHA_ONE = 1;
+__device__ __forceinline__ uint32_t add_fma(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(BSX_SHA_ONE), "r"(b));
+    return r;
+}
+template <int BIT>
+__device__ __forceinline__ uint32_t sha_add(uint32_t a, uint32_t b) {
+    if constexpr ((BSX_SHA_FMA_ADDS & BIT) != 0) return add_fma(a, b);
+    else return a + b;
+}
 #define BSX_SHA_ROUND(wk)                                                                              \
     {                                                                                                  \
-        const uint32_t t1 = h + xor3(rotr32(e, 6), rotr32(e, 11), rotr32(e, 25)) + ch32(e, f, g) + (wk); \
-        const uint32_t t2 = xor3(rotr32(a, 2), rotr32(a, 13), rotr32(a, 22)) + maj32(a, b, c);           \
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;                             \
+        const uint32_t t1 = sha_add<1>(sha_add<1>(sha_add<1>(h, (wk)), ch32(e, f, g)),                   \
+                                       xor3(rotr32(e, 6), rotr32(e, 11), rotr32(e, 25)));               \
+        const uint32_t t2 = sha_add<4>(xor3(rotr32(a, 2), rotr32(a, 13), rotr32(a, 22)), maj32(a, b, c)); \
+        h = g; g = f; f = e; e = sha_add<2>(d, t1); d = c; c = b; b = a; a = sha_add<4>(t1, t2);       \
     }
 __device__ __forceinline__ void sha256_rounds_looped(uint32_t st[8], uint32_t w[16]) {
     constexpr uint32_t K0[16] = {0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5,
@@ -94,8 +116,8 @@ __device__ __forceinline__ void sha256_rounds_looped(uint32_t st[8], uint32_t w[
             const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
             const uint32_t s0 = xor3(rotr32(w15, 7), rotr32(w15, 18), w15 >> 3);
             const uint32_t s1 = xor3(rotr32(w2, 17), rotr32(w2, 19), w2 >> 10);
-            w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
-            BSX_SHA_ROUND(BSX_SHA256_K[16 * p + i] + w[i])
+            w[i] = sha_add<8>(sha_add<8>(sha_add<8>(w[i], w[(i + 9) & 15]), s0), s1);
+            BSX_SHA_ROUND(sha_add<8>(BSX_SHA256_K[16 * p + i], w[i]))
         }
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;

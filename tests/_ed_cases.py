@@ -31,5 +31,18 @@ def stress_inputs(n_valid: int, n_garb: int, seed: int = 20261017, base_n: int =
         else:
             g_sig[j, :32] = np.frombuffer((edge_y[(j // 2) % len(edge_y)] % 2**256).to_bytes(32, "little"), np.uint8)
         g_sig[j, 32:] = np.frombuffer(edge_s[j % len(edge_s)].to_bytes(32, "little"), np.uint8)
+    # edges of the R shortcut of the FP64 witness core (R' = sG - hA compared with the encoded R): A = identity (or undecodable,
+    # which falls back to it) and s = 0 make R' the identity; R encoded canonically, with the sign bit on x = 0, as y = 1 + p
+    k = n_garb - 1
+    for pk_v in (1, 2):
+        for r_v in (1, 1 | 1 << 255, 1 + P, 1 + P | 1 << 255):
+            if k < 0:
+                break
+            g_pk[k] = np.frombuffer(pk_v.to_bytes(32, "little"), np.uint8)
+            g_sig[k, :32] = np.frombuffer(r_v.to_bytes(32, "little"), np.uint8)
+            g_sig[k, 32:] = 0
+            k -= 1
+    if n_valid > 1:
+        sigs[1, 31] ^= 0x80     # -R of a signature: decodes, does not verify (entry 1 is not one of the corrupted ones)
     return (np.concatenate([pks, g_pk]), np.concatenate([sigs, g_sig]), np.concatenate([msgs, g_msg]),
             np.concatenate([lens, g_len]), np.concatenate([act, np.ones(n_garb, np.uint8)]))

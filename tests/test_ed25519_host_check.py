@@ -316,6 +316,19 @@ def test_fp64_witness_records(hc):
         if i % 8 == 7:
             pk, sig, msg = rng.bytes(32), rng.bytes(64), rng.bytes(33)
         cases.append((pk, sig, msg))
+    # edges of the R shortcut (R' = sG - hA compared with the encoded R instead of a decompression): A = the identity makes
+    # hA the identity, s = 0 makes sG the identity, so R' = (0, 1) -- encoded canonically, with the sign bit set on x = 0,
+    # and non-canonically as y = 1 + p; the same with an undecodable public key (A falls back to the identity)
+    ident, zero_s = (1).to_bytes(32, "little"), bytes(32)
+    P25519 = 2**255 - 19
+    for pk in (ident, (2).to_bytes(32, "little")):
+        cases.append((pk, ident + zero_s, b"edge"))
+        cases.append((pk, (1 | 1 << 255).to_bytes(32, "little") + zero_s, b"edge"))
+        cases.append((pk, (1 + P25519).to_bytes(32, "little") + zero_s, b"edge"))
+        cases.append((pk, (1 + P25519 | 1 << 255).to_bytes(32, "little") + zero_s, b"edge"))
+    sk = SigningKey(hashlib.sha256(b"fp-sign").digest())
+    sig = sk.sign(b"sign bit").signature
+    cases.append((bytes(sk.verify_key), sig[:31] + bytes([sig[31] ^ 0x80]) + sig[32:], b"sign bit"))   # -R: decodes, does not verify
     seen = set()
     for pk, sig, msg in cases:
         out = _out(576)
