@@ -843,16 +843,8 @@ BSX_HD ged_p3 ged_scalarmult(const uint8_t s[32], const ged_p3 &P) {
 // R + hA = sG as points, so every byte of the record follows without the chain.  Anything else -- a signature that does not
 // verify, a non-canonical y, an R off the curve -- takes the general path below (decompression, addition, a second
 // inversion), which is the r02b code.  Same bytes either way (tests/test_ed25519_host_check.py, the GPU stress inputs).
-template <bool INL = false>
-BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], const uint8_t digest[64],
-                                 const ed::ge_niels_slot *base_table, uint8_t *out) {
-    for (int i = 0; i < 64; i++) out[i] = digest[i];
-    ed::sc_divrem_l(digest, out + 64, out + 96);
-    uint32_t flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
-    fed ax, ay;
-    if (ged_decompress(pk, ax, ay, out + 200, out + 232, out + 264)) flags |= 2u;
-    const ged_p3 sg = ged_scalarmult_base<INL>(sig + 32, base_table);
-    const ged_p3 ha = ged_scalarmult<INL>(out + 64, ged_from_affine(ax, ay));
+// everything after the two scalar multiplications: R (shortcut or general path), R + hA, affine bytes, flags
+BSX_HD void ed25519_witness_tail(const ged_p3 &sg, const ged_p3 &ha, const uint8_t sig[64], uint32_t flags, uint8_t *out) {
     // R' = sG - hA, and one inversion for the three Z's
     const ged_p3 rp = ged_p1p1_to_p3(ged_add_cached(sg, ged_cached_cneg(ged_to_cached(ha), true)), false);
     const fed z12 = fed_mul(sg.Z, ha.Z);
@@ -882,6 +874,113 @@ BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], co
     }
     out[520] = (uint8_t)flags; out[521] = 0; out[522] = 0; out[523] = 0;
     for (int i = 524; i < 576; i++) out[i] = 0;
+}
+
+template <bool INL = false>
+BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], const uint8_t digest[64],
+                                 const ed::ge_niels_slot *base_table, uint8_t *out) {
+    for (int i = 0; i < 64; i++) out[i] = digest[i];
+    ed::sc_divrem_l(digest, out + 64, out + 96);
+    uint32_t flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
+    fed ax, ay;
+    if (ged_decompress(pk, ax, ay, out + 200, out + 232, out + 264)) flags |= 2u;
+    const ged_p3 sg = ged_scalarmult_base<INL>(sig + 32, base_table);
+    const ged_p3 ha = ged_scalarmult<INL>(out + 64, ged_from_affine(ax, ay));
+    ed25519_witness_tail(sg, ha, sig, flags, out);
+}
+
+// ---- per-key window tables (r02k) ----
+// A batch that repeats public keys (one validator set signs every range of a batch) pays the 252 doublings of h*A and the
+// decompression of A once per KEY instead of once per signature: for every distinct key the windows 16^w A (w = 0..63) and
+// their multiples 1..8 are tabulated in the projective addend form, and h*A becomes 64 table additions over the signed
+// radix-16 digits of h (h < l < 2^253, so the digit recoding leaves no carry out of window 63).  The result is the same
+// group element, hence the same affine bytes.  Layouts (doubles / bytes):
+//   key record  BSX_ED_KEYREC_BYTES: x[32] y[32] root[32] ok[1] of decompress(A) -- exactly the bytes of the signature record
+//   bases       [key][w]    one extended point (X, Y, Z, T) = 20 doubles
+//   table       [key][w][d] addend form of (d+1) 16^w A (YpX, YmX, Z, T2d) = 20 doubles
+#define BSX_ED_KEYREC_BYTES 128
+#define BSX_ED_KEY_WINDOWS 64
+BSX_HD void ged_store20(double *dst, const fed &a, const fed &b, const fed &c, const fed &d) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) { dst[k] = a.v[k]; dst[5 + k] = b.v[k]; dst[10 + k] = c.v[k]; dst[15 + k] = d.v[k]; }
+}
+BSX_HD void ged_load20(const double *src, fed &a, fed &b, fed &c, fed &d) {
+    double t[20];
+#if defined(__CUDA_ARCH__)
+    const double2 *q = reinterpret_cast<const double2 *>(src);   // 160-byte entries of a 256-byte-aligned allocation
+#pragma unroll
+    for (int k = 0; k < 10; k++) { const double2 v = __ldg(q + k); t[2 * k] = v.x; t[2 * k + 1] = v.y; }
+#else
+    for (int k = 0; k < 20; k++) t[k] = src[k];
+#endif
+#pragma unroll
+    for (int k = 0; k < 5; k++) { a.v[k] = t[k]; b.v[k] = t[5 + k]; c.v[k] = t[10 + k]; d.v[k] = t[15 + k]; }
+}
+// one key: decompress, then the 64 window bases (252 dependent doublings -- the part that is shared by every signature of the key)
+BSX_HD void ed25519_key_bases(const uint8_t pk[32], uint8_t *rec, double *bases) {
+    fed ax, ay;
+    rec[96] = ged_decompress(pk, ax, ay, rec, rec + 32, rec + 64) ? 1 : 0;
+    ged_p3 p = ged_from_affine(ax, ay);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int w = 0; w < BSX_ED_KEY_WINDOWS; w++) {
+        ged_store20(bases + 20 * w, p.X, p.Y, p.Z, p.T);
+        if (w + 1 < BSX_ED_KEY_WINDOWS) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 0; k < 4; k++) p = ged_p1p1_to_p3(ged_dbl(p), k == 3);
+        }
+    }
+}
+// one (key, window): the addend forms of 1..8 times the window base
+BSX_HD void ed25519_key_window(const double *base, double *tab) {
+    ged_p3 cur;
+    ged_load20(base, cur.X, cur.Y, cur.Z, cur.T);
+    const ged_cached first = ged_to_cached(cur);
+    ged_store20(tab, first.YpX, first.YmX, first.Z, first.T2d);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int d = 2; d <= 8; d++) {
+        cur = ged_p1p1_to_p3(ged_add_cached(cur, first), true);
+        const ged_cached c = ged_to_cached(cur);
+        ged_store20(tab + 20 * (d - 1), c.YpX, c.YmX, c.Z, c.T2d);
+    }
+}
+// h * A from the key's table: signed radix-16 digits as in ged_scalarmult, one table addition per non-zero digit
+template <bool INL = false>
+BSX_HD ged_p3 ged_scalarmult_keyed(const uint8_t s[32], const double *tab) {
+    ged_p3 acc = ged_identity();
+    int carry = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int w = 0; w < BSX_ED_KEY_WINDOWS; w++) {
+        int d = (int)((s[w >> 1] >> ((w & 1) * 4)) & 15) + carry;
+        carry = d >= 8;
+        d -= 16 * carry;
+        if (d) {
+            ged_cached q;
+            ged_load20(tab + 20 * (8 * w + (d < 0 ? -d : d) - 1), q.YpX, q.YmX, q.Z, q.T2d);
+            acc = ged_p1p1_to_p3<INL>(ged_add_cached<INL>(acc, ged_cached_cneg(q, d < 0)), true);
+        }
+    }
+    return acc;   // carry out of window 63 is impossible for s < 2^255 - 2^251 (the remainder mod l is < 2^253)
+}
+// the record of one signature whose key has been tabulated: same bytes as ed25519_witness_core
+template <bool INL = false>
+BSX_HD void ed25519_witness_core_keyed(const uint8_t sig[64], const uint8_t digest[64], const ed::ge_niels_slot *base_table,
+                                       const uint8_t *key_rec, const double *key_tab, uint8_t *out) {
+    for (int i = 0; i < 64; i++) out[i] = digest[i];
+    ed::sc_divrem_l(digest, out + 64, out + 96);
+    uint32_t flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
+    for (int i = 0; i < 96; i++) out[200 + i] = key_rec[i];
+    if (key_rec[96]) flags |= 2u;
+    const ged_p3 sg = ged_scalarmult_base<INL>(sig + 32, base_table);
+    const ged_p3 ha = ged_scalarmult_keyed<INL>(out + 64, key_tab);
+    ed25519_witness_tail(sg, ha, sig, flags, out);
 }
 
 }  // namespace edd

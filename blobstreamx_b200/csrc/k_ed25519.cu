@@ -47,25 +47,109 @@ struct EdIn {
     uint32_t pk_stride, sig_stride, msg_stride, msg_max, len_stride, active_stride;
 };
 
+// ---- per-key tables (ed25519.cuh, "per-key window tables"): which signatures share a public key is found on the device ----
+// An open-addressing table of BSX_ED_KEY_SLOTS slots holds, per distinct key, the index of the first signature that
+// carries it; a batch with more than BSX_ED_KEY_MAX distinct keys (or a probe sequence that runs too long) sets the
+// overflow word and the whole batch takes the general path.  No host round trip: every later kernel reads the verdict.
+#define BSX_ED_KEY_SLOTS 4096
+#define BSX_ED_KEY_MAX 1024
+#define BSX_ED_KEY_PROBES 64
+#define BSX_ED_KEY_MIN_USE 16        // tables are used when a key serves at least this many signatures on average
+struct EdKeys {
+    int32_t *slots;        // [SLOTS] -1 or the first signature with this key
+    int32_t *slot_id;      // [SLOTS] dense key id (assigned by the bases kernel)
+    int32_t *state;        // [0] distinct keys  [1] overflow  [2] next dense id
+    int32_t *key_slot;     // [n] slot of each signature's key
+    uint8_t *recs;         // [KEY_MAX] BSX_ED_KEYREC_BYTES
+    double *bases;         // [KEY_MAX][64][20]
+    double *tab;           // [KEY_MAX][64][8][20]
+    int32_t force;         // ED_KEYTAB = 1: use the tables whenever the keys fit
+};
+__device__ __forceinline__ bool ed_keys_in_use(const EdKeys &k, uint32_t n) {
+    return k.state != nullptr && k.state[1] == 0 && (k.force || (uint64_t)k.state[0] * BSX_ED_KEY_MIN_USE <= n);
+}
+__device__ __forceinline__ void ed_effective_pk(const EdIn &in, uint32_t i, uint32_t w[8]) {
+    const bool on = !in.active || in.active[(size_t)in.active_stride * i];
+    const uint8_t *p = on ? in.pks + (size_t)in.pk_stride * i : DUMMY_PK;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
+}
+__global__ void __launch_bounds__(128) ed25519_key_assign_kernel(uint32_t n, EdIn in, EdKeys keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[8];
+    ed_effective_pk(in, i, w);
+    uint32_t h = 0x811c9dc5u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) h = (h ^ w[k]) * 0x01000193u + (h >> 15);
+    h ^= h >> 16;
+    int32_t found = -1;
+    for (int probe = 0; probe < BSX_ED_KEY_PROBES; probe++) {
+        const uint32_t slot = (h + probe) & (BSX_ED_KEY_SLOTS - 1);
+        int32_t cur = keys.slots[slot];
+        if (cur < 0) {
+            cur = atomicCAS(&keys.slots[slot], -1, (int32_t)i);
+            if (cur < 0) {                                   // this signature is the key's first
+                if (atomicAdd(&keys.state[0], 1) >= BSX_ED_KEY_MAX) keys.state[1] = 1;
+                found = (int32_t)slot;
+                break;
+            }
+        }
+        uint32_t o[8];
+        ed_effective_pk(in, (uint32_t)cur, o);
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < 8; k++) same = same && o[k] == w[k];
+        if (same) { found = (int32_t)slot; break; }
+    }
+    if (found < 0) keys.state[1] = 1;
+    keys.key_slot[i] = found;
+}
+// one thread per occupied slot: the key's record and its 64 window bases (a dependent chain: ~2 100 field operations)
+__global__ void __launch_bounds__(32) ed25519_key_bases_kernel(uint32_t n, EdIn in, EdKeys keys) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= BSX_ED_KEY_SLOTS || !ed_keys_in_use(keys, n)) return;
+    const int32_t first = keys.slots[s];
+    if (first < 0) return;
+    const int32_t id = atomicAdd(&keys.state[2], 1);
+    keys.slot_id[s] = id;
+    uint32_t w[8];
+    ed_effective_pk(in, (uint32_t)first, w);
+    uint8_t pk[32];
+#pragma unroll
+    for (int k = 0; k < 32; k++) pk[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    edd::ed25519_key_bases(pk, keys.recs + (size_t)BSX_ED_KEYREC_BYTES * id, keys.bases + (size_t)id * BSX_ED_KEY_WINDOWS * 20);
+}
+// one CTA per key, one thread per window: the multiples 1..8 of the window base in addend form
+__global__ void __launch_bounds__(BSX_ED_KEY_WINDOWS) ed25519_key_table_kernel(uint32_t n, EdKeys keys) {
+    const uint32_t id = blockIdx.x, w = threadIdx.x;
+    if (!ed_keys_in_use(keys, n) || (int32_t)id >= keys.state[0]) return;
+    const size_t e = (size_t)id * BSX_ED_KEY_WINDOWS + w;
+    edd::ed25519_key_window(keys.bases + e * 20, keys.tab + e * 8 * 20);
+}
+
 // FP64: the field arithmetic of the whole signature on the FP64 pipe (fe51d.cuh) instead of IMAD.WIDE
 template <bool INL, bool FP64>
-__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out);
+__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out,
+                                                   const EdKeys &keys);
 
 template <int MIN_CTAS, bool INL, bool FP64 = false>
 __global__ void __launch_bounds__(64, MIN_CTAS) ed25519_batch_kernel(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
-                                                           uint8_t *__restrict__ out) {
-    ed25519_batch_body<INL, FP64>(n, in, table, out);
+                                                           uint8_t *__restrict__ out, EdKeys keys) {
+    ed25519_batch_body<INL, FP64>(n, in, table, out, keys);
 }
 // the same kernel under an explicit register cap (64-thread CTAs): still 2 warps per SM sub-partition, but more of the
 // register file left to the SHA-256 warps that run beside it
 template <int REGS, bool INL, bool FP64 = false>
 __global__ void __maxnreg__(REGS) ed25519_batch_kernel_capped(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
-                                                               uint8_t *__restrict__ out) {
-    ed25519_batch_body<INL, FP64>(n, in, table, out);
+                                                               uint8_t *__restrict__ out, EdKeys keys) {
+    ed25519_batch_body<INL, FP64>(n, in, table, out, keys);
 }
 
 template <bool INL, bool FP64>
-__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out) {
+__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out,
+                                                   const EdKeys &keys) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t pk[32], sig[64];
@@ -94,8 +178,17 @@ __device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, c
     for (int k = 0; k < 8; k++)
 #pragma unroll
         for (int j = 0; j < 8; j++) digest[8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
-    if (FP64) edd::ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
-    else ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
+    if (FP64) {
+        if (ed_keys_in_use(keys, n)) {
+            const int32_t id = keys.slot_id[keys.key_slot[i]];
+            edd::ed25519_witness_core_keyed<INL>(sig, digest, table, keys.recs + (size_t)BSX_ED_KEYREC_BYTES * id,
+                                                 keys.tab + (size_t)id * BSX_ED_KEY_WINDOWS * 8 * 20, out + (size_t)BSX_SIG_OUT_BYTES * i);
+        } else {
+            edd::ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
+        }
+    } else {
+        ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
+    }
 }
 
 
@@ -428,10 +521,45 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     // (80 KB of the pinned 114 KB carveout shared between them), which leaves registers and issue slots to the hash kernels
     const int resident = ctx->tun[BSX_TUN_ED_RESIDENT];
     const size_t ballast = resident > 1 ? (size_t)((80 * 1024 / resident) & ~1023) : 0;
-#define BSX_ED_LAUNCH(K)                                  \
-    do {                                                  \
-        BSX_PIN_CARVEOUT((K));                            \
-        K<<<grid, 64, ballast, st>>>(n, in, tab, out);    \
+    // per-key tables (FP64 build): ED_KEYTAB -1 = when keys repeat at least BSX_ED_KEY_MIN_USE times on average, 0 = never,
+    // 1 = whenever the distinct keys fit.  The state is stream-ordered pool memory: nothing of it lives in the ctx.
+    EdKeys keys = {};
+    uint8_t *kmem = nullptr;
+    const int keytab = ctx->tun[BSX_TUN_ED_KEYTAB];
+    if (fp64 && keytab != 0) {
+        const size_t o_slot_id = sizeof(int32_t) * BSX_ED_KEY_SLOTS, o_state = 2 * o_slot_id, o_key_slot = o_state + 256,
+                     o_recs = (o_key_slot + sizeof(int32_t) * (size_t)n + 255) & ~(size_t)255,
+                     o_bases = o_recs + (size_t)BSX_ED_KEY_MAX * BSX_ED_KEYREC_BYTES,
+                     o_tab = o_bases + sizeof(double) * 20 * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX,
+                     total = o_tab + sizeof(double) * 20 * 8 * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX;
+        BSX_CUDA(ctx, cudaMallocAsync((void **)&kmem, total, st));
+        keys.slots = reinterpret_cast<int32_t *>(kmem);
+        keys.slot_id = reinterpret_cast<int32_t *>(kmem + o_slot_id);
+        keys.state = reinterpret_cast<int32_t *>(kmem + o_state);
+        keys.key_slot = reinterpret_cast<int32_t *>(kmem + o_key_slot);
+        keys.recs = kmem + o_recs;
+        keys.bases = reinterpret_cast<double *>(kmem + o_bases);
+        keys.tab = reinterpret_cast<double *>(kmem + o_tab);
+        keys.force = keytab > 0;
+        cudaError_t e = cudaMemsetAsync(keys.slots, 0xff, o_slot_id, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(keys.state, 0, 256, st);
+        if (e == cudaSuccess) {
+            BSX_PIN_CARVEOUT(ed25519_key_assign_kernel); BSX_PIN_CARVEOUT(ed25519_key_bases_kernel); BSX_PIN_CARVEOUT(ed25519_key_table_kernel);
+            ed25519_key_assign_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, in, keys);
+            ed25519_key_bases_kernel<<<BSX_ED_KEY_SLOTS / 32, 32, 0, st>>>(n, in, keys);
+            ed25519_key_table_kernel<<<BSX_ED_KEY_MAX, BSX_ED_KEY_WINDOWS, 0, st>>>(n, keys);
+            ctx->launches += 3;
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) {
+            cudaFreeAsync(kmem, st);
+            return bsx::fail(ctx, BSX_ERR_CUDA, "Ed25519 key tables: %s%s", cudaGetErrorString(e));
+        }
+    }
+#define BSX_ED_LAUNCH(K)                                      \
+    do {                                                      \
+        BSX_PIN_CARVEOUT((K));                                \
+        K<<<grid, 64, ballast, st>>>(n, in, tab, out, keys);  \
     } while (0)
     if (cap && (!alone || env_cap > 0) && !env_occ && !corun && inl <= 0) {
         // (caps of 176 and 160 registers spill and were slower: profiles/r01p_step_ab.txt)
@@ -452,7 +580,10 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
         else BSX_ED_LAUNCH((ed25519_batch_kernel<4, false, false>));
     }
 #undef BSX_ED_LAUNCH
-    BSX_LAUNCHED(ctx);
+    const cudaError_t el = cudaGetLastError();
+    if (kmem) cudaFreeAsync(kmem, st);   // stream-ordered: after the kernel above, also on the error path
+    if (el != cudaSuccess) return bsx::fail(ctx, BSX_ERR_CUDA, "kernel launch: %s%s", cudaGetErrorString(el));
+    ctx->launches++;
     return BSX_OK;
 }
 

@@ -109,6 +109,16 @@ void hc_fp64_scalarmult(const uint8_t *s, const uint8_t *xy, uint8_t *out, int b
     fe_tobytes(out, fe_from_fed(fed_mul(r.X, zi)));
     fe_tobytes(out + 32, fe_from_fed(fed_mul(r.Y, zi)));
 }
+// the per-key table path: bases and window tables of pk built here, then the keyed record
+void hc_fp64_ed25519_witness_keyed(const uint8_t *pk, const uint8_t *sig, const uint8_t *digest, uint8_t *out) {
+    build_table();
+    RoundTowardZero rz;
+    static uint8_t rec[BSX_ED_KEYREC_BYTES];
+    static double bases[BSX_ED_KEY_WINDOWS * 20], tab[BSX_ED_KEY_WINDOWS * 8 * 20];
+    bsx::edd::ed25519_key_bases(pk, rec, bases);
+    for (int w = 0; w < BSX_ED_KEY_WINDOWS; w++) bsx::edd::ed25519_key_window(bases + 20 * w, tab + 160 * w);
+    bsx::edd::ed25519_witness_core_keyed(sig, digest, g_table, rec, tab, out);
+}
 int hc_fp64_decompress(const uint8_t *in, uint8_t *xy, uint8_t *root) {
     RoundTowardZero rz;
     bsx::edd::fed x, y;

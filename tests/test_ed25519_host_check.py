@@ -211,6 +211,9 @@ def test_no_limb_overflow_under_ubsan():
                 out2 = (C.c_uint8 * 576)()
                 hc.hc_fp64_ed25519_witness(buf(pk), buf(sig), buf(hashlib.sha512(sig[:32] + pk + msg).digest()), out2)
                 assert bytes(out2) == bytes(out)
+                out3 = (C.c_uint8 * 576)()   # and the per-key table path
+                hc.hc_fp64_ed25519_witness_keyed(buf(pk), buf(sig), buf(hashlib.sha512(sig[:32] + pk + msg).digest()), out3)
+                assert bytes(out3) == bytes(out)
         print("clean")
     """)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
@@ -335,5 +338,8 @@ def test_fp64_witness_records(hc):
         hc.hc_fp64_ed25519_witness(_buf(pk), _buf(sig), _buf(hashlib.sha512(sig[:32] + pk + msg).digest()), out)
         want = orc.ed25519_witness(pk, sig, msg)
         assert bytes(out) == want, (pk.hex(), sig.hex())
+        out_k = _out(576)      # the per-key table path (h*A from the tabulated windows of the key) gives the same record
+        hc.hc_fp64_ed25519_witness_keyed(_buf(pk), _buf(sig), _buf(hashlib.sha512(sig[:32] + pk + msg).digest()), out_k)
+        assert bytes(out_k) == want, ("keyed", pk.hex(), sig.hex())
         seen.add(want[520])
     assert 0xF in seen and len(seen) >= 3

@@ -27,6 +27,56 @@ def cases():
     return a, orc.ed25519_batch(*a, threads=8)
 
 
+# the per-key table path of the FP64 build (h*A from tabulated windows of each distinct public key, found on the device)
+KEYED = [
+    ("per-key tables", {"ED_MODE": 2, "ED_FP64": 1, "ED_KEYTAB": 1}),
+    ("per-key tables, 128 registers", {"ED_MODE": 2, "ED_FP64": 1, "ED_KEYTAB": 1, "ED_OCC": 8}),
+    ("per-key tables, 168 registers", {"ED_MODE": 2, "ED_FP64": 1, "ED_KEYTAB": 1, "ED_OCC": 6}),
+    ("per-key tables by the repeat rule", {"ED_MODE": 2, "ED_FP64": 1}),
+]
+
+
+@pytest.fixture(scope="module")
+def few_keys():
+    """~450 distinct keys (100 signers, one-bit corruptions of pk / R / s / message, garbage and edge encodings), each
+    valid signer ~6 times: below the 1024-key capacity, so ED_KEYTAB = 1 really takes the table path; tiled 40 times
+    (36 000 signatures, > 16 uses per key) the default rule takes it too."""
+    from oracle import cbind as orc
+    from tests._ed_cases import stress_inputs
+    a = stress_inputs(600, 300, base_n=100)
+    return a, orc.ed25519_batch(*a, threads=8)
+
+
+@pytest.mark.parametrize("name,tun", KEYED, ids=[b[0] for b in KEYED])
+def test_per_key_table_path_matches_oracle(few_keys, name, tun):
+    from blobstreamx_b200 import lib
+    a, want = few_keys
+    reps = 40 if "ED_KEYTAB" not in tun else 1
+    if reps > 1:
+        a = tuple(np.ascontiguousarray(np.concatenate([x] * reps)) for x in a)
+        want = np.concatenate([want] * reps)
+    with lib.Context(0) as ctx:
+        for k, v in tun.items():
+            ctx.set_tunable(k, v)
+        got = ctx.ed25519_batch(*a)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, (name, bad[:10])
+    flags = want[:, 520]
+    assert (flags == 0xF).sum() > 300 * reps and (flags != 0xF).sum() > 300 * reps
+
+
+def test_per_key_tables_overflow_falls_back(cases):
+    """More distinct keys than the table holds (the 3 600-key stress sample): the device-side verdict sends the whole
+    batch down the general path, whatever ED_KEYTAB asks for."""
+    from blobstreamx_b200 import lib
+    a, want = cases
+    with lib.Context(0) as ctx:
+        for k, v in {"ED_MODE": 2, "ED_FP64": 1, "ED_KEYTAB": 1}.items():
+            ctx.set_tunable(k, v)
+        got = ctx.ed25519_batch(*a)
+    assert (got == want).all()
+
+
 @pytest.mark.parametrize("name,tun", BUILDS, ids=[b[0] for b in BUILDS])
 def test_every_ed25519_build_matches_oracle(cases, name, tun):
     from blobstreamx_b200 import lib
