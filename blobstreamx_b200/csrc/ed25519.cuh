@@ -843,19 +843,27 @@ BSX_HD ged_p3 ged_scalarmult(const uint8_t s[32], const ged_p3 &P) {
 // R + hA = sG as points, so every byte of the record follows without the chain.  Anything else -- a signature that does not
 // verify, a non-canonical y, an R off the curve -- takes the general path below (decompression, addition, a second
 // inversion), which is the r02b code.  Same bytes either way (tests/test_ed25519_host_check.py, the GPU stress inputs).
-// everything after the two scalar multiplications: R (shortcut or general path), R + hA, affine bytes, flags
-BSX_HD void ed25519_witness_tail(const ged_p3 &sg, const ged_p3 &ha, const uint8_t sig[64], uint32_t flags, uint8_t *out) {
-    // R' = sG - hA, and one inversion for the three Z's
+// everything after the two scalar multiplications, in two halves around the inversion so that a thread that handles
+// several signatures can share ONE inversion between them (Montgomery's trick):
+//   ed25519_witness_points: R' = sG - hA and z = Z_sG Z_hA Z_R'
+//   ed25519_witness_finish: given 1/z -- affine bytes, R by the shortcut or the general path, R + hA, flags
+struct ed_pending { fed sgX, sgY, sgZ, haX, haY, haZ, haT, rpX, rpY, rpZ, z; };
+BSX_HD ed_pending ed25519_witness_points(const ged_p3 &sg, const ged_p3 &ha) {
     const ged_p3 rp = ged_p1p1_to_p3(ged_add_cached(sg, ged_cached_cneg(ged_to_cached(ha), true)), false);
-    const fed z12 = fed_mul(sg.Z, ha.Z);
-    const fed inv = fed_invert(fed_mul(z12, rp.Z));
-    const fed irp = fed_mul(inv, z12);
-    const fed i12 = fed_mul(inv, rp.Z);
-    const fed isg = fed_mul(i12, ha.Z), iha = fed_mul(i12, sg.Z);
-    ed::fe_tobytes(out + 136, fe_from_fed(fed_mul(sg.X, isg))); ed::fe_tobytes(out + 168, fe_from_fed(fed_mul(sg.Y, isg)));
-    ed::fe_tobytes(out + 296, fe_from_fed(fed_mul(ha.X, iha))); ed::fe_tobytes(out + 328, fe_from_fed(fed_mul(ha.Y, iha)));
-    const fed rpx = fed_mul(rp.X, irp);
-    ed::fe_tobytes(out + 360, fe_from_fed(rpx)); ed::fe_tobytes(out + 392, fe_from_fed(fed_mul(rp.Y, irp)));
+    ed_pending p;
+    p.sgX = sg.X; p.sgY = sg.Y; p.sgZ = sg.Z; p.haX = ha.X; p.haY = ha.Y; p.haZ = ha.Z; p.haT = ha.T;
+    p.rpX = rp.X; p.rpY = rp.Y; p.rpZ = rp.Z;
+    p.z = fed_mul(fed_mul(sg.Z, ha.Z), rp.Z);
+    return p;
+}
+BSX_HD void ed25519_witness_finish(const ed_pending &p, const fed &inv, const uint8_t sig[64], uint32_t flags, uint8_t *out) {
+    const fed irp = fed_mul(inv, fed_mul(p.sgZ, p.haZ));
+    const fed i12 = fed_mul(inv, p.rpZ);
+    const fed isg = fed_mul(i12, p.haZ), iha = fed_mul(i12, p.sgZ);
+    ed::fe_tobytes(out + 136, fe_from_fed(fed_mul(p.sgX, isg))); ed::fe_tobytes(out + 168, fe_from_fed(fed_mul(p.sgY, isg)));
+    ed::fe_tobytes(out + 296, fe_from_fed(fed_mul(p.haX, iha))); ed::fe_tobytes(out + 328, fe_from_fed(fed_mul(p.haY, iha)));
+    const fed rpx = fed_mul(p.rpX, irp);
+    ed::fe_tobytes(out + 360, fe_from_fed(rpx)); ed::fe_tobytes(out + 392, fe_from_fed(fed_mul(p.rpY, irp)));
     const bool sign = (sig[31] >> 7) != 0;
     bool same = ((out[360] & 1) != 0) == sign && out[392 + 31] == (sig[31] & 0x7f);
     for (int i = 0; i < 31; i++) same = same && out[392 + i] == sig[i];
@@ -867,6 +875,7 @@ BSX_HD void ed25519_witness_tail(const ged_p3 &sg, const ged_p3 &ha, const uint8
     } else {
         fed rx, ry;
         if (ged_decompress(sig, rx, ry, out + 360, out + 392, out + 424)) flags |= 4u;
+        ged_p3 ha; ha.X = p.haX; ha.Y = p.haY; ha.Z = p.haZ; ha.T = p.haT;
         const ged_p3 sum = ged_p1p1_to_p3(ged_add_cached(ha, ged_to_cached(ged_from_affine(rx, ry))), false);
         const fed isum = fed_invert(sum.Z);
         ed::fe_tobytes(out + 456, fe_from_fed(fed_mul(sum.X, isum))); ed::fe_tobytes(out + 488, fe_from_fed(fed_mul(sum.Y, isum)));
@@ -874,6 +883,10 @@ BSX_HD void ed25519_witness_tail(const ged_p3 &sg, const ged_p3 &ha, const uint8
     }
     out[520] = (uint8_t)flags; out[521] = 0; out[522] = 0; out[523] = 0;
     for (int i = 524; i < 576; i++) out[i] = 0;
+}
+BSX_HD void ed25519_witness_tail(const ged_p3 &sg, const ged_p3 &ha, const uint8_t sig[64], uint32_t flags, uint8_t *out) {
+    const ed_pending p = ed25519_witness_points(sg, ha);
+    ed25519_witness_finish(p, fed_invert(p.z), sig, flags, out);
 }
 
 template <bool INL = false>
@@ -892,14 +905,18 @@ BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], co
 // ---- per-key window tables (r02k) ----
 // A batch that repeats public keys (one validator set signs every range of a batch) pays the 252 doublings of h*A and the
 // decompression of A once per KEY instead of once per signature: for every distinct key the windows 16^w A (w = 0..63) and
-// their multiples 1..8 are tabulated in the projective addend form, and h*A becomes 64 table additions over the signed
-// radix-16 digits of h (h < l < 2^253, so the digit recoding leaves no carry out of window 63).  The result is the same
+// their multiples 1..2^(b-1) are tabulated in the projective addend form (b = BSX_ED_KEY_BITS = 6: 43 windows of 32 entries),
+// and h*A becomes one table addition per window over the signed radix-2^b digits of h (h < l < 2^253: no carry out of the top).  The result is the same
 // group element, hence the same affine bytes.  Layouts (doubles / bytes):
 //   key record  BSX_ED_KEYREC_BYTES: x[32] y[32] root[32] ok[1] of decompress(A) -- exactly the bytes of the signature record
 //   bases       [key][w]    one extended point (X, Y, Z, T) = 20 doubles
-//   table       [key][w][d] addend form of (d+1) 16^w A (YpX, YmX, Z, T2d) = 20 doubles
+//   table       [key][w][d] addend form of (d+1) 2^(b w) A (YpX, YmX, Z, T2d) = 20 doubles, d < 2^(b-1)
 #define BSX_ED_KEYREC_BYTES 128
-#define BSX_ED_KEY_WINDOWS 64
+#ifndef BSX_ED_KEY_BITS
+#define BSX_ED_KEY_BITS 6                                            // window width: signed digits in [-2^(b-1), 2^(b-1)]
+#endif
+#define BSX_ED_KEY_WINDOWS ((253 + BSX_ED_KEY_BITS - 1) / BSX_ED_KEY_BITS)   // h < l < 2^253
+#define BSX_ED_KEY_ENTRIES (1 << (BSX_ED_KEY_BITS - 1))             // multiples 1 .. 2^(b-1) of a window base
 BSX_HD void ged_store20(double *dst, const fed &a, const fed &b, const fed &c, const fed &d) {
 #pragma unroll
     for (int k = 0; k < 5; k++) { dst[k] = a.v[k]; dst[5 + k] = b.v[k]; dst[10 + k] = c.v[k]; dst[15 + k] = d.v[k]; }
@@ -930,7 +947,7 @@ BSX_HD void ed25519_key_bases(const uint8_t pk[32], uint8_t *rec, double *bases)
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-            for (int k = 0; k < 4; k++) p = ged_p1p1_to_p3(ged_dbl(p), k == 3);
+            for (int k = 0; k < BSX_ED_KEY_BITS; k++) p = ged_p1p1_to_p3(ged_dbl(p), k == BSX_ED_KEY_BITS - 1);
         }
     }
 }
@@ -943,7 +960,7 @@ BSX_HD void ed25519_key_window(const double *base, double *tab) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int d = 2; d <= 8; d++) {
+    for (int d = 2; d <= BSX_ED_KEY_ENTRIES; d++) {
         cur = ged_p1p1_to_p3(ged_add_cached(cur, first), true);
         const ged_cached c = ged_to_cached(cur);
         ged_store20(tab + 20 * (d - 1), c.YpX, c.YmX, c.Z, c.T2d);
@@ -958,29 +975,39 @@ BSX_HD ged_p3 ged_scalarmult_keyed(const uint8_t s[32], const double *tab) {
 #pragma unroll 1
 #endif
     for (int w = 0; w < BSX_ED_KEY_WINDOWS; w++) {
-        int d = (int)((s[w >> 1] >> ((w & 1) * 4)) & 15) + carry;
-        carry = d >= 8;
-        d -= 16 * carry;
+        const int bit = w * BSX_ED_KEY_BITS, byte = bit >> 3;
+        const uint32_t v = (uint32_t)s[byte] | ((uint32_t)(byte + 1 < 32 ? s[byte + 1] : 0) << 8);
+        int d = (int)((v >> (bit & 7)) & ((1u << BSX_ED_KEY_BITS) - 1)) + carry;
+        carry = d > BSX_ED_KEY_ENTRIES;
+        d -= (1 << BSX_ED_KEY_BITS) * carry;
         if (d) {
             ged_cached q;
-            ged_load20(tab + 20 * (8 * w + (d < 0 ? -d : d) - 1), q.YpX, q.YmX, q.Z, q.T2d);
+            ged_load20(tab + 20 * (BSX_ED_KEY_ENTRIES * w + (d < 0 ? -d : d) - 1), q.YpX, q.YmX, q.Z, q.T2d);
             acc = ged_p1p1_to_p3<INL>(ged_add_cached<INL>(acc, ged_cached_cneg(q, d < 0)), true);
         }
     }
-    return acc;   // carry out of window 63 is impossible for s < 2^255 - 2^251 (the remainder mod l is < 2^253)
+    return acc;   // no carry out of the top window: the remainder mod l is < 2^253 and the windows cover >= 253 bits with room
 }
-// the record of one signature whose key has been tabulated: same bytes as ed25519_witness_core
+// the record of one signature whose key has been tabulated: same bytes as ed25519_witness_core.  First half (up to the
+// inversion) and the whole of it for one signature per thread.
 template <bool INL = false>
-BSX_HD void ed25519_witness_core_keyed(const uint8_t sig[64], const uint8_t digest[64], const ed::ge_niels_slot *base_table,
-                                       const uint8_t *key_rec, const double *key_tab, uint8_t *out) {
+BSX_HD ed_pending ed25519_witness_keyed_points(const uint8_t sig[64], const uint8_t digest[64], const ed::ge_niels_slot *base_table,
+                                               const uint8_t *key_rec, const double *key_tab, uint8_t *out, uint32_t &flags) {
     for (int i = 0; i < 64; i++) out[i] = digest[i];
     ed::sc_divrem_l(digest, out + 64, out + 96);
-    uint32_t flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
+    flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
     for (int i = 0; i < 96; i++) out[200 + i] = key_rec[i];
     if (key_rec[96]) flags |= 2u;
     const ged_p3 sg = ged_scalarmult_base<INL>(sig + 32, base_table);
     const ged_p3 ha = ged_scalarmult_keyed<INL>(out + 64, key_tab);
-    ed25519_witness_tail(sg, ha, sig, flags, out);
+    return ed25519_witness_points(sg, ha);
+}
+template <bool INL = false>
+BSX_HD void ed25519_witness_core_keyed(const uint8_t sig[64], const uint8_t digest[64], const ed::ge_niels_slot *base_table,
+                                       const uint8_t *key_rec, const double *key_tab, uint8_t *out) {
+    uint32_t flags;
+    const ed_pending p = ed25519_witness_keyed_points<INL>(sig, digest, base_table, key_rec, key_tab, out, flags);
+    ed25519_witness_finish(p, fed_invert(p.z), sig, flags, out);
 }
 
 }  // namespace edd

@@ -61,9 +61,10 @@ struct EdKeys {
     int32_t *state;        // [0] distinct keys  [1] overflow  [2] next dense id
     int32_t *key_slot;     // [n] slot of each signature's key
     uint8_t *recs;         // [KEY_MAX] BSX_ED_KEYREC_BYTES
-    double *bases;         // [KEY_MAX][64][20]
-    double *tab;           // [KEY_MAX][64][8][20]
+    double *bases;         // [KEY_MAX][WINDOWS][20]
+    double *tab;           // [KEY_MAX][WINDOWS][ENTRIES][20]
     int32_t force;         // ED_KEYTAB = 1: use the tables whenever the keys fit
+    int32_t pair;          // table path: two signatures per thread sharing one inversion (large batches only)
 };
 __device__ __forceinline__ bool ed_keys_in_use(const EdKeys &k, uint32_t n) {
     return k.state != nullptr && k.state[1] == 0 && (k.force || (uint64_t)k.state[0] * BSX_ED_KEY_MIN_USE <= n);
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(BSX_ED_KEY_WINDOWS) ed25519_key_table_kernel(u
     const uint32_t id = blockIdx.x, w = threadIdx.x;
     if (!ed_keys_in_use(keys, n) || (int32_t)id >= keys.state[0]) return;
     const size_t e = (size_t)id * BSX_ED_KEY_WINDOWS + w;
-    edd::ed25519_key_window(keys.bases + e * 20, keys.tab + e * 8 * 20);
+    edd::ed25519_key_window(keys.bases + e * 20, keys.tab + e * BSX_ED_KEY_ENTRIES * 20);
 }
 
 // FP64: the field arithmetic of the whole signature on the FP64 pipe (fe51d.cuh) instead of IMAD.WIDE
@@ -147,12 +148,8 @@ __global__ void __maxnreg__(REGS) ed25519_batch_kernel_capped(uint32_t n, EdIn i
     ed25519_batch_body<INL, FP64>(n, in, table, out, keys);
 }
 
-template <bool INL, bool FP64>
-__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out,
-                                                   const EdKeys &keys) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint8_t pk[32], sig[64];
+// inputs of signature i (the DUMMY triple for an inactive lane, eddsa.rs:28-30,62-63) and SHA-512(R || A || M)
+__device__ __forceinline__ void ed_load_and_hash(const EdIn &in, uint32_t i, uint8_t pk[32], uint8_t sig[64], uint8_t digest[64]) {
     const bool on = !in.active || in.active[(size_t)in.active_stride * i];
     const uint8_t *m = in.msgs + (size_t)in.msg_stride * i;
     uint32_t len = in.msg_max;
@@ -167,25 +164,73 @@ __device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, c
     } else {
         for (int k = 0; k < 32; k++) pk[k] = DUMMY_PK[k];
         for (int k = 0; k < 64; k++) sig[k] = DUMMY_SIG[k];
-        len = 32;  // DUMMY_MSG_LENGTH_BYTES: 32 zero bytes (eddsa.rs:28-30,62-63)
+        len = 32;  // DUMMY_MSG_LENGTH_BYTES: 32 zero bytes
     }
     uint64_t st[8];
     sha512_bytes(
         [&](uint32_t k) -> uint8_t { return k < 32 ? sig[k] : (k < 64 ? pk[k - 32] : (on ? m[k - 64] : (uint8_t)0)); },
         64 + len, st);
-    uint8_t digest[64];
 #pragma unroll
     for (int k = 0; k < 8; k++)
 #pragma unroll
         for (int j = 0; j < 8; j++) digest[8 * k + j] = (uint8_t)(st[k] >> (56 - 8 * j));
-    if (FP64) {
-        if (ed_keys_in_use(keys, n)) {
-            const int32_t id = keys.slot_id[keys.key_slot[i]];
-            edd::ed25519_witness_core_keyed<INL>(sig, digest, table, keys.recs + (size_t)BSX_ED_KEYREC_BYTES * id,
-                                                 keys.tab + (size_t)id * BSX_ED_KEY_WINDOWS * 8 * 20, out + (size_t)BSX_SIG_OUT_BYTES * i);
-        } else {
-            edd::ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
-        }
+}
+__device__ __forceinline__ void ed_load_sig(const EdIn &in, uint32_t i, uint8_t sig[64]) {
+    const bool on = !in.active || in.active[(size_t)in.active_stride * i];
+    for (int k = 0; k < 64; k++) sig[k] = on ? in.sigs[(size_t)in.sig_stride * i + k] : DUMMY_SIG[k];
+}
+
+// the table path: thread t takes signatures t and t + ceil(n / 2) and inverts once for both (Montgomery's trick): with h*A
+// down to 43 table additions the inversion is a quarter of a signature's field operations.  The grid is launched for one
+// signature per thread (the verdict on the tables falls on the device), so the upper half of the threads leaves at once.
+template <bool INL>
+__device__ __forceinline__ void ed25519_keyed_pair(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out,
+                                                   const EdKeys &keys) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, half = (n + 1) / 2;
+    if (t >= half) return;
+    edd::ed_pending pend[2];
+    uint32_t flags[2];
+    const bool two = t + half < n;
+#pragma unroll 1
+    for (int j = 0; j < (two ? 2 : 1); j++) {
+        const uint32_t i = t + j * half;
+        uint8_t pk[32], sig[64], digest[64];
+        ed_load_and_hash(in, i, pk, sig, digest);
+        const int32_t id = keys.slot_id[keys.key_slot[i]];
+        pend[j] = edd::ed25519_witness_keyed_points<INL>(sig, digest, table, keys.recs + (size_t)BSX_ED_KEYREC_BYTES * id,
+                                                         keys.tab + (size_t)id * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_ENTRIES * 20,
+                                                         out + (size_t)BSX_SIG_OUT_BYTES * i, flags[j]);
+    }
+    // Z is never zero (complete addition law; undecodable points were replaced by the identity): the product is invertible
+    const edd::fed inv01 = edd::fed_invert(two ? edd::fed_mul(pend[0].z, pend[1].z) : pend[0].z);
+#pragma unroll 1
+    for (int j = 0; j < (two ? 2 : 1); j++) {
+        const uint32_t i = t + j * half;
+        uint8_t sig[64];
+        ed_load_sig(in, i, sig);
+        const edd::fed inv = two ? edd::fed_mul(inv01, pend[1 - j].z) : inv01;
+        edd::ed25519_witness_finish(pend[j], inv, sig, flags[j], out + (size_t)BSX_SIG_OUT_BYTES * i);
+    }
+}
+
+template <bool INL, bool FP64>
+__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out,
+                                                   const EdKeys &keys) {
+    const bool keyed = FP64 && ed_keys_in_use(keys, n);
+    if (keyed && keys.pair) {
+        ed25519_keyed_pair<INL>(n, in, table, out, keys);
+        return;
+    }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t pk[32], sig[64], digest[64];
+    ed_load_and_hash(in, i, pk, sig, digest);
+    if (keyed) {
+        const int32_t id = keys.slot_id[keys.key_slot[i]];
+        edd::ed25519_witness_core_keyed<INL>(sig, digest, table, keys.recs + (size_t)BSX_ED_KEYREC_BYTES * id,
+                                             keys.tab + (size_t)id * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_ENTRIES * 20, out + (size_t)BSX_SIG_OUT_BYTES * i);
+    } else if (FP64) {
+        edd::ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
     } else {
         ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
     }
@@ -505,7 +550,14 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     const bool fp64 = fp64_t < 0 ? BSX_ED_FP64_DEFAULT : fp64_t != 0;
     // FP64 limbs: the register budget follows the batch size (the widest build whose wave the batch fills, common.cuh);
     // ED_OCC = 4 / 6 / 8 forces one
-    const int wave_occ = fp64 ? bsx_ed_wave_occ(ctx, n) : 0;
+    // Table path, two signatures per thread (one shared inversion): only when half the threads still give every SM five
+    // CTAs -- r02n: 1135 ranges 4.76 -> 4.64 ms per step, but 757 ranges 3.26 -> 3.30 and 378 ranges 1.94 -> 2.33 (too few
+    // warps to hide the latency).  The wave is then counted over n / 2 threads; a batch that falls back to the general path
+    // on the device runs it in a build chosen for half its size.  ED_PAIR = 0 / 1 forces the choice.
+    const int pair_t = ctx->tun[BSX_TUN_ED_PAIR];
+    const bool pairs = fp64 && ctx->tun[BSX_TUN_ED_KEYTAB] != 0 &&
+                       (pair_t >= 0 ? pair_t != 0 : (uint64_t)(n + 1) / 2 >= (uint64_t)ctx->sm_count * 5 * 64);
+    const int wave_occ = fp64 ? bsx_ed_wave_occ(ctx, pairs ? (n + 1) / 2 : n) : 0;
     const int occ = env_occ ? env_occ : corun ? 8 : (wave_occ > 4 ? wave_occ : 4);
     const int inl = ctx->tun[BSX_TUN_ED_INLINE];   // -1: by call site
     const bool use_inl = inl < 0 ? alone : inl != 0;
@@ -531,7 +583,7 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
                      o_recs = (o_key_slot + sizeof(int32_t) * (size_t)n + 255) & ~(size_t)255,
                      o_bases = o_recs + (size_t)BSX_ED_KEY_MAX * BSX_ED_KEYREC_BYTES,
                      o_tab = o_bases + sizeof(double) * 20 * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX,
-                     total = o_tab + sizeof(double) * 20 * 8 * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX;
+                     total = o_tab + sizeof(double) * 20 * BSX_ED_KEY_ENTRIES * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX;
         BSX_CUDA(ctx, cudaMallocAsync((void **)&kmem, total, st));
         keys.slots = reinterpret_cast<int32_t *>(kmem);
         keys.slot_id = reinterpret_cast<int32_t *>(kmem + o_slot_id);
@@ -541,6 +593,7 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
         keys.bases = reinterpret_cast<double *>(kmem + o_bases);
         keys.tab = reinterpret_cast<double *>(kmem + o_tab);
         keys.force = keytab > 0;
+        keys.pair = pairs;
         cudaError_t e = cudaMemsetAsync(keys.slots, 0xff, o_slot_id, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(keys.state, 0, 256, st);
         if (e == cudaSuccess) {

@@ -114,9 +114,9 @@ void hc_fp64_ed25519_witness_keyed(const uint8_t *pk, const uint8_t *sig, const 
     build_table();
     RoundTowardZero rz;
     static uint8_t rec[BSX_ED_KEYREC_BYTES];
-    static double bases[BSX_ED_KEY_WINDOWS * 20], tab[BSX_ED_KEY_WINDOWS * 8 * 20];
+    static double bases[BSX_ED_KEY_WINDOWS * 20], tab[BSX_ED_KEY_WINDOWS * BSX_ED_KEY_ENTRIES * 20];
     bsx::edd::ed25519_key_bases(pk, rec, bases);
-    for (int w = 0; w < BSX_ED_KEY_WINDOWS; w++) bsx::edd::ed25519_key_window(bases + 20 * w, tab + 160 * w);
+    for (int w = 0; w < BSX_ED_KEY_WINDOWS; w++) bsx::edd::ed25519_key_window(bases + 20 * w, tab + 20 * BSX_ED_KEY_ENTRIES * w);
     bsx::edd::ed25519_witness_core_keyed(sig, digest, g_table, rec, tab, out);
 }
 int hc_fp64_decompress(const uint8_t *in, uint8_t *xy, uint8_t *root) {
