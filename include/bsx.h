@@ -53,8 +53,8 @@ uint64_t bsx_launch_count(const bsx_ctx *ctx);
 int bsx_sync(bsx_ctx *ctx);
 /* Measurement knobs of one ctx (kernel-build and stream-arrangement choices; defaults = the measured best; the
  * environment variable BSX_<name> sets the default a new ctx starts with).  Names: ED_MODE, ED_QUAD_MAX, ED_INLINE,
- * ED_OCC, ED_REGS, ED_FP64, HR_HASH_STREAM, HR_TRACE, PIPE_CHUNK, PIPE_ED, PIPE_TRACE, PROOFS_OCC, SUBCHAIN_FUSED,
- * COMMIT_THREADS
+ * ED_OCC, ED_REGS, ED_FP64, ED_KEYTAB, ED_PAIR, ED_RESIDENT, HR_HASH_STREAM, HR_TRACE, PIPE_CHUNK, PIPE_ED, PIPE_TRACE,
+ * PROOFS_OCC, SUBCHAIN_FUSED, COMMIT_THREADS
  * (DESIGN.md section 4).  No reference counterpart: results are identical under every setting. */
 int bsx_set_tunable(bsx_ctx *ctx, const char *name, int value);
 int bsx_get_tunable(const bsx_ctx *ctx, const char *name, int *value);
@@ -272,6 +272,10 @@ int bsx_shard_step_dev(bsx_shard *sh, void *stream, const bsx_shard_in *in, cons
  *   [360..424) Rp (x,y)     [424..456) R_root    [456..520) Rp + h*A   [520..524) flags
  * flags: BSX_SIG_S_LT_L | BSX_SIG_A_OK | BSX_SIG_R_OK | BSX_SIG_EQ ; 0xF = the circuit accepts.
  * A point that fails to decompress (the reference panics) is reported as the identity with root 0.
+ * Batches above 16 384 signatures (one thread per signature): public keys that repeat within the batch
+ * (one validator set signing many ranges) are found on the device and h*A is taken from per-key window
+ * tables, R is checked against s*G - h*A before it is decompressed; the records are the same bytes on
+ * every path.  Such a call draws up to ~250 MB of stream-ordered pool memory (cudaMallocAsync) while it runs.
  * ------------------------------------------------------------------------------------------ */
 #define BSX_SIG_OUT_BYTES 576
 #define BSX_SIG_S_LT_L 1u
