@@ -29,6 +29,7 @@ enum bsx_tun_id {
     BSX_TUN_SUBCHAIN_FUSED,  // 1 = one-CTA-per-job map kernel with TMA-staged inputs (A/B only)
     BSX_TUN_COMMIT_THREADS,  // threads per CTA of the commit kernel (B = 32 / 64): 128, 256, 512 or 1024
     BSX_TUN_ED_KEYTAB,       // per-key window tables for h*A (FP64 build): -1 when keys repeat enough, 0 never, 1 whenever they fit
+    BSX_TUN_ED_KOCC,         // register budget of the table-path kernel: 0 = as the general kernel's, 4 / 6 / 8 CTAs per SM
     BSX_TUN_ED_PAIR,         // table path: two signatures per thread with one shared inversion: -1 by batch size, 0 never, 1 always
     BSX_TUN_ED_RESIDENT,     // thread-per-signature kernel: at most this many CTAs per SM (dynamic shared memory as ballast), 0 = no limit
     BSX_TUN_COUNT

@@ -656,6 +656,35 @@ using ed::fe;
 #define BSX_FED_SQRTM1 {-533094393274192.0, 234908883556510.0, -18285341111200.0, -134597186663265.0, 765476049583134.0}
 BSX_HD fed fed_const(const double c[5]) { fed r; for (int i = 0; i < 5; i++) r.v[i] = c[i]; return r; }
 
+// Record bytes are produced in thread-local arrays and leave as 8-byte words (every field of the 576-byte record starts at a
+// multiple of 8): r02p's capture of the batch kernel had the read-backs of bytes it had just stored to global memory
+// (`long_scoreboard`) and its byte-wide stores (`lg_throttle`) as the top stalls.  dst must be 8-byte aligned.
+template <int N>
+BSX_HD void put_bytes(uint8_t *dst, const uint8_t *src) {
+#if defined(__CUDA_ARCH__)
+    uint2 *q = reinterpret_cast<uint2 *>(dst);
+#pragma unroll
+    for (int k = 0; k < N / 8; k++) {
+        const uint8_t *b = src + 8 * k;
+        q[k] = make_uint2((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24),
+                          (uint32_t)b[4] | ((uint32_t)b[5] << 8) | ((uint32_t)b[6] << 16) | ((uint32_t)b[7] << 24));
+    }
+#else
+    for (int k = 0; k < N; k++) dst[k] = src[k];
+#endif
+}
+BSX_HD void put_flags_and_padding(uint8_t *out, uint32_t flags) {   // [520, 576): flags byte, zeros
+#if defined(__CUDA_ARCH__)
+    uint2 *q = reinterpret_cast<uint2 *>(out + 520);
+    q[0] = make_uint2(flags & 0xffu, 0u);
+#pragma unroll
+    for (int k = 1; k < 7; k++) q[k] = make_uint2(0u, 0u);
+#else
+    out[520] = (uint8_t)flags;
+    for (int i = 521; i < 576; i++) out[i] = 0;
+#endif
+}
+
 // 10 x 25.5-bit integer limbs <-> 5 x 51-bit double limbs (limb pair 2k, 2k+1 = bits 51k .. 51k+50)
 BSX_HD fed fed_from_fe(const fe &f) {
     int64_t E[5];
@@ -860,29 +889,34 @@ BSX_HD void ed25519_witness_finish(const ed_pending &p, const fed &inv, const ui
     const fed irp = fed_mul(inv, fed_mul(p.sgZ, p.haZ));
     const fed i12 = fed_mul(inv, p.rpZ);
     const fed isg = fed_mul(i12, p.haZ), iha = fed_mul(i12, p.sgZ);
-    ed::fe_tobytes(out + 136, fe_from_fed(fed_mul(p.sgX, isg))); ed::fe_tobytes(out + 168, fe_from_fed(fed_mul(p.sgY, isg)));
-    ed::fe_tobytes(out + 296, fe_from_fed(fed_mul(p.haX, iha))); ed::fe_tobytes(out + 328, fe_from_fed(fed_mul(p.haY, iha)));
+    uint8_t sgb[64], t[64], rb[96];      // sG (x, y); scratch; R (x, y, root)
+    ed::fe_tobytes(sgb, fe_from_fed(fed_mul(p.sgX, isg))); ed::fe_tobytes(sgb + 32, fe_from_fed(fed_mul(p.sgY, isg)));
+    put_bytes<64>(out + 136, sgb);
+    ed::fe_tobytes(t, fe_from_fed(fed_mul(p.haX, iha))); ed::fe_tobytes(t + 32, fe_from_fed(fed_mul(p.haY, iha)));
+    put_bytes<64>(out + 296, t);
     const fed rpx = fed_mul(p.rpX, irp);
-    ed::fe_tobytes(out + 360, fe_from_fed(rpx)); ed::fe_tobytes(out + 392, fe_from_fed(fed_mul(p.rpY, irp)));
+    ed::fe_tobytes(rb, fe_from_fed(rpx)); ed::fe_tobytes(rb + 32, fe_from_fed(fed_mul(p.rpY, irp)));
     const bool sign = (sig[31] >> 7) != 0;
-    bool same = ((out[360] & 1) != 0) == sign && out[392 + 31] == (sig[31] & 0x7f);
-    for (int i = 0; i < 31; i++) same = same && out[392 + i] == sig[i];
+    bool same = ((rb[0] & 1) != 0) == sign && rb[32 + 31] == (sig[31] & 0x7f);
+    for (int i = 0; i < 31; i++) same = same && rb[32 + i] == sig[i];
     if (same) {
         flags |= 4u | 8u;
-        if (sign) ed::fe_tobytes(out + 424, fe_from_fed(fed_neg(rpx)));           // x' odd: the even root is p - x'
-        else for (int i = 0; i < 32; i++) out[424 + i] = out[360 + i];
-        for (int i = 0; i < 64; i++) out[456 + i] = out[136 + i];                   // R + hA = sG
+        if (sign) ed::fe_tobytes(rb + 64, fe_from_fed(fed_neg(rpx)));             // x' odd: the even root is p - x'
+        else for (int i = 0; i < 32; i++) rb[64 + i] = rb[i];
+        put_bytes<96>(out + 360, rb);
+        put_bytes<64>(out + 456, sgb);                                              // R + hA = sG
     } else {
         fed rx, ry;
-        if (ged_decompress(sig, rx, ry, out + 360, out + 392, out + 424)) flags |= 4u;
+        if (ged_decompress(sig, rx, ry, rb, rb + 32, rb + 64)) flags |= 4u;
+        put_bytes<96>(out + 360, rb);
         ged_p3 ha; ha.X = p.haX; ha.Y = p.haY; ha.Z = p.haZ; ha.T = p.haT;
         const ged_p3 sum = ged_p1p1_to_p3(ged_add_cached(ha, ged_to_cached(ged_from_affine(rx, ry))), false);
         const fed isum = fed_invert(sum.Z);
-        ed::fe_tobytes(out + 456, fe_from_fed(fed_mul(sum.X, isum))); ed::fe_tobytes(out + 488, fe_from_fed(fed_mul(sum.Y, isum)));
-        if (ed::bytes_eq32(out + 136, out + 456) && ed::bytes_eq32(out + 168, out + 488)) flags |= 8u;
+        ed::fe_tobytes(t, fe_from_fed(fed_mul(sum.X, isum))); ed::fe_tobytes(t + 32, fe_from_fed(fed_mul(sum.Y, isum)));
+        put_bytes<64>(out + 456, t);
+        if (ed::bytes_eq32(sgb, t) && ed::bytes_eq32(sgb + 32, t + 32)) flags |= 8u;
     }
-    out[520] = (uint8_t)flags; out[521] = 0; out[522] = 0; out[523] = 0;
-    for (int i = 524; i < 576; i++) out[i] = 0;
+    put_flags_and_padding(out, flags);
 }
 BSX_HD void ed25519_witness_tail(const ged_p3 &sg, const ged_p3 &ha, const uint8_t sig[64], uint32_t flags, uint8_t *out) {
     const ed_pending p = ed25519_witness_points(sg, ha);
@@ -892,13 +926,16 @@ BSX_HD void ed25519_witness_tail(const ged_p3 &sg, const ged_p3 &ha, const uint8
 template <bool INL = false>
 BSX_HD void ed25519_witness_core(const uint8_t pk[32], const uint8_t sig[64], const uint8_t digest[64],
                                  const ed::ge_niels_slot *base_table, uint8_t *out) {
-    for (int i = 0; i < 64; i++) out[i] = digest[i];
-    ed::sc_divrem_l(digest, out + 64, out + 96);
+    uint8_t h[32], div[40], ab[96];
+    put_bytes<64>(out, digest);
+    ed::sc_divrem_l(digest, h, div);
+    put_bytes<32>(out + 64, h); put_bytes<40>(out + 96, div);
     uint32_t flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
     fed ax, ay;
-    if (ged_decompress(pk, ax, ay, out + 200, out + 232, out + 264)) flags |= 2u;
+    if (ged_decompress(pk, ax, ay, ab, ab + 32, ab + 64)) flags |= 2u;
+    put_bytes<96>(out + 200, ab);
     const ged_p3 sg = ged_scalarmult_base<INL>(sig + 32, base_table);
-    const ged_p3 ha = ged_scalarmult<INL>(out + 64, ged_from_affine(ax, ay));
+    const ged_p3 ha = ged_scalarmult<INL>(h, ged_from_affine(ax, ay));
     ed25519_witness_tail(sg, ha, sig, flags, out);
 }
 
@@ -993,13 +1030,24 @@ BSX_HD ged_p3 ged_scalarmult_keyed(const uint8_t s[32], const double *tab) {
 template <bool INL = false>
 BSX_HD ed_pending ed25519_witness_keyed_points(const uint8_t sig[64], const uint8_t digest[64], const ed::ge_niels_slot *base_table,
                                                const uint8_t *key_rec, const double *key_tab, uint8_t *out, uint32_t &flags) {
-    for (int i = 0; i < 64; i++) out[i] = digest[i];
-    ed::sc_divrem_l(digest, out + 64, out + 96);
+    uint8_t h[32], div[40];
+    put_bytes<64>(out, digest);
+    ed::sc_divrem_l(digest, h, div);
+    put_bytes<32>(out + 64, h); put_bytes<40>(out + 96, div);
     flags = ed::sc_lt_l(sig + 32) ? 1u : 0u;
+#if defined(__CUDA_ARCH__)
+    {   // x, y, root of decompress(A): 96 bytes of the key record, word for word
+        const uint2 *src = reinterpret_cast<const uint2 *>(key_rec);
+        uint2 *dst = reinterpret_cast<uint2 *>(out + 200);
+#pragma unroll
+        for (int k = 0; k < 12; k++) dst[k] = __ldg(src + k);
+    }
+#else
     for (int i = 0; i < 96; i++) out[200 + i] = key_rec[i];
+#endif
     if (key_rec[96]) flags |= 2u;
     const ged_p3 sg = ged_scalarmult_base<INL>(sig + 32, base_table);
-    const ged_p3 ha = ged_scalarmult_keyed<INL>(out + 64, key_tab);
+    const ged_p3 ha = ged_scalarmult_keyed<INL>(h, key_tab);
     return ed25519_witness_points(sg, ha);
 }
 template <bool INL = false>

@@ -213,11 +213,13 @@ __device__ __forceinline__ void ed25519_keyed_pair(uint32_t n, const EdIn &in, c
     }
 }
 
-template <bool INL, bool FP64>
-__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out,
-                                                   const EdKeys &keys) {
-    const bool keyed = FP64 && ed_keys_in_use(keys, n);
-    if (keyed && keys.pair) {
+// The table path as a kernel of its own, so that its registers are allocated for its own code (no 8-entry local table, no
+// doubling chain): does nothing unless the device-side verdict is "tables".
+template <int MIN_CTAS, bool INL>
+__global__ void __launch_bounds__(64, MIN_CTAS) ed25519_keyed_kernel(uint32_t n, EdIn in, const ge_niels_slot *__restrict__ table,
+                                                                      uint8_t *__restrict__ out, EdKeys keys) {
+    if (!ed_keys_in_use(keys, n)) return;
+    if (keys.pair) {
         ed25519_keyed_pair<INL>(n, in, table, out, keys);
         return;
     }
@@ -225,11 +227,22 @@ __device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, c
     if (i >= n) return;
     uint8_t pk[32], sig[64], digest[64];
     ed_load_and_hash(in, i, pk, sig, digest);
-    if (keyed) {
-        const int32_t id = keys.slot_id[keys.key_slot[i]];
-        edd::ed25519_witness_core_keyed<INL>(sig, digest, table, keys.recs + (size_t)BSX_ED_KEYREC_BYTES * id,
-                                             keys.tab + (size_t)id * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_ENTRIES * 20, out + (size_t)BSX_SIG_OUT_BYTES * i);
-    } else if (FP64) {
+    const int32_t id = keys.slot_id[keys.key_slot[i]];
+    edd::ed25519_witness_core_keyed<INL>(sig, digest, table, keys.recs + (size_t)BSX_ED_KEYREC_BYTES * id,
+                                         keys.tab + (size_t)id * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_ENTRIES * 20, out + (size_t)BSX_SIG_OUT_BYTES * i);
+}
+
+template <bool INL, bool FP64>
+__device__ __forceinline__ void ed25519_batch_body(uint32_t n, const EdIn &in, const ge_niels_slot *__restrict__ table, uint8_t *__restrict__ out,
+                                                   const EdKeys &keys) {
+    // the table path has a kernel of its own (ed25519_keyed_kernel, launched just before this one): when the device-side
+    // verdict is "tables", this kernel has nothing to do
+    if (FP64 && ed_keys_in_use(keys, n)) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t pk[32], sig[64], digest[64];
+    ed_load_and_hash(in, i, pk, sig, digest);
+    if (FP64) {
         edd::ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
     } else {
         ed25519_witness_core<INL>(pk, sig, digest, table, out + (size_t)BSX_SIG_OUT_BYTES * i);
@@ -603,6 +616,24 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
             ed25519_key_table_kernel<<<BSX_ED_KEY_MAX, BSX_ED_KEY_WINDOWS, 0, st>>>(n, keys);
             ctx->launches += 3;
             e = cudaGetLastError();
+            if (e == cudaSuccess) {   // the table-path kernel; the general kernel below then returns at once (and vice versa)
+                const int kocc = ctx->tun[BSX_TUN_ED_KOCC] ? ctx->tun[BSX_TUN_ED_KOCC] : occ;
+                if (kocc >= 8) {
+                    BSX_PIN_CARVEOUT((ed25519_keyed_kernel<8, false>));
+                    ed25519_keyed_kernel<8, false><<<grid, 64, 0, st>>>(n, in, tab, out, keys);
+                } else if (kocc >= 6) {
+                    BSX_PIN_CARVEOUT((ed25519_keyed_kernel<6, false>));
+                    ed25519_keyed_kernel<6, false><<<grid, 64, 0, st>>>(n, in, tab, out, keys);
+                } else if (use_inl) {
+                    BSX_PIN_CARVEOUT((ed25519_keyed_kernel<4, true>));
+                    ed25519_keyed_kernel<4, true><<<grid, 64, 0, st>>>(n, in, tab, out, keys);
+                } else {
+                    BSX_PIN_CARVEOUT((ed25519_keyed_kernel<4, false>));
+                    ed25519_keyed_kernel<4, false><<<grid, 64, 0, st>>>(n, in, tab, out, keys);
+                }
+                ctx->launches++;
+                e = cudaGetLastError();
+            }
         }
         if (e != cudaSuccess) {
             cudaFreeAsync(kmem, st);
@@ -645,6 +676,7 @@ static int ed25519_strided(bsx_ctx *ctx, void *stream, uint32_t n, const uint8_t
                            uint32_t msg_max, const uint8_t *msg_lens, uint32_t len_stride, const uint8_t *active,
                            uint32_t active_stride, uint8_t *out, bool alone, bool corun = false) {
     BSX_REQUIRE(ctx, ctx && pks && sigs && (msgs || msg_max == 0) && out);
+    BSX_REQUIRE(ctx, ((uintptr_t)out & 7) == 0);   // the records are stored as 8-byte words (cudaMalloc'd memory always is)
     if (n == 0) return BSX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_base_table(ctx, st);

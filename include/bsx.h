@@ -266,7 +266,7 @@ int bsx_shard_step_dev(bsx_shard *sh, void *stream, const bsx_shard_in *in, cons
  * pks n*32 (compressed), sigs n*64 (R ‖ s little-endian), msgs n*msg_stride (MAX_MSG_LENGTH_BYTES),
  * msg_lens[n] (NULL = every message is msg_stride long), active[n] (NULL = all; 0 = run the lane on
  * DUMMY_PUBLIC_KEY / DUMMY_SIGNATURE / 32 zero bytes, eddsa.rs:28-42,102-115).
- * out: n * BSX_SIG_OUT_BYTES records, all values little-endian canonical (x,y = 16 u16 limbs each):
+ * out: n * BSX_SIG_OUT_BYTES records (device pointers of the _dev forms: 8-byte aligned), all values little-endian canonical (x,y = 16 u16 limbs each):
  *   [0..64) sha512 digest   [64..96) h = LE512(digest) mod l   [96..136) div = LE512(digest) / l
  *   [136..200) s*G (x,y)    [200..264) A (x,y)   [264..296) A_root   [296..360) h*A
  *   [360..424) Rp (x,y)     [424..456) R_root    [456..520) Rp + h*A   [520..524) flags

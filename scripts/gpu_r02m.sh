@@ -7,9 +7,11 @@ run() { local r=$1; shift
   env "$@" timeout 300 python bench.py --ranges $r --no-cpu --e2e-threads 1 --e2e-ranges 64 --no-2048 --steps 20 --warmup 5 2>> $OUT/err.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ranges=$r $*', round(d['value']/1e6,1), 'M headers/s', round(d['ms_per_step'],3), 'ms', {k[:14]: round(v,3) for k,v in d['kernels_alone_ms'].items()}, 'general', round(d['general_path']['value']/1e6,1))"
 }
 run 757 BSX_X=0
-run 757 BSX_ED_PAIR=1
+run 757 BSX_ED_KOCC=4
+run 757 BSX_ED_KEYTAB=0
+run 757 BSX_ED_KOCC=4 BSX_ED_INLINE=1
 run 1514 BSX_X=0
-run 1514 BSX_ED_PAIR=0
+run 1514 BSX_ED_KOCC=4
 run 378 BSX_X=0
 run 1135 BSX_X=0
 for n in 37888 75776; do
