@@ -8,7 +8,7 @@ run() { local r=$1; shift
 }
 run 757 BSX_X=0
 run 757 BSX_ED_KOCC=4
-run 757 BSX_ED_KEYTAB=0
+run 757 BSX_ED_KOCC=6
 run 757 BSX_ED_KOCC=4 BSX_ED_INLINE=1
 run 1514 BSX_X=0
 run 1514 BSX_ED_KOCC=4
