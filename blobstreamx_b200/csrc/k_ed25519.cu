@@ -591,13 +591,16 @@ static int launch_mono(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     EdKeys keys = {};
     uint8_t *kmem = nullptr;
     const int keytab = ctx->tun[BSX_TUN_ED_KEYTAB];
-    if (fp64 && keytab != 0) {
-        const size_t o_slot_id = sizeof(int32_t) * BSX_ED_KEY_SLOTS, o_state = 2 * o_slot_id, o_key_slot = o_state + 256,
-                     o_recs = (o_key_slot + sizeof(int32_t) * (size_t)n + 255) & ~(size_t)255,
-                     o_bases = o_recs + (size_t)BSX_ED_KEY_MAX * BSX_ED_KEYREC_BYTES,
-                     o_tab = o_bases + sizeof(double) * 20 * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX,
-                     total = o_tab + sizeof(double) * 20 * BSX_ED_KEY_ENTRIES * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX;
-        BSX_CUDA(ctx, cudaMallocAsync((void **)&kmem, total, st));
+    const size_t o_slot_id = sizeof(int32_t) * BSX_ED_KEY_SLOTS, o_state = 2 * o_slot_id, o_key_slot = o_state + 256,
+                 o_recs = (o_key_slot + sizeof(int32_t) * (size_t)n + 255) & ~(size_t)255,
+                 o_bases = o_recs + (size_t)BSX_ED_KEY_MAX * BSX_ED_KEYREC_BYTES,
+                 o_tab = o_bases + sizeof(double) * 20 * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX,
+                 k_total = o_tab + sizeof(double) * 20 * BSX_ED_KEY_ENTRIES * BSX_ED_KEY_WINDOWS * BSX_ED_KEY_MAX;
+    if (fp64 && keytab != 0 && cudaMallocAsync((void **)&kmem, k_total, st) != cudaSuccess) {
+        cudaGetLastError();   // no room for the tables: the batch simply takes the general path
+        kmem = nullptr;
+    }
+    if (kmem) {
         keys.slots = reinterpret_cast<int32_t *>(kmem);
         keys.slot_id = reinterpret_cast<int32_t *>(kmem + o_slot_id);
         keys.state = reinterpret_cast<int32_t *>(kmem + o_state);
