@@ -186,7 +186,21 @@ __global__ void __launch_bounds__(256) verify_kernel(VerifyArgs a) {
             if (v[237]) {
                 uint32_t f = v[236] ? 0u : BSX_VFAIL_TRUSTED_PRESENT;
                 bool found = false;
-                for (uint32_t j = 0; j < N; j++) found = found || bytes_eq(v, a.trusted_pubkeys + (inst * N + j) * 32, 32);
+                const uint8_t *tp = a.trusted_pubkeys + inst * N * 32;
+                if ((((uintptr_t)v | (uintptr_t)tp) & 3) == 0) {   // word-aligned inputs: 8 word compares per pair instead of 32 byte pairs
+                    const uint32_t *vw = reinterpret_cast<const uint32_t *>(v), *tw = reinterpret_cast<const uint32_t *>(tp);
+                    uint32_t k8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) k8[k] = vw[k];
+                    for (uint32_t j = 0; j < N; j++) {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) x |= k8[k] ^ __ldg(tw + 8 * j + k);
+                        found = found || x == 0;
+                    }
+                } else {
+                    for (uint32_t j = 0; j < N; j++) found = found || bytes_eq(v, tp + j * 32, 32);
+                }
                 if (!found) f |= BSX_VFAIL_TRUSTED_PRESENT;
                 if (f) atomicOr(&s_fail, f);
             }
