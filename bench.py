@@ -611,6 +611,34 @@ def run_gpu(args):
             assert (g1["map_digests"][0] == w1["map_digests"]).all() and g1["data_commitments"][0].tobytes() == w1["data_commitment"]
             assert (g1["skip"]["ed"][0] == leg.oracle_skip(0)["ed"]).all()
 
+    # ---- BASELINE config 1: next_header, the reference's own fixture (mocha-4 10000 -> 10001, 2 validators padded to 100 with
+    # DUMMY lanes), one call through the host-buffer entry point, the single-thread oracle beside it ----
+    nh = None
+    if rank == 0:
+        try:
+            from blobstreamx_b200 import inputs as I
+            with open(os.path.join(ROOT, "tests", "golden", "mocha4.json")) as f:
+                gold = json.load(f)
+            kstep = I.get_step_inputs(gold["headers"]["10000"], gold["headers"]["10001"], gold["commits"]["10001"], gold["validators"]["10001"])
+            ts = []
+            for i in range(12):
+                t0 = time.perf_counter()
+                gn = ctx.next_header([kstep])
+                ts.append(time.perf_counter() - t0)
+            nh = {"latency_ms": 1e3 * statistics.median(ts[2:]), "fixture": "BX/circuits/fixtures/mocha-4 10000 -> 10001 (tests/golden/mocha4.json)",
+                  "work": "282 SHA-256 digests, 100 Ed25519 records (98 DUMMY lanes), data commitment of [10000, 10001)"}
+            assert int(gn["fail"][0]) == 0
+            assert gn["data_commitments"][0].tobytes().hex().upper() == gold["data_commitments"]["10000-10001"], "next_header: fixture data commitment"
+            if not args.no_check:
+                from oracle import cbind as orc
+                t0 = time.perf_counter()
+                wn = orc.next_header(kstep, threads=1)
+                nh["cpu_oracle_ms_1_thread"] = 1e3 * (time.perf_counter() - t0)
+                assert (gn["sha256_digests"][0] == wn["sha256_digests"]).all() and (gn["ed"][0] == wn["ed"]).all()
+                nh["checked_against_oracle"] = True
+        except FileNotFoundError:
+            nh = None
+
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + kernels + D2H inside every call) ----
     # A ctx belongs to one calling thread (include/bsx.h), so a host that keeps the GPU busy runs one ctx per thread:
     # --e2e-threads T (default 2) threads, each with its own ctx and its own pinned buffers, take the steps in turn; the
@@ -786,6 +814,7 @@ def run_gpu(args):
             "step_ms": st_stats,
             "ranges_checked_against_oracle": ranges_checked,
             "latency_single_range_ms": lat_ms,
+            "next_header": nh,
             "latency_note": "ONE header_range_1024 (the reference proves one range per request) through bsx_header_range with host "
                             "buffers, median of 10 calls: the throughput lines batch hundreds of independent ranges per launch",
             # the time-dominant kernel of the step: the Ed25519 batch
