@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HOT = ["ed25519_batch_kernel", "ed25519_quad_kernel", "subchain_proofs_kernel", "subchain_commit_kernel", "reduce_subchains_kernel",
+HOT = ["ed25519_batch_kernel", "ed25519_keyed_kernel", "ed25519_key_bases_kernel", "ed25519_key_table_kernel", "ed25519_key_assign_kernel", "ed25519_quad_kernel", "subchain_proofs_kernel", "subchain_commit_kernel", "reduce_subchains_kernel",
        "verify_kernel", "gl_gate_eval_kernel", "gl_gate_quotient_kernel", "gl_poseidon_batch_kernel", "ntt_dif_strided_kernel",
        "ntt_dif_contig_kernel", "gl_merkle_leaves_kernel", "gl_merkle_layer_kernel", "sha256_trace_kernel", "pack_bytes_kernel",
        "encode_headers_kernel", "range_inputs_kernel", "prove_subchain_kernel", "data_commitment_kernel"]
