@@ -306,7 +306,10 @@ __global__ void __launch_bounds__(128) ed25519_prep_kernel(uint32_t n, EdIn in, 
     }
     // A -> [200..296), flag byte 522;  R -> [360..456), flag byte 523
     uint8_t *dst = rec + (which ? 360 : 200);
-    const bool ok = ge_decompress(pt, x, y, dst, dst + 32, dst + 64);
+    // the square-root chain (~265 dependent squarings: the latency of this kernel) on the FP64 pipe: 441 against 570 cycles
+    // per squaring with one warp per sub-partition (profiles/r02a_ubench_fp64.txt); same bytes (tests: every build, host check)
+    edd::fed fx, fy;
+    const bool ok = edd::ged_decompress(pt, fx, fy, dst, dst + 32, dst + 64);
     rec[522 + which] = ok ? 1 : 0;
 }
 
@@ -438,6 +441,144 @@ __global__ void __launch_bounds__(64) ed25519_quad_kernel(uint32_t n, const ge_n
         for (int j = 0; j < 10; j++) scr[60 + 10 * k + j] = acc.v[j];
 }
 
+// ---- the same kernel on the FP64 pipe (fe51d.cuh): the quad kernel is a chain of dependent field operations per
+// signature (252 doublings x (one squaring + one multiplication)), and with one warp per sub-partition an FP64-limb
+// squaring / multiplication takes 441 / 652 cycles against 570 / 772 for the integer limbs (profiles/r02a_ubench_fp64.txt).
+// Units (fe51d.cuh: a product needs |f_i| |g_j| < 2^103, i.e. 2u x 2u or 3u x 1u of carried values): a doubling leaves
+// X' = A - YY - XX 3u, Y' 2u, Z' 2u, T' = 2ZZ - YY + XX 4u; quad_p3d multiplies (X' or Z') by a re-carried (Y' or T').
+using edd::fed;
+__device__ __forceinline__ fed fed_quad_get(const fed &a, int src) {
+    fed r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src, 4);
+    return r;
+}
+__device__ __forceinline__ fed fed_quad_swap(const fed &a) {     // lanes 0<->1, 2<->3
+    fed r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], 1, 4);
+    return r;
+}
+__device__ __forceinline__ fed fed_lin(int ca, const fed &a, int cb, const fed &b) {   // small integer coefficients: exact
+    fed r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.v[i] = (double)ca * a.v[i] + (double)cb * b.v[i];
+    return r;
+}
+__device__ __forceinline__ fed fed_small(int c) { fed r = edd::fed_zero(); r.v[0] = (double)c; return r; }
+__device__ __forceinline__ fed quad_p3d(const fed &c, int k) {
+    const fed t = edd::fed_reduce(c);
+    const fed f = fed_quad_get(c, (k == 1 || k == 2) ? 2 : 0);
+    const fed g = fed_quad_get(t, (k & 1) ? 1 : 3);
+    return edd::fed_mul(f, g);
+}
+__device__ __forceinline__ fed quad_dbld(const fed &c, int k) {
+    const fed x = fed_quad_get(c, 0), y = fed_quad_get(c, 1);
+    const fed s = edd::fed_sq(k == 3 ? edd::fed_add(x, y) : c);
+    const fed xx = fed_quad_get(s, 0), yy = fed_quad_get(s, 1);
+    const fed o = fed_quad_get(s, k == 0 ? 3 : 2);          // lane 0 takes A, lane 3 takes ZZ
+    const int co = (k == 0) ? 1 : (k == 3 ? 2 : 0), cy = (k == 0 || k == 3) ? -1 : 1, cx = (k == 0 || k == 2) ? -1 : 1;
+    fed r;
+#pragma unroll
+    for (int i = 0; i < 5; i++) r.v[i] = (double)co * o.v[i] + (double)cy * yy.v[i] + (double)cx * xx.v[i];
+    return r;
+}
+__device__ __forceinline__ fed quad_addd(const fed &c, const fed &g, int k) {
+    const fed o = fed_quad_swap(c);
+    const fed m = edd::fed_mul(fed_lin(1, c, k == 0 ? 1 : (k == 1 ? -1 : 0), o), g);
+    const fed o2 = fed_quad_swap(m);
+    return fed_lin(k == 3 ? -1 : 1, m, k == 0 ? -1 : 1, o2);
+}
+__device__ __forceinline__ fed quad_to_cachedd(const fed &c, int k) {
+    const double d2[5] = BSX_FED_2D;
+    const fed o = fed_quad_swap(c);
+    const fed v = fed_lin(k == 2 ? 2 : 1, c, k == 0 ? 1 : (k == 1 ? -1 : 0), o);
+    return edd::fed_mul(v, k == 3 ? edd::fed_const(d2) : edd::fed_one());
+}
+__device__ __forceinline__ void scr_store_fed(int32_t *scr, int p, const fed &a) {
+    const fe f = edd::fe_from_fed(a);
+#pragma unroll
+    for (int j = 0; j < 10; j++) scr[10 * p + j] = f.v[j];
+}
+
+__global__ void __launch_bounds__(64) ed25519_quad_kernel_fp64(uint32_t n, const ge_niels_slot *__restrict__ table,
+                                                                const uint8_t *__restrict__ out, int32_t *__restrict__ scratch) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = t & 3;
+    uint32_t i = t >> 2;
+    const bool live = i < n;
+    if (!live) i = n - 1;                     // keep whole warps in the shuffles; no stores
+    const uint8_t *rec = out + (size_t)BSX_SIG_OUT_BYTES * i;
+    int32_t *scr = scratch + (size_t)BSX_ED_SCRATCH_WORDS * i;
+    const fed ident = fed_small((k == 1 || k == 2) ? 1 : 0);            // (0, 1, 1, 0)
+    const fed ident_addend = fed_small(k == 3 ? 0 : (k == 2 ? 2 : 1));  // (1, 1, 2, 0)
+    const double d2[5] = BSX_FED_2D;
+    // the two scalars once, into registers (the integer kernel re-reads a byte of the record from global memory per window)
+    uint32_t sw[8], hw[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint8_t *ps = rec + 136 + 4 * j, *ph = rec + 64 + 4 * j;
+        sw[j] = (uint32_t)ps[0] | ((uint32_t)ps[1] << 8) | ((uint32_t)ps[2] << 16) | ((uint32_t)ps[3] << 24);
+        hw[j] = (uint32_t)ph[0] | ((uint32_t)ph[1] << 8) | ((uint32_t)ph[2] << 16) | ((uint32_t)ph[3] << 24);
+    }
+    auto word = [](const uint32_t (&a)[8], int j) {   // a[j] without a local-memory array
+        uint32_t v = a[0];
+#pragma unroll
+        for (int q = 1; q < 8; q++) v = j == q ? a[q] : v;
+        return v;
+    };
+
+    // ---- s*G: 32 windows of 8 bits over the affine table ----
+    fed acc = ident;
+#pragma unroll 1
+    for (int w = 0; w < BSX_ED_BASE_WINDOWS; w++) {
+        const uint32_t dgt = (word(sw, w >> 2) >> (8 * (w & 3))) & 255u;
+        fed g = ident_addend;
+        if (dgt && k != 2) {
+            const int32_t *q = table[w * BSX_ED_BASE_ENTRIES + (dgt - 1)].v + (k == 3 ? 20 : 10 * k);
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const int2 v = __ldg(reinterpret_cast<const int2 *>(q) + j);
+                g.v[j] = (double)v.x + 67108864.0 * (double)v.y;
+            }
+        }
+        acc = quad_p3d(quad_addd(acc, g, k), k);
+    }
+    if (live && k < 3) scr_store_fed(scr, k, acc);
+
+    // ---- table of A: tab[d] = addend form of d*A, d = 0..15 ----
+    const fed ax = edd::fed_from_fe(fe_frombytes(rec + 200)), ay = edd::fed_from_fe(fe_frombytes(rec + 232));
+    const fed axy = edd::fed_mul(ax, ay);
+    fed cur = k == 0 ? ax : (k == 1 ? ay : (k == 2 ? edd::fed_one() : axy));
+    fed tab[16];
+    tab[0] = ident_addend;
+    tab[1] = quad_to_cachedd(cur, k);
+#pragma unroll 1
+    for (int d = 2; d < 16; d++) {
+        cur = quad_p3d(quad_addd(cur, tab[1], k), k);
+        tab[d] = quad_to_cachedd(cur, k);
+    }
+    // ---- h*A: 64 windows of 4 bits, most significant first ----
+    acc = ident;
+#pragma unroll 1
+    for (int w = 63; w >= 0; w--) {
+        if (w != 63) {
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) acc = quad_p3d(quad_dbld(acc, k), k);
+        }
+        const uint32_t dgt = (word(hw, w >> 3) >> (4 * (w & 7))) & 15u;
+        acc = quad_p3d(quad_addd(acc, tab[dgt], k), k);
+    }
+    if (live && k < 3) scr_store_fed(scr, 3 + k, acc);
+
+    // ---- R + h*A ----
+    const fed rx = edd::fed_from_fe(fe_frombytes(rec + 360)), ry = edd::fed_from_fe(fe_frombytes(rec + 392));
+    const fed rt = edd::fed_mul(edd::fed_mul(rx, ry), edd::fed_const(d2));
+    const fed gr = k == 0 ? edd::fed_add(ry, rx) : (k == 1 ? edd::fed_sub(ry, rx) : (k == 2 ? fed_small(2) : rt));
+    acc = quad_p3d(quad_addd(acc, gr, k), k);
+    if (live && k < 3) scr_store_fed(scr, 6 + k, acc);
+}
+
 __device__ __forceinline__ fe scr_load(const int32_t *scr, int p) {
     fe r;
 #pragma unroll
@@ -464,7 +605,8 @@ __global__ void __launch_bounds__(128) ed25519_finish_kernel(uint32_t n, const i
             pre[j] = j ? fe_mul(pre[j - 1], z) : z;
         }
     }
-    fe run = fe_invert(pre[cnt - 1]);  // 1 / (z_0 ... z_{cnt-1})
+    // 1 / (z_0 ... z_{cnt-1}); the inversion chain on the FP64 pipe (as in the prep kernel)
+    fe run = edd::fe_from_fed(edd::fed_invert(edd::fed_from_fe(pre[cnt - 1])));
 #pragma unroll
     for (int j = K - 1; j >= 0; j--) {
         if ((uint32_t)j >= cnt) continue;
@@ -534,7 +676,13 @@ static int launch_quad(bsx_ctx *ctx, cudaStream_t st, uint32_t n, const EdIn &in
     ed25519_prep_kernel<0><<<(2 * n + 127) / 128, 128, 0, st>>>(n, in, out);
     ctx->launches++;
     if ((e = cudaGetLastError()) == cudaSuccess) {
-        ed25519_quad_kernel<<<(4 * n + 63) / 64, 64, 0, st>>>(n, tab, out, scratch);
+        const int fp64_t = ctx->tun[BSX_TUN_ED_FP64];
+        if (fp64_t < 0 ? BSX_ED_FP64_DEFAULT : fp64_t != 0) {
+            BSX_PIN_CARVEOUT(ed25519_quad_kernel_fp64);
+            ed25519_quad_kernel_fp64<<<(4 * n + 63) / 64, 64, 0, st>>>(n, tab, out, scratch);
+        } else {
+            ed25519_quad_kernel<<<(4 * n + 63) / 64, 64, 0, st>>>(n, tab, out, scratch);
+        }
         ctx->launches++;
         e = cudaGetLastError();
     }

@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 # (name, tunables): all force the one-thread-per-signature kernel except "quad"
 BUILDS = [
     ("quad-lane three-stage path", {"ED_MODE": 1}),
+    ("quad-lane three-stage path, integer limbs", {"ED_MODE": 1, "ED_FP64": 0}),
     ("compact, 216 registers", {"ED_MODE": 2, "ED_INLINE": 0, "ED_REGS": 0, "ED_FP64": 0}),
     ("inlined point arithmetic", {"ED_MODE": 2, "ED_INLINE": 1, "ED_REGS": 0, "ED_FP64": 0}),
     ("capped at 192 registers", {"ED_MODE": 2, "ED_REGS": 1, "ED_FP64": 0}),
