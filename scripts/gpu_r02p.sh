@@ -1,6 +1,6 @@
 #!/bin/bash
 # r02p: the round's closing single-GPU run: tests, smoke, default bench + reference arm, sweeps / ed25519 / plonk / trace modes, launch list, (ncu: scripts/gpu_r02p_ncu.sh)
-OUT=gpurun_out/r02z
+OUT=gpurun_out/r03c
 mkdir -p $OUT
 export PATH=/usr/local/cuda/bin:$PATH
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.csv 2>&1
@@ -10,11 +10,11 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench"; S=$(date +%s); timeout 900 python bench.py 2> $OUT/bench.err > $OUT/bench.json; echo "wall $(( $(date +%s) - S )) s"
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r02z/bench.json').read())
+d=json.loads(open('gpurun_out/r03c/bench.json').read())
 print('value', d['value']/1e6, 'ms', d['ms_per_step'], d['step_ms'], d['clocks']); print('next_header', d['next_header'])
 print('general path', d['general_path']['value']/1e6, d['general_path']['ms_per_step'])
 print('alone', d['kernels_alone_ms'])
-print('e2e', d['e2e']['value']/1e6, d['e2e'].get('single_call'), 'lat', d['latency_single_range_ms'])
+print('e2e', d['e2e']['value']/1e6, d['e2e'].get('single_call'), 'lat', d['latency_single_range_ms'], d['latency_single_range_c_abi_pinned_ms'])
 print('2048:', d['header_range_2048']['value']/1e6, d['header_range_2048']['ms_per_step'])
 print('roofline', d['roofline']['frac'], d['roofline']['signatures_per_s'], d['roofline']['capture_stale'], 'map', d['roofline_map']['frac'])
 print('constraints', d['constraints']['value']/1e9, d['constraints']['roofline']['frac'])
