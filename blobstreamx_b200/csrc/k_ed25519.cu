@@ -1,5 +1,7 @@
-// K4+K5: batched Ed25519 witness generation.
-// Default path = three kernels, because the parallel width of the work changes along a signature:
+// K4+K5: batched Ed25519 witness generation.  Two paths, chosen by batch size (BSX_ED_QUAD_MAX = 16 384; BSX_ED_MODE forces one):
+//
+// (a) up to 16 384 signatures -- the latency path (one proof = 100 signatures): three kernels, because the parallel width of
+//     the work changes along a signature:
 //   ed25519_prep_kernel    one thread per POINT (2 per signature): SHA-512, h = digest div/rem l, s < l, and the
 //                          decompression of A or R (a serial chain of ~265 squarings -- nothing to split)
 //   ed25519_quad_kernel    FOUR lanes per signature, one extended coordinate (X, Y, Z, T) each: the four independent
@@ -7,13 +9,18 @@
 //                          conversion run side by side and the operands move between the lanes with warp shuffles;
 //                          s*G (8-bit windows), the 16-entry table of A, h*A and R + h*A
 //   ed25519_finish_kernel  one thread per signature: one inversion for the three Z's, affine bytes, flags
-// The latency of one signature drops from ~3 700 dependent field operations to ~265 + ~750 + ~280, and a batch of
-// 25 600 signatures (256 header ranges) is 3 200 warps instead of 800 -- enough to fill the machine.
-// Measured (profiles/r01l_ed25519_modes.txt): 100 signatures 0.57 ms instead of 1.26, 10 000: 0.96 instead of 1.30,
-// 25 600: 1.67 instead of 1.84 -- but the quad kernel executes ~1.5x the instructions per signature (shuffles,
-// fe_tighten, sign selections), so next to the SHA-256 map kernels of bsx_header_range (256 ranges) the step is slower
-// with it (2.49 vs 2.33 ms).  Batches above BSX_ED_QUAD_MAX (16 384) signatures therefore run the
-// one-thread-per-signature kernel below; BSX_ED_MODE = 1 / 2 forces one path.
+//     The latency of one signature drops from ~3 700 dependent field operations to ~265 + ~750 + ~280.  r01l: 100 signatures
+//     0.57 ms instead of 1.26, 10 000: 0.96 instead of 1.30; r03a/b, all three kernels on the FP64 pipe (441 / 652 cycles per
+//     squaring / multiplication with one warp per sub-partition against 570 / 772): 0.46 and 0.79 ms.  The quad kernel
+//     executes ~1.5x the instructions per signature (shuffles, re-carries, sign selections), hence the size threshold.
+//
+// (b) above it -- the throughput path: one thread per signature (ed25519_batch_kernel: decompression of A, s*G from the
+//     8-bit window table, h*A by 252 doublings + signed 4-bit windows, R checked against sG - hA before a decompression is
+//     spent on it, one inversion), in the register budget whose wave the batch fills.  When public keys repeat in the batch
+//     (one validator set signing many ranges) the key-table kernels below run first and ed25519_keyed_kernel takes h*A from
+//     per-key window tables instead (no doublings, A decompressed once per key); which of the two kernels does the work is
+//     decided on the device, the other returns at once.
+//
 // Replaces, per signature, the CPU hints of curta_eddsa_verify_sigs (PX/frontend/ecc/curve25519/
 // ed25519/eddsa.rs:161-203): HashDigestHint<SHA512> (PX/frontend/hash/sha/sha512/curta.rs:103-111),
 // BigUintDivRemGenerator (PX/frontend/uint/num/biguint/mod.rs:451-488) and the seven EcOpResultHint
