@@ -1,0 +1,76 @@
+// Ed25519 scalar-multiplication execution trace on the device (the EdDSA half): the table a STARK over the
+// Curta Ed25519 accelerator commits to, written column-major (one polynomial per column).
+// Reference: `Ed25519Stark::prove` (PX/frontend/ecc/curve25519/curta/stark.rs:182-219) fills 256 rows per ScalarMul
+// operation -- `write_trace_instructions` per row inside `chunks_par(256)` -- for the two scalar multiplications of every
+// signature (s*G and h*A; collected at stark.rs:93-124).  The AIR is starkyx's `scalar_mul_batch` (UN-VENDORED,
+// starkyx@ad8eb4ba): its column assignment is not on disk, so this LAYOUT IS OURS and PARITY IS UNPINNED.  It carries what
+// that construction constrains: an affine double-and-add, one scalar bit per row, and for each of the 16 field operations
+// of the row's two Edwards additions the starkyx-style witness -- result and quotient (`carry`) as 16 limbs of 16 bits and
+// the polynomial w(x) = (lhs(x) - result(x) - carry(x) p(x)) / (x - 2^16), offset and split into 16-bit halves
+// (include/bsx.h BSX_ED25519_TRACE_COLS has the column table; oracle/ed_trace.py is the CPU restatement).
+// Sizing: one verify_skip circuit = 100 signatures = 200 multiplications = 51 200 rows -> 2^16 rows x 1540 columns x 8 B
+// = 807 MB: an HBM write stream, like the SHA traces.
+//
+// Two kernels, because the work has two shapes:
+//   ed_trace_chain_kernel  one thread per MULTIPLICATION: the 256 dependent steps in extended coordinates (sum = acc + temp
+//                          and dbl = 2 temp at every step, whatever the bit -- the row witnesses both), all 512 Z's inverted
+//                          with one field inversion (prefix products), affine sum / dbl of every row to scratch (128 B / row)
+//   ed_trace_rows_kernel   one thread per ROW: picks temp / acc / sum / dbl of its row from the scratch (acc = the sum of
+//                          the last set bit below j), redoes the 16 field operations on 16-bit limbs with exact integer
+//                          quotients, and stores its 1540 values; a warp stores 32 consecutive rows of a column (256 B).
+#include "common.cuh"
+#include "ed_trace.cuh"
+
+namespace bsx {
+
+using namespace edt;
+
+// chain[(m * 256 + j) * 80 ..]: working values of step j; aff[(m * 256 + j) * 32 ..]: sum.x sum.y dbl.x dbl.y (8 words each,
+// canonical little-endian); results[m] = k * P (64 bytes), when asked for
+__global__ void __launch_bounds__(64) ed_trace_chain_kernel(const uint8_t *__restrict__ scalars, const uint8_t *__restrict__ points, uint32_t n_muls,
+                                                            int32_t *__restrict__ chain, uint32_t *__restrict__ aff, uint8_t *__restrict__ results) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_muls) return;
+    edt_chain_core(scalars + (size_t)m * 32, points + (size_t)m * 64, chain + (size_t)m * 256 * EDT_CHAIN_WORDS,
+                   aff + (size_t)m * 256 * EDT_AFF_WORDS, results ? results + (size_t)m * 64 : nullptr);
+}
+
+__global__ void __launch_bounds__(128) ed_trace_rows_kernel(const uint8_t *__restrict__ scalars, const uint8_t *__restrict__ points, uint32_t n_muls,
+                                                            const uint32_t *__restrict__ aff, size_t n_rows, uint64_t *__restrict__ trace) {
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint32_t m = (uint32_t)(row >> 8), j = (uint32_t)row & 255;
+    const bool real = m < n_muls;
+    edt_row_core(real, j, real ? scalars + (size_t)m * 32 : nullptr, real ? points + (size_t)m * 64 : nullptr,
+                 real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows);
+}
+
+}  // namespace bsx
+
+using namespace bsx;
+
+// bytes of device scratch bsx_ed25519_trace_dev needs for n_muls multiplications
+extern "C" size_t bsx_ed25519_trace_scratch_bytes(uint32_t n_muls) { return (size_t)n_muls * 256 * (EDT_CHAIN_WORDS + EDT_AFF_WORDS) * 4; }
+
+// Execution trace of n_muls scalar multiplications k_m * P_m: trace = BSX_ED25519_TRACE_COLS columns of 2^log_rows rows
+// (column-major u64 field elements), 256 rows per multiplication, the rest padded with rows of 0 * (0, 1).
+// scalars: n_muls x 32 bytes little-endian (any 256-bit value); points: n_muls x 64 bytes (x, y little-endian, canonical,
+// ON THE CURVE -- the outputs of the decompressions); results (may be null): n_muls x 64 bytes, k_m * P_m affine.
+extern "C" int bsx_ed25519_trace_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
+                                     uint32_t log_rows, void *scratch, uint8_t *results, uint64_t *trace) {
+    static_assert(BSX_ED25519_TRACE_COLS == 68 + 16 * EDT_OP, "column table");
+    BSX_REQUIRE(ctx, ctx && trace && log_rows >= 8 && log_rows <= 30);
+    const size_t n_rows = (size_t)1 << log_rows;
+    BSX_REQUIRE(ctx, (size_t)n_muls * 256 <= n_rows);
+    BSX_REQUIRE(ctx, n_muls == 0 || (scalars && points && scratch));
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *chain = reinterpret_cast<int32_t *>(scratch);
+    uint32_t *aff = reinterpret_cast<uint32_t *>(chain + (size_t)n_muls * 256 * EDT_CHAIN_WORDS);
+    if (n_muls) {
+        ed_trace_chain_kernel<<<(n_muls + 63) / 64, 64, 0, st>>>(scalars, points, n_muls, chain, aff, results);
+        BSX_LAUNCHED(ctx);
+    }
+    ed_trace_rows_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(scalars, points, n_muls, aff, n_rows, trace);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}

@@ -624,6 +624,28 @@ int bsx_sha512_trace_dev(bsx_ctx *ctx, void *stream, const uint64_t *padded_chun
                          const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace);
 int bsx_sha256_trace_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chunks, const uint8_t *end_bits,
                          const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace);
+/* Ed25519 scalar-multiplication execution trace (the EdDSA accelerator): 256 rows per ScalarMul operation
+ * (two per signature: s*G and h*A), one scalar bit per row, an affine double-and-add whose 16 field operations per row
+ * carry starkyx-style witnesses (16-bit limbs; quotient `carry`; witness polynomial of the division by x - 2^16).
+ * replaces: the trace fill of Ed25519Stark::prove (PX/frontend/ecc/curve25519/curta/stark.rs:182-219, write_trace_instructions
+ *   over chunks_par(256)); operations collected at stark.rs:93-124.  The AIR (`scalar_mul_batch`) is starkyx's, un-vendored:
+ *   this column assignment is our own and PARITY IS UNPINNED; the CPU restatement is oracle/ed_trace.py, pinned by
+ *   re-checking every operation's polynomial identity, k * P against an independent scalar multiplication and the
+ *   mocha-4 fixture signatures' s*G / h*A (tests/test_oracle_ed_trace.py).
+ * Row 256 m + j = step j of multiplication m; temp = 2^j P, acc = (k mod 2^j) P; next row: temp' = dbl, acc' = bit ? sum : acc.
+ *   0 bit j of k | 1 real row (0 on padding) | 2 j == 0 | 3 j == 255 | 4..19 temp.x 20..35 temp.y 36..51 acc.x 52..67 acc.y
+ *   68 + 92 o, o = 0..15: result[16] carry[16] witness_low[30] witness_high[30] of field operation o, where
+ *     o = 0..7 is sum = acc + temp and o = 8..15 is dbl = temp + temp, an addition (x1,y1) + (x2,y2) being
+ *     0 xn = x1 y2 + x2 y1 | 1 yn = y1 y2 + x1 x2 | 2 m1 = x1 y1 | 3 m2 = x2 y2 | 4 f = m1 m2 | 5 df = d f |
+ *     6 x3 = xn / (1 + df): df x3 + x3 - xn = carry p | 7 y3 = yn / (1 - df): df y3 + yn - y3 = carry p
+ *   witness: w(x) = (lhs(x) - result(x) - carry(x) p(x)) / (x - 2^16), stored as w_k + 2^22 in two 16-bit halves.
+ * Padding rows (beyond 256 * n_muls) are the rows of 0 * (0, 1) with column 1 = 0.
+ * scalars: n_muls x 32 bytes little-endian; points: n_muls x 64 bytes (x, y canonical little-endian, on the curve);
+ * scratch: bsx_ed25519_trace_scratch_bytes(n_muls) bytes of device memory; results: n_muls x 64 bytes k * P, or NULL. */
+#define BSX_ED25519_TRACE_COLS 1540
+size_t bsx_ed25519_trace_scratch_bytes(uint32_t n_muls);
+int bsx_ed25519_trace_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
+                          uint32_t log_rows, void *scratch, uint8_t *results, uint64_t *trace);
 uint32_t bsx_hash_input_chunks(int sha512, uint32_t buf_len, int variable);
 int bsx_hash_input_data(bsx_ctx *ctx, int sha512, uint32_t n_req, const uint8_t *bufs, const uint32_t *buf_offsets,
                         const uint32_t *lens, const uint8_t *kinds, void *padded_chunks, uint8_t *end_bits,

@@ -2,6 +2,7 @@
 // for the HOST with plain g++, so its logic can be checked against the oracle on a machine without a
 // GPU.  Never linked into libbsx.so; the product has no CPU path.
 #include "../../blobstreamx_b200/csrc/ed25519.cuh"
+#include "../../blobstreamx_b200/csrc/ed_trace.cuh"
 
 #include <fenv.h>
 #include <stdlib.h>
@@ -123,5 +124,22 @@ int hc_fp64_decompress(const uint8_t *in, uint8_t *xy, uint8_t *root) {
     RoundTowardZero rz;
     bsx::edd::fed x, y;
     return bsx::edd::ged_decompress(in, x, y, xy, xy + 32, root) ? 1 : 0;
+}
+// the Ed25519 scalar-multiplication trace (ed_trace.cuh): chain + every row, exactly as the two kernels call the cores
+void hc_ed25519_trace(const uint8_t *scalars, const uint8_t *points, uint32_t n_muls, uint32_t log_rows, uint8_t *results, uint64_t *trace) {
+    using namespace bsx::edt;
+    const size_t n_rows = (size_t)1 << log_rows;
+    int32_t *chain = (int32_t *)malloc((size_t)(n_muls + 1) * 256 * EDT_CHAIN_WORDS * 4);
+    uint32_t *aff = (uint32_t *)malloc((size_t)(n_muls + 1) * 256 * EDT_AFF_WORDS * 4);
+    for (uint32_t m = 0; m < n_muls; m++)
+        edt_chain_core(scalars + (size_t)m * 32, points + (size_t)m * 64, chain + (size_t)m * 256 * EDT_CHAIN_WORDS,
+                       aff + (size_t)m * 256 * EDT_AFF_WORDS, results ? results + (size_t)m * 64 : nullptr);
+    for (size_t row = 0; row < n_rows; row++) {
+        const uint32_t m = (uint32_t)(row >> 8), j = (uint32_t)row & 255;
+        const bool real = m < n_muls;
+        edt_row_core(real, j, real ? scalars + (size_t)m * 32 : nullptr, real ? points + (size_t)m * 64 : nullptr,
+                     real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows);
+    }
+    free(chain); free(aff);
 }
 }

@@ -201,3 +201,71 @@ def test_sha512_trace_matches_oracle(pv):
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(pv.dev)
     got = pv.sha512_trace(dev(hid["padded_chunks"].view(np.int64)), dev(hid["end_bits"]), dev(hid["digest_bits"]), log_rows)
     assert (_host(got) == orc.sha512_trace(hid["padded_chunks"], hid["end_bits"], hid["digest_bits"], log_rows)).all()
+
+
+def _ed_dev(pv, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(pv.dev)
+
+
+@pytest.mark.parametrize("log_rows", [12, 13])
+def test_ed25519_trace_matches_oracle(pv, log_rows):
+    """Ed25519 scalar-multiplication trace (EdDSA accelerator) on the device == oracle/ed_trace.py (pinned by
+    tests/test_oracle_ed_trace.py): edge scalars (0, 1, 2^256 - 1, l), the identity and the order-2 point, random
+    multiplications, s*G and h*A of a mocha-4 fixture signature, padding multiplications; k * P out of the same call."""
+    import json, os
+    from oracle import ed_trace as T
+    from oracle import pyoracle as po
+    from tests.test_oracle_ed_trace import _cases, _fixture_muls, pack
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mocha4.json")) as f:
+        golden = json.load(f)
+    rng = np.random.default_rng(8 + log_rows)
+    scalars, points = _cases(rng, 2)
+    fs, fp, fw = _fixture_muls(golden, "10000", 1)
+    scalars, points = scalars + fs, points + fp
+    want, results = T.ed25519_trace(scalars, points, log_rows)
+    assert results[-2:] == fw
+    sc, pt = pack(scalars, points)
+    n = len(scalars)
+    got, res = pv.ed25519_trace(_ed_dev(pv, sc.reshape(n, 32)), _ed_dev(pv, pt.reshape(n, 64)), log_rows)
+    assert (_host(got) == want).all()
+    assert res.cpu().numpy().tobytes() == b"".join(po.ed_point_bytes(p) for p in results)
+
+
+def test_ed25519_trace_of_a_signature_batch_closes_on_the_witness_records(pv):
+    """At batch size: 2 x 256 signatures' multiplications (s, G) and (h, A), taken from the 576-byte records of
+    bsx_ed25519_batch (h at 64, s*G at 136, A at 200, h*A at 296; parity-green vs the oracle elsewhere) -> 2^17 rows.  Size-
+    independent properties read off the trace: k * P equals the record's s*G / h*A, the last row's selected accumulator is k * P,
+    rows chain (temp' = dbl, acc' = bit ? sum : acc) across the whole table, every limb is 16 bits, padding rows are flagged."""
+    import torch
+    from blobstreamx_b200 import synthetic as S
+    from oracle import pyoracle as po
+    n_sig = 256
+    pks, sigs, msgs, lens, _ = S.ed25519_batch_inputs(n_sig)
+    rec = pv.ctx.ed25519_batch(pks, sigs, msgs, lens)          # every lane active: s is the signature's own
+    assert (rec[:, 520] == 0xF).all()
+    G = np.frombuffer(po.ed_point_bytes(po.G), np.uint8)
+    scalars = np.empty((2 * n_sig, 32), np.uint8)
+    points = np.empty((2 * n_sig, 64), np.uint8)
+    scalars[0::2], points[0::2] = sigs[:, 32:64], G
+    scalars[1::2], points[1::2] = rec[:, 64:96], rec[:, 200:264]
+    want = np.empty((2 * n_sig, 64), np.uint8)
+    want[0::2], want[1::2] = rec[:, 136:200], rec[:, 296:360]
+    log_rows = 18                                                    # 131 072 real rows + as many padding rows: 3.2 GB
+    tr, res = pv.ed25519_trace(_ed_dev(pv, scalars), _ed_dev(pv, points), log_rows)
+    assert (res.cpu().numpy() == want).all()
+    n_real = 2 * n_sig * 256
+    assert int(tr.max()) < 65536 and int(tr.min()) >= 0
+    assert bool((tr[1, :n_real] == 1).all()) and bool((tr[1, n_real:] == 0).all())
+    bit = tr[0] == 1
+    last = tr[3] == 1
+    inner = ~last
+    inner[-1] = False
+    nxt = torch.roll(tr, -1, dims=1)
+    sum_xy = torch.cat([tr[68 + 92 * 6:68 + 92 * 6 + 16], tr[68 + 92 * 7:68 + 92 * 7 + 16]])
+    dbl_xy = torch.cat([tr[68 + 92 * 14:68 + 92 * 14 + 16], tr[68 + 92 * 15:68 + 92 * 15 + 16]])
+    sel = torch.where(bit[None, :], sum_xy, tr[36:68])
+    assert bool((nxt[4:36][:, inner] == dbl_xy[:, inner]).all())
+    assert bool((nxt[36:68][:, inner] == sel[:, inner]).all())
+    fin = sel[:, last][:, :2 * n_sig].cpu().numpy().astype(np.uint16).T.copy()      # [mul, 32 limbs] -> 64 bytes little-endian
+    assert (fin.view(np.uint8) == want).all()
