@@ -11,10 +11,11 @@
 // Sizing: one verify_skip circuit = 100 signatures = 200 multiplications = 51 200 rows -> 2^16 rows x 1540 columns x 8 B
 // = 807 MB: an HBM write stream, like the SHA traces.
 //
-// Two kernels, because the work has two shapes:
+// Three kernels, because the work has three shapes:
 //   ed_trace_chain_kernel  one thread per MULTIPLICATION: the 256 dependent steps in extended coordinates (sum = acc + temp
-//                          and dbl = 2 temp at every step, whatever the bit -- the row witnesses both), all 512 Z's inverted
-//                          with one field inversion (prefix products), affine sum / dbl of every row to scratch (128 B / row)
+//                          and dbl = 2 temp at every step, whatever the bit -- the row witnesses both), X Y Z to scratch
+//   ed_trace_affine_kernel one thread per 16 STEPS: their 32 Z's inverted with one field inversion (prefix products),
+//                          affine sum / dbl of every row to scratch (128 B / row)
 //   ed_trace_rows_kernel   one thread per ROW: picks temp / acc / sum / dbl of its row from the scratch (acc = the sum of
 //                          the last set bit below j), redoes the 16 field operations on 16-bit limbs with exact integer
 //                          quotients, and stores its 1540 values; a warp stores 32 consecutive rows of a column (256 B).
@@ -25,24 +26,35 @@ namespace bsx {
 
 using namespace edt;
 
-// chain[(m * 256 + j) * 80 ..]: working values of step j; aff[(m * 256 + j) * 32 ..]: sum.x sum.y dbl.x dbl.y (8 words each,
-// canonical little-endian); results[m] = k * P (64 bytes), when asked for
+// resident CTAs of the row kernel per SM the register budget is set for (2: 255 registers, no spills; 2 / 3 / 4 / 5 measured: profiles/r04c_ed_trace_minb.txt)
+#ifndef EDT_ROWS_MINB
+#define EDT_ROWS_MINB 2
+#endif
+
+// chain[(m * 256 + j) * 64 ..]: sum and dbl of step j in extended coordinates; aff[(m * 256 + j) * 32 ..]: sum.x sum.y dbl.x dbl.y
+// (8 words each, canonical little-endian)
 __global__ void __launch_bounds__(64) ed_trace_chain_kernel(const uint8_t *__restrict__ scalars, const uint8_t *__restrict__ points, uint32_t n_muls,
-                                                            int32_t *__restrict__ chain, uint32_t *__restrict__ aff, uint8_t *__restrict__ results) {
+                                                            int32_t *__restrict__ chain) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_muls) return;
-    edt_chain_core(scalars + (size_t)m * 32, points + (size_t)m * 64, chain + (size_t)m * 256 * EDT_CHAIN_WORDS,
-                   aff + (size_t)m * 256 * EDT_AFF_WORDS, results ? results + (size_t)m * 64 : nullptr);
+    edt_forward_core<true>(scalars + (size_t)m * 32, points + (size_t)m * 64, chain + (size_t)m * 256 * EDT_CHAIN_WORDS);
 }
 
-__global__ void __launch_bounds__(128) ed_trace_rows_kernel(const uint8_t *__restrict__ scalars, const uint8_t *__restrict__ points, uint32_t n_muls,
-                                                            const uint32_t *__restrict__ aff, size_t n_rows, uint64_t *__restrict__ trace) {
+__global__ void __launch_bounds__(128) ed_trace_affine_kernel(const int32_t *__restrict__ chain, uint32_t n_groups, uint32_t *__restrict__ aff) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    edt_affine_core(chain + (size_t)g * EDT_GROUP * EDT_CHAIN_WORDS, aff + (size_t)g * EDT_GROUP * EDT_AFF_WORDS);
+}
+
+__global__ void __launch_bounds__(128, EDT_ROWS_MINB) ed_trace_rows_kernel(const uint8_t *__restrict__ scalars, const uint8_t *__restrict__ points, uint32_t n_muls,
+                                                            const uint32_t *__restrict__ aff, size_t n_rows, uint64_t *__restrict__ trace,
+                                                            uint8_t *__restrict__ results) {
     const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
     const uint32_t m = (uint32_t)(row >> 8), j = (uint32_t)row & 255;
     const bool real = m < n_muls;
     edt_row_core(real, j, real ? scalars + (size_t)m * 32 : nullptr, real ? points + (size_t)m * 64 : nullptr,
-                 real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows);
+                 real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows, real && results ? results + (size_t)m * 64 : nullptr);
 }
 
 }  // namespace bsx
@@ -56,21 +68,41 @@ extern "C" size_t bsx_ed25519_trace_scratch_bytes(uint32_t n_muls) { return (siz
 // (column-major u64 field elements), 256 rows per multiplication, the rest padded with rows of 0 * (0, 1).
 // scalars: n_muls x 32 bytes little-endian (any 256-bit value); points: n_muls x 64 bytes (x, y little-endian, canonical,
 // ON THE CURVE -- the outputs of the decompressions); results (may be null): n_muls x 64 bytes, k_m * P_m affine.
-extern "C" int bsx_ed25519_trace_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
-                                     uint32_t log_rows, void *scratch, uint8_t *results, uint64_t *trace) {
+// Two halves, callable apart so that a caller with several batches can run the latency-bound first half of one batch
+// beside the bandwidth-bound second half of the previous one (two streams, two scratch buffers: bench.py --mode trace):
+//   bsx_ed25519_trace_points_dev  chain + affine kernels: the affine sum / dbl of every step -> scratch
+//   bsx_ed25519_trace_rows_dev    row kernel: scratch -> trace (+ results)
+extern "C" int bsx_ed25519_trace_points_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls, void *scratch) {
+    BSX_REQUIRE(ctx, ctx && (n_muls == 0 || (scalars && points && scratch)) && n_muls <= (1u << 22));
+    if (n_muls == 0) return BSX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *chain = reinterpret_cast<int32_t *>(scratch);
+    uint32_t *aff = reinterpret_cast<uint32_t *>(chain + (size_t)n_muls * 256 * EDT_CHAIN_WORDS);
+    ed_trace_chain_kernel<<<(n_muls + 63) / 64, 64, 0, st>>>(scalars, points, n_muls, chain);
+    BSX_LAUNCHED(ctx);
+    const uint32_t n_groups = n_muls * (256 / EDT_GROUP);
+    ed_trace_affine_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(chain, n_groups, aff);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
+
+extern "C" int bsx_ed25519_trace_rows_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
+                                          uint32_t log_rows, const void *scratch, uint8_t *results, uint64_t *trace) {
     static_assert(BSX_ED25519_TRACE_COLS == 68 + 16 * EDT_OP, "column table");
     BSX_REQUIRE(ctx, ctx && trace && log_rows >= 8 && log_rows <= 30);
     const size_t n_rows = (size_t)1 << log_rows;
     BSX_REQUIRE(ctx, (size_t)n_muls * 256 <= n_rows);
     BSX_REQUIRE(ctx, n_muls == 0 || (scalars && points && scratch));
-    cudaStream_t st = (cudaStream_t)stream;
-    int32_t *chain = reinterpret_cast<int32_t *>(scratch);
-    uint32_t *aff = reinterpret_cast<uint32_t *>(chain + (size_t)n_muls * 256 * EDT_CHAIN_WORDS);
-    if (n_muls) {
-        ed_trace_chain_kernel<<<(n_muls + 63) / 64, 64, 0, st>>>(scalars, points, n_muls, chain, aff, results);
-        BSX_LAUNCHED(ctx);
-    }
-    ed_trace_rows_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(scalars, points, n_muls, aff, n_rows, trace);
+    const uint32_t *aff = reinterpret_cast<const uint32_t *>(reinterpret_cast<const int32_t *>(scratch) + (size_t)n_muls * 256 * EDT_CHAIN_WORDS);
+    ed_trace_rows_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(scalars, points, n_muls, aff, n_rows, trace, results);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
+}
+
+extern "C" int bsx_ed25519_trace_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
+                                     uint32_t log_rows, void *scratch, uint8_t *results, uint64_t *trace) {
+    BSX_REQUIRE(ctx, ctx && trace && log_rows >= 8 && log_rows <= 30 && ((size_t)n_muls * 256 <= ((size_t)1 << log_rows)));
+    const int rc = bsx_ed25519_trace_points_dev(ctx, stream, scalars, points, n_muls, scratch);
+    if (rc != BSX_OK) return rc;
+    return bsx_ed25519_trace_rows_dev(ctx, stream, scalars, points, n_muls, log_rows, scratch, results, trace);
 }

@@ -119,17 +119,22 @@ class Prover:
                           L.ptr(digest_bits.data_ptr()), L.u32(padded_chunks.shape[0]), L.u32(log_rows), L.ptr(out.data_ptr()))
         return out
 
+    def ed25519_trace_scratch_bytes(self, n: int) -> int:
+        lb = self.ctx._lib
+        lb.bsx_ed25519_trace_scratch_bytes.restype = C.c_size_t
+        return max(int(lb.bsx_ed25519_trace_scratch_bytes(C.c_uint32(n))), 256)
+
+    def ed25519_trace_scratch(self, n: int) -> torch.Tensor:
+        return torch.empty(self.ed25519_trace_scratch_bytes(n), dtype=torch.uint8, device=self.dev)
+
     def ed25519_trace(self, scalars: torch.Tensor, points: torch.Tensor, log_rows: int, out: torch.Tensor = None, results: bool = True):
         """n scalar multiplications k * P (device tensors: [n, 32] uint8 little-endian scalars, [n, 64] uint8 affine points,
         the s / G and h / A of the EdDSA schedule) -> (trace [BSX_ED25519_TRACE_COLS, 2^log_rows], [n, 64] uint8 k * P).
         Replaces the trace fill of Ed25519Stark::prove (PX/frontend/ecc/curve25519/curta/stark.rs:182-219); layout our own,
         parity unpinned (include/bsx.h)."""
         n = scalars.shape[0]
-        lb = self.ctx._lib
-        lb.bsx_ed25519_trace_scratch_bytes.restype = C.c_size_t
-        need = int(lb.bsx_ed25519_trace_scratch_bytes(C.c_uint32(n)))
-        if getattr(self, "_edt_scratch", None) is None or self._edt_scratch.numel() < need:
-            self._edt_scratch = torch.empty(max(need, 256), dtype=torch.uint8, device=self.dev)
+        if getattr(self, "_edt_scratch", None) is None or self._edt_scratch.numel() < self.ed25519_trace_scratch_bytes(n):
+            self._edt_scratch = self.ed25519_trace_scratch(n)
         if out is None:
             out = torch.empty((ED25519_TRACE_COLS, 1 << log_rows), dtype=torch.int64, device=self.dev)
         res = torch.empty((n, 64), dtype=torch.uint8, device=self.dev) if results else None
@@ -137,6 +142,17 @@ class Prover:
                           L.u32(n), L.u32(log_rows), L.ptr(self._edt_scratch.data_ptr()), L.ptr(res.data_ptr() if results and n else 0),
                           L.ptr(out.data_ptr()))
         return out, res
+
+    def ed25519_trace_points(self, scalars: torch.Tensor, points: torch.Tensor, scratch: torch.Tensor, stream: int = None):
+        """first half of ed25519_trace (multiplication chains -> scratch), on `stream`"""
+        self.ctx.call_dev("bsx_ed25519_trace_points_dev", self.stream if stream is None else stream, L.ptr(scalars.data_ptr()),
+                          L.ptr(points.data_ptr()), L.u32(scalars.shape[0]), L.ptr(scratch.data_ptr()))
+
+    def ed25519_trace_rows(self, scalars: torch.Tensor, points: torch.Tensor, scratch: torch.Tensor, log_rows: int, out: torch.Tensor,
+                           stream: int = None):
+        """second half of ed25519_trace (scratch -> trace), on `stream`"""
+        self.ctx.call_dev("bsx_ed25519_trace_rows_dev", self.stream if stream is None else stream, L.ptr(scalars.data_ptr()),
+                          L.ptr(points.data_ptr()), L.u32(scalars.shape[0]), L.u32(log_rows), L.ptr(scratch.data_ptr()), L.ptr(0), L.ptr(out.data_ptr()))
 
 
 SHA256_TRACE_COLS = 176

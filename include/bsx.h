@@ -646,6 +646,12 @@ int bsx_sha256_trace_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chun
 size_t bsx_ed25519_trace_scratch_bytes(uint32_t n_muls);
 int bsx_ed25519_trace_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
                           uint32_t log_rows, void *scratch, uint8_t *results, uint64_t *trace);
+/* the two halves of bsx_ed25519_trace_dev, for callers that overlap batches (two streams, two scratch buffers): the
+ * latency-bound multiplication chains (-> scratch), then the bandwidth-bound row expansion (scratch -> trace) */
+int bsx_ed25519_trace_points_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
+                                 void *scratch);
+int bsx_ed25519_trace_rows_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
+                               uint32_t log_rows, const void *scratch, uint8_t *results, uint64_t *trace);
 uint32_t bsx_hash_input_chunks(int sha512, uint32_t buf_len, int variable);
 int bsx_hash_input_data(bsx_ctx *ctx, int sha512, uint32_t n_req, const uint8_t *bufs, const uint32_t *buf_offsets,
                         const uint32_t *lens, const uint8_t *kinds, void *padded_chunks, uint8_t *end_bits,

@@ -132,13 +132,14 @@ void hc_ed25519_trace(const uint8_t *scalars, const uint8_t *points, uint32_t n_
     int32_t *chain = (int32_t *)malloc((size_t)(n_muls + 1) * 256 * EDT_CHAIN_WORDS * 4);
     uint32_t *aff = (uint32_t *)malloc((size_t)(n_muls + 1) * 256 * EDT_AFF_WORDS * 4);
     for (uint32_t m = 0; m < n_muls; m++)
-        edt_chain_core(scalars + (size_t)m * 32, points + (size_t)m * 64, chain + (size_t)m * 256 * EDT_CHAIN_WORDS,
-                       aff + (size_t)m * 256 * EDT_AFF_WORDS, results ? results + (size_t)m * 64 : nullptr);
+        edt_forward_core<false>(scalars + (size_t)m * 32, points + (size_t)m * 64, chain + (size_t)m * 256 * EDT_CHAIN_WORDS);
+    for (uint32_t g = 0; g < n_muls * (256 / EDT_GROUP); g++)
+        edt_affine_core(chain + (size_t)g * EDT_GROUP * EDT_CHAIN_WORDS, aff + (size_t)g * EDT_GROUP * EDT_AFF_WORDS);
     for (size_t row = 0; row < n_rows; row++) {
         const uint32_t m = (uint32_t)(row >> 8), j = (uint32_t)row & 255;
         const bool real = m < n_muls;
         edt_row_core(real, j, real ? scalars + (size_t)m * 32 : nullptr, real ? points + (size_t)m * 64 : nullptr,
-                     real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows);
+                     real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows, real && results ? results + (size_t)m * 64 : nullptr);
     }
     free(chain); free(aff);
 }

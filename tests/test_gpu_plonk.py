@@ -230,6 +230,13 @@ def test_ed25519_trace_matches_oracle(pv, log_rows):
     got, res = pv.ed25519_trace(_ed_dev(pv, sc.reshape(n, 32)), _ed_dev(pv, pt.reshape(n, 64)), log_rows)
     assert (_host(got) == want).all()
     assert res.cpu().numpy().tobytes() == b"".join(po.ed_point_bytes(p) for p in results)
+    # the two halves called apart (what a caller overlapping batches does) give the same table
+    import torch
+    d_sc, d_pt = _ed_dev(pv, sc.reshape(n, 32)), _ed_dev(pv, pt.reshape(n, 64))
+    scratch, out2 = pv.ed25519_trace_scratch(n), torch.zeros_like(got)
+    pv.ed25519_trace_points(d_sc, d_pt, scratch)
+    pv.ed25519_trace_rows(d_sc, d_pt, scratch, log_rows, out2)
+    assert torch.equal(out2, got)
 
 
 def test_ed25519_trace_of_a_signature_batch_closes_on_the_witness_records(pv):
