@@ -1734,7 +1734,7 @@ def ed25519_trace_block(args, ctx, pv, dev, peak):
     out2 = torch.empty_like(out)
     scr = [pv.ed25519_trace_scratch(n) for _ in range(2)]
     outs = [out, out2]
-    s_pts, s_rows = torch.cuda.Stream(), torch.cuda.Stream()
+    s_pts, s_rows = torch.cuda.Stream(priority=-1), torch.cuda.Stream()     # the few chain CTAs must not queue behind the row kernel's thousands
     pts_done = [torch.cuda.Event() for _ in range(2)]
     rows_done = [torch.cuda.Event() for _ in range(2)]
 
@@ -1791,7 +1791,7 @@ def ed25519_trace_block(args, ctx, pv, dev, peak):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--ed-trace-circuits", type=int, default=8, help="--mode trace: verify_skip circuits per Ed25519 trace step")
+    ap.add_argument("--ed-trace-circuits", type=int, default=16, help="--mode trace: verify_skip circuits per Ed25519 trace step")
     ap.add_argument("--mode", default="header_range", choices=["header_range", "ed25519", "gates", "tree", "poseidon", "shape", "encode", "pack", "sweeps", "plonk", "trace"])
     ap.add_argument("--trees", type=int, default=4096)
     ap.add_argument("--hashes", type=int, default=1 << 20)
