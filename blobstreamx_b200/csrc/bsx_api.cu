@@ -22,6 +22,7 @@ static const struct { const char *name; int dflt; } TUNABLES[BSX_TUN_COUNT] = {
     {"ED_FP64", -1},     {"HR_HASH_STREAM", -1}, {"HR_TRACE", 0},    {"PIPE_CHUNK", 0}, {"PIPE_ED", 0},
     {"PIPE_TRACE", 0},   {"PROOFS_OCC", 8},      {"SUBCHAIN_FUSED", 0}, {"COMMIT_THREADS", 128},
     {"ED_KEYTAB", -1},   {"ED_KOCC", 0},        {"ED_PAIR", -1},       {"ED_RESIDENT", 0},
+    {"ED_TRACE_LANES", 0},
 };
 
 static int tunable_index(const char *name) {

@@ -32,6 +32,7 @@ enum bsx_tun_id {
     BSX_TUN_ED_KOCC,         // register budget of the table-path kernel: 0 = as the general kernel's, 4 / 6 / 8 CTAs per SM
     BSX_TUN_ED_PAIR,         // table path: two signatures per thread with one shared inversion: -1 by batch size, 0 never, 1 always
     BSX_TUN_ED_RESIDENT,     // thread-per-signature kernel: at most this many CTAs per SM (dynamic shared memory as ballast), 0 = no limit
+    BSX_TUN_ED_TRACE_LANES,  // Ed25519 trace, lanes per multiplication in the chain kernel: 0 by batch size, 1 or 8
     BSX_TUN_COUNT
 };
 

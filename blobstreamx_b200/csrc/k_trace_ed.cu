@@ -40,6 +40,98 @@ __global__ void __launch_bounds__(64) ed_trace_chain_kernel(const uint8_t *__res
     edt_forward_core<true>(scalars + (size_t)m * 32, points + (size_t)m * 64, chain + (size_t)m * 256 * EDT_CHAIN_WORDS);
 }
 
+// The same chain with EIGHT lanes per multiplication: lanes 0..3 of a group hold X, Y, Z, T of temp (the doubling chain),
+// lanes 4..7 those of acc (the addition chain), and every lane does ONE field multiplication per time slot:
+//   slot 1   D: X^2, Y^2, Z * 2Z, (X + Y)^2                A: (Y1 + X1)(Yt + Xt), (Y1 - X1)(Yt - Xt), Z1 Zt, T1 (2d Tt)
+//   slot 2   completed -> extended, both groups: X' T', Z' Y', Z' T', X' Y'
+//   slot 3   2d T of the new temp (one lane's worth of work, the other seven idle along)
+// with the operands moved by warp shuffles and chosen by lane role, so that one instruction stream serves all roles.  A
+// step's dependent path is 3 multiplications instead of 18: 24 multiplication slots of work instead of 18, but a small
+// batch (one circuit = 200 multiplications) is bound by that path, not by issue slots.  Same formulas as ge_dbl /
+// ge_add_cached / ge_p1p1_to_p3 (ed25519.cuh), same limb bounds (f <= 3 units, g <= 2 units).
+__device__ __forceinline__ fe shfl_fe(const fe &a, int src) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+    return r;
+}
+
+__global__ void __launch_bounds__(128) ed_trace_chain8_kernel(const uint8_t *__restrict__ scalars, const uint8_t *__restrict__ points, uint32_t n_muls,
+                                                              int32_t *__restrict__ chain) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t m_raw = gid >> 3;
+    const bool live = m_raw < n_muls;
+    const uint32_t m = live ? m_raw : n_muls - 1;              // idle groups compute along (the shuffles need every lane)
+    const int lane = threadIdx.x & 31, gb = lane & ~7, c = lane & 3;
+    const bool isA = (lane & 4) != 0;
+    const int gq = gb + (isA ? 4 : 0);
+    const int32_t d2c[10] = BSX_FE_2D;
+    const fe d2 = fe_const(d2c);
+    uint32_t k[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) k[i] = ld_le32(scalars + (size_t)m * 32 + 4 * i);
+    fe own;
+    {
+        const fe px = fe_frombytes(points + (size_t)m * 64), py = fe_frombytes(points + (size_t)m * 64 + 32);
+        const fe pt = fe_mul(px, py);
+        // D: X Y Z T of P;  A: the identity (0, 1, 1, 0)
+        own = isA ? ((c == 1 || c == 2) ? fe_one() : fe_zero()) : (c == 0 ? px : c == 1 ? py : c == 2 ? fe_one() : pt);
+    }
+    fe t2d = fe_mul(own, d2);                                  // used from lane D3 only
+    const int srcC = isA ? (c == 0 ? gb + 5 : c == 1 ? gb + 4 : c == 2 ? gb + 2 : gb + 3) : lane;
+    int32_t *out = chain + (size_t)m * 256 * EDT_CHAIN_WORDS + (isA ? 0 : 32) + 10 * c;
+    // Role masks: every choice below is a bitwise blend, so the warp runs ONE instruction stream (written with ?: the
+    // compiler makes branches of them and the eight roles run one after the other: 1.30 ms instead of the time below).
+    const int32_t mA = isA ? -1 : 0, m0 = c == 0 ? -1 : 0, m1 = c == 1 ? -1 : 0, m2 = c == 2 ? -1 : 0, m3 = c == 3 ? -1 : 0;
+    const int32_t mD3 = ~mA & m3, mA0 = mA & m0, mA1 = mA & m1;
+    const int32_t gS = mA0 | mD3, gV = mA & (m2 | m3), gOO = ~mA & m2, gO = ~mA & (m0 | m1);
+    const int32_t mX = m0 | m3, mT = m0 | m2;
+#pragma unroll 1
+    for (int j = 0; j < 256; j++) {
+        const fe Xt = shfl_fe(own, gb), Yt = shfl_fe(own, gb + 1);
+        fe give;
+#pragma unroll
+        for (int i = 0; i < 10; i++) give.v[i] = (t2d.v[i] & mD3) | (own.v[i] & ~mD3);
+        const fe vc = shfl_fe(give, srcC);                       // A0 <- Y1, A1 <- X1, A2 <- Zt, A3 <- 2d Tt
+        fe f, g;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            const int32_t o = own.v[i], v = vc.v[i], s = Xt.v[i] + Yt.v[i], dm = Yt.v[i] - Xt.v[i];
+            // f: A0 X1 + Y1, A1 Y1 - X1, A2 Z1, A3 T1;  D0 X, D1 Y, D2 Z, D3 X + Y
+            f.v[i] = ((o + (v & mA0) - (v & mA1)) & ~mD3) | (s & mD3);
+            // g: A0 Yt + Xt, A1 Yt - Xt, A2 Zt, A3 2d Tt;  D0 X, D1 Y, D2 2Z, D3 X + Y
+            g.v[i] = (s & gS) | (dm & mA1) | (v & gV) | ((o + o) & gOO) | (o & gO);
+        }
+        const fe p = fe_mul(f, g);
+        const fe p0 = shfl_fe(p, gq), p1 = shfl_fe(p, gq + 1), p2 = shfl_fe(p, gq + 2), p3 = shfl_fe(p, gq + 3);
+        fe Tc;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            // D: xx yy 2zz (x+y)^2 -> Y' = yy + xx, Z' = yy - xx, X' = a - Y', T' = 2zz - Z'
+            // A: a b zz c          -> X' = a - b, Y' = a + b, Z' = 2zz + c, T' = 2zz - c
+            const int32_t yy = p1.v[i] + p0.v[i], zD = p1.v[i] - p0.v[i], dA = p2.v[i] + p2.v[i];
+            const int32_t Xc = ((p0.v[i] - p1.v[i]) & mA) | ((p3.v[i] - yy) & ~mA);
+            const int32_t Zc = ((dA + p3.v[i]) & mA) | (zD & ~mA);
+            Tc.v[i] = ((dA - p3.v[i]) & mA) | ((p2.v[i] - zD) & ~mA);
+            f.v[i] = (Xc & mX) | (Zc & ~mX);                      // slot 2: X' T', Z' Y', Z' T', X' Y'
+            g.v[i] = yy;                                         // Y' is yy + xx resp. a + b: the same sum
+        }
+        const fe tt = fe_tighten(Tc);
+#pragma unroll
+        for (int i = 0; i < 10; i++) g.v[i] = (tt.v[i] & mT) | (g.v[i] & ~mT);
+        const fe q = fe_mul(f, g);                                // D: coordinate c of 2 temp;  A: coordinate c of acc + temp
+        if (live && c < 3) {
+            int2 *o2 = reinterpret_cast<int2 *>(out + (size_t)j * EDT_CHAIN_WORDS);
+#pragma unroll
+            for (int i = 0; i < 5; i++) o2[i] = make_int2(q.v[2 * i], q.v[2 * i + 1]);
+        }
+        const int32_t take = ~mA | -(int32_t)((k[j >> 5] >> (j & 31)) & 1);
+#pragma unroll
+        for (int i = 0; i < 10; i++) own.v[i] = (q.v[i] & take) | (own.v[i] & ~take);
+        t2d = fe_mul(own, d2);
+    }
+}
+
 __global__ void __launch_bounds__(128) ed_trace_affine_kernel(const int32_t *__restrict__ chain, uint32_t n_groups, uint32_t *__restrict__ aff) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
@@ -78,7 +170,11 @@ extern "C" int bsx_ed25519_trace_points_dev(bsx_ctx *ctx, void *stream, const ui
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *chain = reinterpret_cast<int32_t *>(scratch);
     uint32_t *aff = reinterpret_cast<uint32_t *>(chain + (size_t)n_muls * 256 * EDT_CHAIN_WORDS);
-    ed_trace_chain_kernel<<<(n_muls + 63) / 64, 64, 0, st>>>(scalars, points, n_muls, chain);
+    // one circuit's worth of multiplications is bound by the chain's dependent path: eight lanes each; large batches fill the
+    // machine with one thread each (less work per multiplication)
+    const int lanes = ctx->tun[BSX_TUN_ED_TRACE_LANES] ? ctx->tun[BSX_TUN_ED_TRACE_LANES] : (n_muls <= 16384 ? 8 : 1);
+    if (lanes == 8) ed_trace_chain8_kernel<<<(n_muls + 15) / 16, 128, 0, st>>>(scalars, points, n_muls, chain);
+    else ed_trace_chain_kernel<<<(n_muls + 63) / 64, 64, 0, st>>>(scalars, points, n_muls, chain);
     BSX_LAUNCHED(ctx);
     const uint32_t n_groups = n_muls * (256 / EDT_GROUP);
     ed_trace_affine_kernel<<<(n_groups + 127) / 128, 128, 0, st>>>(chain, n_groups, aff);

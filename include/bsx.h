@@ -54,7 +54,7 @@ int bsx_sync(bsx_ctx *ctx);
 /* Measurement knobs of one ctx (kernel-build and stream-arrangement choices; defaults = the measured best; the
  * environment variable BSX_<name> sets the default a new ctx starts with).  Names: ED_MODE, ED_QUAD_MAX, ED_INLINE,
  * ED_OCC, ED_REGS, ED_FP64, ED_KEYTAB, ED_PAIR, ED_RESIDENT, HR_HASH_STREAM, HR_TRACE, PIPE_CHUNK, PIPE_ED, PIPE_TRACE,
- * PROOFS_OCC, SUBCHAIN_FUSED, COMMIT_THREADS
+ * PROOFS_OCC, SUBCHAIN_FUSED, COMMIT_THREADS, ED_TRACE_LANES
  * (DESIGN.md section 4).  No reference counterpart: results are identical under every setting. */
 int bsx_set_tunable(bsx_ctx *ctx, const char *name, int value);
 int bsx_get_tunable(const bsx_ctx *ctx, const char *name, int *value);

@@ -208,8 +208,8 @@ def _ed_dev(pv, a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(pv.dev)
 
 
-@pytest.mark.parametrize("log_rows", [12, 13])
-def test_ed25519_trace_matches_oracle(pv, log_rows):
+@pytest.mark.parametrize("log_rows,lanes", [(12, 0), (13, 1), (12, 8)])
+def test_ed25519_trace_matches_oracle(pv, log_rows, lanes):
     """Ed25519 scalar-multiplication trace (EdDSA accelerator) on the device == oracle/ed_trace.py (pinned by
     tests/test_oracle_ed_trace.py): edge scalars (0, 1, 2^256 - 1, l), the identity and the order-2 point, random
     multiplications, s*G and h*A of a mocha-4 fixture signature, padding multiplications; k * P out of the same call."""
@@ -219,7 +219,8 @@ def test_ed25519_trace_matches_oracle(pv, log_rows):
     from tests.test_oracle_ed_trace import _cases, _fixture_muls, pack
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mocha4.json")) as f:
         golden = json.load(f)
-    rng = np.random.default_rng(8 + log_rows)
+    pv.ctx.set_tunable("ED_TRACE_LANES", lanes)        # chain kernel: by batch size / one thread / eight lanes per multiplication
+    rng = np.random.default_rng(8 + log_rows + lanes)
     scalars, points = _cases(rng, 2)
     fs, fp, fw = _fixture_muls(golden, "10000", 1)
     scalars, points = scalars + fs, points + fp
@@ -237,6 +238,7 @@ def test_ed25519_trace_matches_oracle(pv, log_rows):
     pv.ed25519_trace_points(d_sc, d_pt, scratch)
     pv.ed25519_trace_rows(d_sc, d_pt, scratch, log_rows, out2)
     assert torch.equal(out2, got)
+    pv.ctx.set_tunable("ED_TRACE_LANES", 0)
 
 
 def test_ed25519_trace_of_a_signature_batch_closes_on_the_witness_records(pv):
@@ -260,6 +262,11 @@ def test_ed25519_trace_of_a_signature_batch_closes_on_the_witness_records(pv):
     want[0::2], want[1::2] = rec[:, 136:200], rec[:, 296:360]
     log_rows = 18                                                    # 131 072 real rows + as many padding rows: 3.2 GB
     tr, res = pv.ed25519_trace(_ed_dev(pv, scalars), _ed_dev(pv, points), log_rows)
+    pv.ctx.set_tunable("ED_TRACE_LANES", 1)                          # the other chain kernel: identical table
+    tr1, res1 = pv.ed25519_trace(_ed_dev(pv, scalars), _ed_dev(pv, points), log_rows)
+    pv.ctx.set_tunable("ED_TRACE_LANES", 0)
+    assert torch.equal(tr1, tr) and torch.equal(res1, res)
+    del tr1
     assert (res.cpu().numpy() == want).all()
     n_real = 2 * n_sig * 256
     assert int(tr.max()) < 65536 and int(tr.min()) >= 0
