@@ -92,13 +92,18 @@ __device__ __forceinline__ void tr_expand_row(const TraceRow &o, int t, const ui
     o.put(175, TR_K[t]);
 }
 
+// blockIdx.y = circuit: its chunks / flags start chunk_stride chunks further, its table TR_COLS * n_rows elements further
 __global__ void __launch_bounds__(128) sha256_trace_kernel(const uint32_t *__restrict__ chunks, const uint8_t *__restrict__ end_bits,
-                                                           const uint8_t *__restrict__ digest_bits, uint32_t n_chunks, size_t n_rows,
-                                                           uint64_t *__restrict__ trace) {
+                                                           const uint8_t *__restrict__ digest_bits, uint32_t n_chunks, size_t chunk_stride,
+                                                           size_t n_rows, uint64_t *__restrict__ trace) {
     __shared__ uint32_t sW[4][64], sS[4][64][8];
     const uint32_t wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t blk = blockIdx.x * 4 + wid;
     if (blk >= n_chunks) return;
+    chunks += (size_t)blockIdx.y * chunk_stride * 16;
+    end_bits += (size_t)blockIdx.y * chunk_stride;
+    digest_bits += (size_t)blockIdx.y * chunk_stride;
+    trace += (size_t)blockIdx.y * TR_COLS * n_rows;
     if (lane == 0) {
         // entering state: IV at the first chunk of a request, else the chaining value of the chunks before it
         uint32_t s0 = blk;
@@ -248,19 +253,28 @@ using namespace bsx;
 
 // SHA-256 trace of n_chunks padded chunks (bsx_hash_input_data layout): trace = BSX_SHA256_TRACE_COLS columns of
 // 2^log_rows rows each (column-major, u64 field elements), rows beyond 64 * n_chunks zero.
-extern "C" int bsx_sha256_trace_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chunks, const uint8_t *end_bits,
-                                    const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace) {
-    BSX_REQUIRE(ctx, ctx && padded_chunks && end_bits && digest_bits && trace && log_rows <= 30);
+// _batch_: n_circuits accelerators of the same shape in ONE launch (the map circuits of a range have the same request
+// schedule): circuit c reads its chunks / flags at c * chunk_stride chunks and writes its own table after the others'.  One
+// circuit is 312 CTAs -- two per SM, all ramp-up and tail; 32 of them in one grid keep the machine full.
+extern "C" int bsx_sha256_trace_batch_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chunks, const uint8_t *end_bits,
+                                          const uint8_t *digest_bits, uint32_t n_chunks, uint32_t n_circuits, size_t chunk_stride,
+                                          uint32_t log_rows, uint64_t *trace) {
+    BSX_REQUIRE(ctx, ctx && padded_chunks && end_bits && digest_bits && trace && log_rows <= 30 && n_circuits <= 65535);
     const size_t n_rows = (size_t)1 << log_rows;
-    BSX_REQUIRE(ctx, (size_t)n_chunks * 64 <= n_rows);
+    BSX_REQUIRE(ctx, (size_t)n_chunks * 64 <= n_rows && (n_circuits <= 1 || chunk_stride >= n_chunks));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t used = (size_t)n_chunks * 64;
-    if (used < n_rows)
-        BSX_CUDA(ctx, cudaMemset2DAsync(trace + used, n_rows * sizeof(uint64_t), 0, (n_rows - used) * sizeof(uint64_t), TR_COLS, st));
-    if (n_chunks == 0) return BSX_OK;
-    sha256_trace_kernel<<<(n_chunks + 3) / 4, 128, 0, st>>>(padded_chunks, end_bits, digest_bits, n_chunks, n_rows, trace);
+    if (used < n_rows && n_circuits)
+        BSX_CUDA(ctx, cudaMemset2DAsync(trace + used, n_rows * sizeof(uint64_t), 0, (n_rows - used) * sizeof(uint64_t), (size_t)TR_COLS * n_circuits, st));
+    if (n_chunks == 0 || n_circuits == 0) return BSX_OK;
+    sha256_trace_kernel<<<dim3((n_chunks + 3) / 4, n_circuits), 128, 0, st>>>(padded_chunks, end_bits, digest_bits, n_chunks, chunk_stride, n_rows, trace);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
+}
+
+extern "C" int bsx_sha256_trace_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chunks, const uint8_t *end_bits,
+                                    const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace) {
+    return bsx_sha256_trace_batch_dev(ctx, stream, padded_chunks, end_bits, digest_bits, n_chunks, 1, n_chunks, log_rows, trace);
 }
 
 // SHA-512 trace: BSX_SHA512_TRACE_COLS columns of 2^log_rows rows, 80 rows per 128-byte chunk (padded_chunks = u64 words,

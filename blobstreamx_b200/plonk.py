@@ -112,6 +112,17 @@ class Prover:
                           L.ptr(digest_bits.data_ptr()), L.u32(n), L.u32(log_rows), L.ptr(out.data_ptr()))
         return out
 
+    def sha256_trace_batch(self, padded_chunks: torch.Tensor, end_bits: torch.Tensor, digest_bits: torch.Tensor, log_rows: int,
+                           out: torch.Tensor = None) -> torch.Tensor:
+        """[circuits, chunks, 16] int32 words + [circuits, chunks] uint8 flags (same request schedule in every circuit) ->
+        [circuits, BSX_SHA256_TRACE_COLS, 2^log_rows] in one launch."""
+        nc, n = padded_chunks.shape[0], padded_chunks.shape[1]
+        if out is None:
+            out = torch.empty((nc, SHA256_TRACE_COLS, 1 << log_rows), dtype=torch.int64, device=self.dev)
+        self.ctx.call_dev("bsx_sha256_trace_batch_dev", self.stream, L.ptr(padded_chunks.data_ptr()), L.ptr(end_bits.data_ptr()),
+                          L.ptr(digest_bits.data_ptr()), L.u32(n), L.u32(nc), C.c_size_t(n), L.u32(log_rows), L.ptr(out.data_ptr()))
+        return out
+
     def sha512_trace(self, padded_chunks: torch.Tensor, end_bits: torch.Tensor, digest_bits: torch.Tensor, log_rows: int) -> torch.Tensor:
         """As sha256_trace for the SHA-512 (EdDSA) accelerator: [chunks, 16] int64 words -> [BSX_SHA512_TRACE_COLS, 2^log_rows]."""
         out = torch.empty((SHA512_TRACE_COLS, 1 << log_rows), dtype=torch.int64, device=self.dev)

@@ -624,6 +624,11 @@ int bsx_sha512_trace_dev(bsx_ctx *ctx, void *stream, const uint64_t *padded_chun
                          const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace);
 int bsx_sha256_trace_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chunks, const uint8_t *end_bits,
                          const uint8_t *digest_bits, uint32_t n_chunks, uint32_t log_rows, uint64_t *trace);
+/* n_circuits accelerators of the same shape (the map circuits of a range) in one launch: circuit c reads its chunks and
+ * flags chunk_stride chunks after circuit c - 1's and writes table c (BSX_SHA256_TRACE_COLS * 2^log_rows elements each) */
+int bsx_sha256_trace_batch_dev(bsx_ctx *ctx, void *stream, const uint32_t *padded_chunks, const uint8_t *end_bits,
+                               const uint8_t *digest_bits, uint32_t n_chunks, uint32_t n_circuits, size_t chunk_stride,
+                               uint32_t log_rows, uint64_t *trace);
 /* Ed25519 scalar-multiplication execution trace (the EdDSA accelerator): 256 rows per ScalarMul operation
  * (two per signature: s*G and h*A), one scalar bit per row, an affine double-and-add whose 16 field operations per row
  * carry starkyx-style witnesses (16-bit limbs; quotient `carry`; witness polynomial of the division by x - 2^16).

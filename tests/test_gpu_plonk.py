@@ -183,6 +183,12 @@ def test_sha256_trace_matches_oracle(pv, n_req):
     got = pv.sha256_trace(dev(hid["padded_chunks"].view(np.int32)), dev(hid["end_bits"]), dev(hid["digest_bits"]), log_rows)
     want = orc.sha256_trace(hid["padded_chunks"], hid["end_bits"], hid["digest_bits"], log_rows)
     assert (_host(got) == want).all()
+    # three circuits of the same schedule in one launch (bsx_sha256_trace_batch_dev), different words in each
+    pcs = np.stack([hid["padded_chunks"], hid["padded_chunks"] ^ np.uint32(0x5A5A5A5A), rng.integers(0, 2**32, hid["padded_chunks"].shape, dtype=np.uint32)])
+    ebs, dbs = np.stack([hid["end_bits"]] * 3), np.stack([hid["digest_bits"]] * 3)
+    gotb = _host(pv.sha256_trace_batch(dev(pcs.view(np.int32)), dev(ebs), dev(dbs), log_rows))
+    for c in range(3):
+        assert (gotb[c] == orc.sha256_trace(pcs[c], hid["end_bits"], hid["digest_bits"], log_rows)).all()
 
 
 def test_sha512_trace_matches_oracle(pv):
