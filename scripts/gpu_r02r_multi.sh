@@ -1,7 +1,7 @@
 #!/bin/bash
 # r02r (N GPUs): the sharded bench of this build exactly as the driver launches it, at every N the box has, plus the distributed GPU tests
 N=${1:-2}
-OUT=gpurun_out/r03e_multi_$N
+OUT=gpurun_out/r04z_multi_$N
 mkdir -p $OUT
 export PATH=/usr/local/cuda/bin:$PATH
 nproc > $OUT/nproc.txt
