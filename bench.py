@@ -1702,13 +1702,13 @@ def ed25519_trace_block(args, ctx, pv, dev, peak):
     rec = ctx.ed25519_batch(pks, sigs, msgs, lens)
     gx = 15112221349535400772501151409588531511454012693041857206046113283949847762202
     gy = 46316835694926478169428394003475163141307993866256225615783033603165251855960
-    G = np.frombuffer(gx.to_bytes(32, "little") + gy.to_bytes(32, "little"), np.uint8)
     n = 2 * n_sig
-    scalars, points, want = np.empty((n, 32), np.uint8), np.empty((n, 64), np.uint8), np.empty((n, 64), np.uint8)
-    scalars[0::2], points[0::2], want[0::2] = sigs[:, 32:64], G, rec[:, 136:200]
-    scalars[1::2], points[1::2], want[1::2] = rec[:, 64:96], rec[:, 200:264], rec[:, 296:360]
+    want = np.empty((n, 64), np.uint8)
+    want[0::2], want[1::2] = rec[:, 136:200], rec[:, 296:360]
     log_rows = int(np.ceil(np.log2(256 * n)))
-    d_sc, d_pt = torch.from_numpy(scalars).to(dev), torch.from_numpy(points).to(dev)
+    # the ScalarMul operands (s, G), (h, A) gathered on the device from the signatures and their witness records
+    d_sc, d_pt = pv.ed25519_trace_operands(torch.from_numpy(sigs).to(dev), torch.from_numpy(rec).to(dev))
+    scalars, points = d_sc.cpu().numpy(), d_pt.cpu().numpy()
     out = torch.empty((ED25519_TRACE_COLS, 1 << log_rows), dtype=torch.int64, device=dev)
     _, res = pv.ed25519_trace(d_sc, d_pt, log_rows, out=out)
     torch.cuda.synchronize()

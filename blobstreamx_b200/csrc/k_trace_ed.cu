@@ -149,12 +149,47 @@ __global__ void __launch_bounds__(128, EDT_ROWS_MINB) ed_trace_rows_kernel(const
                  real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows, real && results ? results + (size_t)m * 64 : nullptr);
 }
 
+// ScalarMul operands of a batch of signatures, on the device: (s, G) and (h, A) per signature from the signature bytes and
+// the 576-byte witness records of bsx_ed25519_batch (h at 64, A at 200) -- the requests Ed25519Stark::new collects
+// (PX/frontend/ecc/curve25519/curta/stark.rs:93-124), in the order of the EdDSA schedule (eddsa.rs:161-203: s*G, then h*A).
+// s of the DUMMY signature inactive lanes run on (eddsa.rs:28-30; the bytes 32..63 of DUMMY_SIG in k_ed25519.cu)
+__constant__ uint8_t EDT_DUMMY_S[32] = {1, 41, 22, 121, 249, 46, 198, 145, 155, 102, 3, 210, 168, 135, 173, 55,
+                                        252, 72, 45, 126, 169, 178, 191, 7, 153, 67, 112, 90, 150, 33, 140, 7};
+__global__ void ed_trace_operands_kernel(uint32_t n_sigs, const uint8_t *__restrict__ sigs, uint32_t sig_stride, const uint8_t *__restrict__ active,
+                                         uint32_t active_stride, const uint8_t *__restrict__ ed_out, uint8_t *__restrict__ scalars,
+                                         uint8_t *__restrict__ points) {
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
+    if (i >= n_sigs) return;
+    const int32_t gx[10] = BSX_FE_GX, gy[10] = BSX_FE_GY;
+    uint8_t g[64];
+    fe_tobytes(g, fe_const(gx)); fe_tobytes(g + 32, fe_const(gy));
+    const uint8_t *rec = ed_out + (size_t)i * BSX_SIG_OUT_BYTES;
+    const bool on = !active || active[(size_t)i * active_stride] != 0;
+    scalars[(size_t)(2 * i) * 32 + l] = on ? sigs[(size_t)i * sig_stride + 32 + l] : EDT_DUMMY_S[l];
+    scalars[(size_t)(2 * i + 1) * 32 + l] = rec[64 + l];
+    points[(size_t)(2 * i) * 64 + l] = g[l];
+    points[(size_t)(2 * i) * 64 + 32 + l] = g[32 + l];
+    points[(size_t)(2 * i + 1) * 64 + l] = rec[200 + l];
+    points[(size_t)(2 * i + 1) * 64 + 32 + l] = rec[232 + l];
+}
+
 }  // namespace bsx
 
 using namespace bsx;
 
 // bytes of device scratch bsx_ed25519_trace_dev needs for n_muls multiplications
 extern "C" size_t bsx_ed25519_trace_scratch_bytes(uint32_t n_muls) { return (size_t)n_muls * 256 * (EDT_CHAIN_WORDS + EDT_AFF_WORDS) * 4; }
+
+extern "C" int bsx_ed25519_trace_operands_dev(bsx_ctx *ctx, void *stream, uint32_t n_sigs, const uint8_t *sigs, uint32_t sig_stride,
+                                              const uint8_t *active, uint32_t active_stride, const uint8_t *ed_out, uint8_t *scalars,
+                                              uint8_t *points) {
+    BSX_REQUIRE(ctx, ctx && (n_sigs == 0 || (sigs && ed_out && scalars && points && sig_stride >= 64)));
+    if (n_sigs == 0) return BSX_OK;
+    ed_trace_operands_kernel<<<(n_sigs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(n_sigs, sigs, sig_stride, active, active_stride, ed_out, scalars,
+                                                                                  points);
+    BSX_LAUNCHED(ctx);
+    return BSX_OK;
+}
 
 // Execution trace of n_muls scalar multiplications k_m * P_m: trace = BSX_ED25519_TRACE_COLS columns of 2^log_rows rows
 // (column-major u64 field elements), 256 rows per multiplication, the rest padded with rows of 0 * (0, 1).

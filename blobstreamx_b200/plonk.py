@@ -154,6 +154,17 @@ class Prover:
                           L.ptr(out.data_ptr()))
         return out, res
 
+    def ed25519_trace_operands(self, sigs: torch.Tensor, ed_out: torch.Tensor, active: torch.Tensor = None):
+        """[n, 64] uint8 signatures (+ [n] uint8 lane flags) + [n, 576] uint8 witness records (device; rows may be strided views,
+        e.g. validators[:, 32:96]) -> ([2n, 32] scalars, [2n, 64] points): (s, G), (h, A); inactive lanes take the DUMMY s"""
+        n = sigs.shape[0]
+        scalars = torch.empty((2 * n, 32), dtype=torch.uint8, device=self.dev)
+        points = torch.empty((2 * n, 64), dtype=torch.uint8, device=self.dev)
+        self.ctx.call_dev("bsx_ed25519_trace_operands_dev", self.stream, L.u32(n), L.ptr(sigs.data_ptr()), L.u32(sigs.stride(0)),
+                          L.ptr(active.data_ptr() if active is not None else 0), L.u32(active.stride(0) if active is not None else 0),
+                          L.ptr(ed_out.data_ptr()), L.ptr(scalars.data_ptr()), L.ptr(points.data_ptr()))
+        return scalars, points
+
     def ed25519_trace_points(self, scalars: torch.Tensor, points: torch.Tensor, scratch: torch.Tensor, stream: int = None):
         """first half of ed25519_trace (multiplication chains -> scratch), on `stream`"""
         self.ctx.call_dev("bsx_ed25519_trace_points_dev", self.stream if stream is None else stream, L.ptr(scalars.data_ptr()),

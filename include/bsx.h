@@ -649,6 +649,15 @@ int bsx_sha256_trace_batch_dev(bsx_ctx *ctx, void *stream, const uint32_t *padde
  * scratch: bsx_ed25519_trace_scratch_bytes(n_muls) bytes of device memory; results: n_muls x 64 bytes k * P, or NULL. */
 #define BSX_ED25519_TRACE_COLS 1540
 size_t bsx_ed25519_trace_scratch_bytes(uint32_t n_muls);
+/* The ScalarMul operands of n_sigs signatures, gathered on the device: scalars[2i] = s_i, points[2i] = G, scalars[2i+1] =
+ * h_i, points[2i+1] = A_i, from the signature bytes (sigs + i * sig_stride: R ‖ s), the lane flags (active + i *
+ * active_stride; NULL = all active; an inactive lane ran on the DUMMY signature, eddsa.rs:28-30, and takes its s) and the
+ * witness records ed_out of bsx_ed25519_batch[_dev] / bsx_verify_skip (BSX_SIG_OUT_BYTES each; with the validator records of
+ * bsx_verify_skip: sigs = validators + 32, active = validators + 236, strides BSX_VAL_IN_BYTES) -- the operations
+ * Ed25519Stark::new collects (stark.rs:93-124), in the order of the EdDSA schedule (s*G, then h*A). */
+int bsx_ed25519_trace_operands_dev(bsx_ctx *ctx, void *stream, uint32_t n_sigs, const uint8_t *sigs, uint32_t sig_stride,
+                                   const uint8_t *active, uint32_t active_stride, const uint8_t *ed_out, uint8_t *scalars,
+                                   uint8_t *points);
 int bsx_ed25519_trace_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls,
                           uint32_t log_rows, void *scratch, uint8_t *results, uint64_t *trace);
 /* the two halves of bsx_ed25519_trace_dev, for callers that overlap batches (two streams, two scratch buffers): the

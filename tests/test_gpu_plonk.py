@@ -256,18 +256,22 @@ def test_ed25519_trace_of_a_signature_batch_closes_on_the_witness_records(pv):
     from blobstreamx_b200 import synthetic as S
     from oracle import pyoracle as po
     n_sig = 256
-    pks, sigs, msgs, lens, _ = S.ed25519_batch_inputs(n_sig)
-    rec = pv.ctx.ed25519_batch(pks, sigs, msgs, lens)          # every lane active: s is the signature's own
-    assert (rec[:, 520] == 0xF).all()
+    pks, sigs, msgs, lens, act = S.ed25519_batch_inputs(n_sig, inactive_every=50)      # 5 lanes run on the DUMMY signature
+    rec = pv.ctx.ed25519_batch(pks, sigs, msgs, lens, act)
+    assert (rec[:, 520] == 0xF).all() and (act == 0).sum() == 5
     G = np.frombuffer(po.ed_point_bytes(po.G), np.uint8)
+    s_used = np.where(act[:, None] != 0, sigs[:, 32:64], np.frombuffer(po.DUMMY_SIGNATURE[32:], np.uint8)[None, :])
     scalars = np.empty((2 * n_sig, 32), np.uint8)
     points = np.empty((2 * n_sig, 64), np.uint8)
-    scalars[0::2], points[0::2] = sigs[:, 32:64], G
+    scalars[0::2], points[0::2] = s_used, G
     scalars[1::2], points[1::2] = rec[:, 64:96], rec[:, 200:264]
     want = np.empty((2 * n_sig, 64), np.uint8)
     want[0::2], want[1::2] = rec[:, 136:200], rec[:, 296:360]
+    # the operands gathered on the device from signatures + records (bsx_ed25519_trace_operands_dev) are those
+    d_sc, d_pt = pv.ed25519_trace_operands(_ed_dev(pv, sigs), _ed_dev(pv, rec), _ed_dev(pv, act))
+    assert (d_sc.cpu().numpy() == scalars).all() and (d_pt.cpu().numpy() == points).all()
     log_rows = 18                                                    # 131 072 real rows + as many padding rows: 3.2 GB
-    tr, res = pv.ed25519_trace(_ed_dev(pv, scalars), _ed_dev(pv, points), log_rows)
+    tr, res = pv.ed25519_trace(d_sc, d_pt, log_rows)
     pv.ctx.set_tunable("ED_TRACE_LANES", 1)                          # the other chain kernel: identical table
     tr1, res1 = pv.ed25519_trace(_ed_dev(pv, scalars), _ed_dev(pv, points), log_rows)
     pv.ctx.set_tunable("ED_TRACE_LANES", 0)
