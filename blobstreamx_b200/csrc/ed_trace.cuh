@@ -14,12 +14,53 @@ using namespace ed;
 #define EDT_CHAIN_WORDS 64        // per row: sum and dbl in extended coordinates, X Y Z (3 x 10 limbs) padded to 32 words each
 #define EDT_AFF_WORDS 32          // per row: sum.x sum.y dbl.x dbl.y, 8 little-endian words each
 
+// Row kernel output path.  Default: every thread stores its own 8 bytes (a warp = 256 B of a column).  EDT_STAGE = 1 (A/B
+// build, measured and NOT kept): a CTA's 128 rows of an operation's 92 columns are staged in shared memory ([column][row])
+// and leave as TMA bulk stores of 1 KB per column (cp.async.bulk shared -> global), the tile in two halves with their own
+// issuing threads so that a half is only waited for one operation later -- 2.98 ms against 2.43 ms for 2^20 rows: the four
+// barriers per operation put the CTA's warps in lockstep and the kernel is not short of store bandwidth but of independent
+// work (without any global store the staged form takes 1.47 ms, profiles/r04k_ed_trace_stage.txt).
+#ifndef EDT_STAGE
+#define EDT_STAGE 0
+#endif
+#define EDT_TILE 128              // rows per CTA of the row kernel = its threads
 #if defined(__CUDA_ARCH__)
+#if EDT_STAGE
+#define EDT_ST(ptr, val) (*(ptr) = (val))
+#else
 #define EDT_ST(ptr, val) __stcs((ptr), (val))
+#endif
 #define EDT_CLZ(x) __clz(x)
 #else
 #define EDT_ST(ptr, val) (*(ptr) = (val))
 #define EDT_CLZ(x) __builtin_clz(x)
+#endif
+
+// Staged output (EDT_STAGE): the tile [92 columns][128 rows] has two halves with their own issuing threads, so that a half
+// is only waited for when it is written again, one whole operation after its bulk stores were issued:
+//   A = columns 0..31 (result, carry), issued by threads 64..95;  B = columns 32..91 (the witness halves), by threads 0..59.
+#if defined(__CUDA_ARCH__) && EDT_STAGE
+#define EDT_BULK(gdst, ssrc) \
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), \
+                 "r"((uint32_t)(EDT_TILE * 8)) : "memory")
+#define EDT_BULK_COMMIT() asm volatile("cp.async.bulk.commit_group;" ::: "memory")
+#define EDT_BULK_WAIT() asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory")
+#define EDT_IS_A (threadIdx.x >= 64 && threadIdx.x < 96)
+#define EDT_IS_B (threadIdx.x < 60)
+#define EDT_PRE(is)  do { if (is) EDT_BULK_WAIT(); __syncthreads(); } while (0)
+#define EDT_POST(is, c0, stage, gcol, grows)                                                        \
+    do {                                                                                            \
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                                \
+        __syncthreads();                                                                            \
+        if (is) {                                                                                   \
+            const uint32_t c_ = (c0) + (threadIdx.x & 63);                                          \
+            if (EDT_STAGE != 2) EDT_BULK((gcol) + (size_t)c_ * (grows), (stage) + (size_t)c_ * EDT_TILE); \
+            EDT_BULK_COMMIT();                                                                      \
+        }                                                                                           \
+    } while (0)
+#else
+#define EDT_PRE(is) do { } while (0)
+#define EDT_POST(is, c0, stage, gcol, grows) do { } while (0)
 #endif
 
 BSX_HD uint32_t ld_le32(const uint8_t *s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24); }
@@ -124,7 +165,8 @@ BSX_HD void edt_limbs(uint32_t *l, const uint32_t *w) {
 //   KIND 1  inner    lhs = a1 b1 + a2 b2            res <- lhs mod p
 //   KIND 2  den (+)  lhs = a1 res + res - a2 = carry p   (res = a2 / (1 + a1), given)
 //   KIND 3  den (-)  lhs = a1 res + a2 - res = carry p   (res = a2 / (1 - a1), given)
-// Columns at col (stride n_rows): result[16] carry[16] witness_low[30] witness_high[30], where
+// Columns at col (n_rows = distance between columns there: the table's, or the staging tile's): result[16] carry[16]
+// witness_low[30] witness_high[30], where
 // lhs(x) - result(x) [KIND 0, 1] - carry(x) p(x) = (x - 2^16) w(x) and the stored witness is w_k + EDT_OFFSET.
 //
 // Quotient by p = 2^255 - 19:  N = q p + r  <=>  N + 19 q = q 2^255 + r.  Iterate q <- (N + 19 q) >> 255 from q = 0: the first
@@ -132,7 +174,8 @@ BSX_HD void edt_limbs(uint32_t *l, const uint32_t *w) {
 // particular for every exact division); the third pass only forms T = N + 19 q, whose top part tells which, and whose low
 // 255 bits are r or r + p - 2^255.
 template <int KIND>
-BSX_CALL void edt_op(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *res, uint64_t *col, size_t n_rows) {
+BSX_CALL void edt_op(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *res, uint64_t *col, size_t n_rows,
+                     uint64_t *gcol, size_t grows) {
     int64_t V[31];
 #pragma unroll
     for (int i = 0; i < 31; i++) V[i] = 0;
@@ -223,11 +266,13 @@ BSX_CALL void edt_op(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2,
             V[2 * i] -= w & 0xffff; V[2 * i + 1] -= w >> 16;
         }
     }
+    EDT_PRE(EDT_IS_A);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         EDT_ST(col + (size_t)k * n_rows, (uint64_t)res[k]);
         EDT_ST(col + (size_t)(16 + k) * n_rows, (uint64_t)cl[k]);
     }
+    EDT_POST(EDT_IS_A, 0, col - threadIdx.x, gcol, grows);
     // V -= carry(x) p(x): p = [0xffed, 0xffff x 14, 0x7fff] = 0xffff (1 + x + .. + x^15) - 0x12 - 0x8000 x^15
     {
         uint32_t S = 0;
@@ -241,6 +286,7 @@ BSX_CALL void edt_op(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2,
             V[k] -= cp;
         }
     }
+    EDT_PRE(EDT_IS_B);
     int64_t prev = 0;
 #pragma unroll
     for (int k = 0; k < 30; k++) {
@@ -249,24 +295,43 @@ BSX_CALL void edt_op(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2,
         EDT_ST(col + (size_t)(32 + k) * n_rows, (uint64_t)(sh & 0xffff));
         EDT_ST(col + (size_t)(62 + k) * n_rows, (uint64_t)(sh >> 16));
     }
+    EDT_POST(EDT_IS_B, 32, col - threadIdx.x, gcol, grows);
+}
+
+// Where a row's values go.  dst / stride: this thread's slot of column 0 of the current group of columns and the distance
+// between columns there (the table itself, or the CTA's staging tile); gcol: the table at the CTA's first row, same column.
+struct EdtSink {
+    uint64_t *dst;
+    size_t stride;
+    uint64_t *gcol;
+    size_t n_rows;
+};
+// the group of ncols columns is complete: move on to the next group (staged: the tile leaves through the bulk-copy engine;
+// every thread of the CTA calls this)
+BSX_HD void edt_flush(EdtSink &s, int ncols) {
+#if defined(__CUDA_ARCH__) && EDT_STAGE
+    s.gcol += (size_t)ncols * s.n_rows;
+#else
+    s.dst += (size_t)ncols * s.n_rows;
+    s.gcol += (size_t)ncols * s.n_rows;
+#endif
 }
 
 // the eight operations of (x1, y1) + (x2, y2) = (x3, y3), x3 / y3 known (the chain's affine values)
 BSX_HD void edt_add_emit(const uint32_t *x1, const uint32_t *y1, const uint32_t *x2, const uint32_t *y2, uint32_t *x3, uint32_t *y3,
-                         uint64_t *col, size_t n_rows) {
+                         EdtSink &sink) {
     // d = -121665 / 121666 mod p
     const uint32_t D16[16] = {0x78a3, 0x1359, 0x4dca, 0x75eb, 0xd8ab, 0x4141, 0x0a4d, 0x0070,
                               0xe898, 0x7779, 0x4079, 0x8cc7, 0xfe73, 0x2b6f, 0x6cee, 0x5203};
     uint32_t xn[16], yn[16], m1[16], m2[16], f[16], df[16];
-    const size_t op = (size_t)EDT_OP * n_rows;
-    edt_op<1>(x1, y2, x2, y1, xn, col, n_rows);
-    edt_op<1>(y1, y2, x1, x2, yn, col + op, n_rows);
-    edt_op<0>(x1, y1, nullptr, nullptr, m1, col + 2 * op, n_rows);
-    edt_op<0>(x2, y2, nullptr, nullptr, m2, col + 3 * op, n_rows);
-    edt_op<0>(m1, m2, nullptr, nullptr, f, col + 4 * op, n_rows);
-    edt_op<0>(D16, f, nullptr, nullptr, df, col + 5 * op, n_rows);
-    edt_op<2>(df, nullptr, xn, nullptr, x3, col + 6 * op, n_rows);
-    edt_op<3>(df, nullptr, yn, nullptr, y3, col + 7 * op, n_rows);
+    edt_op<1>(x1, y2, x2, y1, xn, sink.dst, sink.stride, sink.gcol, sink.n_rows); edt_flush(sink, EDT_OP);
+    edt_op<1>(y1, y2, x1, x2, yn, sink.dst, sink.stride, sink.gcol, sink.n_rows); edt_flush(sink, EDT_OP);
+    edt_op<0>(x1, y1, nullptr, nullptr, m1, sink.dst, sink.stride, sink.gcol, sink.n_rows); edt_flush(sink, EDT_OP);
+    edt_op<0>(x2, y2, nullptr, nullptr, m2, sink.dst, sink.stride, sink.gcol, sink.n_rows); edt_flush(sink, EDT_OP);
+    edt_op<0>(m1, m2, nullptr, nullptr, f, sink.dst, sink.stride, sink.gcol, sink.n_rows); edt_flush(sink, EDT_OP);
+    edt_op<0>(D16, f, nullptr, nullptr, df, sink.dst, sink.stride, sink.gcol, sink.n_rows); edt_flush(sink, EDT_OP);
+    edt_op<2>(df, nullptr, xn, nullptr, x3, sink.dst, sink.stride, sink.gcol, sink.n_rows); edt_flush(sink, EDT_OP);
+    edt_op<3>(df, nullptr, yn, nullptr, y3, sink.dst, sink.stride, sink.gcol, sink.n_rows); edt_flush(sink, EDT_OP);
 }
 
 BSX_HD void edt_ld_point(uint32_t *x, uint32_t *y, const uint32_t *src) {
@@ -287,9 +352,8 @@ BSX_HD void edt_identity(uint32_t *x, uint32_t *y) {
 }
 
 // Row j of one multiplication (real) or a padding row: scalar / point / af belong to the multiplication (unused for padding);
-// col = &trace[row], column stride n_rows; result (may be null): 64 bytes k * P, written by the last row.
-BSX_HD void edt_row_core(bool real, uint32_t j, const uint8_t *scalar, const uint8_t *point, const uint32_t *af, uint64_t *col, size_t n_rows,
-                         uint8_t *result) {
+// sink: where the row's 1540 values go (EdtSink); result (may be null): 64 bytes k * P, written by the last row.
+BSX_HD void edt_row_core(bool real, uint32_t j, const uint8_t *scalar, const uint8_t *point, const uint32_t *af, EdtSink sink, uint8_t *result) {
     uint32_t tx[16], ty[16], ax[16], ay[16], sx[16], sy[16], dx[16], dy[16];
     uint32_t bit = 0;
     edt_identity(tx, ty); edt_identity(ax, ay); edt_identity(sx, sy); edt_identity(dx, dy);
@@ -317,19 +381,35 @@ BSX_HD void edt_row_core(bool real, uint32_t j, const uint8_t *scalar, const uin
         }
         if (top >= 0) edt_ld_point(ax, ay, af + top * EDT_AFF_WORDS);
     }
-    EDT_ST(col, (uint64_t)bit);
-    EDT_ST(col + n_rows, (uint64_t)(real ? 1 : 0));
-    EDT_ST(col + 2 * n_rows, (uint64_t)(j == 0));
-    EDT_ST(col + 3 * n_rows, (uint64_t)(j == 255));
+    {
+        uint64_t *col = sink.dst;
+        const size_t st = sink.stride;
+        EDT_ST(col, (uint64_t)bit);
+        EDT_ST(col + st, (uint64_t)(real ? 1 : 0));
+        EDT_ST(col + 2 * st, (uint64_t)(j == 0));
+        EDT_ST(col + 3 * st, (uint64_t)(j == 255));
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        EDT_ST(col + (size_t)(4 + i) * n_rows, (uint64_t)tx[i]);
-        EDT_ST(col + (size_t)(20 + i) * n_rows, (uint64_t)ty[i]);
-        EDT_ST(col + (size_t)(36 + i) * n_rows, (uint64_t)ax[i]);
-        EDT_ST(col + (size_t)(52 + i) * n_rows, (uint64_t)ay[i]);
+        for (int i = 0; i < 16; i++) {
+            EDT_ST(col + (size_t)(4 + i) * st, (uint64_t)tx[i]);
+            EDT_ST(col + (size_t)(20 + i) * st, (uint64_t)ty[i]);
+            EDT_ST(col + (size_t)(36 + i) * st, (uint64_t)ax[i]);
+            EDT_ST(col + (size_t)(52 + i) * st, (uint64_t)ay[i]);
+        }
+        // the 68 header columns span both halves of the tile: first use of each, nothing to wait for
+        EDT_POST(EDT_IS_A, 0, col - threadIdx.x, sink.gcol, sink.n_rows);
+#if defined(__CUDA_ARCH__) && EDT_STAGE
+        if (threadIdx.x < 36) {
+            if (EDT_STAGE != 2) EDT_BULK(sink.gcol + (size_t)(32 + threadIdx.x) * sink.n_rows, (col - threadIdx.x) + (size_t)(32 + threadIdx.x) * EDT_TILE);
+            EDT_BULK_COMMIT();
+        }
+#endif
+        edt_flush(sink, 68);
     }
-    edt_add_emit(ax, ay, tx, ty, sx, sy, col + (size_t)68 * n_rows, n_rows);
-    edt_add_emit(tx, ty, tx, ty, dx, dy, col + (size_t)(68 + 8 * EDT_OP) * n_rows, n_rows);
+    edt_add_emit(ax, ay, tx, ty, sx, sy, sink);
+    edt_add_emit(tx, ty, tx, ty, dx, dy, sink);
+#if defined(__CUDA_ARCH__) && EDT_STAGE
+    if (EDT_IS_A || EDT_IS_B) EDT_BULK_WAIT();              // the tile must outlive its last bulk reads
+#endif
     if (result && real && j == 255) {                        // k * P = the accumulator leaving the last row
 #pragma unroll
         for (int i = 0; i < 16; i++) {

@@ -19,6 +19,7 @@
 //   ed_trace_rows_kernel   one thread per ROW: picks temp / acc / sum / dbl of its row from the scratch (acc = the sum of
 //                          the last set bit below j), redoes the 16 field operations on 16-bit limbs with exact integer
 //                          quotients, and stores its 1540 values; a warp stores 32 consecutive rows of a column (256 B).
+//                          (EDT_STAGE = 1: the same through a shared-memory tile and TMA bulk stores -- measured slower, ed_trace.cuh)
 #include "common.cuh"
 #include "ed_trace.cuh"
 
@@ -138,15 +139,21 @@ __global__ void __launch_bounds__(128) ed_trace_affine_kernel(const int32_t *__r
     edt_affine_core(chain + (size_t)g * EDT_GROUP * EDT_CHAIN_WORDS, aff + (size_t)g * EDT_GROUP * EDT_AFF_WORDS);
 }
 
-__global__ void __launch_bounds__(128, EDT_ROWS_MINB) ed_trace_rows_kernel(const uint8_t *__restrict__ scalars, const uint8_t *__restrict__ points, uint32_t n_muls,
-                                                            const uint32_t *__restrict__ aff, size_t n_rows, uint64_t *__restrict__ trace,
-                                                            uint8_t *__restrict__ results) {
-    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
+__global__ void __launch_bounds__(EDT_TILE, EDT_ROWS_MINB) ed_trace_rows_kernel(const uint8_t *__restrict__ scalars, const uint8_t *__restrict__ points,
+                                                                                uint32_t n_muls, const uint32_t *__restrict__ aff, size_t n_rows,
+                                                                                uint64_t *__restrict__ trace, uint8_t *__restrict__ results) {
+    // n_rows is a multiple of EDT_TILE (a power of two >= 256): every thread has a row, every CTA a whole tile
+    const size_t row0 = (size_t)blockIdx.x * EDT_TILE, row = row0 + threadIdx.x;
     const uint32_t m = (uint32_t)(row >> 8), j = (uint32_t)row & 255;
     const bool real = m < n_muls;
+#if EDT_STAGE
+    extern __shared__ __align__(128) uint64_t edt_stage[];      // [EDT_OP columns][EDT_TILE rows]
+    const EdtSink sink{edt_stage + threadIdx.x, EDT_TILE, trace + row0, n_rows};
+#else
+    const EdtSink sink{trace + row, n_rows, trace + row0, n_rows};
+#endif
     edt_row_core(real, j, real ? scalars + (size_t)m * 32 : nullptr, real ? points + (size_t)m * 64 : nullptr,
-                 real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows, real && results ? results + (size_t)m * 64 : nullptr);
+                 real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, sink, real && results ? results + (size_t)m * 64 : nullptr);
 }
 
 // ScalarMul operands of a batch of signatures, on the device: (s, G) and (h, A) per signature from the signature bytes and
@@ -201,6 +208,7 @@ extern "C" int bsx_ed25519_trace_operands_dev(bsx_ctx *ctx, void *stream, uint32
 //   bsx_ed25519_trace_rows_dev    row kernel: scratch -> trace (+ results)
 extern "C" int bsx_ed25519_trace_points_dev(bsx_ctx *ctx, void *stream, const uint8_t *scalars, const uint8_t *points, uint32_t n_muls, void *scratch) {
     BSX_REQUIRE(ctx, ctx && (n_muls == 0 || (scalars && points && scratch)) && n_muls <= (1u << 22));
+    BSX_REQUIRE(ctx, ((uintptr_t)scratch & 15) == 0);               // 16-byte vector accesses
     if (n_muls == 0) return BSX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int32_t *chain = reinterpret_cast<int32_t *>(scratch);
@@ -224,8 +232,11 @@ extern "C" int bsx_ed25519_trace_rows_dev(bsx_ctx *ctx, void *stream, const uint
     const size_t n_rows = (size_t)1 << log_rows;
     BSX_REQUIRE(ctx, (size_t)n_muls * 256 <= n_rows);
     BSX_REQUIRE(ctx, n_muls == 0 || (scalars && points && scratch));
+    BSX_REQUIRE(ctx, ((uintptr_t)scratch & 15) == 0 && ((uintptr_t)trace & 15) == 0);
     const uint32_t *aff = reinterpret_cast<const uint32_t *>(reinterpret_cast<const int32_t *>(scratch) + (size_t)n_muls * 256 * EDT_CHAIN_WORDS);
-    ed_trace_rows_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(scalars, points, n_muls, aff, n_rows, trace, results);
+    const size_t smem = EDT_STAGE ? sizeof(uint64_t) * EDT_OP * EDT_TILE : 0;
+    if (smem) BSX_CUDA(ctx, cudaFuncSetAttribute(ed_trace_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ed_trace_rows_kernel<<<(unsigned)(n_rows / EDT_TILE), EDT_TILE, smem, (cudaStream_t)stream>>>(scalars, points, n_muls, aff, n_rows, trace, results);
     BSX_LAUNCHED(ctx);
     return BSX_OK;
 }

@@ -138,8 +138,9 @@ void hc_ed25519_trace(const uint8_t *scalars, const uint8_t *points, uint32_t n_
     for (size_t row = 0; row < n_rows; row++) {
         const uint32_t m = (uint32_t)(row >> 8), j = (uint32_t)row & 255;
         const bool real = m < n_muls;
+        const EdtSink sink{trace + row, n_rows, trace + row, n_rows};
         edt_row_core(real, j, real ? scalars + (size_t)m * 32 : nullptr, real ? points + (size_t)m * 64 : nullptr,
-                     real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, trace + row, n_rows, real && results ? results + (size_t)m * 64 : nullptr);
+                     real ? aff + (size_t)m * 256 * EDT_AFF_WORDS : nullptr, sink, real && results ? results + (size_t)m * 64 : nullptr);
     }
     free(chain); free(aff);
 }
