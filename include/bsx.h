@@ -647,8 +647,8 @@ int bsx_sha256_trace_batch_dev(bsx_ctx *ctx, void *stream, const uint32_t *padde
  * Padding rows (beyond 256 * n_muls) are the rows of 0 * (0, 1) with column 1 = 0.
  * scalars: n_muls x 32 bytes little-endian; points: n_muls x 64 bytes (x, y canonical little-endian, on the curve);
  * scratch: bsx_ed25519_trace_scratch_bytes(n_muls) bytes of device memory, 16-byte aligned; results: n_muls x 64 bytes
- * k * P, or NULL.  Points that are not on the curve give rows that satisfy the field-operation identities but no meaningful
- * k * P (the reference only ever multiplies decompressed points). */
+ * k * P, or NULL.  The points MUST be on the curve (the reference only ever multiplies decompressed points): the chains double
+ * with the dedicated doubling formulas, which use the curve equation, so for any other (x, y) the rows are meaningless. */
 #define BSX_ED25519_TRACE_COLS 1540
 size_t bsx_ed25519_trace_scratch_bytes(uint32_t n_muls);
 /* The ScalarMul operands of n_sigs signatures, gathered on the device: scalars[2i] = s_i, points[2i] = G, scalars[2i+1] =

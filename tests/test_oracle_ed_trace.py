@@ -193,3 +193,57 @@ def test_kernel_source_on_the_host_reproduces_the_oracle_trace(hc, golden):
                         res.ctypes.data_as(C.c_void_p), tr.ctypes.data_as(C.c_void_p))
     assert np.array_equal(tr, want)
     assert res.tobytes() == b"".join(po.ed_point_bytes(p) for p in results)
+
+
+def _sqrt(a):
+    a %= P
+    if a == 0:
+        return 0
+    if pow(a, (P - 1) // 2, P) != 1:
+        return None
+    r = pow(a, (P + 3) // 8, P)
+    if r * r % P != a:
+        r = r * pow(2, (P - 1) // 4, P) % P
+    return r
+
+
+def _points_with_small_xy(t_max):
+    """curve points with x * y = t for small t: -x^2 + t^2 / x^2 = 1 + d t^2 is a quadratic in x^2"""
+    out = []
+    for t in range(1, t_max):
+        c = (1 + T.D * t * t) % P
+        disc = _sqrt(c * c + 4 * t * t)
+        if disc is None:
+            continue
+        for sgn in (1, -1):
+            x = _sqrt((-c + sgn * disc) * pow(2, P - 2, P))
+            if x:
+                y = t * pow(x, P - 2, P) % P
+                assert (-x * x + y * y - 1 - T.D * x * x * y * y) % P == 0
+                out.append((t, (x, y)))
+                break
+    return out
+
+
+def test_quotient_corner_remainders_below_19(hc):
+    """The kernel-side quotient by p = 2^255 - 19 iterates q <- (N + 19 q) >> 255 and lands one below the quotient when the
+    remainder is smaller than 19 (q* - q) -- always for the exact divisions, never by chance for a product.  Curve points with
+    x * y = t, t = 5, 8, 10, 16, 17 (and 25, 28, 32, 37 on the other side of 19), put such remainders into the products
+    m1 = x1 y1 / m2 = x2 y2 of the first row: kernel source on the host == Python integers on every row, and the independent
+    checker accepts the rows."""
+    rng = np.random.default_rng(19)
+    pts = _points_with_small_xy(40)
+    assert [t for t, _ in pts if t < 19] == [5, 8, 10, 16, 17] and len(pts) >= 8
+    points = [p for _, p in pts]
+    scalars = [int.from_bytes(rng.bytes(32), "little") | 1 for _ in points]
+    n, log_rows = len(scalars), 12
+    want, results = T.ed25519_trace(scalars, points, log_rows)
+    for m, (t, _) in enumerate(pts):
+        assert _val(want, 68 + 92 * 10, 256 * m) == t and _val(want, 68 + 92 * 3, 256 * m) == t   # m1 of the doubling, m2 of the sum
+        assert results[m] == po.ed_mul(scalars[m], points[m])
+    sc, pt = pack(scalars, points)
+    tr = np.zeros((T.COLS, 1 << log_rows), np.uint64)
+    hc.hc_ed25519_trace(sc.ctypes.data_as(C.c_void_p), pt.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(log_rows), None,
+                        tr.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(tr, want)
+    check_trace(tr, scalars, points, [256 * m for m in range(n)] + [256 * m + 1 for m in range(n)])
