@@ -296,3 +296,43 @@ def test_ed25519_trace_of_a_signature_batch_closes_on_the_witness_records(pv):
     assert bool((nxt[36:68][:, inner] == sel[:, inner]).all())
     fin = sel[:, last][:, :2 * n_sig].cpu().numpy().astype(np.uint16).T.copy()      # [mul, 32 limbs] -> 64 bytes little-endian
     assert (fin.view(np.uint8) == want).all()
+
+
+def test_verify_skip_records_to_ed25519_trace(pv):
+    """The EC accelerator of a verify_skip circuit end to end: the reference's 10000 -> 10500 fixture (2 real signatures, 98
+    DUMMY lanes) through bsx_verify_skip, the 200 ScalarMul operands gathered on the device straight from the 240-byte
+    validator records (signature at 32, lane flag at 236, strides BSX_VAL_IN_BYTES) and the 576-byte witness records, the
+    2^16-row trace, and k * P of every multiplication equal to the records' s*G / h*A; the first real and the first DUMMY
+    signature's rows against the oracle."""
+    import json, os
+    import torch
+    from blobstreamx_b200 import inputs as I
+    from oracle import ed_trace as T
+    from oracle import pyoracle as po
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mocha4.json")) as f:
+        golden = json.load(f)
+    k = I.get_skip_inputs(golden["headers"]["10000"], golden["validators"]["10000"], golden["headers"]["10500"],
+                          golden["commits"]["10500"], golden["validators"]["10500"])
+    got = pv.ctx.verify_skip([k])
+    assert got["fail"][0] == 0
+    rec = np.ascontiguousarray(got["ed"][0])                                   # [100, 576]
+    val = np.ascontiguousarray(np.asarray(k["target"]["validators"], np.uint8).reshape(100, 240))
+    active = val[:, 236]
+    assert 0 < int(active.sum()) < 100
+    d_val, d_rec = _ed_dev(pv, val), _ed_dev(pv, rec)
+    d_sc, d_pt = pv.ed25519_trace_operands(d_val[:, 32:96], d_rec, d_val[:, 236])
+    sc, pt = d_sc.cpu().numpy(), d_pt.cpu().numpy()
+    dummy_s = np.frombuffer(po.DUMMY_SIGNATURE[32:], np.uint8)
+    assert (sc[0::2] == np.where(active[:, None] != 0, val[:, 64:96], dummy_s[None, :])).all() and (sc[1::2] == rec[:, 64:96]).all()
+    assert (pt[0::2] == np.frombuffer(po.ed_point_bytes(po.G), np.uint8)).all() and (pt[1::2] == rec[:, 200:264]).all()
+    tr, res = pv.ed25519_trace(d_sc, d_pt, 16)
+    want = np.empty((200, 64), np.uint8)
+    want[0::2], want[1::2] = rec[:, 136:200], rec[:, 296:360]
+    assert (res.cpu().numpy() == want).all()
+    assert bool((tr[1, :51200] == 1).all()) and bool((tr[1, 51200:] == 0).all())
+    first_real, first_dummy = int(np.argmax(active != 0)), int(np.argmax(active == 0))
+    for i in (first_real, first_dummy):
+        ks = [int.from_bytes(sc[2 * i + j].tobytes(), "little") for j in range(2)]
+        ps = [(int.from_bytes(pt[2 * i + j, :32].tobytes(), "little"), int.from_bytes(pt[2 * i + j, 32:].tobytes(), "little")) for j in range(2)]
+        w, _ = T.ed25519_trace(ks, ps, 9)
+        assert (_host(tr[:, 512 * i:512 * (i + 1)]) == w).all()
