@@ -1690,18 +1690,17 @@ def run_trace(args):
 def ed25519_trace_block(args, ctx, pv, dev, peak):
     """Ed25519 scalar-multiplication trace of verify_skip circuits (the EdDSA accelerator): per circuit 100
     signatures = 200 multiplications (s, G), (h, A) -> 2^16 rows x 1540 columns = 807 MB.  `circuits` per step, the multiplications
-    taken from the witness records of bsx_ed25519_batch on synthetic CanonicalVote signatures; oracle-checked on the first
-    two multiplications of the batch (pure-Python restatement: 1 s per multiplication) and, for every multiplication, by
+    taken from the witness records of bsx_ed25519_batch on synthetic CanonicalVote signatures; oracle-checked on one circuit's
+    multiplications (C restatement), on two of them also against the pure-Python one, and, for every multiplication, by
     k * P == the record's s*G / h*A."""
     import torch
     from blobstreamx_b200 import synthetic as S
     from blobstreamx_b200.plonk import ED25519_TRACE_COLS
+    from oracle import cbind as orc
     circuits = args.ed_trace_circuits
     n_sig = 100 * circuits
     pks, sigs, msgs, lens, _ = S.ed25519_batch_inputs(n_sig)
     rec = ctx.ed25519_batch(pks, sigs, msgs, lens)
-    gx = 15112221349535400772501151409588531511454012693041857206046113283949847762202
-    gy = 46316835694926478169428394003475163141307993866256225615783033603165251855960
     n = 2 * n_sig
     want = np.empty((n, 64), np.uint8)
     want[0::2], want[1::2] = rec[:, 136:200], rec[:, 296:360]
@@ -1719,8 +1718,13 @@ def ed25519_trace_block(args, ctx, pv, dev, peak):
         ks = [int.from_bytes(scalars[i].tobytes(), "little") for i in range(2)]
         ps = [(int.from_bytes(points[i, :32].tobytes(), "little"), int.from_bytes(points[i, 32:].tobytes(), "little")) for i in range(2)]
         w, _ = T.ed25519_trace(ks, ps, 9)
-        assert (out[:, :512].cpu().numpy().view(np.uint64) == w).all(), "Ed25519 trace differs from the oracle"
-        checked = "k * P of every multiplication vs the witness records; rows of 2 multiplications vs oracle/ed_trace.py"
+        assert (out[:, :512].cpu().numpy().view(np.uint64) == w).all(), "Ed25519 trace differs from the Python oracle"
+        n_chk = min(n, 200)                                     # one circuit's worth against the C restatement
+        lr = int(np.ceil(np.log2(256 * n_chk)))
+        wc, _ = orc.ed25519_trace(scalars[:n_chk], points[:n_chk], lr, threads=orc.max_threads())
+        assert (out[:, :256 * n_chk].cpu().numpy().view(np.uint64) == wc[:, :256 * n_chk]).all(), "Ed25519 trace differs from the C oracle"
+        checked = (f"k * P of every multiplication vs the witness records; all rows of {n_chk} multiplications vs oracle/ed25519.c, "
+                   "of 2 vs oracle/ed_trace.py")
     # the two kernels apart (events on torch's current stream, the one the calls are issued on)
     lb = ctx._lib
     for _ in range(3):
@@ -1781,11 +1785,10 @@ def ed25519_trace_block(args, ctx, pv, dev, peak):
     alg = 8 * ED25519_TRACE_COLS * (1 << log_rows) + 96 * n
     cpu = None
     if not args.no_cpu:
-        from oracle import ed_trace as T
         t0 = time.perf_counter()
-        T.scalar_mul_rows(int.from_bytes(scalars[2].tobytes(), "little"), (gx, gy))
-        cpu = {"value": 256 / (time.perf_counter() - t0), "unit": "trace rows/s", "cores": 1, "kind": "port",
-               "sample": "one multiplication (256 rows), pure-Python integers (oracle/ed_trace.py)"}
+        orc.ed25519_trace(scalars[:64], points[:64], 14, threads=1)
+        cpu = {"value": 64 * 256 / (time.perf_counter() - t0), "unit": "trace rows/s", "cores": 1, "kind": "port",
+               "sample": "64 multiplications (2^14 rows), the C restatement oracle/ed25519.c orc_ed25519_trace on one thread"}
     return {"metric": "trace rows/sec, Ed25519 scalar-multiplication trace of verify_skip circuits", "value": 256 * n / (ms_pipe * 1e-3), "unit": "rows/s",
             "ms_per_step": ms_pipe, "steps": batches, "gpu_launches": 3 * batches,
             "single_call": {"ms": ms, "rows_per_s": 256 * n / (ms * 1e-3), "GBps": alg / (ms * 1e-3) / 1e9,

@@ -255,6 +255,10 @@ void orc_sha256_trace(const uint32_t *chunks, const uint8_t *end_bits, const uin
                       uint32_t log_rows, uint64_t *trace);
 void orc_sha512_trace(const uint64_t *chunks, const uint8_t *end_bits, const uint8_t *digest_bits, uint32_t n_chunks,
                       uint32_t log_rows, uint64_t *trace);
+/* Ed25519 scalar-multiplication trace (oracle/ed25519.c, restated a second time in Python: oracle/ed_trace.py): columns in
+ * include/bsx.h (BSX_ED25519_TRACE_COLS = 1540); returns 1 (0 = an identity failed to hold, which cannot happen for curve points) */
+int orc_ed25519_trace(const uint8_t *scalars, const uint8_t *points, uint32_t n_muls, uint32_t log_rows, uint8_t *results,
+                      uint64_t *trace, int threads);
 void orc_gl_fri_fold(const uint64_t *in, uint32_t n_in, uint32_t arity_bits, uint64_t beta0, uint64_t beta1, uint64_t *out);
 
 int orc_max_threads(void);

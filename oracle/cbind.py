@@ -578,3 +578,19 @@ def sha512_trace(chunks, end_bits, digest_bits, log_rows: int) -> np.ndarray:
     out = np.zeros((SHA512_TRACE_COLS, 1 << log_rows), np.uint64)
     lib().orc_sha512_trace(_p(c), _p(eb), _p(db), C.c_uint32(len(c)), C.c_uint32(log_rows), _p(out))
     return out
+
+
+ED25519_TRACE_COLS = 1540
+
+
+def ed25519_trace(scalars, points, log_rows: int, threads: int = 1):
+    """scalars [n, 32] u8 little-endian, points [n, 64] u8 (x, y canonical, on the curve) -> (trace [1540, 2^log_rows] u64,
+    results [n, 64] u8 = k * P).  The C restatement (oracle/ed25519.c); oracle/ed_trace.py is the Python-integer one."""
+    sc = np.ascontiguousarray(scalars, np.uint8).reshape(-1, 32)
+    pt = np.ascontiguousarray(points, np.uint8).reshape(-1, 64)
+    out = np.zeros((ED25519_TRACE_COLS, 1 << log_rows), np.uint64)
+    res = np.zeros((len(sc), 64), np.uint8)
+    lib().orc_ed25519_trace.restype = C.c_int
+    ok = lib().orc_ed25519_trace(_p(sc), _p(pt), C.c_uint32(len(sc)), C.c_uint32(log_rows), _p(res), _p(out), C.c_int(threads))
+    assert ok == 1, "orc_ed25519_trace: an operation's identity did not hold (points off the curve?)"
+    return out, res

@@ -310,3 +310,179 @@ void orc_ed25519_batch(uint32_t n, const uint8_t *pks, const uint8_t *sigs, cons
             orc_ed25519_witness(DUMMY_PK, DUMMY_SIG, zero_msg, 32, out + ORC_SIG_OUT_BYTES * (size_t)i);
     }
 }
+
+/* =====================================================================================================================
+ * Ed25519 scalar-multiplication execution trace (EdDSA accelerator) -- the C restatement beside the
+ * Python-integer one (oracle/ed_trace.py, which documents the construction and the layout; columns: include/bsx.h
+ * BSX_ED25519_TRACE_COLS).  Reference: Ed25519Stark::prove, PX/frontend/ecc/curve25519/curta/stark.rs:182-219; the AIR
+ * is starkyx's (un-vendored): layout our own, PARITY UNPINNED.  Deliberately NOT the kernels' way where there is a
+ * choice: affine additions with a field inversion each (the kernels: extended coordinates + batched inversion), results
+ * from the 51-bit-limb field arithmetic above (the kernels: from the integer division), quotients by an exact division
+ * from the LOW end with p^-1 mod 2^64 (the kernels: an iteration from the high end).
+ * ===================================================================================================================== */
+#define EDT_COLS 1540
+#define EDT_OFFSET (1 << 22)
+static const uint64_t P_LIMBS64[4] = {0xffffffffffffffedULL, 0xffffffffffffffffULL, 0xffffffffffffffffULL, 0x7fffffffffffffffULL};
+
+static void fe_limbs16(uint32_t l[16], const fe *a) {
+    uint8_t s[32];
+    fe_tobytes(s, a);
+    for (int i = 0; i < 16; i++) l[i] = (uint32_t)s[2 * i] | ((uint32_t)s[2 * i + 1] << 8);
+}
+static void poly_mac(int64_t V[31], const uint32_t a[16], const uint32_t b[16]) {
+    for (int i = 0; i < 16; i++)
+        for (int j = 0; j < 16; j++) V[i + j] += (int64_t)((uint64_t)a[i] * b[j]);
+}
+/* M = V(2^16) - r >= 0, a multiple of p -> quotient limbs (16 x 16 bits); returns 0 if M is not an exact multiple */
+static int exact_quotient(const int64_t V[31], const uint32_t r[16], uint32_t q16[16]) {
+    /* V(2^16) - r as 9 x 64-bit limbs (two's complement while accumulating) */
+    uint64_t M[9] = {0};
+    __int128 c = 0;
+    int64_t limbs[36] = {0};
+    for (int k = 0; k < 31; k++) limbs[k] = V[k] - (r && k < 16 ? (int64_t)r[k] : 0);
+    for (int k = 0; k < 36; k++) {           /* to 16-bit digits */
+        c += limbs[k];
+        limbs[k] = (int64_t)(c & 0xffff);
+        c >>= 16;
+    }
+    if (c != 0) return 0;
+    for (int k = 0; k < 36; k++) M[k / 4] |= (uint64_t)limbs[k] << (16 * (k % 4));
+    /* p^-1 mod 2^64 by Newton's iteration (p odd) */
+    uint64_t inv = 1;
+    for (int i = 0; i < 6; i++) inv *= 2 - P_LIMBS64[0] * inv;
+    uint64_t q[5];
+    for (int i = 0; i < 5; i++) {
+        q[i] = M[i] * inv;
+        /* M -= q[i] * p << (64 i) */
+        unsigned __int128 borrow = 0, carry = 0;
+        for (int j = 0; j < 4 && i + j < 9; j++) {
+            const unsigned __int128 prod = (unsigned __int128)q[i] * P_LIMBS64[j] + carry;
+            carry = prod >> 64;
+            const unsigned __int128 sub = (unsigned __int128)(uint64_t)prod + borrow;
+            const uint64_t before = M[i + j];
+            M[i + j] = before - (uint64_t)sub;
+            borrow = (sub >> 64) + (before < (uint64_t)sub ? 1 : 0);
+        }
+        for (int j = i + 4; j < 9; j++) {
+            const unsigned __int128 sub = carry + borrow;
+            carry = 0;
+            const uint64_t before = M[j];
+            M[j] = before - (uint64_t)sub;
+            borrow = (sub >> 64) + (before < (uint64_t)sub ? 1 : 0);
+            if (!borrow) break;
+        }
+    }
+    for (int i = 0; i < 9; i++)
+        if (M[i]) return 0;
+    if (q[4] != 0) return 0;                 /* quotient below 2^256 */
+    for (int i = 0; i < 16; i++) q16[i] = (uint32_t)(q[i / 4] >> (16 * (i % 4))) & 0xffff;
+    return 1;
+}
+/* one operation's 92 columns at col (stride = rows per column).  V: left-hand-side polynomial; res: the result limbs
+ * (subtracted from V unless the operation is a division, whose left-hand side already contains it) */
+static int emit_op(int64_t V[31], const uint32_t res[16], int den, uint64_t *col, size_t stride) {
+    uint32_t q[16];
+    if (!exact_quotient(V, den ? NULL : res, q)) return 0;
+    static const uint32_t P16[16] = {0xffed, 0xffff, 0xffff, 0xffff, 0xffff, 0xffff, 0xffff, 0xffff,
+                                     0xffff, 0xffff, 0xffff, 0xffff, 0xffff, 0xffff, 0xffff, 0x7fff};
+    int64_t van[31];
+    for (int k = 0; k < 31; k++) van[k] = V[k] - (!den && k < 16 ? (int64_t)res[k] : 0);
+    for (int i = 0; i < 16; i++)
+        for (int j = 0; j < 16; j++) van[i + j] -= (int64_t)((uint64_t)q[i] * P16[j]);
+    for (int k = 0; k < 16; k++) { col[(size_t)k * stride] = res[k]; col[(size_t)(16 + k) * stride] = q[k]; }
+    int64_t prev = 0;
+    for (int k = 0; k < 30; k++) {
+        const int64_t num = prev - van[k];
+        if (num & 0xffff) return 0;
+        prev = num >> 16;                    /* arithmetic shift of an exact multiple */
+        const int64_t sh = prev + EDT_OFFSET;
+        if (sh < 0 || sh >= ((int64_t)1 << 32)) return 0;
+        col[(size_t)(32 + k) * stride] = (uint64_t)sh & 0xffff;
+        col[(size_t)(62 + k) * stride] = (uint64_t)sh >> 16;
+    }
+    return van[30] == prev;
+}
+/* the eight witnessed operations of (x1, y1) + (x2, y2); the sum leaves in (x3, y3) */
+static int add_rows(const fe *x1, const fe *y1, const fe *x2, const fe *y2, fe *x3, fe *y3, uint64_t *col, size_t stride) {
+    fe d, one, xn, yn, m1, m2, f, df, t, u, den, inv;
+    uint32_t lx1[16], ly1[16], lx2[16], ly2[16], lr[16], la[16], lb[16];
+    int64_t V[31];
+    int ok = 1;
+    fe_frombytes(&d, D_BYTES); fe_1(&one);
+    fe_limbs16(lx1, x1); fe_limbs16(ly1, y1); fe_limbs16(lx2, x2); fe_limbs16(ly2, y2);
+    const size_t op = 92 * stride;
+    /* 0: xn = x1 y2 + x2 y1 */
+    fe_mul(&t, x1, y2); fe_mul(&u, x2, y1); fe_add(&xn, &t, &u); fe_carry(&xn);
+    memset(V, 0, sizeof V); poly_mac(V, lx1, ly2); poly_mac(V, lx2, ly1); fe_limbs16(lr, &xn); ok &= emit_op(V, lr, 0, col, stride);
+    /* 1: yn = y1 y2 + x1 x2 */
+    fe_mul(&t, y1, y2); fe_mul(&u, x1, x2); fe_add(&yn, &t, &u); fe_carry(&yn);
+    memset(V, 0, sizeof V); poly_mac(V, ly1, ly2); poly_mac(V, lx1, lx2); fe_limbs16(lr, &yn); ok &= emit_op(V, lr, 0, col + op, stride);
+    /* 2, 3: m1 = x1 y1, m2 = x2 y2 */
+    fe_mul(&m1, x1, y1);
+    memset(V, 0, sizeof V); poly_mac(V, lx1, ly1); fe_limbs16(lr, &m1); ok &= emit_op(V, lr, 0, col + 2 * op, stride);
+    fe_mul(&m2, x2, y2);
+    memset(V, 0, sizeof V); poly_mac(V, lx2, ly2); fe_limbs16(lr, &m2); ok &= emit_op(V, lr, 0, col + 3 * op, stride);
+    /* 4: f = m1 m2 */
+    fe_mul(&f, &m1, &m2);
+    fe_limbs16(la, &m1); fe_limbs16(lb, &m2);
+    memset(V, 0, sizeof V); poly_mac(V, la, lb); fe_limbs16(lr, &f); ok &= emit_op(V, lr, 0, col + 4 * op, stride);
+    /* 5: df = d f */
+    fe_mul(&df, &d, &f);
+    fe_limbs16(la, &d); fe_limbs16(lb, &f);
+    memset(V, 0, sizeof V); poly_mac(V, la, lb); fe_limbs16(lr, &df); ok &= emit_op(V, lr, 0, col + 5 * op, stride);
+    /* 6: x3 = xn / (1 + df):  df x3 + x3 - xn = carry p */
+    fe_add(&den, &one, &df); fe_carry(&den); fe_invert(&inv, &den); fe_mul(x3, &xn, &inv);
+    fe_limbs16(la, &df); fe_limbs16(lr, x3); fe_limbs16(lb, &xn);
+    memset(V, 0, sizeof V); poly_mac(V, la, lr);
+    for (int k = 0; k < 16; k++) V[k] += (int64_t)lr[k] - (int64_t)lb[k];
+    ok &= emit_op(V, lr, 1, col + 6 * op, stride);
+    /* 7: y3 = yn / (1 - df):  df y3 + yn - y3 = carry p */
+    fe_sub(&den, &one, &df); fe_invert(&inv, &den); fe_mul(y3, &yn, &inv);
+    fe_limbs16(lr, y3); fe_limbs16(lb, &yn);
+    memset(V, 0, sizeof V); poly_mac(V, la, lr);
+    for (int k = 0; k < 16; k++) V[k] += (int64_t)lb[k] - (int64_t)lr[k];
+    ok &= emit_op(V, lr, 1, col + 7 * op, stride);
+    return ok;
+}
+static int mul_rows(const uint8_t *scalar, const fe *px, const fe *py, int real, uint64_t *col0, size_t stride, uint8_t *result) {
+    fe tx = *px, ty = *py, ax, ay, sx, sy, dx, dy;
+    int ok = 1;
+    fe_0(&ax); fe_1(&ay);
+    for (int j = 0; j < 256; j++) {
+        uint64_t *col = col0 + j;
+        const int bit = scalar ? (scalar[j >> 3] >> (j & 7)) & 1 : 0;
+        uint32_t l[16];
+        col[0] = (uint64_t)bit; col[stride] = (uint64_t)real; col[2 * stride] = j == 0; col[3 * stride] = j == 255;
+        fe_limbs16(l, &tx); for (int i = 0; i < 16; i++) col[(size_t)(4 + i) * stride] = l[i];
+        fe_limbs16(l, &ty); for (int i = 0; i < 16; i++) col[(size_t)(20 + i) * stride] = l[i];
+        fe_limbs16(l, &ax); for (int i = 0; i < 16; i++) col[(size_t)(36 + i) * stride] = l[i];
+        fe_limbs16(l, &ay); for (int i = 0; i < 16; i++) col[(size_t)(52 + i) * stride] = l[i];
+        ok &= add_rows(&ax, &ay, &tx, &ty, &sx, &sy, col + 68 * stride, stride);
+        ok &= add_rows(&tx, &ty, &tx, &ty, &dx, &dy, col + (68 + 8 * 92) * stride, stride);
+        if (bit) { ax = sx; ay = sy; }
+        tx = dx; ty = dy;
+    }
+    if (result) { fe_tobytes(result, &ax); fe_tobytes(result + 32, &ay); }
+    return ok;
+}
+/* trace[EDT_COLS][2^log_rows]; results: n_muls x 64 bytes or NULL; returns 1, or 0 if an identity failed to hold (it cannot) */
+int orc_ed25519_trace(const uint8_t *scalars, const uint8_t *points, uint32_t n_muls, uint32_t log_rows, uint8_t *results,
+                      uint64_t *trace, int threads) {
+    const size_t n_rows = (size_t)1 << log_rows;
+    if ((size_t)n_muls * 256 > n_rows || log_rows < 8) return 0;
+    const uint32_t slots = (uint32_t)(n_rows / 256);
+    int ok = 1;
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic) num_threads(threads) reduction(& : ok)
+    for (uint32_t m = 0; m < slots; m++) {
+        fe px, py;
+        if (m < n_muls) {
+            fe_frombytes(&px, points + (size_t)m * 64); fe_frombytes(&py, points + (size_t)m * 64 + 32);
+            ok &= mul_rows(scalars + (size_t)m * 32, &px, &py, 1, trace + (size_t)m * 256, n_rows, results ? results + (size_t)m * 64 : NULL);
+        } else {
+            fe_0(&px); fe_1(&py);
+            ok &= mul_rows(NULL, &px, &py, 0, trace + (size_t)m * 256, n_rows, NULL);
+        }
+    }
+    return ok;
+}

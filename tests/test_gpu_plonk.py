@@ -296,6 +296,10 @@ def test_ed25519_trace_of_a_signature_batch_closes_on_the_witness_records(pv):
     assert bool((nxt[36:68][:, inner] == sel[:, inner]).all())
     fin = sel[:, last][:, :2 * n_sig].cpu().numpy().astype(np.uint16).T.copy()      # [mul, 32 limbs] -> 64 bytes little-endian
     assert (fin.view(np.uint8) == want).all()
+    # the first 2^14 rows (64 multiplications) and the padding tail against the C restatement
+    from oracle import cbind as orc
+    ctr, _ = orc.ed25519_trace(scalars[:64], points[:64], 15, threads=orc.max_threads())
+    assert (_host(tr[:, :1 << 14]) == ctr[:, :1 << 14]).all() and (_host(tr[:, -256:]) == ctr[:, -256:]).all()
 
 
 def test_verify_skip_records_to_ed25519_trace(pv):
@@ -330,6 +334,10 @@ def test_verify_skip_records_to_ed25519_trace(pv):
     want[0::2], want[1::2] = rec[:, 136:200], rec[:, 296:360]
     assert (res.cpu().numpy() == want).all()
     assert bool((tr[1, :51200] == 1).all()) and bool((tr[1, 51200:] == 0).all())
+    # the whole 2^16-row table against the C restatement (oracle/ed25519.c), then two signatures against the Python one
+    from oracle import cbind as orc
+    want_tr, want_res = orc.ed25519_trace(sc, pt, 16, threads=orc.max_threads())
+    assert (want_res == want).all() and (_host(tr) == want_tr).all()
     first_real, first_dummy = int(np.argmax(active != 0)), int(np.argmax(active == 0))
     for i in (first_real, first_dummy):
         ks = [int.from_bytes(sc[2 * i + j].tobytes(), "little") for j in range(2)]

@@ -247,3 +247,27 @@ def test_quotient_corner_remainders_below_19(hc):
                         tr.ctypes.data_as(C.c_void_p))
     assert np.array_equal(tr, want)
     check_trace(tr, scalars, points, [256 * m for m in range(n)] + [256 * m + 1 for m in range(n)])
+
+
+def test_c_restatement_equals_the_python_one(golden):
+    """oracle/ed25519.c orc_ed25519_trace (affine additions with an inversion each, results from 51-bit-limb field arithmetic,
+    quotients by exact division from the low end) == oracle/ed_trace.py (Python divmod) on the edge cases, the quotient-corner
+    points and fixture signatures; then ALL 98 real signatures of the 157001 commit through the C one: s*G and h*A as the pinned
+    signature oracle computes them, rows accepted by the independent checker."""
+    from oracle import cbind as orc
+    rng = np.random.default_rng(23)
+    scalars, points = _cases(rng, 2)
+    corner = [p for _, p in _points_with_small_xy(19)]
+    scalars, points = scalars + [int.from_bytes(rng.bytes(32), "little") | 1 for _ in corner], points + corner
+    fs, fp, _ = _fixture_muls(golden, "10000", 1)
+    scalars, points = scalars + fs, points + fp
+    want, results = T.ed25519_trace(scalars, points, 13)
+    sc, pt = pack(scalars, points)
+    got, res = orc.ed25519_trace(sc, pt, 13, threads=orc.max_threads())
+    assert np.array_equal(got, want) and res.tobytes() == b"".join(po.ed_point_bytes(p) for p in results)
+    scalars, points, want_pts = _fixture_muls(golden, "157001", 98)
+    assert len(scalars) == 196
+    sc, pt = pack(scalars, points)
+    tr, res = orc.ed25519_trace(sc, pt, 16, threads=orc.max_threads())
+    assert res.tobytes() == b"".join(po.ed_point_bytes(p) for p in want_pts)
+    check_trace(tr, scalars, points, list(range(0, 196 * 256, 997)) + [196 * 256 - 1, 196 * 256, 65535])
