@@ -634,7 +634,8 @@ int bsx_sha256_trace_batch_dev(bsx_ctx *ctx, void *stream, const uint32_t *padde
  * carry starkyx-style witnesses (16-bit limbs; quotient `carry`; witness polynomial of the division by x - 2^16).
  * replaces: the trace fill of Ed25519Stark::prove (PX/frontend/ecc/curve25519/curta/stark.rs:182-219, write_trace_instructions
  *   over chunks_par(256)); operations collected at stark.rs:93-124.  The AIR (`scalar_mul_batch`) is starkyx's, un-vendored:
- *   this column assignment is our own and PARITY IS UNPINNED; the CPU restatement is oracle/ed_trace.py, pinned by
+ *   this column assignment is our own and PARITY IS UNPINNED; the CPU restatements are oracle/ed_trace.py (Python integers)
+ *   and oracle/ed25519.c orc_ed25519_trace (C), pinned by
  *   re-checking every operation's polynomial identity, k * P against an independent scalar multiplication and the
  *   mocha-4 fixture signatures' s*G / h*A (tests/test_oracle_ed_trace.py).
  * Row 256 m + j = step j of multiplication m; temp = 2^j P, acc = (k mod 2^j) P; next row: temp' = dbl, acc' = bit ? sum : acc.
