@@ -1673,6 +1673,7 @@ def run_trace(args):
         orc.sha256_trace(hid["padded_chunks"], hid["end_bits"], hid["digest_bits"], log_rows)
         cpu = {"value": 64 * n / (time.perf_counter() - t0), "unit": "trace rows/s", "cores": 1, "kind": "port", "sample": "one map circuit (1246 chunks)"}
     ed = ed25519_trace_block(args, ctx, pv, dev, peak)
+    skip_circuit = skip_circuit_traces_block(args, ctx, pv, dev)
     print(json.dumps({"metric": "trace rows/sec, SHA-256 execution trace of the header_range_1024 map circuits", "value": jobs * 64 * n / (ms * 1e-3),
                       "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "dtype": "u32 -> u64 elements",
                       "data": "synthetic",
@@ -1684,7 +1685,76 @@ def run_trace(args):
                       "roofline": {"kernel": "sha256_trace_kernel", "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": alg // jobs,
                                    "note": "almost write-only; peak = measured COPY bandwidth (read + write): a write-only stream has no read/write turnarounds and can exceed it; all circuits in one grid (one launch per circuit: one_launch_per_circuit_ms)"},
-                      "ed25519_trace": ed, "cpu_baseline": cpu}))
+                      "ed25519_trace": ed, "verify_skip_circuit_traces": skip_circuit, "cpu_baseline": cpu}))
+
+
+def skip_circuit_traces_block(args, ctx, pv, dev):
+    """The three accelerator traces of ONE verify_skip circuit (the reference proves one at a time), request schedule of
+    SURVEY A.5 / A.4: SHA-256 490 requests = 978 chunks -> 2^16 rows x 176 columns, SHA-512 100 requests = 200 chunks -> 2^14
+    rows x 338 columns, EC 200 scalar multiplications -> 2^16 rows x 1540 columns (sizes: SURVEY 'STARK sizes implied')."""
+    import torch
+    from blobstreamx_b200 import synthetic as S
+    from blobstreamx_b200.plonk import ED25519_TRACE_COLS, SHA256_TRACE_COLS, SHA512_TRACE_COLS
+    rng = np.random.default_rng(5)
+    proof = lambda leaf: [(leaf, 0)] + [(65, 0)] * 8                    # A.1: leaf, then both orderings of 4 levels
+    proof_hashed = [(65, 0)] * 8
+    valset = [(64, 1)] * 100 + [(65, 0)] * 127                          # A.3: 100 variable leaves over 64-byte buffers + the tree
+    header = valset + proof(35) + [(64, 1)] + proof_hashed + [(64, 1)] + proof_hashed   # A.4 = 254 requests
+    sched = proof(35) + valset + header                                 # A.5 = 490 requests
+    assert len(sched) == 490
+    sizes = [b for b, _ in sched]
+    kinds = np.array([k for _, k in sched], np.uint8)
+    lens = np.array([int(rng.integers(40, 48)) if k else b for b, k in sched], np.uint32)
+    bufs = rng.integers(0, 256, sum(sizes), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    h256 = ctx.hash_input_data(bufs, offs, lens, kinds)
+    assert len(h256["padded_chunks"]) == 978, len(h256["padded_chunks"])
+    lens512 = (64 + rng.integers(100, 125, 100)).astype(np.uint32)
+    h512 = ctx.hash_input_data(rng.integers(0, 256, 188 * 100, dtype=np.uint8), (np.arange(101) * 188).astype(np.uint32), lens512,
+                               np.ones(100, np.uint8), sha512=True)
+    assert len(h512["padded_chunks"]) == 200
+    pks, sigs, msgs, mlens, act = S.ed25519_batch_inputs(100, inactive_every=50)
+    rec = ctx.ed25519_batch(pks, sigs, msgs, mlens, act)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    a256 = (to(h256["padded_chunks"].view(np.int32)), to(h256["end_bits"]), to(h256["digest_bits"]))
+    a512 = (to(h512["padded_chunks"].view(np.int64)), to(h512["end_bits"]), to(h512["digest_bits"]))
+    d_sig, d_rec, d_act = to(sigs), to(rec), to(act)
+    o256 = torch.empty((SHA256_TRACE_COLS, 1 << 16), dtype=torch.int64, device=dev)
+    oed = torch.empty((ED25519_TRACE_COLS, 1 << 16), dtype=torch.int64, device=dev)
+
+    def one():
+        pv.sha256_trace(*a256, 16, out=o256)
+        t512 = pv.sha512_trace(*a512, 14)
+        sc, pt = pv.ed25519_trace_operands(d_sig, d_rec, d_act)
+        pv.ed25519_trace(sc, pt, 16, out=oed, results=False)
+        return t512
+
+    t512 = one()
+    torch.cuda.synchronize()
+    checked = None
+    if not args.no_check:
+        from oracle import cbind as orc
+        assert (o256.cpu().numpy().view(np.uint64) == orc.sha256_trace(h256["padded_chunks"], h256["end_bits"], h256["digest_bits"], 16)).all()
+        assert (t512.cpu().numpy().view(np.uint64) == orc.sha512_trace(h512["padded_chunks"], h512["end_bits"], h512["digest_bits"], 14)).all()
+        sc, pt = pv.ed25519_trace_operands(d_sig, d_rec, d_act)
+        want, _ = orc.ed25519_trace(sc.cpu().numpy(), pt.cpu().numpy(), 16, threads=orc.max_threads())
+        assert (oed.cpu().numpy().view(np.uint64) == want).all()
+        checked = "all three tables against the C oracle"
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    steps = max(5, min(args.steps, 50))
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    e[0].record()
+    for _ in range(steps):
+        one()
+    e[1].record()
+    torch.cuda.synchronize()
+    ms = e[0].elapsed_time(e[1]) / steps
+    nbytes = 8 * ((SHA256_TRACE_COLS + ED25519_TRACE_COLS) * (1 << 16) + SHA512_TRACE_COLS * (1 << 14))
+    return {"ms_per_circuit": ms, "bytes": nbytes, "GBps": nbytes / (ms * 1e-3) / 1e9, "gpu_launches_per_circuit": 8, "checked": checked,
+            "workload": "one verify_skip circuit: SHA-256 978 chunks -> 2^16 x 176, SHA-512 200 chunks -> 2^14 x 338, EC 200 multiplications "
+                        "(2 DUMMY lanes) -> 2^16 x 1540, operands gathered on the device; one circuit at a time (latency, not the batched rates above)"}
 
 
 def ed25519_trace_block(args, ctx, pv, dev, peak):
