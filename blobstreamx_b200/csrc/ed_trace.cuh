@@ -173,6 +173,41 @@ BSX_HD void edt_limbs(uint32_t *l, const uint32_t *w) {
 // pass gives N >> 255, at most 39 below the quotient; the second lands on it or one below (one below when r < 19 (q* - q), in
 // particular for every exact division); the third pass only forms T = N + 19 q, whose top part tells which, and whose low
 // 255 bits are r or r + p - 2^255.
+// EDT_UNIFIED (default): ONE copy of the operation's code with the kind as a run-time (warp-uniform) argument -- the four
+// template instances are 7.5 k instructions = 120 KB of code for the row kernel, and ncu shows 0.9 instruction-fetch stall
+// cycles per issue; a doubling's x1 y2 + x2 y1 (same operands twice) is one product, doubled.
+#ifndef EDT_UNIFIED
+#define EDT_UNIFIED 1
+#endif
+#if EDT_UNIFIED
+BSX_CALL void edt_op_rt(int KIND, const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *res, uint64_t *col,
+                        size_t n_rows, uint64_t *gcol, size_t grows) {
+    int64_t V[31];
+#pragma unroll
+    for (int i = 0; i < 31; i++) V[i] = 0;
+    const bool twice = KIND == 1 && a1 == a2 && b1 == b2;        // the doubling's inner product: 2 (x y)
+    const int n_prod = (KIND == 1 && !twice) ? 2 : 1;
+#pragma unroll 1
+    for (int p = 0; p < n_prod; p++) {
+        const uint32_t *xa = p ? a2 : a1, *yb = p ? b2 : (KIND >= 2 ? res : b1);
+        uint32_t x[16], y[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { x[i] = xa[i]; y[i] = yb[i]; }
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+#pragma unroll
+            for (int j = 0; j < 16; j++) V[i + j] += (int64_t)((uint64_t)x[i] * y[j]);
+    }
+    if (twice) {
+#pragma unroll
+        for (int i = 0; i < 31; i++) V[i] += V[i];
+    }
+    if (KIND >= 2) {                                             // res (1 + a1) - a2  resp.  a2 - res (1 - a1)
+        const int64_t sg = KIND == 2 ? 1 : -1;
+#pragma unroll
+        for (int k = 0; k < 16; k++) V[k] += sg * ((int64_t)res[k] - (int64_t)a2[k]);
+    }
+#else
 template <int KIND>
 BSX_CALL void edt_op(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *res, uint64_t *col, size_t n_rows,
                      uint64_t *gcol, size_t grows) {
@@ -205,6 +240,7 @@ BSX_CALL void edt_op(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2,
 #pragma unroll
             for (int j = 0; j < 16; j++) V[i + j] += (int64_t)((uint64_t)x[i] * y[j]);
     }
+#endif
     // N = V(2^16) >= 0, below 2^512
     uint32_t N[16];
     {
@@ -316,6 +352,14 @@ BSX_HD void edt_flush(EdtSink &s, int ncols) {
     s.gcol += (size_t)ncols * s.n_rows;
 #endif
 }
+
+#if EDT_UNIFIED
+template <int KIND>
+BSX_HD void edt_op(const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *res, uint64_t *col, size_t n_rows,
+                   uint64_t *gcol, size_t grows) {
+    edt_op_rt(KIND, a1, b1, a2, b2, res, col, n_rows, gcol, grows);
+}
+#endif
 
 // the eight operations of (x1, y1) + (x2, y2) = (x3, y3), x3 / y3 known (the chain's affine values)
 BSX_HD void edt_add_emit(const uint32_t *x1, const uint32_t *y1, const uint32_t *x2, const uint32_t *y2, uint32_t *x3, uint32_t *y3,
