@@ -344,3 +344,27 @@ def test_verify_skip_records_to_ed25519_trace(pv):
         ps = [(int.from_bytes(pt[2 * i + j, :32].tobytes(), "little"), int.from_bytes(pt[2 * i + j, 32:].tobytes(), "little")) for j in range(2)]
         w, _ = T.ed25519_trace(ks, ps, 9)
         assert (_host(tr[:, 512 * i:512 * (i + 1)]) == w).all()
+
+
+def test_ed25519_trace_to_commitment_on_device(pv):
+    """The Ed25519 trace stays on the device into the first commitment of a STARK over it: its 1540 columns are polynomials in
+    the layout the transforms read -- iNTT -> coset LDE (rate 2) -> Poseidon Merkle cap over leaves of 1540 elements, every
+    stage against the CPU restatements (the trace against oracle/ed25519.c).  Which blow-up and cap height starkyx's CurtaConfig
+    uses is not on disk: rate 2 / cap height 4 here, parity unpinned like the rest of the prover loops."""
+    from blobstreamx_b200.plonk import bitrev_indices
+    from oracle import cbind as orc
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(77)
+    scalars = rng.integers(0, 256, (3, 32), dtype=np.uint8)
+    pts = [po.G, po.ed_mul(12345, po.G), po.ed_mul(int.from_bytes(rng.bytes(32), "little"), po.G)]
+    points = np.frombuffer(b"".join(po.ed_point_bytes(p) for p in pts), np.uint8).reshape(3, 64).copy()
+    log_rows = 10
+    tr, _ = pv.ed25519_trace(_ed_dev(pv, scalars), _ed_dev(pv, points), log_rows)
+    want_tr, _ = orc.ed25519_trace(scalars, points, log_rows, threads=orc.max_threads())
+    assert (_host(tr) == want_tr).all()
+    coeffs = pv.ntt(tr, inverse=True, natural_out=True)
+    ext = pv.lde(coeffs, 1)
+    _, cap = pv.merkle_caps(ext, 4)
+    want_ext = orc.gl_lde(orc.gl_ntt(want_tr, inverse=True), 1)[:, bitrev_indices(log_rows + 1)]
+    assert (_host(ext) == want_ext).all()
+    assert (_host(cap) == orc.gl_merkle(np.ascontiguousarray(want_ext.T), 4)[-16:]).all()
