@@ -144,4 +144,10 @@ void hc_ed25519_trace(const uint8_t *scalars, const uint8_t *points, uint32_t n_
     }
     free(chain); free(aff);
 }
+// one witnessed field operation of the trace (ed_trace.cuh edt_op_rt) on arbitrary canonical operands: 92 values out
+// kind 0 mul a1 b1, 1 inner a1 b1 + a2 b2, 2 / 3 division with the given result res (16-bit limbs, 16 each)
+void hc_edt_op(int kind, const uint32_t *a1, const uint32_t *b1, const uint32_t *a2, const uint32_t *b2, uint32_t *res, uint64_t *out92) {
+    bsx::edt::edt_op_rt(kind, a1, b1, a2, b2, res, out92, 1, out92, 1);
 }
+}
+

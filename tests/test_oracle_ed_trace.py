@@ -271,3 +271,46 @@ def test_c_restatement_equals_the_python_one(golden):
     tr, res = orc.ed25519_trace(sc, pt, 16, threads=orc.max_threads())
     assert res.tobytes() == b"".join(po.ed_point_bytes(p) for p in want_pts)
     check_trace(tr, scalars, points, list(range(0, 196 * 256, 997)) + [196 * 256 - 1, 196 * 256, 65535])
+
+
+def test_field_operation_at_operand_extremes(hc):
+    """One witnessed operation (ed_trace.cuh edt_op_rt, host build) on operands at the ends of [0, p): the limb products, the
+    quotient and the witness offset are at their largest for p - 1 everywhere (an inner product of four such operands), at
+    their smallest for 0 / 1; divisions with the matching result.  Every output equals the Python restatement's, whose own
+    assertions bound the witness (0 <= w + 2^22 < 2^32) and whose columns the checker above accepts."""
+    rng = np.random.default_rng(41)
+    ext = [0, 1, 2, 18, 19, P - 1, P - 2, P - 19, 2**255 - 20, 1 << 254, (1 << 255) - (1 << 240), int("55" * 32, 16) % P, int("aa" * 32, 16) % P]
+    vals = ext + [int.from_bytes(rng.bytes(32), "little") % P for _ in range(12)]
+    u32 = C.c_uint32 * 16
+
+    def run(kind, a1, b1, a2, b2, res, alias=False):
+        r = u32(*T.limbs(res))
+        out = (C.c_uint64 * 92)()
+        pa1, pb1 = u32(*T.limbs(a1)), u32(*T.limbs(b1))
+        pa2, pb2 = (pa1, pb1) if alias else (u32(*T.limbs(a2)), u32(*T.limbs(b2)))     # alias: the doubling's x y + x y, computed once
+        hc.hc_edt_op(kind, pa1, pb1, pa2, pb2, r, out)
+        return list(out), sum(int(x) << (16 * i) for i, x in enumerate(r))
+
+    n = 0
+    for i, a in enumerate(vals):
+        for b in (vals[(i * 5 + 1) % len(vals)], vals[(i * 3 + 2) % len(vals)], a, P - 1, 0):
+            want_r, want_cols = T.fp_mul(a, b)
+            cols, r = run(0, a, b, 0, 0, 0)
+            assert cols == want_cols and r == want_r
+            c, d = vals[(i * 7 + 3) % len(vals)], vals[(i + 4) % len(vals)]
+            for (x1, y1, x2, y2) in ((a, b, c, d), (a, b, a, b), (P - 1, P - 1, P - 1, P - 1)):
+                want_r, want_cols = T.fp_inner(x1, y1, x2, y2)
+                cols, r = run(1, x1, y1, x2, y2, 0)
+                assert cols == want_cols and r == want_r
+                if (x1, y1) == (x2, y2):
+                    cols, r = run(1, x1, y1, x2, y2, 0, alias=True)
+                    assert cols == want_cols and r == want_r
+            for plus in (True, False):
+                den = (1 + b) % P if plus else (1 - b) % P
+                if den == 0:
+                    continue
+                want_r, want_cols = T.fp_den(a, b, plus)
+                cols, _ = run(2 if plus else 3, b, 0, a, 0, want_r)
+                assert cols == want_cols
+                n += 1
+    assert n > 200
